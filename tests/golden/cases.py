@@ -1,0 +1,85 @@
+"""Seeded synthetic inputs shared by the golden-vector generator and the parity tests.
+
+Everything is drawn from numpy RandomState (portable across machines/torch builds), so
+the fixtures under tests/golden/ only need to store the REFERENCE OUTPUTS.
+"""
+import numpy as np
+import torch
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+
+
+def disparity_fields(rng, B, H, W, maxd):
+    """The disparity distributions SURVEY.md section 4/8d asks for."""
+    xs = np.arange(W)[None, None, None, :]
+    ys = np.arange(H)[None, None, :, None]
+    return {
+        "uniform": rng.uniform(0, maxd, size=(B, 1, H, W)),
+        "smooth": 0.4 * maxd + 0.2 * maxd * np.sin(2 * np.pi * xs / W) * np.cos(2 * np.pi * ys / H)
+                  + rng.normal(0, 0.25, size=(B, 1, H, W)),
+        "integer": np.floor(rng.uniform(0, maxd, size=(B, 1, H, W))),
+        "negative": -rng.uniform(0, maxd, size=(B, 1, H, W)),
+        "far_oob": rng.uniform(3 * maxd + 3 * W, 5 * maxd + 5 * W, size=(B, 1, H, W)),
+        "edge": rng.choice([-4.5, -0.25, 0.0, 0.5, maxd - 1.0, maxd - 0.5, maxd + 3.75, W - 1.0, W - 0.5],
+                           size=(B, 1, H, W)),
+    }
+
+
+def raft_corr_case(seed=1, B=2, D=16, H=5, W=23, L=4):
+    rng = np.random.RandomState(seed)
+    f1 = _t(rng.standard_normal((B, D, H, W)))
+    f2 = _t(rng.standard_normal((B, D, H, W)))
+    disps = {k: _t(v) for k, v in disparity_fields(rng, B, H, W, 12).items()}
+    return dict(f1=f1, f2=f2, L=L, r=4, disps=disps)
+
+
+def igev_geo_case(seed=2, B=2, D=24, H=4, W=20, G=8, Dg=16, L=2):
+    rng = np.random.RandomState(seed)
+    f1 = _t(rng.standard_normal((B, D, H, W)))
+    f2 = _t(rng.standard_normal((B, D, H, W)))
+    geo = _t(rng.standard_normal((B, G, Dg, H, W)))
+    disps = {k: _t(v) for k, v in disparity_fields(rng, B, H, W, Dg).items()}
+    return dict(f1=f1, f2=f2, geo=geo, L=L, r=4, disps=disps)
+
+
+def gwc_cases():
+    out = {}
+    for name, (seed, B, C, H, W, maxd, G) in {
+        "small_wide_disp": (3, 2, 24, 3, 11, 16, 8),     # maxdisp > W: empty slices (submodule.py:266)
+        "igev_shape": (4, 1, 96, 4, 40, 48, 8),
+        "odd": (5, 2, 32, 2, 17, 7, 4),
+    }.items():
+        rng = np.random.RandomState(seed)
+        out[name] = dict(left=_t(rng.standard_normal((B, C, H, W))),
+                         right=_t(rng.standard_normal((B, C, H, W))), maxdisp=maxd, groups=G)
+    return out
+
+
+def update_block_case(family, seed=6, B=1, H=8, W=12, hidden=128):
+    """net/inp at 1/4, 1/8, 1/16 (sizes follow the reference encoder's stride-2 convs:
+    ceil halves), corr features and disparity."""
+    rng = np.random.RandomState(seed + (0 if family == "igev" else 100))
+    cor_planes = 162 if family == "igev" else 36
+    sizes = [(H, W), ((H + 1) // 2, (W + 1) // 2), (((H + 1) // 2 + 1) // 2, ((W + 1) // 2 + 1) // 2)]
+    net = [_t(np.tanh(rng.standard_normal((B, hidden, h, w)))) for h, w in sizes]
+    inp = [[_t(0.5 * rng.standard_normal((B, hidden, h, w))) for _ in range(3)] for h, w in sizes]
+    corr = _t(rng.standard_normal((B, cor_planes, H, W)))
+    disp = _t(rng.uniform(0, 10, size=(B, 1, H, W)))
+    return dict(net=net, inp=inp, corr=corr, disp=disp, cor_planes=cor_planes)
+
+
+def loop_case(family, seed=7, B=1, H=16, W=24, hidden=128):
+    rng = np.random.RandomState(seed + (0 if family == "igev" else 100))
+    D = 96 if family == "igev" else 256
+    f1 = _t(rng.standard_normal((B, D, H, W)) / np.sqrt(D) * 2.0)
+    f2 = _t(rng.standard_normal((B, D, H, W)) / np.sqrt(D) * 2.0)
+    sizes = [(H, W), ((H + 1) // 2, (W + 1) // 2), (((H + 1) // 2 + 1) // 2, ((W + 1) // 2 + 1) // 2)]
+    net = [_t(np.tanh(rng.standard_normal((B, hidden, h, w)))) for h, w in sizes]
+    inp = [[_t(0.5 * rng.standard_normal((B, hidden, h, w))) for _ in range(3)] for h, w in sizes]
+    case = dict(f1=f1, f2=f2, net=net, inp=inp, cor_planes=162 if family == "igev" else 36)
+    if family == "igev":
+        case["geo"] = _t(rng.standard_normal((B, 8, 12, H, W)))
+        case["init_disp"] = _t(rng.uniform(0, 11, size=(B, 1, H, W)))
+    return case
