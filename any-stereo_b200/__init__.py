@@ -1,0 +1,29 @@
+"""anystereo_b200 -- B200-native (sm_100a) implementation of Any-Stereo's iterative cost-volume hot path.
+
+The public names are the reference's operator surface:
+
+    CorrBlock1D                    models/corePrune_RAFT/geometry.py
+    Combined_Geo_Encoding_Volume   models/coreContinuous_IGEV/geometry.py
+    build_gwc_volume               models/coreContinuous_IGEV/submodule.py
+    corr_sampler.forward/backward  sampler/ (pybind module `corr_sampler`)
+    BasicMultiUpdateBlock          models/*/update.py
+
+Everything computes in hand-written CUDA kernels behind the C ABI of include/anystereo_b200.h
+(csrc/libanystereo_b200.so).  There is no CPU path: importing works anywhere, calling needs a B200.
+"""
+from . import _lib
+from . import corr_sampler
+from .geometry import CorrBlock1D, Combined_Geo_Encoding_Volume, set_corr_mode, get_corr_mode
+from .submodule import build_gwc_volume
+from .update import (BasicMultiUpdateBlock, BasicMultiUpdateBlockRAFT, BasicMotionEncoder, ConvGRU, DispHead,
+                     set_update_engine, get_update_engine)
+from .hotpath import igev_iterations, raft_iterations, install_into_reference, HotLoopGraph
+from .parallel import shard_pairs, allreduce_gradients
+
+__all__ = [
+    "CorrBlock1D", "Combined_Geo_Encoding_Volume", "build_gwc_volume", "corr_sampler",
+    "BasicMultiUpdateBlock", "BasicMultiUpdateBlockRAFT", "BasicMotionEncoder", "ConvGRU", "DispHead",
+    "set_corr_mode", "get_corr_mode", "set_update_engine", "get_update_engine",
+    "igev_iterations", "raft_iterations", "install_into_reference", "HotLoopGraph",
+    "shard_pairs", "allreduce_gradients",
+]

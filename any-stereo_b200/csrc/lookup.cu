@@ -1,0 +1,514 @@
+// a3 / a4: per-iteration radius lookups over the correlation pyramid (RAFT) and over the combined
+// geometry-encoding + correlation pyramids (IGEV), forward and adjoint.
+//
+// Reference behaviour: CorrBlock1D.__call__ (models/corePrune_RAFT/geometry.py:24-43),
+// Combined_Geo_Encoding_Volume.__call__ (models/coreContinuous_IGEV/geometry.py:34-60), both through
+// bilinear_sampler -> F.grid_sample (models/*/utils/utils.py:59-72); index math as in
+// sampler/sampler_kernel.cu:39-58.
+//
+// B200 design (HBM-bound kernels):
+//  * ONE launch per iteration produces the final [B,C,H,W] tensor for all levels (the reference runs
+//    ~20-40 small torch kernels and 1 host sync per level per sampler).
+//  * Every pixel needs a private, data-dependent window of its own pyramid row, so lane=pixel loads are
+//    32-lines-per-request.  Instead a CTA loads the windows of P consecutive pixels with 128-bit loads in
+//    which neighbouring lanes cover the SAME pixel's window (sector-exact traffic), transposes them
+//    through shared memory (conflict-free strides), and then lane=pixel threads interpolate and write
+//    each output channel as full 128-byte lines.
+//  * The geometry pyramid is stored [pixel][disparity][group] (see pyramid.cu) so the (2r+2) taps x 8
+//    groups of one pixel are ONE contiguous, 32-byte aligned 320-byte run: zero sector waste.
+#include "common.cuh"
+
+namespace {
+
+struct LevelSet {
+  const float* ptr[AS_MAX_LEVELS];
+  int width[AS_MAX_LEVELS];
+  int pitch[AS_MAX_LEVELS];
+};
+struct LevelSetRW {
+  float* ptr[AS_MAX_LEVELS];
+  int width[AS_MAX_LEVELS];
+  int pitch[AS_MAX_LEVELS];
+};
+
+__device__ __forceinline__ void split_pos(float x, int r, int& t0, float& f) {
+  const float fl = floorf(x);
+  f = x - fl;                                                   // sampler_kernel.cu:42
+  t0 = (int)fminf(fmaxf(fl, -1.0e6f), 1.0e6f) - r;              // sampler_kernel.cu:47 (clamped: far OOB)
+}
+
+__device__ __forceinline__ float level_scale(int l) { return __int_as_float((127 - l) << 23); }  // 2^-l
+
+// ------------------------------------------------------------------------------------------------
+// RAFT: correlation pyramid only
+// ------------------------------------------------------------------------------------------------
+constexpr int kRP = 128;   // pixels per CTA
+constexpr int kRSP = 130;  // smem row stride (floats): 4*kRSP % 32 == 8 -> conflict-free transposing stores
+
+__global__ void __launch_bounds__(kRP) corr_lookup_fwd_kernel(LevelSet lv, int L, const float* __restrict__ disp,
+                                                              const float* __restrict__ coords,
+                                                              float* __restrict__ out, int HW, int W, int r,
+                                                              int NV) {
+  extern __shared__ __align__(16) float s_win[];  // [L][4*NV][kRSP]
+  __shared__ int s_t0[AS_MAX_LEVELS][kRP];
+  __shared__ float s_f[AS_MAX_LEVELS][kRP];
+  const int tid = threadIdx.x;
+  const int b = blockIdx.y;
+  const int p0 = blockIdx.x * kRP;
+  const long long nbase = (long long)b * HW;
+  {
+    const int p = p0 + tid;
+    float d = 0.f, c = 0.f;
+    if (p < HW) {
+      d = disp[nbase + p];
+      c = coords ? coords[nbase + p] : (float)(p % W);
+    }
+    for (int l = 0; l < L; ++l) {
+      const float sc = level_scale(l);
+      int t0; float f;
+      split_pos(c * sc - d * sc, r, t0, f);   // geometry.py:35 (coords/2^i - disp/2^i)
+      s_t0[l][tid] = t0;
+      s_f[l][tid] = f;
+    }
+  }
+  __syncthreads();
+
+  // phase 1: 128-bit window loads; lanes = 8 pixels x 4 quads (NV==4) -> transposed smem
+  const int items = L * kRP * NV;
+  for (int i0 = tid; i0 < items; i0 += kRP * 4) {
+    float4 v[4];
+    int dst[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int item = i0 + u * kRP;
+      dst[u] = -1;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (item < items) {
+        const int q = item % NV;
+        const int rest = item / NV;
+        const int pix = rest % kRP;
+        const int l = rest / kRP;
+        const int p = p0 + pix;
+        dst[u] = (l * 4 * NV + q * 4) * kRSP + pix;
+        const int c0 = as_floor4(s_t0[l][pix]) * 4 + q * 4;
+        if (p < HW && c0 >= 0 && c0 < lv.pitch[l])
+          v[u] = __ldg(reinterpret_cast<const float4*>(lv.ptr[l] + (nbase + p) * lv.pitch[l] + c0));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (dst[u] >= 0) {
+        s_win[dst[u]] = v[u].x;
+        s_win[dst[u] + kRSP] = v[u].y;
+        s_win[dst[u] + 2 * kRSP] = v[u].z;
+        s_win[dst[u] + 3 * kRSP] = v[u].w;
+      }
+    }
+  }
+  __syncthreads();
+
+  // phase 2: lane = pixel
+  const int p = p0 + tid;
+  if (p >= HW) return;
+  const int K = 2 * r + 1;
+  float* o = out + (long long)b * L * K * HW + p;
+  for (int l = 0; l < L; ++l) {
+    const int t0 = s_t0[l][tid];
+    const float f = s_f[l][tid], omf = 1.0f - f;
+    const int off = t0 - as_floor4(t0) * 4;
+    const float* w = s_win + (l * 4 * NV + off) * kRSP + tid;
+    const int Wl = lv.width[l];
+    float prev = (t0 >= 0 && t0 < Wl) ? w[0] : 0.f;
+    for (int k = 0; k < K; ++k) {
+      const int x1 = t0 + k + 1;
+      const float cur = (x1 >= 0 && x1 < Wl) ? w[(k + 1) * kRSP] : 0.f;
+      o[(long long)(l * K + k) * HW] = prev * omf + cur * f;
+      prev = cur;
+    }
+  }
+}
+
+// adjoint w.r.t. the levels; one thread per (pixel, level); rows are pixel-private -> no atomics
+__global__ void corr_lookup_bwd_kernel(LevelSetRW lv, int L, const float* __restrict__ disp,
+                                       const float* __restrict__ coords, const float* __restrict__ gout,
+                                       int HW, int W, int r, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int l = (int)(idx / ((long long)total / L));
+  const long long n = idx - (long long)l * (total / L);
+  const int b = (int)(n / HW);
+  const int p = (int)(n - (long long)b * HW);
+  const float d = disp[n];
+  const float c = coords ? coords[n] : (float)(p % W);
+  const float sc = level_scale(l);
+  int t0; float f;
+  split_pos(c * sc - d * sc, r, t0, f);
+  const float omf = 1.0f - f;
+  const int K = 2 * r + 1;
+  const float* g = gout + ((long long)b * L * K + (long long)l * K) * HW + p;
+  float* row = lv.ptr[l] + n * lv.pitch[l];
+  const int Wl = lv.width[l];
+  float gm1 = 0.f;
+  for (int j = 0; j <= K; ++j) {
+    const float g0 = (j < K) ? g[(long long)j * HW] : 0.f;
+    const int x1 = t0 + j;
+    if (x1 >= 0 && x1 < Wl) row[x1] += gm1 * f + g0 * omf;   // sampler_kernel.cu:90-103
+    gm1 = g0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// IGEV: geometry volume (8 groups) + correlation, fast path G == 8, r == 4
+// ------------------------------------------------------------------------------------------------
+constexpr int kGP = 64;    // pixels per CTA
+constexpr int kGT = 192;   // threads per CTA (6 warps)
+constexpr int kGSP = 66;   // smem row stride: 4*66 % 32 == 8
+constexpr int kG = 8, kR = 4, kTaps = 10, kK = 9;
+
+template <int L>
+__global__ void __launch_bounds__(kGT) geo_lookup_fwd_kernel(LevelSet geo, int Dg, LevelSet corr,
+                                                             const float* __restrict__ disp,
+                                                             const float* __restrict__ coords,
+                                                             float* __restrict__ out, int HW, int W) {
+  extern __shared__ __align__(16) float smem[];
+  float* s_geo = smem;                                   // [L][kTaps*kG = 80][kGSP]
+  float* s_cor = smem + L * kTaps * kG * kGSP;           // [L][16][kGSP]
+  __shared__ int s_tg[L][kGP], s_tc[L][kGP];
+  __shared__ float s_fg[L][kGP], s_fc[L][kGP];
+
+  const int tid = threadIdx.x;
+  const int b = blockIdx.y;
+  const int p0 = blockIdx.x * kGP;
+  const long long nbase = (long long)b * HW;
+
+  if (tid < kGP) {
+    const int p = p0 + tid;
+    float d = 0.f, c = 0.f;
+    if (p < HW) {
+      d = disp[nbase + p];
+      c = coords ? coords[nbase + p] : (float)(p % W);
+    }
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+      const float sc = level_scale(l);
+      int t0; float f;
+      split_pos(d * sc, kR, t0, f);                 // geometry.py:43  x0 = dx + disp/2^i
+      s_tg[l][tid] = t0; s_fg[l][tid] = f;
+      split_pos(c * sc - d * sc, kR, t0, f);        // geometry.py:52
+      s_tc[l][tid] = t0; s_fc[l][tid] = f;
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 1: window loads.  A warp instruction covers 8 pixels x 4 consecutive 16-byte chunks.
+  const int warp = tid >> 5, lane = tid & 31;
+  const int pix8 = lane >> 2, q4 = lane & 3;
+  constexpr int kGeoJobs = L * (kGP / 8) * 5;    // (level, pixel-group, chunk-quad): 20 chunks/pixel
+  constexpr int kCorJobs = L * (kGP / 8);        // 4 chunks/pixel
+  constexpr int kJobs = kGeoJobs + kCorJobs;
+  constexpr int kWarps = kGT / 32;
+  constexpr int kPerWarp = (kJobs + kWarps - 1) / kWarps;
+  float4 v[kPerWarp];
+  int dst[kPerWarp];
+#pragma unroll
+  for (int i = 0; i < kPerWarp; ++i) {
+    const int job = warp + i * kWarps;
+    dst[i] = -1;
+    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (job < kGeoJobs) {
+      const int l = job / ((kGP / 8) * 5);
+      const int rem = job - l * ((kGP / 8) * 5);
+      const int pg = rem / 5, qq = rem - pg * 5;
+      const int pix = pg * 8 + pix8;
+      const int q = qq * 4 + q4;            // chunk 0..19 : tap j = q>>1, groups (q&1)*4..+3
+      const int p = p0 + pix;
+      const int Dl = Dg >> l;
+      const int x1 = s_tg[l][pix] + (q >> 1);
+      dst[i] = (l * kTaps * kG + q * 4) * kGSP + pix;
+      if (p < HW && x1 >= 0 && x1 < Dl)
+        v[i] = as_ldg_stream(reinterpret_cast<const float4*>(geo.ptr[l] + ((nbase + p) * Dl + x1) * kG + (q & 1) * 4));
+    } else if (job < kJobs) {
+      const int cj = job - kGeoJobs;
+      const int l = cj / (kGP / 8);
+      const int pg = cj - l * (kGP / 8);
+      const int pix = pg * 8 + pix8;
+      const int p = p0 + pix;
+      const int c0 = as_floor4(s_tc[l][pix]) * 4 + q4 * 4;
+      dst[i] = -2 - ((l * 16 + q4 * 4) * kGSP + pix);
+      if (p < HW && c0 >= 0 && c0 < corr.pitch[l])
+        v[i] = as_ldg_stream(reinterpret_cast<const float4*>(corr.ptr[l] + (nbase + p) * corr.pitch[l] + c0));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kPerWarp; ++i) {
+    if (dst[i] != -1) {
+      float* s = dst[i] >= 0 ? (s_geo + dst[i]) : (s_cor + (-2 - dst[i]));
+      s[0] = v[i].x; s[kGSP] = v[i].y; s[2 * kGSP] = v[i].z; s[3 * kGSP] = v[i].w;
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: lane = pixel; 3 thread groups share the 9*L (group|corr) rows
+  const int pix = tid & (kGP - 1);
+  const int part = tid / kGP;          // 0..2
+  const int p = p0 + pix;
+  if (p >= HW) return;
+  constexpr int C = L * (kG + 1) * kK;
+  float* o = out + (long long)b * C * HW + p;
+#pragma unroll
+  for (int l = 0; l < L; ++l) {
+    for (int g = part; g <= kG; g += kGT / kGP) {
+      if (g < kG) {
+        const int t0 = s_tg[l][pix];
+        const float f = s_fg[l][pix], omf = 1.0f - f;
+        const int Dl = Dg >> l;
+        const float* w = s_geo + (l * kTaps * kG + g) * kGSP + pix;
+        float* oc = o + (long long)(l * (kG + 1) * kK + g * kK) * HW;
+        float prev = (t0 >= 0 && t0 < Dl) ? w[0] : 0.f;
+#pragma unroll
+        for (int k = 0; k < kK; ++k) {
+          const int x1 = t0 + k + 1;
+          const float cur = (x1 >= 0 && x1 < Dl) ? w[(k + 1) * kG * kGSP] : 0.f;
+          oc[(long long)k * HW] = prev * omf + cur * f;
+          prev = cur;
+        }
+      } else {
+        const int t0 = s_tc[l][pix];
+        const float f = s_fc[l][pix], omf = 1.0f - f;
+        const int Wl = corr.width[l];
+        const int off = t0 - as_floor4(t0) * 4;
+        const float* w = s_cor + (l * 16 + off) * kGSP + pix;
+        float* oc = o + (long long)(l * (kG + 1) * kK + kG * kK) * HW;
+        float prev = (t0 >= 0 && t0 < Wl) ? w[0] : 0.f;
+#pragma unroll
+        for (int k = 0; k < kK; ++k) {
+          const int x1 = t0 + k + 1;
+          const float cur = (x1 >= 0 && x1 < Wl) ? w[(k + 1) * kGSP] : 0.f;
+          oc[(long long)k * HW] = prev * omf + cur * f;
+          prev = cur;
+        }
+      }
+    }
+  }
+}
+
+// generic (any G, radius, L): one thread per (pixel, level, row) with row in [0,G] (G = the corr row)
+__global__ void geo_lookup_fwd_generic_kernel(LevelSet geo, int G, int Dg, LevelSet corr, int L,
+                                              const float* __restrict__ disp, const float* __restrict__ coords,
+                                              float* __restrict__ out, int HW, int W, int r, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const long long N = total / ((long long)L * (G + 1));
+  const long long n = idx % N;
+  const int rest = (int)(idx / N);
+  const int g = rest % (G + 1);
+  const int l = rest / (G + 1);
+  const int b = (int)(n / HW);
+  const int p = (int)(n - (long long)b * HW);
+  const float d = disp[n];
+  const float c = coords ? coords[n] : (float)(p % W);
+  const float sc = level_scale(l);
+  const int K = 2 * r + 1;
+  int t0; float f;
+  const float* base; int stride, limit;
+  if (g < G) {
+    split_pos(d * sc, r, t0, f);
+    limit = Dg >> l;
+    base = geo.ptr[l] + n * limit * G + g;
+    stride = G;
+  } else {
+    split_pos(c * sc - d * sc, r, t0, f);
+    limit = corr.width[l];
+    base = corr.ptr[l] + n * corr.pitch[l];
+    stride = 1;
+  }
+  const float omf = 1.0f - f;
+  float* o = out + ((long long)b * L * (G + 1) * K + (long long)(l * (G + 1) + g) * K) * HW + p;
+  float prev = (t0 >= 0 && t0 < limit) ? base[(long long)t0 * stride] : 0.f;
+  for (int k = 0; k < K; ++k) {
+    const int x1 = t0 + k + 1;
+    const float cur = (x1 >= 0 && x1 < limit) ? base[(long long)x1 * stride] : 0.f;
+    o[(long long)k * HW] = prev * omf + cur * f;
+    prev = cur;
+  }
+}
+
+__global__ void geo_lookup_bwd_kernel(LevelSetRW ggeo, int G, int Dg, LevelSetRW gcorr, int L,
+                                      const float* __restrict__ disp, const float* __restrict__ coords,
+                                      const float* __restrict__ gout, int HW, int W, int r, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const long long N = total / ((long long)L * (G + 1));
+  const long long n = idx % N;
+  const int rest = (int)(idx / N);
+  const int g = rest % (G + 1);
+  const int l = rest / (G + 1);
+  const int b = (int)(n / HW);
+  const int p = (int)(n - (long long)b * HW);
+  const float d = disp[n];
+  const float c = coords ? coords[n] : (float)(p % W);
+  const float sc = level_scale(l);
+  const int K = 2 * r + 1;
+  int t0; float f;
+  float* base; int stride, limit;
+  if (g < G) {
+    split_pos(d * sc, r, t0, f);
+    limit = Dg >> l;
+    base = ggeo.ptr[l] + n * limit * G + g;
+    stride = G;
+  } else {
+    split_pos(c * sc - d * sc, r, t0, f);
+    limit = gcorr.width[l];
+    base = gcorr.ptr[l] + n * gcorr.pitch[l];
+    stride = 1;
+  }
+  const float omf = 1.0f - f;
+  const float* go = gout + ((long long)b * L * (G + 1) * K + (long long)(l * (G + 1) + g) * K) * HW + p;
+  float gm1 = 0.f;
+  for (int j = 0; j <= K; ++j) {
+    const float g0 = (j < K) ? go[(long long)j * HW] : 0.f;
+    const int x1 = t0 + j;
+    if (x1 >= 0 && x1 < limit) base[(long long)x1 * stride] += gm1 * f + g0 * omf;
+    gm1 = g0;
+  }
+}
+
+__global__ void lookup_taps_kernel(const float* __restrict__ disp, const float* __restrict__ coords, int HW,
+                                   int W, int r, int level, int kind, int32_t* __restrict__ tap0,
+                                   float* __restrict__ frac, long long N) {
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int p = (int)(n % HW);
+  const float d = disp[n];
+  const float c = coords ? coords[n] : (float)(p % W);
+  const float sc = level_scale(level);
+  int t0; float f;
+  split_pos(kind == 0 ? d * sc : c * sc - d * sc, r, t0, f);
+  tap0[n] = t0;
+  frac[n] = f;
+}
+
+int fill_levels(LevelSet& ls, const float* const* ptrs, const int* widths, const int* pitches, int L) {
+  for (int l = 0; l < L; ++l) {
+    if (!ptrs[l] || widths[l] < 0 || pitches[l] < widths[l]) return AS_ERR_BAD_ARG;
+    if ((pitches[l] & 3) || !as_aligned16(ptrs[l])) return AS_ERR_ALIGNMENT;
+    ls.ptr[l] = ptrs[l];
+    ls.width[l] = widths[l];
+    ls.pitch[l] = pitches[l];
+  }
+  return AS_OK;
+}
+
+}  // namespace
+
+extern "C" int as_corr_lookup_fwd(const float* const* levels, const int* widths, const int* pitches,
+                                  int num_levels, const float* disp, const float* coords, float* out, int B,
+                                  int H, int W, int radius, as_stream_t stream) {
+  if (!levels || !widths || !pitches || !disp || !out) return AS_ERR_BAD_ARG;
+  if (num_levels < 1 || num_levels > AS_MAX_LEVELS || B <= 0 || H <= 0 || W <= 0 || radius < 0) return AS_ERR_BAD_ARG;
+  if (B > 65535 || radius > 15) return AS_ERR_UNSUPPORTED;
+  LevelSet ls{};
+  int rc = fill_levels(ls, levels, widths, pitches, num_levels);
+  if (rc != AS_OK) return rc;
+  const int HW = H * W;
+  const int NV = (2 * radius + 5 + 3) / 4;
+  const size_t smem = sizeof(float) * num_levels * 4 * NV * kRSP;
+  if (smem > 200 * 1024) return AS_ERR_UNSUPPORTED;
+  cudaError_t e = cudaFuncSetAttribute(corr_lookup_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  dim3 grid(as_ceil_div(HW, kRP), B);
+  corr_lookup_fwd_kernel<<<grid, kRP, smem, as_cu(stream)>>>(ls, num_levels, disp, coords, out, HW, W, radius, NV);
+  AS_RETURN_IF_LAUNCH_FAILED();
+  return AS_OK;
+}
+
+extern "C" int as_corr_lookup_bwd(float* const* g_levels, const int* widths, const int* pitches, int num_levels,
+                                  const float* disp, const float* coords, const float* g_out, int B, int H,
+                                  int W, int radius, as_stream_t stream) {
+  if (!g_levels || !widths || !pitches || !disp || !g_out) return AS_ERR_BAD_ARG;
+  if (num_levels < 1 || num_levels > AS_MAX_LEVELS || B <= 0 || H <= 0 || W <= 0 || radius < 0) return AS_ERR_BAD_ARG;
+  LevelSetRW ls{};
+  for (int l = 0; l < num_levels; ++l) {
+    if (!g_levels[l] || pitches[l] < widths[l]) return AS_ERR_BAD_ARG;
+    ls.ptr[l] = g_levels[l]; ls.width[l] = widths[l]; ls.pitch[l] = pitches[l];
+  }
+  const long long total = (long long)B * H * W * num_levels;
+  corr_lookup_bwd_kernel<<<(unsigned)as_ceil_div_ll(total, 256), 256, 0, as_cu(stream)>>>(
+      ls, num_levels, disp, coords, g_out, H * W, W, radius, total);
+  AS_RETURN_IF_LAUNCH_FAILED();
+  return AS_OK;
+}
+
+extern "C" int as_geo_lookup_fwd(const float* const* geo_levels, int G, int Dg, const float* const* corr_levels,
+                                 const int* corr_widths, const int* corr_pitches, int num_levels,
+                                 const float* disp, const float* coords, float* out, int B, int H, int W,
+                                 int radius, as_stream_t stream) {
+  if (!geo_levels || !corr_levels || !corr_widths || !corr_pitches || !disp || !out) return AS_ERR_BAD_ARG;
+  if (num_levels < 1 || num_levels > AS_MAX_LEVELS || B <= 0 || H <= 0 || W <= 0 || radius < 0 || G < 1 || Dg < 1)
+    return AS_ERR_BAD_ARG;
+  if (B > 65535) return AS_ERR_UNSUPPORTED;
+  LevelSet cs{}, gs{};
+  int rc = fill_levels(cs, corr_levels, corr_widths, corr_pitches, num_levels);
+  if (rc != AS_OK) return rc;
+  for (int l = 0; l < num_levels; ++l) {
+    if (!geo_levels[l]) return AS_ERR_BAD_ARG;
+    if (!as_aligned16(geo_levels[l])) return AS_ERR_ALIGNMENT;
+    gs.ptr[l] = geo_levels[l]; gs.width[l] = Dg >> l; gs.pitch[l] = (Dg >> l) * G;
+  }
+  const int HW = H * W;
+  cudaStream_t st = as_cu(stream);
+  if (G == kG && radius == kR && num_levels <= 4) {
+    dim3 grid(as_ceil_div(HW, kGP), B);
+    const size_t smem = sizeof(float) * num_levels * (kTaps * kG + 16) * kGSP;
+#define AS_LAUNCH_GEO(LV)                                                                                      \
+  case LV: {                                                                                                   \
+    cudaError_t e = cudaFuncSetAttribute(geo_lookup_fwd_kernel<LV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         (int)smem);                                                           \
+    if (e != cudaSuccess) return (int)e;                                                                       \
+    geo_lookup_fwd_kernel<LV><<<grid, kGT, smem, st>>>(gs, Dg, cs, disp, coords, out, HW, W);                  \
+  } break;
+    switch (num_levels) {
+      AS_LAUNCH_GEO(1)
+      AS_LAUNCH_GEO(2)
+      AS_LAUNCH_GEO(3)
+      AS_LAUNCH_GEO(4)
+    }
+#undef AS_LAUNCH_GEO
+  } else {
+    const long long total = (long long)B * HW * num_levels * (G + 1);
+    geo_lookup_fwd_generic_kernel<<<(unsigned)as_ceil_div_ll(total, 256), 256, 0, st>>>(
+        gs, G, Dg, cs, num_levels, disp, coords, out, HW, W, radius, total);
+  }
+  AS_RETURN_IF_LAUNCH_FAILED();
+  return AS_OK;
+}
+
+extern "C" int as_geo_lookup_bwd(float* const* g_geo_levels, int G, int Dg, float* const* g_corr_levels,
+                                 const int* corr_widths, const int* corr_pitches, int num_levels,
+                                 const float* disp, const float* coords, const float* g_out, int B, int H,
+                                 int W, int radius, as_stream_t stream) {
+  if (!g_geo_levels || !g_corr_levels || !corr_widths || !corr_pitches || !disp || !g_out) return AS_ERR_BAD_ARG;
+  if (num_levels < 1 || num_levels > AS_MAX_LEVELS || B <= 0 || H <= 0 || W <= 0 || radius < 0 || G < 1 || Dg < 1)
+    return AS_ERR_BAD_ARG;
+  LevelSetRW cs{}, gs{};
+  for (int l = 0; l < num_levels; ++l) {
+    if (!g_geo_levels[l] || !g_corr_levels[l] || corr_pitches[l] < corr_widths[l]) return AS_ERR_BAD_ARG;
+    cs.ptr[l] = g_corr_levels[l]; cs.width[l] = corr_widths[l]; cs.pitch[l] = corr_pitches[l];
+    gs.ptr[l] = g_geo_levels[l]; gs.width[l] = Dg >> l; gs.pitch[l] = (Dg >> l) * G;
+  }
+  const long long total = (long long)B * H * W * num_levels * (G + 1);
+  geo_lookup_bwd_kernel<<<(unsigned)as_ceil_div_ll(total, 256), 256, 0, as_cu(stream)>>>(
+      gs, G, Dg, cs, num_levels, disp, coords, g_out, H * W, W, radius, total);
+  AS_RETURN_IF_LAUNCH_FAILED();
+  return AS_OK;
+}
+
+extern "C" int as_lookup_taps(const float* disp, const float* coords, int B, int H, int W, int radius, int level,
+                              int kind, int32_t* tap0, float* frac, as_stream_t stream) {
+  if (!disp || !tap0 || !frac || B <= 0 || H <= 0 || W <= 0 || level < 0 || level >= 30) return AS_ERR_BAD_ARG;
+  const long long N = (long long)B * H * W;
+  lookup_taps_kernel<<<(unsigned)as_ceil_div_ll(N, 256), 256, 0, as_cu(stream)>>>(disp, coords, H * W, W, radius,
+                                                                               level, kind, tap0, frac, N);
+  AS_RETURN_IF_LAUNCH_FAILED();
+  return AS_OK;
+}

@@ -1,0 +1,304 @@
+"""Drop-in replacements for the reference's cost-volume objects, backed by the sm_100a kernels.
+
+  CorrBlock1D                  <- models/corePrune_RAFT/geometry.py:6-56
+  Combined_Geo_Encoding_Volume <- models/coreContinuous_IGEV/geometry.py:6-72
+
+Same constructor/``__call__``/``corr`` signatures, same public attributes (``num_levels``, ``radius``,
+``init_corr_pyramid``, ``geo_volume_pyramid``), same output tensors.  Internals differ:
+
+* the pyramid levels live in row-pitched buffers (pitch = width rounded up to 4 floats, so every window
+  load is a 16-byte aligned vector); ``init_corr_pyramid[i]`` are ``[N,1,1,w_i]`` views of them;
+* the geometry pyramid is stored ``[pixel][disparity][group]``; ``geo_volume_pyramid[i]`` exposes the
+  reference's ``[N,G,1,D_i]`` shape as a (strided) view of the same memory;
+* ``__call__`` is ONE kernel launch with no host synchronisation (the reference's ``bilinear_sampler``
+  syncs through ``torch.unique`` once per level per sampler, utils/utils.py:64).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+
+#: default arithmetic of the all-pairs correlation: "fp32" (CUDA cores, exact), "bf16x3" (tcgen05,
+#: fp32-parity split), "bf16" (tcgen05, fast).  Set by anystereo_b200.set_corr_mode().
+_CORR_MODE = {"mode": "fp32"}
+_MODE_ID = {"fp32": L.CORR_FP32_SIMT, "bf16x3": L.CORR_BF16X3, "bf16": L.CORR_BF16}
+
+
+def set_corr_mode(mode: str):
+    if mode not in _MODE_ID:
+        raise ValueError("corr mode must be one of %s" % sorted(_MODE_ID))
+    _CORR_MODE["mode"] = mode
+
+
+def get_corr_mode() -> str:
+    return _CORR_MODE["mode"]
+
+
+def _pitch(w: int) -> int:
+    return max(4, (w + 3) // 4 * 4)
+
+
+def _check_pair(fmap1, fmap2):
+    L.require_cuda(fmap1, "fmap1", torch.float32, contiguous=False)
+    L.require_cuda(fmap2, "fmap2", torch.float32, contiguous=False)
+    if fmap1.dim() != 4 or fmap2.dim() != 4 or fmap1.shape[:3] != fmap2.shape[:3]:
+        raise RuntimeError("fmap1/fmap2 must be [B,D,H,W1] and [B,D,H,W2]")
+    return fmap1.contiguous(), fmap2.contiguous()
+
+
+def _build_corr_levels(fmap1, fmap2, num_levels, mode=None):
+    """all-pairs correlation + pooled levels -> (buffers [N,pitch_l], widths, pitches)."""
+    fmap1, fmap2 = _check_pair(fmap1, fmap2)
+    B, D, H, W1 = fmap1.shape
+    W2 = fmap2.shape[3]
+    N = B * H * W1
+    widths = [W2 >> l for l in range(num_levels)]
+    pitches = [_pitch(w) for w in widths]
+    with torch.cuda.device(fmap1.device):
+        bufs = [torch.empty((N, p), device=fmap1.device, dtype=torch.float32) for p in pitches]
+        mode_id = _MODE_ID[mode or _CORR_MODE["mode"]]
+        ws_bytes = L.lib().as_corr1d_workspace_bytes(B, D, H, W1, W2, mode_id)
+        ws = torch.empty((max(ws_bytes, 1),), device=fmap1.device, dtype=torch.uint8) if ws_bytes else None
+        L.call("as_corr1d_build", fmap1.data_ptr(), fmap2.data_ptr(), B, D, H, W1, W2, num_levels,
+               L.ptr_array(bufs), L.int_array(pitches), mode_id, L.ptr(ws), ws_bytes, L.stream_ptr())
+    return bufs, widths, pitches
+
+
+class _CorrBuildFn(torch.autograd.Function):
+    """Differentiable pyramid build (training, config 5): grads flow to the feature maps."""
+
+    @staticmethod
+    def forward(ctx, fmap1, fmap2, num_levels, mode):
+        bufs, widths, pitches = _build_corr_levels(fmap1, fmap2, num_levels, mode)
+        ctx.save_for_backward(fmap1, fmap2)
+        ctx.meta = (widths, pitches)
+        return tuple(bufs)
+
+    @staticmethod
+    def backward(ctx, *g_levels):
+        fmap1, fmap2 = ctx.saved_tensors
+        widths, pitches = ctx.meta
+        B, D, H, W1 = fmap1.shape
+        W2 = fmap2.shape[3]
+        N = B * H * W1
+        st = L.stream_ptr()
+        gl = [None if g is None else g.contiguous() for g in g_levels]
+        # pool adjoint, coarse -> fine
+        acc = None
+        for l in range(len(gl) - 1, -1, -1):
+            cur = gl[l].clone() if gl[l] is not None else torch.zeros((N, pitches[l]), device=fmap1.device)
+            if acc is not None:
+                L.call("as_pool1d_halve_bwd_acc", acc.data_ptr(), cur.data_ptr(), N, widths[l], pitches[l + 1],
+                       pitches[l], st)
+            acc = cur
+        g1 = torch.empty_like(fmap1)
+        g2 = torch.empty_like(fmap2)
+        L.call("as_corr1d_bwd", acc.data_ptr(), pitches[0], fmap1.data_ptr(), fmap2.data_ptr(), g1.data_ptr(),
+               g2.data_ptr(), B, D, H, W1, W2, st)
+        return g1, g2, None, None
+
+
+class _CorrLookupFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, disp, coords, meta, *bufs):
+        widths, pitches, radius = meta
+        out = _corr_lookup(bufs, widths, pitches, radius, disp, coords)
+        ctx.save_for_backward(disp, coords)
+        ctx.meta = (widths, pitches, radius, [tuple(b.shape) for b in bufs])
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        disp, coords = ctx.saved_tensors
+        widths, pitches, radius, shapes = ctx.meta
+        B, _, H, W = disp.shape
+        g_out = g_out.contiguous()
+        gb = [torch.zeros(s, device=disp.device, dtype=torch.float32) for s in shapes]
+        L.call("as_corr_lookup_bwd", L.ptr_array(gb), L.int_array(widths), L.int_array(pitches), len(gb),
+               disp.data_ptr(), L.ptr(coords), g_out.data_ptr(), B, H, W, radius, L.stream_ptr())
+        return (None, None, None) + tuple(gb)
+
+
+def _check_disp_coords(disp, coords):
+    L.require_cuda(disp, "disp", torch.float32, contiguous=False)
+    if disp.dim() != 4 or disp.shape[1] != 1:
+        raise RuntimeError("disp must be [B,1,H,W]")
+    B, _, H, W = disp.shape
+    disp = disp.contiguous()
+    if coords is not None:
+        L.require_cuda(coords, "coords", torch.float32, contiguous=False)
+        if coords.numel() != B * H * W:
+            raise RuntimeError("coords must be [B,H,W,1]")
+        coords = coords.contiguous()
+    return disp, coords
+
+
+def _corr_lookup(bufs, widths, pitches, radius, disp, coords):
+    B, _, H, W = disp.shape
+    Lv = len(bufs)
+    with torch.cuda.device(disp.device):
+        out = torch.empty((B, Lv * (2 * radius + 1), H, W), device=disp.device, dtype=torch.float32)
+        L.call("as_corr_lookup_fwd", L.ptr_array(bufs), L.int_array(widths), L.int_array(pitches), Lv,
+               disp.data_ptr(), L.ptr(coords), out.data_ptr(), B, H, W, radius, L.stream_ptr())
+    return out
+
+
+class CorrBlock1D:
+    """RAFT-style 1-D all-pairs correlation pyramid + radius lookup
+    (reference: models/corePrune_RAFT/geometry.py:6-56; call site prune_raft_stereo.py:267-278)."""
+
+    def __init__(self, init_fmap1, init_fmap2, num_levels=2, radius=4, mask_invalid=False):
+        self.num_levels = num_levels
+        self.radius = radius
+        # mask_invalid is accepted and ignored: in the reference it is a discarded comparison
+        # (geometry.py:53-54), i.e. a no-op.
+        needs_grad = torch.is_grad_enabled() and (init_fmap1.requires_grad or init_fmap2.requires_grad)
+        if needs_grad:
+            f1, f2 = _check_pair(init_fmap1, init_fmap2)
+            bufs = list(_CorrBuildFn.apply(f1, f2, num_levels, None))
+            W2 = f2.shape[3]
+            self._widths = [W2 >> l for l in range(num_levels)]
+            self._pitches = [_pitch(w) for w in self._widths]
+        else:
+            bufs, self._widths, self._pitches = _build_corr_levels(init_fmap1.detach(), init_fmap2.detach(), num_levels)
+        self._bufs = bufs
+        N = bufs[0].shape[0]
+        self.init_corr_pyramid = [b[:, :w].unflatten(1, (1, 1, w)) if w > 0 else b[:, :0].reshape(N, 1, 1, 0)
+                                  for b, w in zip(bufs, self._widths)]
+
+    def __call__(self, disp, coords):
+        disp, coords = _check_disp_coords(disp, coords)
+        if torch.is_grad_enabled() and any(b.requires_grad for b in self._bufs):
+            return _CorrLookupFn.apply(disp, coords, (self._widths, self._pitches, self.radius), *self._bufs)
+        return _corr_lookup(self._bufs, self._widths, self._pitches, self.radius, disp, coords)
+
+    @staticmethod
+    def corr(fmap1, fmap2, mask_invalid=False):
+        """[B,D,H,W1] x [B,D,H,W2] -> [B,H,W1,1,W2] (geometry.py:46-56); no 1/sqrt(D) scaling."""
+        f1, f2 = _check_pair(fmap1, fmap2)
+        B, D, H, W1 = f1.shape
+        W2 = f2.shape[3]
+        bufs, widths, pitches = _build_corr_levels(f1.detach(), f2.detach(), 1)
+        lvl = bufs[0]
+        if pitches[0] != W2:
+            lvl = lvl[:, :W2].contiguous()
+        return lvl.view(B, H, W1, 1, W2)
+
+
+# ------------------------------------------------------------------------------------------------
+# IGEV
+# ------------------------------------------------------------------------------------------------
+
+def _build_geo_levels(geo_volume, num_levels):
+    L.require_cuda(geo_volume, "geo_volume", torch.float32, contiguous=False)
+    if geo_volume.dim() != 5:
+        raise RuntimeError("geo_volume must be [B,G,D,H,W]")
+    geo_volume = geo_volume.contiguous()
+    B, G, Dg, H, W = geo_volume.shape
+    N = B * H * W
+    with torch.cuda.device(geo_volume.device):
+        bufs = [torch.empty((N, max(Dg >> l, 0), G), device=geo_volume.device, dtype=torch.float32)
+                for l in range(num_levels)]
+        L.call("as_geo_pyramid_build", geo_volume.data_ptr(), B, G, Dg, H, W, num_levels, L.ptr_array(bufs),
+               L.stream_ptr())
+    return bufs
+
+
+class _GeoBuildFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, geo_volume, num_levels):
+        ctx.shape = tuple(geo_volume.shape)
+        return tuple(_build_geo_levels(geo_volume, num_levels))
+
+    @staticmethod
+    def backward(ctx, *g_levels):
+        B, G, Dg, H, W = ctx.shape
+        N = B * H * W
+        dev = g_levels[0].device if g_levels[0] is not None else None
+        gl = [g.contiguous() if g is not None else torch.zeros((N, Dg >> l, G), device=dev)
+              for l, g in enumerate(g_levels)]
+        g_geo = torch.empty(ctx.shape, device=gl[0].device, dtype=torch.float32)
+        L.call("as_geo_pyramid_bwd", L.ptr_array(gl), B, G, Dg, H, W, len(gl), g_geo.data_ptr(), L.stream_ptr())
+        return g_geo, None
+
+
+def _geo_lookup(geo_bufs, G, Dg, corr_bufs, widths, pitches, radius, disp, coords):
+    B, _, H, W = disp.shape
+    Lv = len(geo_bufs)
+    with torch.cuda.device(disp.device):
+        out = torch.empty((B, Lv * (G + 1) * (2 * radius + 1), H, W), device=disp.device, dtype=torch.float32)
+        L.call("as_geo_lookup_fwd", L.ptr_array(geo_bufs), G, Dg, L.ptr_array(corr_bufs), L.int_array(widths),
+               L.int_array(pitches), Lv, disp.data_ptr(), L.ptr(coords), out.data_ptr(), B, H, W, radius,
+               L.stream_ptr())
+    return out
+
+
+class _GeoLookupFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, disp, coords, meta, *bufs):
+        G, Dg, widths, pitches, radius, Lv = meta
+        out = _geo_lookup(bufs[:Lv], G, Dg, bufs[Lv:], widths, pitches, radius, disp, coords)
+        ctx.save_for_backward(disp, coords)
+        ctx.meta = meta
+        ctx.shapes = [tuple(b.shape) for b in bufs]
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        disp, coords = ctx.saved_tensors
+        G, Dg, widths, pitches, radius, Lv = ctx.meta
+        B, _, H, W = disp.shape
+        g_out = g_out.contiguous()
+        gb = [torch.zeros(s, device=disp.device, dtype=torch.float32) for s in ctx.shapes]
+        L.call("as_geo_lookup_bwd", L.ptr_array(gb[:Lv]), G, Dg, L.ptr_array(gb[Lv:]), L.int_array(widths),
+               L.int_array(pitches), Lv, disp.data_ptr(), L.ptr(coords), g_out.data_ptr(), B, H, W, radius,
+               L.stream_ptr())
+        return (None, None, None) + tuple(gb)
+
+
+class Combined_Geo_Encoding_Volume:
+    """IGEV combined geometry-encoding volume: all-pairs correlation pyramid + pooled GWC/geometry volume,
+    looked up together every iteration
+    (reference: models/coreContinuous_IGEV/geometry.py:6-72; call site continuous_IGEVstereo.py:275-286)."""
+
+    def __init__(self, init_fmap1, init_fmap2, geo_volume, num_levels=2, radius=4):
+        self.num_levels = num_levels
+        self.radius = radius
+        grad_on = torch.is_grad_enabled()
+        if grad_on and (init_fmap1.requires_grad or init_fmap2.requires_grad):
+            f1, f2 = _check_pair(init_fmap1, init_fmap2)
+            corr_bufs = list(_CorrBuildFn.apply(f1, f2, num_levels, None))
+            W2 = f2.shape[3]
+            self._widths = [W2 >> l for l in range(num_levels)]
+            self._pitches = [_pitch(w) for w in self._widths]
+        else:
+            corr_bufs, self._widths, self._pitches = _build_corr_levels(init_fmap1.detach(), init_fmap2.detach(),
+                                                                        num_levels)
+        if grad_on and geo_volume.requires_grad:
+            L.require_cuda(geo_volume, "geo_volume", torch.float32, contiguous=False)
+            geo_bufs = list(_GeoBuildFn.apply(geo_volume.contiguous(), num_levels))
+        else:
+            geo_bufs = _build_geo_levels(geo_volume.detach(), num_levels)
+        self._corr_bufs = corr_bufs
+        self._geo_bufs = geo_bufs
+        B, G, Dg, H, W = geo_volume.shape
+        self._G, self._Dg = G, Dg
+        N = B * H * W
+        # reference-shaped views: [N,1,1,w_i] and [N,G,1,D_i]
+        self.init_corr_pyramid = [b[:, :w].unflatten(1, (1, 1, w)) for b, w in zip(corr_bufs, self._widths)]
+        self.geo_volume_pyramid = [b.permute(0, 2, 1).unsqueeze(2) for b in geo_bufs]
+
+    def __call__(self, disp, coords):
+        disp, coords = _check_disp_coords(disp, coords)
+        bufs = list(self._geo_bufs) + list(self._corr_bufs)
+        if torch.is_grad_enabled() and any(b.requires_grad for b in bufs):
+            meta = (self._G, self._Dg, self._widths, self._pitches, self.radius, self.num_levels)
+            return _GeoLookupFn.apply(disp, coords, meta, *bufs)
+        return _geo_lookup(self._geo_bufs, self._G, self._Dg, self._corr_bufs, self._widths, self._pitches,
+                           self.radius, disp, coords)
+
+    @staticmethod
+    def corr(fmap1, fmap2):
+        """coreContinuous_IGEV/geometry.py:63-72."""
+        return CorrBlock1D.corr(fmap1, fmap2)

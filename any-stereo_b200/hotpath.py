@@ -1,0 +1,146 @@
+"""Loop glue of the hot path (a12) and the hook that installs the operators into the reference models.
+
+  igev_iterations  <- models/coreContinuous_IGEV/continuous_IGEVstereo.py:275-297
+  raft_iterations  <- models/corePrune_RAFT/prune_raft_stereo.py:267-288
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+from .geometry import CorrBlock1D, Combined_Geo_Encoding_Volume
+from .submodule import build_gwc_volume
+from .update import BasicMultiUpdateBlock
+
+
+def pixel_coords(B, H, W, device):
+    """coords[b,y,x,0] = x (continuous_IGEVstereo.py:280 / prune_raft_stereo.py:272)."""
+    return torch.arange(W, device=device, dtype=torch.float32).reshape(1, 1, W, 1).repeat(B, H, 1, 1)
+
+
+def _add(a, b):
+    a = a.contiguous()
+    b = b.contiguous()
+    y = torch.empty_like(a)
+    L.call("as_add_f32", a.data_ptr(), b.data_ptr(), y.data_ptr(), a.numel(), L.stream_ptr())
+    return y
+
+
+def _iterate(lookup, update_block, net_list, inp_list, disp, coords, iters, slow_fast_gru=False, keep_all=False):
+    n_layers = update_block.args.n_gru_layers
+    hist = []
+    net_list = list(net_list)
+    for _ in range(iters):
+        disp = disp.detach()
+        feat = lookup(disp, coords)
+        if n_layers == 3 and slow_fast_gru:
+            net_list = update_block(net_list, inp_list, iter16=True, iter08=False, iter04=False, update=False)
+        if n_layers >= 2 and slow_fast_gru:
+            net_list = update_block(net_list, inp_list, iter16=n_layers == 3, iter08=True, iter04=False, update=False)
+        net_list, delta = update_block(net_list, inp_list, feat, disp, iter16=n_layers == 3, iter08=n_layers >= 2)
+        disp = _add(disp, delta)
+        if keep_all:
+            hist.append(disp)
+    return (disp, net_list, hist) if keep_all else (disp, net_list)
+
+
+@torch.no_grad()
+def igev_iterations(update_block: BasicMultiUpdateBlock, match_left, match_right, geo_encoding_volume, net_list,
+                    inp_list, init_disp, iters, radius=4, num_levels=2, slow_fast_gru=False, keep_all=False):
+    """Build the combined volume, then ``iters`` x {lookup -> update -> disp += delta}."""
+    geo_fn = Combined_Geo_Encoding_Volume(match_left.float(), match_right.float(), geo_encoding_volume.float(),
+                                          radius=radius, num_levels=num_levels)
+    B, _, H, W = match_left.shape
+    coords = pixel_coords(B, H, W, match_left.device)
+    return _iterate(geo_fn, update_block, net_list, inp_list, init_disp, coords, iters, slow_fast_gru, keep_all)
+
+
+@torch.no_grad()
+def raft_iterations(update_block: BasicMultiUpdateBlock, match_left, match_right, net_list, inp_list, iters,
+                    radius=4, num_levels=4, slow_fast_gru=False, keep_all=False):
+    corr_fn = CorrBlock1D(match_left.float(), match_right.float(), radius=radius, num_levels=num_levels)
+    B, _, H, W = match_left.shape
+    coords = pixel_coords(B, H, W, match_left.device)
+    disp = match_left.new_zeros((B, 1, H, W))       # prune_raft_stereo.py:274
+    return _iterate(corr_fn, update_block, net_list, inp_list, disp, coords, iters, slow_fast_gru, keep_all)
+
+
+class HotLoopGraph:
+    """CUDA-graph replay of one IGEV hot-path step (volume build + all iterations) on static buffers.
+
+    The per-iteration work is ~20 short launches; at small shapes the loop is launch-bound, so the whole
+    step is captured once and replayed (no tracing compiler involved: the graph records exactly the
+    library's kernels)."""
+
+    def __init__(self, update_block, match_left, match_right, geo_volume, net_list, inp_list, init_disp, iters,
+                 radius=4, num_levels=2):
+        self.static_in = dict(ml=match_left.clone(), mr=match_right.clone(), geo=geo_volume.clone(),
+                              net=[t.clone() for t in net_list],
+                              inp=[[t.clone() for t in lst] for lst in inp_list], disp=init_disp.clone())
+        self.args = (update_block, iters, radius, num_levels)
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):   # warm-up: fills the weight/context caches outside capture
+                self._run()
+        torch.cuda.current_stream().wait_stream(s)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out_disp, self.out_net = self._run()
+
+    def _run(self):
+        ub, iters, radius, num_levels = self.args
+        si = self.static_in
+        return igev_iterations(ub, si["ml"], si["mr"], si["geo"], si["net"], si["inp"], si["disp"], iters,
+                               radius=radius, num_levels=num_levels)
+
+    def load(self, match_left, match_right, geo_volume, net_list, inp_list, init_disp):
+        si = self.static_in
+        si["ml"].copy_(match_left, non_blocking=True)
+        si["mr"].copy_(match_right, non_blocking=True)
+        si["geo"].copy_(geo_volume, non_blocking=True)
+        for d, s in zip(si["net"], net_list):
+            d.copy_(s, non_blocking=True)
+        for dl, sl in zip(si["inp"], inp_list):
+            for d, s in zip(dl, sl):
+                d.copy_(s, non_blocking=True)
+        si["disp"].copy_(init_disp, non_blocking=True)
+
+    def replay(self):
+        self.graph.replay()
+        return self.out_disp, self.out_net
+
+
+def install_into_reference(ref_igev_module=None, ref_raft_module=None):
+    """Rebind the names the reference's model graphs resolve at call time:
+
+        models.coreContinuous_IGEV.continuous_IGEVstereo.{Combined_Geo_Encoding_Volume, build_gwc_volume}
+        models.corePrune_RAFT.prune_raft_stereo.CorrBlock1D
+
+    ``model.update_block`` is swapped per model instance with ``adopt_update_block``."""
+    if ref_igev_module is not None:
+        ref_igev_module.Combined_Geo_Encoding_Volume = Combined_Geo_Encoding_Volume
+        ref_igev_module.build_gwc_volume = build_gwc_volume
+    if ref_raft_module is not None:
+        ref_raft_module.CorrBlock1D = CorrBlock1D
+
+
+def adopt_update_block(ref_update_block, family="igev"):
+    """Build our update block around the SAME nn.Parameter objects as a reference BasicMultiUpdateBlock."""
+    from .update import BasicMultiUpdateBlockRAFT
+    cls = BasicMultiUpdateBlock if family == "igev" else BasicMultiUpdateBlockRAFT
+    hd = [ref_update_block.gru16.convz.out_channels, ref_update_block.gru08.convz.out_channels,
+          ref_update_block.gru04.convz.out_channels]
+    ours = cls(ref_update_block.args, hidden_dims=hd)
+    ours.load_state_dict(ref_update_block.state_dict(), strict=True)
+    for (n1, p1), (n2, p2) in zip(ours.named_parameters(), ref_update_block.named_parameters()):
+        assert n1 == n2
+    # share storage: point our modules' parameters at the reference's Parameter objects
+    ref_params = dict(ref_update_block.named_parameters())
+    for name, _ in list(ours.named_parameters()):
+        mod = ours
+        parts = name.split(".")
+        for p in parts[:-1]:
+            mod = getattr(mod, p)
+        mod._parameters[parts[-1]] = ref_params[name]
+    return ours.to(next(ref_update_block.parameters()).device)

@@ -1,0 +1,58 @@
+"""``build_gwc_volume`` -- drop-in for models/coreContinuous_IGEV/submodule.py:253-271."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+
+
+def _gwc_fwd(left, right, maxdisp, num_groups):
+    B, C, H, W = left.shape
+    with torch.cuda.device(left.device):
+        out = torch.empty((B, num_groups, maxdisp, H, W), device=left.device, dtype=torch.float32)
+        L.call("as_gwc_build_fwd", left.data_ptr(), right.data_ptr(), out.data_ptr(), B, C, H, W, maxdisp,
+               num_groups, L.stream_ptr())
+    return out
+
+
+class _GwcFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, left, right, maxdisp, num_groups):
+        ctx.save_for_backward(left, right)
+        ctx.meta = (maxdisp, num_groups)
+        return _gwc_fwd(left, right, maxdisp, num_groups)
+
+    @staticmethod
+    def backward(ctx, g):
+        left, right = ctx.saved_tensors
+        maxdisp, G = ctx.meta
+        B, C, H, W = left.shape
+        g = g.contiguous().float()
+        gl = torch.empty_like(left)
+        gr = torch.empty_like(right)
+        L.call("as_gwc_build_bwd", g.data_ptr(), left.data_ptr(), right.data_ptr(), gl.data_ptr(), gr.data_ptr(),
+               B, C, H, W, maxdisp, G, L.stream_ptr())
+        return gl, gr, None, None
+
+
+def build_gwc_volume(refimg_fea, targetimg_fea, maxdisp, num_groups):
+    """[B,C,H,W] x2 -> [B,num_groups,maxdisp,H,W], same dtype/device as the inputs.
+
+    vol[b,g,d,y,x] = mean_{c in group g} ref[b,c,y,x] * tgt[b,c,y,x-d] for x >= d, else 0.
+    The arithmetic is fp32; half inputs (the reference calls this under autocast,
+    continuous_IGEVstereo.py:244,262) are widened on the way in and narrowed on the way out.
+    """
+    if refimg_fea.shape != targetimg_fea.shape or refimg_fea.dim() != 4:
+        raise RuntimeError("refimg_fea/targetimg_fea must both be [B,C,H,W]")
+    C = refimg_fea.shape[1]
+    assert C % num_groups == 0  # submodule.py:255
+    L.require_cuda(refimg_fea, "refimg_fea", contiguous=False)
+    L.require_cuda(targetimg_fea, "targetimg_fea", contiguous=False)
+    dt = refimg_fea.dtype
+    left = refimg_fea.float().contiguous()
+    right = targetimg_fea.float().contiguous()
+    if torch.is_grad_enabled() and (left.requires_grad or right.requires_grad):
+        vol = _GwcFn.apply(left, right, int(maxdisp), int(num_groups))
+    else:
+        vol = _gwc_fwd(left, right, int(maxdisp), int(num_groups))
+    return vol if dt == torch.float32 else vol.to(dt)

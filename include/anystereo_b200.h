@@ -1,0 +1,218 @@
+/*
+ * anystereo_b200 -- C ABI of the B200-native (sm_100a) Any-Stereo iterative cost-volume hot path.
+ *
+ * Plain pointers + sizes + a CUDA stream; no torch types, no exceptions across the boundary.
+ * Every entry point
+ *   - takes DEVICE pointers (unless the parameter is documented "host array"),
+ *   - launches asynchronously on `stream` (pass the caller's current stream; 0 = legacy default),
+ *   - never allocates, never synchronises, is CUDA-graph capturable and re-entrant
+ *     (no global mutable state; the caller selects the device),
+ *   - returns AS_OK (0), a negative AS_ERR_* argument error, or a positive cudaError_t
+ *     observed by cudaGetLastError() right after the launch.
+ *
+ * Each function names the reference interface it replaces (paths relative to the reference
+ * repository, Zhaohuai-L/Any-Stereo).  The Python layer in any-stereo_b200/ binds these with ctypes and
+ * re-exposes the reference's operator names (CorrBlock1D, Combined_Geo_Encoding_Volume,
+ * build_gwc_volume, corr_sampler.forward/backward, BasicMultiUpdateBlock).
+ */
+#ifndef ANYSTEREO_B200_H
+#define ANYSTEREO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* as_stream_t; /* cudaStream_t */
+
+#define AS_OK 0
+#define AS_ERR_BAD_ARG (-1)      /* null pointer / non-positive size                       */
+#define AS_ERR_UNSUPPORTED (-2)  /* shape or option outside what the kernels implement     */
+#define AS_ERR_INDEX_RANGE (-3)  /* tensor exceeds 32-bit element indexing                  */
+#define AS_ERR_ALIGNMENT (-4)    /* pointer / pitch alignment requirement violated          */
+#define AS_ERR_DRIVER (-5)       /* could not resolve a CUDA driver entry point (TMA maps)  */
+
+#define AS_MAX_LEVELS 8
+
+/* dtype tags for the dtype-dispatched entry points (reference: AT_DISPATCH_FLOATING_TYPES_AND_HALF,
+ * sampler/sampler_kernel.cu:126,157) */
+#define AS_DTYPE_F32 0
+#define AS_DTYPE_F16 1
+#define AS_DTYPE_F64 2
+
+int as_abi_version(void);
+const char* as_error_string(int code);
+/* compiled-in SM target, e.g. 100 for sm_100a */
+int as_compiled_sm(void);
+
+/* ------------------------------------------------------------------------------------------
+ * a6  corr_sampler.forward / corr_sampler.backward
+ *     replaces sampler/sampler.cpp:24-45 (pybind boundary) and sampler/sampler_kernel.cu:19-166.
+ *
+ * volume [B,H,W1,W2] (dtype), coords [B,coords_ch,H,W1] float32 (channel 0 is used; the reference
+ * also reads an unused channel 1), out [B,2r+1,H,W1] (dtype).
+ *   out[b,k,y,x] = (1-f)*V[b,y,x,t+k] + f*V[b,y,x,t+k+1],  t = floor(x0)-r, f = x0-floor(x0),
+ * taps outside [0,W2) contribute 0.  `out` is fully written (no pre-zeroing needed).
+ * ------------------------------------------------------------------------------------------ */
+int as_sampler_fwd(const void* volume, const float* coords, int coords_ch, void* out,
+                   int B, int H, int W1, int W2, int radius, int dtype, as_stream_t stream);
+/* volume_grad [B,H,W1,W2] is fully written (zero-fill fused; the reference memsets then scatters). */
+int as_sampler_bwd(const float* coords, int coords_ch, const void* corr_grad, void* volume_grad,
+                   int B, int H, int W1, int W2, int radius, int dtype, as_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a1 + a2  all-pairs row correlation and its average-pool pyramid
+ *     replaces CorrBlock1D.corr / __init__ (models/corePrune_RAFT/geometry.py:7-19,46-56) and
+ *     Combined_Geo_Encoding_Volume.corr / __init__ (models/coreContinuous_IGEV/geometry.py:14-29,63-72).
+ *
+ * f1 [B,D,H,W1], f2 [B,D,H,W2] float32 NCHW.  levels[l] (host array of device pointers) receives
+ * level l as [B*H*W1][pitch[l]] float32 with valid width W2>>l; pitches in floats, >= width.
+ * Level 0 = sum_d f1*f2 (no scaling); level l+1[j] = (level l[2j] + level l[2j+1]) * 0.5.
+ * mode: AS_CORR_FP32_SIMT  exact fp32 FMA accumulation on CUDA cores,
+ *       AS_CORR_BF16X3     tcgen05 tensor cores, operands split hi+lo bf16, 3 MMAs, fp32 accumulate
+ *                          (fp32-parity mode, ~1e-5 relative to max|corr|),
+ *       AS_CORR_BF16       tcgen05, single bf16 MMA (fast mode; ~2e-3, reported separately).
+ * The tensor-core modes need `workspace` of as_corr1d_workspace_bytes() bytes (256-B aligned).
+ * ------------------------------------------------------------------------------------------ */
+#define AS_CORR_FP32_SIMT 0
+#define AS_CORR_BF16X3 1
+#define AS_CORR_BF16 2
+size_t as_corr1d_workspace_bytes(int B, int D, int H, int W1, int W2, int mode);
+int as_corr1d_build(const float* f1, const float* f2, int B, int D, int H, int W1, int W2,
+                    int num_levels, float* const* levels, const int* pitches, int mode,
+                    void* workspace, size_t workspace_bytes, as_stream_t stream);
+/* one pooling step on its own: in [rows][pitch_in] width w_in -> out [rows][pitch_out] width w_in/2 */
+int as_pool1d_halve(const float* in, float* out, long long rows, int w_in, int pitch_in, int pitch_out,
+                    as_stream_t stream);
+/* adjoints (training, config 5): g_fine += halve^T(g_coarse); dF1,dF2 from dCorr (fp32 SIMT) */
+int as_pool1d_halve_bwd_acc(const float* g_coarse, float* g_fine, long long rows, int w_fine,
+                            int pitch_coarse, int pitch_fine, as_stream_t stream);
+int as_corr1d_bwd(const float* g_corr, int pitch, const float* f1, const float* f2,
+                  float* g_f1, float* g_f2, int B, int D, int H, int W1, int W2, as_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a2 (IGEV)  geometry-encoding-volume pyramid
+ *     replaces the permute+reshape copy and avg_pool2d at coreContinuous_IGEV/geometry.py:17-25.
+ * geo [B,G,Dg,H,W] float32 -> levels[l] = [B*H*W][Dg>>l][G] float32 (disparity-major, group-minor:
+ * the 2r+2 taps x G groups one lookup needs are one contiguous, 32-byte aligned run).
+ * ------------------------------------------------------------------------------------------ */
+int as_geo_pyramid_build(const float* geo, int B, int G, int Dg, int H, int W, int num_levels,
+                         float* const* levels, as_stream_t stream);
+/* adjoint: g_levels (same layout) -> g_geo [B,G,Dg,H,W] (pool-bwd + inverse permute, one pass) */
+int as_geo_pyramid_bwd(const float* const* g_levels, int B, int G, int Dg, int H, int W,
+                       int num_levels, float* g_geo, as_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a3  CorrBlock1D.__call__   (models/corePrune_RAFT/geometry.py:24-43 + utils/utils.py:59-72)
+ * levels/pitches/widths: host arrays (num_levels entries) describing the pyramid from
+ * as_corr1d_build.  disp [B,1,H,W]; coords [B,H,W,1] or NULL (NULL => coords[b,y,x] = x, which is
+ * what both model forwards pass: prune_raft_stereo.py:272).  out [B, L*(2r+1), H, W] float32,
+ * channel = level*(2r+1)+tap, sample position (coords - disp)/2^level + tap - r.
+ * ------------------------------------------------------------------------------------------ */
+int as_corr_lookup_fwd(const float* const* levels, const int* widths, const int* pitches,
+                       int num_levels, const float* disp, const float* coords, float* out,
+                       int B, int H, int W, int radius, as_stream_t stream);
+/* adjoint w.r.t. the pyramid levels: g_levels[l] must be zero-initialised [N][pitch]; rows are
+ * owned by one pixel so no atomics (sampler/sampler_kernel.cu:83-103 semantics per level). */
+int as_corr_lookup_bwd(float* const* g_levels, const int* widths, const int* pitches,
+                       int num_levels, const float* disp, const float* coords, const float* g_out,
+                       int B, int H, int W, int radius, as_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a4  Combined_Geo_Encoding_Volume.__call__  (models/coreContinuous_IGEV/geometry.py:34-60)
+ * geo_levels from as_geo_pyramid_build ([N][Dg>>l][G]); corr levels as above.
+ * out [B, L*(G+1)*(2r+1), H, W]; per level: G*(2r+1) geo channels (g*(2r+1)+k, sampled at
+ * disp/2^l + k - r along Dg) then (2r+1) corr channels (sampled at (coords-disp)/2^l + k - r).
+ * ------------------------------------------------------------------------------------------ */
+int as_geo_lookup_fwd(const float* const* geo_levels, int G, int Dg,
+                      const float* const* corr_levels, const int* corr_widths, const int* corr_pitches,
+                      int num_levels, const float* disp, const float* coords, float* out,
+                      int B, int H, int W, int radius, as_stream_t stream);
+int as_geo_lookup_bwd(float* const* g_geo_levels, int G, int Dg,
+                      float* const* g_corr_levels, const int* corr_widths, const int* corr_pitches,
+                      int num_levels, const float* disp, const float* coords, const float* g_out,
+                      int B, int H, int W, int radius, as_stream_t stream);
+/* index-parity probe: integer base tap (floor(x)-r) and fractional weight per pixel for one level.
+ * kind 0 = geo position disp/2^l, kind 1 = corr position (coords-disp)/2^l. */
+int as_lookup_taps(const float* disp, const float* coords, int B, int H, int W, int radius,
+                   int level, int kind, int32_t* tap0, float* frac, as_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a7  build_gwc_volume  (models/coreContinuous_IGEV/submodule.py:253-271)
+ * left,right [B,C,H,W] float32 -> out [B,G,maxdisp,H,W] float32, fully written:
+ *   out[b,g,d,y,x] = (G/C) * sum_{c in group g} left[b,c,y,x]*right[b,c,y,x-d]  (x>=d), else 0.
+ * ------------------------------------------------------------------------------------------ */
+int as_gwc_build_fwd(const float* left, const float* right, float* out,
+                     int B, int C, int H, int W, int maxdisp, int G, as_stream_t stream);
+int as_gwc_build_bwd(const float* g_out, const float* left, const float* right,
+                     float* g_left, float* g_right,
+                     int B, int C, int H, int W, int maxdisp, int G, as_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a8-a11  per-iteration update block  (models/(all families)/update.py:16-41,73-136)
+ *
+ * Activations are pixel-major ("NHWC": [B*H*W][C], C contiguous).  A convolution reads up to
+ * AS_MAX_SRC sources concatenated along C (this is how torch.cat of update.py:35-36,39,90 is never
+ * materialised) and fuses its consumer into the epilogue.
+ * ------------------------------------------------------------------------------------------ */
+#define AS_MAX_SRC 4
+#define AS_LAYOUT_NHWC 0
+#define AS_LAYOUT_NCHW 1
+
+/* epilogues */
+#define AS_EPI_BIAS 0       /* y = acc + bias                                                       */
+#define AS_EPI_BIAS_RELU 1  /* y = relu(acc + bias)                                                 */
+#define AS_EPI_GRU_ZR 2     /* Cout = 2*Hd: z = sigmoid(acc+bias+ctx) -> aux0 ; r likewise, r*h -> out
+                               (update.py:37-38 and the r*h of :39)                                 */
+#define AS_EPI_GRU_Q 3      /* q = tanh(acc+bias+ctx); out = (1-z)*h + z*q  (update.py:39-40)        */
+
+typedef struct as_conv_src {
+  const float* ptr; /* activation                                            */
+  int channels;     /* channels this source contributes                      */
+  int pitch;        /* NHWC: floats between consecutive pixels (>= channels) ; NCHW: ignored */
+  int layout;       /* AS_LAYOUT_*                                           */
+} as_conv_src;
+
+typedef struct as_conv_desc {
+  int B, H, W;          /* output (= input) spatial size, stride 1, zero padding KH/2, KW/2          */
+  int KH, KW;           /* 1x1, 3x3, 7x7                                                           */
+  int Cout;
+  int num_src;
+  as_conv_src src[AS_MAX_SRC];
+  const float* weight;  /* packed [KH*KW][Cin_total][Cout] from as_pack_conv_weight                */
+  const float* bias;    /* [Cout] or NULL                                                          */
+  int epilogue;         /* AS_EPI_*                                                                */
+  float* out;           /* NHWC [N][out_pitch] at channel offset out_coff, or NCHW [B,Cout,H,W]    */
+  int out_pitch, out_coff, out_layout;
+  /* GRU epilogues (all NHWC, pitch = Hd = Cout/2 for ZR, Cout for Q unless noted) */
+  const float* ctx;     /* ZR: [N][2*Hd] = (cz | cr) ; Q: [N][Hd] = cq   (context terms, update.py:37-39) */
+  int ctx_pitch;
+  const float* h;       /* hidden state [N][Hd]                                                    */
+  float* z;             /* ZR: written ; Q: read                                                   */
+} as_conv_desc;
+
+/* nn.Conv2d weight [Cout][Cin][KH][KW] (update.py:29-31,78-82) -> GEMM operand [KH*KW][Cin][Cout];
+ * run once per weight version, outside the iteration loop */
+int as_pack_conv_weight(const float* w_oihw, float* w_packed, int Cout, int Cin, int KH, int KW,
+                        as_stream_t stream);
+/* exact-fp32 CUDA-core implicit-GEMM convolution (parity baseline for the tensor-core path) */
+int as_conv2d_fp32(const as_conv_desc* desc, as_stream_t stream);
+
+/* helpers between the GRU scales (update.py:94-102), NHWC float32, C contiguous */
+int as_pool2x_nhwc(const float* in, float* out, int B, int H, int W, int C, as_stream_t stream);
+int as_interp_bilinear_nhwc(const float* in, float* out, int B, int Hin, int Win, int Hout, int Wout,
+                            int C, as_stream_t stream);
+/* layout moves at the torch boundary: [B,C,H,W] <-> [B*H*W][pitch] (+ channel offset) */
+int as_nchw_to_nhwc(const float* in, float* out, int B, int C, int H, int W, int out_pitch,
+                    int out_coff, as_stream_t stream);
+int as_nhwc_to_nchw(const float* in, float* out, int B, int C, int H, int W, int in_pitch,
+                    int in_coff, as_stream_t stream);
+/* y[i] = a[i] + b[i] (disp = disp + delta, continuous_IGEVstereo.py:295) */
+int as_add_f32(const float* a, const float* b, float* y, long long n, as_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ANYSTEREO_B200_H */

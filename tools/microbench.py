@@ -1,0 +1,143 @@
+"""Per-kernel micro-benchmarks at BASELINE.json config-2 shapes (IGEV 384x1248 -> 96x312, B=8) and config-3
+for the RAFT lookup: CUDA-event timing, >=20 reps after warm-up, L2 flushed between reps.  Algorithmic bytes
+per SURVEY.md 8(d).  Usage: python tools/microbench.py [--B 8] [--json out.json]"""
+import argparse
+import json
+import os
+import sys
+import types
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import anystereo_b200 as A  # noqa: E402
+
+PEAK = 6543.1
+try:
+    PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    pass
+
+_flush = None
+
+
+def flush_l2():
+    global _flush
+    if _flush is None:
+        _flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    _flush.zero_()
+
+
+def timeit(fn, reps=20, warm=3, flush=True):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        if flush:
+            flush_l2()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)   # us
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--B", type=int, default=8)
+    ap.add_argument("--json", default=None)
+    ap.add_argument("--update", action="store_true", help="also time the update block")
+    a = ap.parse_args()
+    torch.manual_seed(0)
+    dev = "cuda"
+    B, D, H, W, Dg = a.B, 96, 96, 312, 48
+    N = B * H * W
+    res = {}
+
+    def rec(name, med_us, best_us, bytes_):
+        res[name] = dict(us_median=round(med_us, 2), us_best=round(best_us, 2), alg_MB=round(bytes_ / 1e6, 2),
+                         GBps=round(bytes_ / med_us / 1e3, 1), frac_of_peak=round(bytes_ / med_us / 1e3 / PEAK, 3))
+        print(name, res[name], flush=True)
+
+    f1 = torch.randn(B, D, H, W, device=dev)
+    f2 = torch.randn(B, D, H, W, device=dev)
+    # a7 GWC
+    med, best = timeit(lambda: A.build_gwc_volume(f1, f2, Dg, 8))
+    rec("gwc_build", med, best, 2 * 4 * B * D * H * W + 4 * B * 8 * Dg * H * W)
+    gwc = A.build_gwc_volume(f1, f2, Dg, 8)
+    # a1+a2 corr pyramid, per mode
+    for mode in ("fp32", "bf16x3", "bf16"):
+        try:
+            A.set_corr_mode(mode)
+            med, best = timeit(lambda: A.geometry._build_corr_levels(f1, f2, 2))
+            rec("corr_build_" + mode, med, best, 2 * 4 * B * D * H * W + 4 * B * H * W * W * 1.5)
+            res["corr_build_" + mode]["TFLOPs"] = round(2.0 * B * H * W * W * D / med / 1e6, 2)
+        except RuntimeError as e:
+            print("corr mode", mode, "unavailable:", str(e)[:80])
+    A.set_corr_mode("fp32")
+    # a2 geo pyramid
+    med, best = timeit(lambda: A.geometry._build_geo_levels(gwc, 2))
+    rec("geo_pyramid", med, best, 4 * B * 8 * Dg * H * W * 2.5)
+    blk = A.Combined_Geo_Encoding_Volume(f1, f2, gwc, num_levels=2, radius=4)
+    coords = torch.arange(W, device=dev, dtype=torch.float32).reshape(1, 1, W, 1).repeat(B, H, 1, 1)
+    xs = torch.arange(W, device=dev).view(1, 1, 1, W)
+    ys = torch.arange(H, device=dev).view(1, 1, H, 1)
+    disps = {
+        "uniform": torch.rand(B, 1, H, W, device=dev) * Dg,
+        "smooth": 20 + 10 * torch.sin(2 * 3.14159265 * xs / W) * torch.cos(2 * 3.14159265 * ys / H)
+                  + 0.5 * torch.randn(B, 1, H, W, device=dev),
+    }
+    for name, d in disps.items():
+        d = d.float().contiguous()
+        med, best = timeit(lambda: blk(d, coords))
+        rec("geo_lookup_" + name, med, best, 1372 * N)
+    # a6 sampler on the level-0 volume
+    vol = blk.init_corr_pyramid[0].reshape(B, H, W, W)
+    x0 = (coords.reshape(B, 1, H, W) - disps["uniform"]).contiguous()
+    med, best = timeit(lambda: A.corr_sampler.forward(vol, x0, 4))
+    rec("sampler_fwd", med, best, 80 * N)
+    g = torch.randn(B, 9, H, W, device=dev)
+    med, best = timeit(lambda: A.corr_sampler.backward(vol, x0, g, 4))
+    rec("sampler_bwd", med, best, (36 + 4) * N + 4 * N * W)
+    # a3 RAFT lookup at config 3 (496x720, L=4), D reduced to keep the build short: only the lookup is timed
+    Br, Hr, Wr = 1, 496, 720
+    r1 = torch.randn(Br, 64, Hr, Wr, device=dev)
+    r2 = torch.randn(Br, 64, Hr, Wr, device=dev)
+    rb = A.CorrBlock1D(r1, r2, num_levels=4, radius=4)
+    rc = torch.arange(Wr, device=dev, dtype=torch.float32).reshape(1, 1, Wr, 1).repeat(Br, Hr, 1, 1)
+    rd = (torch.rand(Br, 1, Hr, Wr, device=dev) * 64).contiguous()
+    med, best = timeit(lambda: rb(rd, rc))
+    rec("raft_lookup_c3", med, best, 308 * Br * Hr * Wr)
+    del rb, r1, r2
+    if a.update:
+        args = types.SimpleNamespace(corr_levels=2, corr_radius=4, n_gru_layers=3)
+        for engine in ("fp32", "bf16x3", "bf16"):
+            try:
+                A.set_update_engine(engine)
+                m = A.BasicMultiUpdateBlock(args, hidden_dims=[128, 128, 128]).cuda().eval()
+                sizes = [(H, W), (H // 2, W // 2), (H // 4, W // 4)]
+                net = [torch.tanh(torch.randn(B, 128, h, w, device=dev)) for h, w in sizes]
+                inp = [[torch.randn(B, 128, h, w, device=dev) for _ in range(3)] for h, w in sizes]
+                feat = blk(disps["uniform"].contiguous(), coords)
+                dsp = disps["uniform"].contiguous()
+                with torch.no_grad():
+                    med, best = timeit(lambda: m(list(net), inp, feat, dsp), reps=5, warm=2, flush=False)
+                flops = 2.0 * (N * (1847488 + 64 * 162) + N / 4 * 1327104 + N / 16 * 884736)
+                res["update_block_" + engine] = dict(us_median=round(med, 1), TFLOPs=round(flops / med / 1e6, 2))
+                print("update_block_" + engine, res["update_block_" + engine], flush=True)
+            except (RuntimeError, NotImplementedError, ImportError) as e:
+                print("update engine", engine, "unavailable:", str(e)[:100])
+        A.set_update_engine("fp32")
+    if a.json:
+        os.makedirs(os.path.dirname(a.json) or ".", exist_ok=True)
+        json.dump(res, open(a.json, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
