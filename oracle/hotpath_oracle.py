@@ -109,8 +109,9 @@ def lookup_rows_exact(rows: torch.Tensor, x: torch.Tensor, radius: int) -> torch
     ok = (idx >= 0) & (idx < W)
     g = torch.gather(rows, 2, idx.clamp(0, W - 1)[:, None, :].expand(N, C, -1))
     g = g * ok[:, None, :].to(rows.dtype)
+    omf = (1.0 - f).to(rows.dtype)[:, None, None]      # scalar_t(1.0f - dx): fp32 subtraction, then cast (:56)
     f = f.to(rows.dtype)[:, None, None]
-    return g[:, :, :-1] * (1 - f) + g[:, :, 1:] * f
+    return g[:, :, :-1] * omf + g[:, :, 1:] * f
 
 
 def lookup_rows_gridsample(rows: torch.Tensor, x: torch.Tensor, radius: int) -> torch.Tensor:
@@ -153,9 +154,10 @@ def sampler_backward(volume: torch.Tensor, coords: torch.Tensor, corr_grad: torc
     x = coords[:, 0].reshape(-1).to(torch.float32)
     t0, f = tap_indices(x, radius)
     g = corr_grad.permute(0, 2, 3, 1).reshape(N, 2 * radius + 1)
+    omf = (1.0 - f).to(g.dtype)[:, None]
     f = f.to(g.dtype)[:, None]
     z = torch.zeros(N, 1, dtype=g.dtype)
-    contrib = torch.cat([z, g], 1) * f + torch.cat([g, z], 1) * (1 - f)   # [N,2r+2]
+    contrib = torch.cat([z, g], 1) * f + torch.cat([g, z], 1) * omf        # [N,2r+2]
     idx = t0.to(torch.int64)[:, None] + torch.arange(2 * radius + 2)[None, :]
     ok = (idx >= 0) & (idx < W2)
     out = torch.zeros(N, W2, dtype=g.dtype)
@@ -358,9 +360,10 @@ def lookup_rows_bwd(g: torch.Tensor, x: torch.Tensor, radius: int, W: int) -> to
     (sampler/sampler_kernel.cu:83-103 generalised to C channels)."""
     N, C, _ = g.shape
     t0, f = tap_indices(x, radius)
+    omf = (1.0 - f).to(g.dtype)[:, None, None]
     f = f.to(g.dtype)[:, None, None]
     z = g.new_zeros(N, C, 1)
-    contrib = torch.cat([z, g], 2) * f + torch.cat([g, z], 2) * (1 - f)
+    contrib = torch.cat([z, g], 2) * f + torch.cat([g, z], 2) * omf
     idx = t0.to(torch.int64)[:, None] + torch.arange(2 * radius + 2)[None, :]
     ok = (idx >= 0) & (idx < W)
     out = g.new_zeros(N, C, W)
