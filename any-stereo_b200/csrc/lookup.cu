@@ -128,6 +128,89 @@ __global__ void __launch_bounds__(kRP) corr_lookup_fwd_kernel(LevelSet lv, int L
   }
 }
 
+// fast path: radius 4, L <= 4.  32 pixels per CTA (each output channel = one 128-byte line per warp),
+// 4 warps; a warp-wide 128-bit load covers 8 pixels x 64 contiguous bytes.
+constexpr int kFP = 32, kFT = 128, kFSP = 34;
+
+template <int L>
+__global__ void __launch_bounds__(kFT) corr_lookup_fwd_r4_kernel(LevelSet lv, const float* __restrict__ disp,
+                                                                 const float* __restrict__ coords,
+                                                                 float* __restrict__ out, int HW, int W) {
+  __shared__ __align__(16) float s_win[L * 16 * kFSP];
+  __shared__ int s_t0[L][kFP];
+  __shared__ float s_f[L][kFP];
+  const int tid = threadIdx.x;
+  const int b = blockIdx.y;
+  const int p0 = blockIdx.x * kFP;
+  const long long nbase = (long long)b * HW;
+  if (tid < kFP) {
+    const int p = p0 + tid;
+    float d = 0.f, c = 0.f;
+    if (p < HW) {
+      d = disp[nbase + p];
+      c = coords ? coords[nbase + p] : (float)(p % W);
+    }
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+      const float sc = level_scale(l);
+      int t0; float f;
+      split_pos(c * sc - d * sc, 4, t0, f);
+      s_t0[l][tid] = t0;
+      s_f[l][tid] = f;
+    }
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  const int pix8 = lane >> 2, q4 = lane & 3;
+  constexpr int kJobs = L * (kFP / 8);
+  constexpr int kPerWarp = (kJobs + 3) / 4;
+  float4 v[kPerWarp];
+  int dst[kPerWarp];
+#pragma unroll
+  for (int i = 0; i < kPerWarp; ++i) {
+    const int job = warp + 4 * i;
+    dst[i] = -1;
+    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (job < kJobs) {
+      const int l = job / (kFP / 8);
+      const int pix = (job - l * (kFP / 8)) * 8 + pix8;
+      const int p = p0 + pix;
+      const int c0 = as_floor4(s_t0[l][pix]) * 4 + q4 * 4;
+      dst[i] = (l * 16 + q4 * 4) * kFSP + pix;
+      if (p < HW && c0 >= 0 && c0 < lv.pitch[l])
+        v[i] = as_ldg_stream(reinterpret_cast<const float4*>(lv.ptr[l] + (nbase + p) * lv.pitch[l] + c0));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kPerWarp; ++i) {
+    if (dst[i] >= 0) {
+      float* sp = s_win + dst[i];
+      sp[0] = v[i].x; sp[kFSP] = v[i].y; sp[2 * kFSP] = v[i].z; sp[3 * kFSP] = v[i].w;
+    }
+  }
+  __syncthreads();
+  const int pix = lane, part = warp;
+  const int p = p0 + pix;
+  if (p >= HW) return;
+  float* o = out + (long long)b * L * 9 * HW + p;
+  for (int l = part; l < L; l += 4) {
+    const int t0 = s_t0[l][pix];
+    const float f = s_f[l][pix], omf = 1.0f - f;
+    const int off = t0 - as_floor4(t0) * 4;
+    const float* w = s_win + (l * 16 + off) * kFSP + pix;
+    const int Wl = lv.width[l];
+    float* oc = o + (long long)(l * 9) * HW;
+    float prev = (t0 >= 0 && t0 < Wl) ? w[0] : 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const int x1 = t0 + k + 1;
+      const float cur = (x1 >= 0 && x1 < Wl) ? w[(k + 1) * kFSP] : 0.f;
+      oc[(long long)k * HW] = prev * omf + cur * f;
+      prev = cur;
+    }
+  }
+}
+
 // adjoint w.r.t. the levels; one thread per (pixel, level); rows are pixel-private -> no atomics
 __global__ void corr_lookup_bwd_kernel(LevelSetRW lv, int L, const float* __restrict__ disp,
                                        const float* __restrict__ coords, const float* __restrict__ gout,
@@ -160,13 +243,13 @@ __global__ void corr_lookup_bwd_kernel(LevelSetRW lv, int L, const float* __rest
 // ------------------------------------------------------------------------------------------------
 // IGEV: geometry volume (8 groups) + correlation, fast path G == 8, r == 4
 // ------------------------------------------------------------------------------------------------
-constexpr int kGP = 64;    // pixels per CTA
-constexpr int kGT = 192;   // threads per CTA (6 warps)
-constexpr int kGSP = 66;   // smem row stride: 4*66 % 32 == 8
+constexpr int kGP = 32;    // pixels per CTA (one 128-byte output line per channel)
+constexpr int kGT = 192;   // threads per CTA (6 warps): 8 x 128-bit loads in flight per thread, <=64 regs
+constexpr int kGSP = 34;   // smem row stride: 4*34 % 32 == 8 -> conflict-free transposing stores
 constexpr int kG = 8, kR = 4, kTaps = 10, kK = 9;
 
 template <int L>
-__global__ void __launch_bounds__(kGT) geo_lookup_fwd_kernel(LevelSet geo, int Dg, LevelSet corr,
+__global__ void __launch_bounds__(kGT, 5) geo_lookup_fwd_kernel(LevelSet geo, int Dg, LevelSet corr,
                                                              const float* __restrict__ disp,
                                                              const float* __restrict__ coords,
                                                              float* __restrict__ out, int HW, int W) {
@@ -248,16 +331,17 @@ __global__ void __launch_bounds__(kGT) geo_lookup_fwd_kernel(LevelSet geo, int D
   }
   __syncthreads();
 
-  // ---- phase 2: lane = pixel; 3 thread groups share the 9*L (group|corr) rows
+  // ---- phase 2: lane = pixel; kGT/kGP thread groups share the 9*L (group|corr) rows
   const int pix = tid & (kGP - 1);
-  const int part = tid / kGP;          // 0..2
+  const int part = tid / kGP;          // 0..5
   const int p = p0 + pix;
   if (p >= HW) return;
   constexpr int C = L * (kG + 1) * kK;
   float* o = out + (long long)b * C * HW + p;
-#pragma unroll
-  for (int l = 0; l < L; ++l) {
-    for (int g = part; g <= kG; g += kGT / kGP) {
+  for (int row = part; row < L * (kG + 1); row += kGT / kGP) {
+    const int l = row / (kG + 1);
+    const int g = row - l * (kG + 1);
+    {
       if (g < kG) {
         const int t0 = s_tg[l][pix];
         const float f = s_fg[l][pix], omf = 1.0f - f;
@@ -411,6 +495,18 @@ extern "C" int as_corr_lookup_fwd(const float* const* levels, const int* widths,
   int rc = fill_levels(ls, levels, widths, pitches, num_levels);
   if (rc != AS_OK) return rc;
   const int HW = H * W;
+  if (radius == 4 && num_levels <= 4) {
+    dim3 grid(as_ceil_div(HW, kFP), B);
+    cudaStream_t st = as_cu(stream);
+    switch (num_levels) {
+      case 1: corr_lookup_fwd_r4_kernel<1><<<grid, kFT, 0, st>>>(ls, disp, coords, out, HW, W); break;
+      case 2: corr_lookup_fwd_r4_kernel<2><<<grid, kFT, 0, st>>>(ls, disp, coords, out, HW, W); break;
+      case 3: corr_lookup_fwd_r4_kernel<3><<<grid, kFT, 0, st>>>(ls, disp, coords, out, HW, W); break;
+      default: corr_lookup_fwd_r4_kernel<4><<<grid, kFT, 0, st>>>(ls, disp, coords, out, HW, W); break;
+    }
+    AS_RETURN_IF_LAUNCH_FAILED();
+    return AS_OK;
+  }
   const int NV = (2 * radius + 5 + 3) / 4;
   const size_t smem = sizeof(float) * num_levels * 4 * NV * kRSP;
   if (smem > 200 * 1024) return AS_ERR_UNSUPPORTED;

@@ -62,6 +62,8 @@ def _build_corr_levels(fmap1, fmap2, num_levels, mode=None):
         ws = torch.empty((max(ws_bytes, 1),), device=fmap1.device, dtype=torch.uint8) if ws_bytes else None
         L.call("as_corr1d_build", fmap1.data_ptr(), fmap2.data_ptr(), B, D, H, W1, W2, num_levels,
                L.ptr_array(bufs), L.int_array(pitches), mode_id, L.ptr(ws), ws_bytes, L.stream_ptr())
+        if mode_id == L.CORR_FP32_SIMT:
+            L.launch_count += num_levels - 1      # one pooling kernel per extra level
     return bufs, widths, pitches
 
 

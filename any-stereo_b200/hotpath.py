@@ -26,13 +26,22 @@ def _add(a, b):
     return y
 
 
-def _iterate(lookup, update_block, net_list, inp_list, disp, coords, iters, slow_fast_gru=False, keep_all=False):
+def _iterate(lookup, update_block, net_list, inp_list, disp, coords, iters, slow_fast_gru=False, keep_all=False,
+             lookup_events=None):
     n_layers = update_block.args.n_gru_layers
     hist = []
     net_list = list(net_list)
     for _ in range(iters):
         disp = disp.detach()
-        feat = lookup(disp, coords)
+        if lookup_events is not None:      # bench.py: CUDA events around the lookup launch, on its stream
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            feat = lookup(disp, coords)
+            e1.record()
+            lookup_events.append((e0, e1))
+        else:
+            feat = lookup(disp, coords)
         if n_layers == 3 and slow_fast_gru:
             net_list = update_block(net_list, inp_list, iter16=True, iter08=False, iter04=False, update=False)
         if n_layers >= 2 and slow_fast_gru:
@@ -46,13 +55,15 @@ def _iterate(lookup, update_block, net_list, inp_list, disp, coords, iters, slow
 
 @torch.no_grad()
 def igev_iterations(update_block: BasicMultiUpdateBlock, match_left, match_right, geo_encoding_volume, net_list,
-                    inp_list, init_disp, iters, radius=4, num_levels=2, slow_fast_gru=False, keep_all=False):
+                    inp_list, init_disp, iters, radius=4, num_levels=2, slow_fast_gru=False, keep_all=False,
+                    lookup_events=None):
     """Build the combined volume, then ``iters`` x {lookup -> update -> disp += delta}."""
     geo_fn = Combined_Geo_Encoding_Volume(match_left.float(), match_right.float(), geo_encoding_volume.float(),
                                           radius=radius, num_levels=num_levels)
     B, _, H, W = match_left.shape
     coords = pixel_coords(B, H, W, match_left.device)
-    return _iterate(geo_fn, update_block, net_list, inp_list, init_disp, coords, iters, slow_fast_gru, keep_all)
+    return _iterate(geo_fn, update_block, net_list, inp_list, init_disp, coords, iters, slow_fast_gru, keep_all,
+                    lookup_events)
 
 
 @torch.no_grad()

@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""Benchmark of the Any-Stereo iterative cost-volume hot path (BASELINE.json metric:
+"pairs/s @384x1248, 32 iters, 1-8 B200; corr-lookup HBM GB/s vs peak").
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # reference CPU path (oracle port), rank 0 only
+
+One "step" = one pass of the hot path over one batch of 8 synthetic KITTI-shaped pairs per GPU
+(BASELINE.json configs[1]: coreContinuous_IGEV, 384x1248 -> 96x312 at 1/4, 32 iterations):
+    build_gwc_volume -> Combined_Geo_Encoding_Volume(...) (all-pairs correlation + both pyramids)
+    -> 32 x { geo/corr lookup -> BasicMultiUpdateBlock -> disp += delta }.
+Backbones, the 3-D hourglass and the LIIF upsampler are outside the path and outside the
+step; the GWC volume stands in for the aggregated geometry volume (same shape, same traffic).
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H4, W4, FEAT_D, GEO_D, GROUPS, ITERS = 96, 312, 96, 48, 8, 32     # 384x1248 at 1/4 resolution
+LOOKUP_BYTES_PER_PIXEL = 1372                                      # IGEV L=2, r=4, G=8
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self._halt = threading.Event()
+
+    def run(self):
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 7:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def stop(self):
+        self._halt.set()
+        self.join(3)
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port of the reference's torch path on the host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_sample(sample_iters=8, threads=None):
+    """Time the reference's CPU implementation of the path (oracle/hotpath_oracle.py: the same
+    einsum/avg_pool/grid_sample/conv2d calls the reference makes) on ONE 384x1248 pair:
+    volume build + `sample_iters` of the 32 iterations, iteration time scaled to 32."""
+    import torch
+    from oracle import hotpath_oracle as O
+
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    with torch.no_grad():
+        f1 = torch.randn(1, FEAT_D, H4, W4)
+        f2 = torch.randn(1, FEAT_D, H4, W4)
+        sizes = [(H4, W4), (H4 // 2, W4 // 2), (H4 // 4, W4 // 4)]
+        net = [torch.tanh(torch.randn(1, 128, h, w)) for h, w in sizes]
+        inp = [[torch.relu(torch.randn(1, 128, h, w)) for _ in range(3)] for h, w in sizes]
+        disp = torch.rand(1, 1, H4, W4) * GEO_D
+        p = O.make_update_block_params(162, seed=0)
+        t0 = time.perf_counter()
+        geo = O.gwc_volume(f1, f2, GEO_D, GROUPS)
+        cp = O.corr_pyramid(O.all_pairs_corr(f1, f2), 2)
+        gp = O.geo_pyramid(geo, 2)
+        t_build = time.perf_counter() - t0
+        coords = O.pixel_coords(1, H4, W4)
+        # one untimed iteration (thread pools, allocator)
+        feat = O.geo_lookup(gp, cp, disp, coords, 4)
+        O.update_block(p, net, inp, feat, disp)
+        t0 = time.perf_counter()
+        for _ in range(sample_iters):
+            feat = O.geo_lookup(gp, cp, disp, coords, 4)
+            net, delta = O.update_block(p, net, inp, feat, disp)
+            disp = disp + delta
+        t_iters = time.perf_counter() - t0
+    s_per_pair = t_build + t_iters * (ITERS / sample_iters)
+    return {"pairs_per_s": 1.0 / s_per_pair, "s_per_pair": s_per_pair, "cores": threads,
+            "sample": "1 pair 384x1248: volume build + %d of %d iterations timed, iteration time scaled x%g"
+                      % (sample_iters, ITERS, ITERS / sample_iters)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_sample(sample_iters=1)
+    vals = []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        vals.append(cpu_reference_sample(sample_iters=args.ref_sample_iters))
+    wall = time.perf_counter() - t0
+    v = sum(x["pairs_per_s"] for x in vals) / len(vals)
+    ms = 1e3 * sum(x["s_per_pair"] for x in vals) / len(vals)
+    line = {
+        "impl": "reference", "metric": "pairs/s @384x1248, 32 iters", "value": v, "unit": "pairs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "coreContinuous_IGEV hot path, 384x1248 (96x312 @1/4), 32 iters, 1 pair per step on CPU",
+                   "impl_detail": "oracle port of the reference torch-CPU path (the reference tree is not on the GPU box)"},
+        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": vals[0]["cores"], "kind": "port",
+                         "sample": vals[0]["sample"]},
+        "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": wall,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def make_inputs(torch, B, device, seed, pinned=False):
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    sizes = [(H4, W4), (H4 // 2, W4 // 2), (H4 // 4, W4 // 4)]
+
+    def mk(*shape, fn=None):
+        t = torch.randn(*shape, generator=g)
+        if fn is not None:
+            t = fn(t)
+        if pinned:
+            return t.pin_memory()
+        return t.to(device)
+
+    d = {
+        "ml": mk(B, FEAT_D, H4, W4), "mr": mk(B, FEAT_D, H4, W4),
+        "net": [mk(B, 128, h, w, fn=torch.tanh) for h, w in sizes],
+        "inp": [[mk(B, 128, h, w, fn=torch.relu) for _ in range(3)] for h, w in sizes],
+        "disp": mk(B, 1, H4, W4, fn=lambda t: t.abs() * 12.0),
+    }
+    return d
+
+
+def host_bytes(d):
+    n = d["ml"].numel() + d["mr"].numel() + d["disp"].numel()
+    n += sum(t.numel() for t in d["net"]) + sum(t.numel() for l in d["inp"] for t in l)
+    return 4 * n
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import anystereo_b200 as A
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    A.set_update_engine(args.engine)
+    A.set_corr_mode(args.corr_mode or ("fp32" if args.engine == "fp32" else args.engine))
+    B = args.pairs_per_gpu
+    torch.manual_seed(0)
+    uargs = types.SimpleNamespace(corr_levels=2, corr_radius=4, n_gru_layers=3)
+    block = A.BasicMultiUpdateBlock(uargs, hidden_dims=[128, 128, 128]).to(dev).eval()   # random init, seed 0
+    dd = make_inputs(torch, B, dev, seed=rank)                    # device-resident inputs for `value`
+    hh = make_inputs(torch, B, dev, seed=rank, pinned=True)      # pinned host inputs for `e2e`
+    stage = make_inputs(torch, B, dev, seed=1234 + rank)         # device staging buffers the H2D copies fill
+    host_out = torch.empty(B, 1, H4, W4).pin_memory()
+    L = A._lib
+
+    def step(d, events=None):
+        geo = A.build_gwc_volume(d["ml"], d["mr"], GEO_D, GROUPS)
+        disp, net = A.igev_iterations(block, d["ml"], d["mr"], geo, d["net"], d["inp"], d["disp"], ITERS,
+                                      radius=4, num_levels=2, lookup_events=events)
+        return disp
+
+    def e2e_step():
+        stage["ml"].copy_(hh["ml"], non_blocking=True)
+        stage["mr"].copy_(hh["mr"], non_blocking=True)
+        stage["disp"].copy_(hh["disp"], non_blocking=True)
+        for dst, src in zip(stage["net"], hh["net"]):
+            dst.copy_(src, non_blocking=True)
+        for dl, sl in zip(stage["inp"], hh["inp"]):
+            for dst, src in zip(dl, sl):
+                dst.copy_(src, non_blocking=True)
+        disp = step(stage)
+        host_out.copy_(disp, non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            step(dd)
+        sampler = ClockSampler(local) if rank == 0 else None
+        if sampler:
+            sampler.start()
+        events = []
+        l0 = L.launch_count
+        ms = timed(lambda: step(dd, events), args.steps)
+        launches = L.launch_count - l0
+        clocks = sampler.stop() if sampler else None
+        torch.cuda.synchronize()
+        look_us = [a.elapsed_time(b) * 1e3 for a, b in events]
+        for _ in range(2):
+            e2e_step()
+        ms_e2e = timed(e2e_step, args.steps)
+
+    pairs = world * B * args.steps
+    value = pairs / (ms / 1e3)
+    e2e_value = pairs / (ms_e2e / 1e3)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = load_peaks()
+    n_pix = B * H4 * W4
+    look_avg_us = sum(look_us) / max(len(look_us), 1)
+    achieved = LOOKUP_BYTES_PER_PIXEL * n_pix / (look_avg_us * 1e-6) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f).get("geo_lookup_fwd_bytes_per_launch")
+    except Exception:
+        pass
+    cpu = cpu_reference_sample(sample_iters=args.ref_sample_iters) if not args.no_cpu_baseline else None
+    line = {
+        "metric": "pairs/s @384x1248, 32 iters", "value": value, "unit": "pairs/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {"fp32": "f32", "bf16x3": "f32 (3x split-bf16 on tcgen05, fp32 accumulate)", "bf16": "bf16"}[args.engine],
+        "data": "synthetic",
+        "config": {"workload": "coreContinuous_IGEV hot path (BASELINE configs[1]): 384x1248 -> 96x312 @1/4, "
+                               "batch %d pairs/GPU, 32 iters, corr_levels=2, radius=4" % B,
+                   "pairs_per_gpu": B, "iters": ITERS, "engine": args.engine, "corr_mode": A.get_corr_mode(),
+                   "parallelism": "pairs sharded across ranks, no data-path collective",
+                   "l2": "working set per step (~1 GB of pyramids + 155 MB lookup output per iteration) exceeds the 126 MB L2; no explicit flush"},
+        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": host_bytes(hh),
+                "d2h_bytes_per_step": 4 * B * H4 * W4, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "roofline": {"kernel": "geo_lookup_fwd_kernel<2> (Combined_Geo_Encoding_Volume.__call__)", "bound": "hbm",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": LOOKUP_BYTES_PER_PIXEL * n_pix,
+                     "avg_launch_us": look_avg_us, "launches_timed": len(look_us)},
+        "cpu_baseline": None if cpu is None else {"value": cpu["pairs_per_s"], "unit": "pairs/s", "cores": cpu["cores"],
+                                                  "kind": "port", "sample": cpu["sample"]},
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--engine", default=os.environ.get("ANYSTEREO_ENGINE", "fp32"), choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--corr-mode", default=None, choices=[None, "fp32", "bf16x3", "bf16"])
+    ap.add_argument("--pairs-per-gpu", type=int, default=8)
+    ap.add_argument("--ref-sample-iters", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
