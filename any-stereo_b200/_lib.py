@@ -18,6 +18,7 @@ DTYPE_F32, DTYPE_F16, DTYPE_F64 = 0, 1, 2
 CORR_FP32_SIMT, CORR_BF16X3, CORR_BF16 = 0, 1, 2
 LAYOUT_NHWC, LAYOUT_NCHW = 0, 1
 EPI_BIAS, EPI_BIAS_RELU, EPI_GRU_ZR, EPI_GRU_Q = 0, 1, 2, 3
+UEPI_RELU_SPLIT, UEPI_MOTION, UEPI_GRU_ZR, UEPI_GRU_Q, UEPI_DISPHEAD = 0, 1, 2, 3, 4
 
 _vp = C.c_void_p
 _i = C.c_int
@@ -29,6 +30,22 @@ _ip = C.POINTER(C.c_int)
 
 class ConvSrc(C.Structure):
     _fields_ = [("ptr", _vp), ("channels", _i), ("pitch", _i), ("layout", _i)]
+
+
+class UmmaSrc(C.Structure):
+    _fields_ = [("hi", _vp), ("lo", _vp), ("channels", _i)]
+
+
+class ConvUmmaDesc(C.Structure):
+    _fields_ = [
+        ("B", _i), ("H", _i), ("W", _i), ("KH", _i), ("KW", _i), ("Cout", _i), ("num_src", _i),
+        ("src", UmmaSrc * 3),
+        ("w_hi", _vp), ("w_lo", _vp), ("nsplit", _i), ("epilogue", _i),
+        ("bias", _vp), ("ctx", _vp), ("ctx_pitch", _i), ("h", _vp), ("z", _vp),
+        ("out_f32", _vp), ("out_hi", _vp), ("out_lo", _vp),
+        ("out_pitch", _i), ("out_coff", _i), ("cout_valid", _i),
+        ("disp", _vp), ("w2", _vp), ("u", _vp),
+    ]
 
 
 class ConvDesc(C.Structure):
@@ -69,6 +86,15 @@ SIGNATURES = {
     "as_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "as_nhwc_to_nchw": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "as_add_f32": (_i, [_vp, _vp, _vp, _ll, _vp]),
+    "as_nchw_to_nhwc_bias": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "as_conv2d_umma": (_i, [C.POINTER(ConvUmmaDesc), _vp]),
+    "as_pack_conv_weight_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "as_split_f32": (_i, [_vp, _vp, _vp, _ll, _vp]),
+    "as_nchw_to_nhwc_split": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "as_pool2x_nhwc_split": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "as_interp_bilinear_nhwc_split": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "as_convd1_split": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "as_disp_delta": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
 }
 
 _lib = None

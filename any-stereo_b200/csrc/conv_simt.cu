@@ -210,7 +210,8 @@ __global__ void interp_nhwc_kernel(const float* __restrict__ in, float* __restri
 
 // [B,C,HW] -> [B*HW][pitch] (+coff): 32x32 smem transpose tiles
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, int C,
-                                                           long long HW, int pitch, int coff) {
+                                                           long long HW, int pitch, int coff,
+                                                           const float* __restrict__ bias = nullptr) {
   __shared__ float t[32][33];
   const int b = blockIdx.z;
   const long long p0 = (long long)blockIdx.x * 32;
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
   for (int r = ly; r < 32; r += 8) {
     const long long pp = p0 + r;
     const int c = c0 + lx;
-    if (c < C && pp < HW) out[((long long)b * HW + pp) * pitch + coff + c] = t[lx][r];
+    if (c < C && pp < HW) out[((long long)b * HW + pp) * pitch + coff + c] = t[lx][r] + (bias ? __ldg(bias + c) : 0.f);
   }
 }
 
@@ -341,6 +342,17 @@ extern "C" int as_nchw_to_nhwc(const float* in, float* out, int B, int C, int H,
   const long long HW = (long long)H * W;
   dim3 grid((unsigned)as_ceil_div_ll(HW, 32), as_ceil_div(C, 32), B);
   nchw_to_nhwc_kernel<<<grid, 256, 0, as_cu(stream)>>>(in, out, C, HW, out_pitch, out_coff);
+  AS_RETURN_IF_LAUNCH_FAILED();
+  return AS_OK;
+}
+
+extern "C" int as_nchw_to_nhwc_bias(const float* in, const float* bias, float* out, int B, int C, int H, int W,
+                                    int out_pitch, int out_coff, as_stream_t stream) {
+  if (!in || !bias || !out || B <= 0 || C <= 0 || H <= 0 || W <= 0 || out_pitch < out_coff + C) return AS_ERR_BAD_ARG;
+  if (B > 65535 || as_ceil_div(C, 32) > 65535) return AS_ERR_UNSUPPORTED;
+  const long long HW = (long long)H * W;
+  dim3 grid((unsigned)as_ceil_div_ll(HW, 32), as_ceil_div(C, 32), B);
+  nchw_to_nhwc_kernel<<<grid, 256, 0, as_cu(stream)>>>(in, out, C, HW, out_pitch, out_coff, bias);
   AS_RETURN_IF_LAUNCH_FAILED();
   return AS_OK;
 }

@@ -1,0 +1,381 @@
+// a8-a11 on tensor cores: 3x3 / 1x1 convolutions of the update block as implicit GEMMs on tcgen05.
+//
+// Reference: models/*/update.py -- ConvGRU :26-41, BasicMotionEncoder :73-92, DispHead :16-24.
+//
+// GEMM view: M = 128 output pixels (a TW x TH spatial patch), N = Cout (<= 256, z|r share one N = 256 pass),
+// K = taps x Cin.  Activations are pixel-major bf16 planes [B][H][W][C] (hi, and lo = x - hi in the
+// fp32-parity mode).  For every (tap, 64-channel chunk) the TMA producer fetches the patch SHIFTED by the tap
+// as one 4-D box {64ch, TW, TH, 1}: out-of-image coordinates are zero-filled by the TMA unit, which IS the
+// convolution's zero padding; the box lands in shared memory as a K-major, 128B-swizzled [128 x 64] UMMA
+// operand -- no im2col buffer, no halo code.  torch.cat of update.py:35-36,39,90 is a loop over source tensors.
+//   warp 0 TMA producer | warp 1 tcgen05.mma issuer (3 MMAs per K-step in split mode) | warp 2 TMEM allocator
+//   warps 4-7 epilogue: tcgen05.ld -> gates (sigmoid / r*h / tanh / GRU blend / relu / disparity-head dot)
+//   -> per-pixel contiguous stores (fp32 state and/or bf16 hi/lo planes for the next convolution).
+// Two 256-column TMEM accumulators let the epilogue of tile i overlap the MMAs of tile i+1.
+#include "umma.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kAPlane = 128 * 128;      // one [128 px x 64 ch] bf16 tile
+constexpr int kMaxStages = 4;
+constexpr int kW2Floats = 9 * 256;
+constexpr int kSmemBudget = 227 * 1024;
+
+struct ConvMaps {
+  CUtensorMap a_hi[3];
+  CUtensorMap a_lo[3];
+  CUtensorMap b_hi;
+  CUtensorMap b_lo;
+};
+
+struct ConvUmmaParams {
+  int B, H, W, TW, TH, tiles_x, tiles_y, num_tiles;
+  int KH, KW, num_src, src_ch[3], cin_total;
+  int N, nsplit, nstages, stage_bytes, epilogue;
+  const float* bias; const float* ctx; int ctx_pitch; const float* h; float* z;
+  float* out_f32; __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; int out_pitch, out_coff, cout_valid;
+  const float* disp; const float* w2; float* u;
+};
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
+  __nv_bfloat162 t = __halves2bfloat162(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// 8 floats -> 8 bf16 hi (+ 8 bf16 lo = x - hi)
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
+    h[i] = pack_bf16(h0, h1);
+    l[i] = pack_bf16(__float2bfloat16_rn(v[2 * i] - __bfloat162float(h0)),
+                     __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(h1)));
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// store 32 consecutive channels of one pixel as bf16 hi (/lo) planes
+__device__ __forceinline__ void store_split32(const float* v, __nv_bfloat16* hi, __nv_bfloat16* lo, long long off) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    uint4 h, l;
+    split8(v + j, h, l);
+    *reinterpret_cast<uint4*>(hi + off + j) = h;
+    if (lo) *reinterpret_cast<uint4*>(lo + off + j) = l;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_constant__ ConvMaps maps,
+                                                                const ConvUmmaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* stages = smem;
+  float* w2s = reinterpret_cast<float*>(smem + p.nstages * p.stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w2s + kW2Floats);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kMaxStages;
+  uint64_t* tfull = bars + 2 * kMaxStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b_bytes = p.N * 128;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.num_src; ++s) {
+      umma::prefetch_tmap(&maps.a_hi[s]);
+      if (p.nsplit == 3) umma::prefetch_tmap(&maps.a_lo[s]);
+    }
+    umma::prefetch_tmap(&maps.b_hi);
+    if (p.nsplit == 3) umma::prefetch_tmap(&maps.b_lo);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.nstages; ++s) { umma::mbar_init(&full[s], 1); umma::mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { umma::mbar_init(&tfull[a], 1); umma::mbar_init(&tempty[a], 4); }
+    umma::fence_barrier_init();
+  }
+  if (warp == 2) {
+    umma::tmem_alloc(tmem_slot, 512);
+    umma::tmem_relinquish();
+  }
+  if (p.epilogue == AS_UEPI_DISPHEAD) {
+    for (int i = threadIdx.x; i < kW2Floats; i += kThreads) w2s[i] = p.w2[i];
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int taps = p.KH * p.KW;
+  const int chunks = p.cin_total >> 6;           // 64-channel chunks per tap
+  const int nkb = taps * chunks;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      const uint32_t tx = (uint32_t)(kAPlane + b_bytes) * (p.nsplit == 3 ? 2u : 1u);
+      const int ph = p.KH >> 1, pw = p.KW >> 1;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int b = tile / tiles_per_img;
+        const int r = tile - b * tiles_per_img;
+        const int ty = r / p.tiles_x, txi = r - ty * p.tiles_x;
+        const int x0 = txi * p.TW, y0 = ty * p.TH;
+        for (int tap = 0; tap < taps; ++tap) {
+          const int dy = tap / p.KW - ph, dx = tap - (tap / p.KW) * p.KW - pw;
+          int coff = 0;
+          for (int s = 0; s < p.num_src; ++s) {
+            for (int c0 = 0; c0 < p.src_ch[s]; c0 += 64) {
+              umma::mbar_wait(&empty[stage], phase ^ 1);
+              uint8_t* st = stages + stage * p.stage_bytes;
+              umma::mbar_expect_tx(&full[stage], tx);
+              const int kcoord = tap * p.cin_total + coff + c0;
+              umma::tma_load_4d(st, &maps.a_hi[s], &full[stage], c0, x0 + dx, y0 + dy, b);
+              umma::tma_load_2d(st + 2 * kAPlane, &maps.b_hi, &full[stage], kcoord, 0);
+              if (p.nsplit == 3) {
+                umma::tma_load_4d(st + kAPlane, &maps.a_lo[s], &full[stage], c0, x0 + dx, y0 + dy, b);
+                umma::tma_load_2d(st + 2 * kAPlane + b_bytes, &maps.b_lo, &full[stage], kcoord, 0);
+              }
+              if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+            }
+            coff += p.src_ch[s];
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      const uint32_t idesc = umma::idesc_bf16_f32(128, p.N);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+        umma::mbar_wait(&tempty[acc], acc_phase ^ 1);
+        umma::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)acc * 256u;
+        for (int kb = 0; kb < nkb; ++kb) {
+          umma::mbar_wait(&full[stage], phase);
+          umma::tc_fence_after();
+          const uint32_t st = umma::smem_u32(stages + stage * p.stage_bytes);
+          const uint32_t a_hi = st, a_lo = st + kAPlane, b_hi = st + 2 * kAPlane, b_lo = b_hi + b_bytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t ko = (uint32_t)k * 32u;
+            const uint64_t dah = umma::smem_desc_k_sw128(a_hi + ko), dbh = umma::smem_desc_k_sw128(b_hi + ko);
+            umma::mma_bf16_ss(tmem_d, dah, dbh, idesc, (kb | k) != 0);
+            if (p.nsplit == 3) {
+              const uint64_t dal = umma::smem_desc_k_sw128(a_lo + ko), dbl = umma::smem_desc_k_sw128(b_lo + ko);
+              umma::mma_bf16_ss(tmem_d, dah, dbl, idesc, 1u);
+              umma::mma_bf16_ss(tmem_d, dal, dbh, idesc, 1u);
+            }
+          }
+          umma::mma_commit(&empty[stage]);
+          if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+        }
+        umma::mma_commit(&tfull[acc]);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int q = warp - 4;
+    const int m = q * 32 + lane;                 // accumulator row == TMEM lane == pixel within the patch
+    const int py = m / p.TW, px = m - py * p.TW;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int b = tile / tiles_per_img;
+      const int r = tile - b * tiles_per_img;
+      const int ty = r / p.tiles_x, txi = r - ty * p.tiles_x;
+      const int x = txi * p.TW + px, y = ty * p.TH + py;
+      const bool valid = (x < p.W) && (y < p.H);
+      const long long n = ((long long)b * p.H + y) * p.W + x;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      umma::mbar_wait(&tfull[acc], acc_phase);
+      umma::tc_fence_after();
+      const uint32_t trow = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(q * 32) << 16);
+      float u[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) u[t] = 0.f;
+      for (int c0 = 0; c0 < p.N; c0 += 32) {
+        float v[32];
+        umma::tmem_ld_32x32(trow + (uint32_t)c0, v);
+        umma::tmem_ld_wait();
+        if (valid) {
+        if (p.epilogue == AS_UEPI_GRU_ZR) {
+          const int Hd = p.N >> 1;
+          const float* cx = p.ctx + n * p.ctx_pitch + c0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 c4 = __ldg(reinterpret_cast<const float4*>(cx + j));
+            v[j] = sigmoidf_(v[j] + c4.x); v[j + 1] = sigmoidf_(v[j + 1] + c4.y);
+            v[j + 2] = sigmoidf_(v[j + 2] + c4.z); v[j + 3] = sigmoidf_(v[j + 3] + c4.w);
+          }
+          if (c0 < Hd) {                                     // z = sigmoid(convz + cz)      update.py:37
+            float* zp = p.z + n * Hd + c0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(zp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {                                           // r*h feeds convq                update.py:38-39
+            const float* hp = p.h + n * Hd + (c0 - Hd);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 h4 = __ldg(reinterpret_cast<const float4*>(hp + j));
+              v[j] *= h4.x; v[j + 1] *= h4.y; v[j + 2] *= h4.z; v[j + 3] *= h4.w;
+            }
+            store_split32(v, p.out_hi, p.out_lo, n * p.out_pitch + p.out_coff + (c0 - Hd));
+          }
+        } else if (p.epilogue == AS_UEPI_GRU_Q) {            // h' = (1-z) h + z tanh(convq + cq)   update.py:39-40
+          const float* cx = p.ctx + n * p.ctx_pitch + c0;
+          const float* zp = p.z + n * p.N + c0;
+          const float* hp = p.h + n * p.N + c0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 c4 = __ldg(reinterpret_cast<const float4*>(cx + j));
+            const float4 z4 = *reinterpret_cast<const float4*>(zp + j);
+            const float4 h4 = __ldg(reinterpret_cast<const float4*>(hp + j));
+            v[j] = (1.0f - z4.x) * h4.x + z4.x * tanhf(v[j] + c4.x);
+            v[j + 1] = (1.0f - z4.y) * h4.y + z4.y * tanhf(v[j + 1] + c4.y);
+            v[j + 2] = (1.0f - z4.z) * h4.z + z4.z * tanhf(v[j + 2] + c4.z);
+            v[j + 3] = (1.0f - z4.w) * h4.w + z4.w * tanhf(v[j + 3] + c4.w);
+          }
+          float* op = p.out_f32 + n * p.N + c0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          store_split32(v, p.out_hi, p.out_lo, n * p.out_pitch + p.out_coff + c0);
+        } else if (p.epilogue == AS_UEPI_DISPHEAD) {         // relu(conv1) dotted with conv2's 9 taps  update.py:23-24
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
+            const float y0 = fmaxf(v[j] + b4.x, 0.f), y1 = fmaxf(v[j + 1] + b4.y, 0.f);
+            const float y2 = fmaxf(v[j + 2] + b4.z, 0.f), y3 = fmaxf(v[j + 3] + b4.w, 0.f);
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+              const float4 w4 = *reinterpret_cast<const float4*>(w2s + t * 256 + c0 + j);
+              u[t] = fmaf(w4.x, y0, fmaf(w4.y, y1, fmaf(w4.z, y2, fmaf(w4.w, y3, u[t]))));
+            }
+          }
+        } else {                                             // relu(conv + bias) [+ disp in the last channel]
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
+            v[j] = fmaxf(v[j] + b4.x, 0.f); v[j + 1] = fmaxf(v[j + 1] + b4.y, 0.f);
+            v[j + 2] = fmaxf(v[j + 2] + b4.z, 0.f); v[j + 3] = fmaxf(v[j + 3] + b4.w, 0.f);
+          }
+          if (p.epilogue == AS_UEPI_MOTION && c0 + 32 == p.N) v[31] = __ldg(p.disp + n);   // cat(out, disp) update.py:92
+          store_split32(v, p.out_hi, p.out_lo, n * p.out_pitch + p.out_coff + c0);
+        }
+        }
+        __syncwarp();     // reconverge before the next warp-aligned tcgen05.ld
+      }
+      if (p.epilogue == AS_UEPI_DISPHEAD && valid) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t) p.u[n * 9 + t] = u[t];
+      }
+      umma::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(&tempty[acc]);
+    }
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) umma::tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace
+
+extern "C" int as_conv2d_umma(const as_conv_umma_desc* d, as_stream_t stream) {
+  if (!d || !d->w_hi) return AS_ERR_BAD_ARG;
+  if (d->B <= 0 || d->H <= 0 || d->W <= 0 || d->num_src < 1 || d->num_src > 3) return AS_ERR_BAD_ARG;
+  if (!((d->KH == 1 && d->KW == 1) || (d->KH == 3 && d->KW == 3))) return AS_ERR_UNSUPPORTED;
+  if (d->Cout < 32 || d->Cout > 256 || (d->Cout & 31)) return AS_ERR_UNSUPPORTED;
+  if (d->nsplit != 1 && d->nsplit != 3) return AS_ERR_BAD_ARG;
+  if (d->nsplit == 3 && !d->w_lo) return AS_ERR_BAD_ARG;
+  ConvUmmaParams p{};
+  p.B = d->B; p.H = d->H; p.W = d->W; p.KH = d->KH; p.KW = d->KW;
+  p.TW = 16; p.TH = 8;
+  if (d->W <= 8) { p.TW = 8; p.TH = 16; }
+  p.tiles_x = as_ceil_div(d->W, p.TW); p.tiles_y = as_ceil_div(d->H, p.TH);
+  p.num_tiles = p.tiles_x * p.tiles_y * d->B;
+  p.num_src = d->num_src;
+  int cin = 0;
+  for (int s = 0; s < d->num_src; ++s) {
+    if (!d->src[s].hi || (d->nsplit == 3 && !d->src[s].lo)) return AS_ERR_BAD_ARG;
+    if (d->src[s].channels <= 0 || (d->src[s].channels & 63)) return AS_ERR_UNSUPPORTED;
+    if (!as_aligned16(d->src[s].hi) || (d->src[s].lo && !as_aligned16(d->src[s].lo))) return AS_ERR_ALIGNMENT;
+    p.src_ch[s] = d->src[s].channels;
+    cin += d->src[s].channels;
+  }
+  p.cin_total = cin;
+  p.N = d->Cout; p.nsplit = d->nsplit; p.epilogue = d->epilogue;
+  p.stage_bytes = 2 * kAPlane + 2 * p.N * 128;
+  const int fixed = 1024 + kW2Floats * 4 + 256;
+  p.nstages = (kSmemBudget - fixed) / p.stage_bytes;
+  if (p.nstages > kMaxStages) p.nstages = kMaxStages;
+  if (p.nstages < 2) return AS_ERR_UNSUPPORTED;
+  p.bias = d->bias; p.ctx = d->ctx; p.ctx_pitch = d->ctx_pitch; p.h = d->h; p.z = d->z;
+  p.out_f32 = d->out_f32; p.out_hi = (__nv_bfloat16*)d->out_hi; p.out_lo = (__nv_bfloat16*)d->out_lo;
+  p.out_pitch = d->out_pitch; p.out_coff = d->out_coff; p.cout_valid = d->cout_valid;
+  p.disp = d->disp; p.w2 = d->w2; p.u = d->u;
+  switch (d->epilogue) {
+    case AS_UEPI_RELU_SPLIT:
+      if (!d->bias || !d->out_hi) return AS_ERR_BAD_ARG;
+      break;
+    case AS_UEPI_MOTION:
+      if (!d->bias || !d->out_hi || !d->disp) return AS_ERR_BAD_ARG;
+      break;
+    case AS_UEPI_GRU_ZR:
+      if (!d->ctx || !d->h || !d->z || !d->out_hi || (d->Cout & 63)) return AS_ERR_BAD_ARG;
+      break;
+    case AS_UEPI_GRU_Q:
+      if (!d->ctx || !d->h || !d->z || !d->out_f32 || !d->out_hi) return AS_ERR_BAD_ARG;
+      break;
+    case AS_UEPI_DISPHEAD:
+      if (!d->bias || !d->w2 || !d->u || d->Cout != 256) return AS_ERR_BAD_ARG;
+      break;
+    default: return AS_ERR_UNSUPPORTED;
+  }
+  if ((d->out_pitch & 7) || (d->out_coff & 7)) return AS_ERR_ALIGNMENT;
+
+  ConvMaps maps;
+  int rc;
+  for (int s = 0; s < d->num_src; ++s) {
+    const uint64_t C = (uint64_t)d->src[s].channels;
+    const uint64_t dims[4] = {C, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
+    const uint64_t str[3] = {C * 2, (uint64_t)d->W * C * 2, (uint64_t)d->H * d->W * C * 2};
+    const uint32_t box[4] = {64u, (uint32_t)p.TW, (uint32_t)p.TH, 1u};
+    if ((rc = umma::make_tmap_bf16(&maps.a_hi[s], d->src[s].hi, 4, dims, str, box)) != AS_OK) return rc;
+    if (d->nsplit == 3) {
+      if ((rc = umma::make_tmap_bf16(&maps.a_lo[s], d->src[s].lo, 4, dims, str, box)) != AS_OK) return rc;
+    } else {
+      maps.a_lo[s] = maps.a_hi[s];
+    }
+  }
+  for (int s = d->num_src; s < 3; ++s) { maps.a_hi[s] = maps.a_hi[0]; maps.a_lo[s] = maps.a_lo[0]; }
+  {
+    const uint64_t Kt = (uint64_t)d->KH * d->KW * cin;
+    const uint64_t dims[2] = {Kt, (uint64_t)p.N};
+    const uint64_t str[1] = {Kt * 2};
+    const uint32_t box[2] = {64u, (uint32_t)p.N};
+    if ((rc = umma::make_tmap_bf16(&maps.b_hi, d->w_hi, 2, dims, str, box)) != AS_OK) return rc;
+    if (d->nsplit == 3) {
+      if ((rc = umma::make_tmap_bf16(&maps.b_lo, d->w_lo, 2, dims, str, box)) != AS_OK) return rc;
+    } else {
+      maps.b_lo = maps.b_hi;
+    }
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int smem = fixed + p.nstages * p.stage_bytes;
+  cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return (int)e;
+  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
+  conv_umma_kernel<<<grid, kThreads, smem, as_cu(stream)>>>(maps, p);
+  AS_RETURN_IF_LAUNCH_FAILED();
+  return AS_OK;
+}

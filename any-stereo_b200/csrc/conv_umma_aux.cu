@@ -1,0 +1,254 @@
+// Small memory-bound kernels around the tcgen05 convolutions: fp32 -> bf16 hi/lo plane conversion (with the
+// layout move, pooling or bilinear resize fused in), weight packing, the 7x7 single-channel convd1 and the
+// disparity-head gather.  Reference: models/*/update.py:80,87 (convd1), :94-95 (pool2x), :100-102 (interp),
+// :23-24 (DispHead.conv2).
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ void split1(float v, __nv_bfloat16& h, __nv_bfloat16& l) {
+  h = __float2bfloat16_rn(v);
+  l = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+__device__ __forceinline__ void store_split4(float4 v, __nv_bfloat16* hi, __nv_bfloat16* lo, long long off) {
+  __nv_bfloat16 h[4], l[4];
+  split1(v.x, h[0], l[0]); split1(v.y, h[1], l[1]); split1(v.z, h[2], l[2]); split1(v.w, h[3], l[3]);
+  __nv_bfloat162 a = __halves2bfloat162(h[0], h[1]), b = __halves2bfloat162(h[2], h[3]);
+  uint2 pk;
+  pk.x = *reinterpret_cast<uint32_t*>(&a); pk.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(hi + off) = pk;
+  if (lo) {
+    a = __halves2bfloat162(l[0], l[1]); b = __halves2bfloat162(l[2], l[3]);
+    pk.x = *reinterpret_cast<uint32_t*>(&a); pk.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(lo + off) = pk;
+  }
+}
+
+__global__ void split_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                             long long n4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  store_split4(__ldg(reinterpret_cast<const float4*>(in) + i), hi, lo, i * 4);
+}
+
+// [B,C,HW] fp32 -> [B*HW][Cp] bf16 hi/lo, channels >= C zero-filled
+__global__ void __launch_bounds__(256) nchw_to_nhwc_split_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi,
+                                                                 __nv_bfloat16* __restrict__ lo, int C, long long HW, int Cp) {
+  __shared__ float t[32][33];
+  const int b = blockIdx.z;
+  const long long p0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+#pragma unroll
+  for (int r = ly; r < 32; r += 8) {
+    const int c = c0 + r;
+    const long long pp = p0 + lx;
+    t[r][lx] = (c < C && pp < HW) ? __ldg(in + ((long long)b * C + c) * HW + pp) : 0.f;
+  }
+  __syncthreads();
+  // each thread writes 4 consecutive channels of one pixel
+  const int pr = threadIdx.x >> 3, cq = (threadIdx.x & 7) * 4;
+  const long long pp = p0 + pr;
+  if (pp < HW && c0 + cq < Cp)
+    store_split4(make_float4(t[cq][pr], t[cq + 1][pr], t[cq + 2][pr], t[cq + 3][pr]), hi, lo,
+                 ((long long)b * HW + pp) * Cp + c0 + cq);
+}
+
+__global__ void pool2x_split_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                    int H, int W, int Ho, int Wo, int C4, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c4 = (int)(idx % C4);
+  long long t = idx / C4;
+  const int xo = (int)(t % Wo); t /= Wo;
+  const int yo = (int)(t % Ho);
+  const int b = (int)(t / Ho);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int y = 2 * yo - 1 + i;
+    if (y < 0 || y >= H) continue;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int x = 2 * xo - 1 + j;
+      if (x < 0 || x >= W) continue;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(in) + (((long long)b * H + y) * W + x) * C4 + c4);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+  }
+  const float inv = 1.0f / 9.0f;
+  store_split4(make_float4(s.x * inv, s.y * inv, s.z * inv, s.w * inv), hi, lo, idx * 4);
+}
+
+__global__ void interp_split_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                    int Hi, int Wi, int Ho, int Wo, int C4, float sy, float sx, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c4 = (int)(idx % C4);
+  long long t = idx / C4;
+  const int xo = (int)(t % Wo); t /= Wo;
+  const int yo = (int)(t % Ho);
+  const int b = (int)(t / Ho);
+  const float fy = sy * yo, fx = sx * xo;
+  const int y0 = (int)fy, x0 = (int)fx;
+  const int y1 = min(y0 + 1, Hi - 1), x1 = min(x0 + 1, Wi - 1);
+  const float ly = fy - y0, lx = fx - x0, hy = 1.0f - ly, hx = 1.0f - lx;
+  const float4* base = reinterpret_cast<const float4*>(in) + (long long)b * Hi * Wi * C4 + c4;
+  const float4 v00 = __ldg(base + ((long long)y0 * Wi + x0) * C4), v01 = __ldg(base + ((long long)y0 * Wi + x1) * C4);
+  const float4 v10 = __ldg(base + ((long long)y1 * Wi + x0) * C4), v11 = __ldg(base + ((long long)y1 * Wi + x1) * C4);
+  float4 o;
+  o.x = hy * (hx * v00.x + lx * v01.x) + ly * (hx * v10.x + lx * v11.x);
+  o.y = hy * (hx * v00.y + lx * v01.y) + ly * (hx * v10.y + lx * v11.y);
+  o.z = hy * (hx * v00.z + lx * v01.z) + ly * (hx * v10.z + lx * v11.z);
+  o.w = hy * (hx * v00.w + lx * v01.w) + ly * (hx * v10.w + lx * v11.w);
+  store_split4(o, hi, lo, idx * 4);
+}
+
+__global__ void pack_weight_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi,
+                                        __nv_bfloat16* __restrict__ lo, int Cout, int Cin, int T, int n_pad, int cin_pad,
+                                        long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  // idx = (n * T + tap) * cin_pad + c
+  const int c = (int)(idx % cin_pad);
+  const long long r = idx / cin_pad;
+  const int tap = (int)(r % T);
+  const int n = (int)(r / T);
+  float v = 0.f;
+  if (n < Cout && c < Cin) v = w[((long long)n * Cin + c) * T + tap];
+  __nv_bfloat16 h, l;
+  split1(v, h, l);
+  hi[idx] = h;
+  if (lo) lo[idx] = l;
+}
+
+// 7x7 conv, 1 input channel -> 64, + bias, relu; one thread = one pixel x 8 output channels
+__global__ void __launch_bounds__(256) convd1_split_kernel(const float* __restrict__ disp, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, __nv_bfloat16* __restrict__ hi,
+                                                           __nv_bfloat16* __restrict__ lo, int H, int W, int pitch, int coff,
+                                                           long long N) {
+  __shared__ float ws[64 * 49];
+  __shared__ float bs[64];
+  for (int i = threadIdx.x; i < 64 * 49; i += 256) ws[i] = w[i];
+  if (threadIdx.x < 64) bs[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long n = idx >> 3;
+  const int cg = (int)(idx & 7) * 8;
+  if (n >= N) return;
+  const long long HW = (long long)H * W;
+  const int b = (int)(n / HW);
+  const int rem = (int)(n - (long long)b * HW);
+  const int y = rem / W, x = rem - y * W;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = bs[cg + j];
+  for (int dy = 0; dy < 7; ++dy) {
+    const int yy = y + dy - 3;
+    if (yy < 0 || yy >= H) continue;
+    for (int dx = 0; dx < 7; ++dx) {
+      const int xx = x + dx - 3;
+      if (xx < 0 || xx >= W) continue;
+      const float d = __ldg(disp + (long long)b * HW + (long long)yy * W + xx);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(ws[(cg + j) * 49 + dy * 7 + dx], d, acc[j]);
+    }
+  }
+  float4 a = make_float4(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f), fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
+  float4 c = make_float4(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f), fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f));
+  store_split4(a, hi, lo, n * pitch + coff + cg);
+  store_split4(c, hi, lo, n * pitch + coff + cg + 4);
+}
+
+__global__ void disp_delta_kernel(const float* __restrict__ u, const float* __restrict__ bias2, float* __restrict__ delta,
+                                  int H, int W, long long N) {
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const long long HW = (long long)H * W;
+  const int rem = (int)(n % HW);
+  const int y = rem / W, x = rem - y * W;
+  float acc = __ldg(bias2);
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int dy = t / 3 - 1, dx = t % 3 - 1;
+    const int yy = y + dy, xx = x + dx;
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) acc += __ldg(u + (n + (long long)dy * W + dx) * 9 + t);
+  }
+  delta[n] = acc;
+}
+
+}  // namespace
+
+extern "C" int as_split_f32(const float* in, void* hi, void* lo, long long n, as_stream_t stream) {
+  if (!in || !hi || n <= 0) return AS_ERR_BAD_ARG;
+  if ((n & 3) || !as_aligned16(in)) return AS_ERR_ALIGNMENT;
+  split_kernel<<<(unsigned)as_ceil_div_ll(n / 4, 256), 256, 0, as_cu(stream)>>>(in, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n / 4);
+  AS_RETURN_IF_LAUNCH_FAILED();
+  return AS_OK;
+}
+
+extern "C" int as_nchw_to_nhwc_split(const float* in, void* hi, void* lo, int B, int C, int H, int W, int c_pad,
+                                     as_stream_t stream) {
+  if (!in || !hi || B <= 0 || C <= 0 || H <= 0 || W <= 0 || c_pad < C) return AS_ERR_BAD_ARG;
+  if ((c_pad & 31) || B > 65535) return AS_ERR_UNSUPPORTED;
+  const long long HW = (long long)H * W;
+  dim3 grid((unsigned)as_ceil_div_ll(HW, 32), c_pad / 32, B);
+  nchw_to_nhwc_split_kernel<<<grid, 256, 0, as_cu(stream)>>>(in, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, C, HW, c_pad);
+  AS_RETURN_IF_LAUNCH_FAILED();
+  return AS_OK;
+}
+
+extern "C" int as_pool2x_nhwc_split(const float* in, void* hi, void* lo, int B, int H, int W, int C, as_stream_t stream) {
+  if (!in || !hi || B <= 0 || H <= 0 || W <= 0 || C <= 0) return AS_ERR_BAD_ARG;
+  if ((C & 3) || !as_aligned16(in)) return AS_ERR_ALIGNMENT;
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  const long long total = (long long)B * Ho * Wo * (C / 4);
+  pool2x_split_kernel<<<(unsigned)as_ceil_div_ll(total, 256), 256, 0, as_cu(stream)>>>(
+      in, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, H, W, Ho, Wo, C / 4, total);
+  AS_RETURN_IF_LAUNCH_FAILED();
+  return AS_OK;
+}
+
+extern "C" int as_interp_bilinear_nhwc_split(const float* in, void* hi, void* lo, int B, int Hin, int Win, int Hout,
+                                             int Wout, int C, as_stream_t stream) {
+  if (!in || !hi || B <= 0 || Hin <= 0 || Win <= 0 || Hout <= 0 || Wout <= 0 || C <= 0) return AS_ERR_BAD_ARG;
+  if ((C & 3) || !as_aligned16(in)) return AS_ERR_ALIGNMENT;
+  const float sy = Hout > 1 ? (float)(Hin - 1) / (float)(Hout - 1) : 0.f;
+  const float sx = Wout > 1 ? (float)(Win - 1) / (float)(Wout - 1) : 0.f;
+  const long long total = (long long)B * Hout * Wout * (C / 4);
+  interp_split_kernel<<<(unsigned)as_ceil_div_ll(total, 256), 256, 0, as_cu(stream)>>>(
+      in, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, Hin, Win, Hout, Wout, C / 4, sy, sx, total);
+  AS_RETURN_IF_LAUNCH_FAILED();
+  return AS_OK;
+}
+
+extern "C" int as_pack_conv_weight_bf16(const float* w_oihw, void* w_hi, void* w_lo, int Cout, int Cin, int KH, int KW,
+                                        int n_pad, int cin_pad, as_stream_t stream) {
+  if (!w_oihw || !w_hi || Cout <= 0 || Cin <= 0 || KH <= 0 || KW <= 0 || n_pad < Cout || cin_pad < Cin) return AS_ERR_BAD_ARG;
+  const long long total = (long long)n_pad * KH * KW * cin_pad;
+  pack_weight_bf16_kernel<<<(unsigned)as_ceil_div_ll(total, 256), 256, 0, as_cu(stream)>>>(
+      w_oihw, (__nv_bfloat16*)w_hi, (__nv_bfloat16*)w_lo, Cout, Cin, KH * KW, n_pad, cin_pad, total);
+  AS_RETURN_IF_LAUNCH_FAILED();
+  return AS_OK;
+}
+
+extern "C" int as_convd1_split(const float* disp, const float* w, const float* bias, void* hi, void* lo, int B, int H,
+                               int W, int out_pitch, int out_coff, as_stream_t stream) {
+  if (!disp || !w || !bias || !hi || B <= 0 || H <= 0 || W <= 0 || out_pitch < out_coff + 64) return AS_ERR_BAD_ARG;
+  if ((out_pitch & 3) || (out_coff & 3)) return AS_ERR_ALIGNMENT;
+  const long long N = (long long)B * H * W;
+  convd1_split_kernel<<<(unsigned)as_ceil_div_ll(N * 8, 256), 256, 0, as_cu(stream)>>>(
+      disp, w, bias, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, H, W, out_pitch, out_coff, N);
+  AS_RETURN_IF_LAUNCH_FAILED();
+  return AS_OK;
+}
+
+extern "C" int as_disp_delta(const float* u, const float* bias2, float* delta, int B, int H, int W, as_stream_t stream) {
+  if (!u || !bias2 || !delta || B <= 0 || H <= 0 || W <= 0) return AS_ERR_BAD_ARG;
+  const long long N = (long long)B * H * W;
+  disp_delta_kernel<<<(unsigned)as_ceil_div_ll(N, 256), 256, 0, as_cu(stream)>>>(u, bias2, delta, H, W, N);
+  AS_RETURN_IF_LAUNCH_FAILED();
+  return AS_OK;
+}

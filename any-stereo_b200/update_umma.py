@@ -1,0 +1,249 @@
+"""Tensor-core (tcgen05 + TMA) execution of BasicMultiUpdateBlock.forward (models/*/update.py:116-136).
+
+Data flow per iteration (all tensors pixel-major; "S" = bf16 hi/lo plane pair, the A operand format):
+
+  corr [B,C,h,w] --nchw_to_nhwc_split--> corrS --1x1 convc1--> c1S --3x3 convc2--> encS[:, 0:64]
+  disp ---------------convd1 7x7 (CUDA cores, K = 49)--------> d1S --3x3 convd2--> encS[:, 64:128]
+  encS --3x3 conv, epilogue puts disp in channel 127--> motionS            (torch.cat never materialises)
+  gru(h, x...):  [hS, x...] --3x3, N = 256--> z (fp32) and (r*h)S ;  [(r*h)S, x...] --3x3--> h' (fp32 + S)
+  h04S --3x3 conv1, epilogue dots relu(.) with conv2's 9 taps--> u [N,9] --gather--> delta_disp
+
+engine "bf16x3": every operand is split hi+lo and each K-step issues hi*hi + hi*lo + lo*hi (fp32 accumulate
+in TMEM) -- fp32-parity mode; engine "bf16": hi planes only -- fast mode, reported separately.
+"""
+from __future__ import annotations
+
+import weakref
+
+import torch
+
+from . import _lib as L
+
+
+class _Planes:
+    """bf16 hi (+lo) planes of a pixel-major activation [B,H,W,C]."""
+    __slots__ = ("hi", "lo", "shape")
+
+    def __init__(self, shape, device, split):
+        self.shape = tuple(shape)
+        self.hi = torch.empty(shape, device=device, dtype=torch.bfloat16)
+        self.lo = torch.empty(shape, device=device, dtype=torch.bfloat16) if split else None
+
+
+def _state(ub):
+    st = ub.__dict__.get("_umma_state")
+    if st is None:
+        st = {"w": {}, "ctx": {}, "planes": {}}
+        ub.__dict__["_umma_state"] = st
+    return st
+
+
+def _weights(ub, name, convs, n_pad=None, cin_pad=None, split=True):
+    """bf16 hi/lo GEMM weights [n_pad][taps*cin_pad] + padded fp32 bias, cached per parameter version."""
+    st = _state(ub)["w"]
+    key = (split,) + tuple((c.weight.data_ptr(), c.weight._version, c.bias.data_ptr(), c.bias._version) for c in convs)
+    hit = st.get(name)
+    if hit is not None and hit["key"] == key:
+        return hit
+    with torch.no_grad():
+        w = torch.cat([c.weight.detach().float() for c in convs], dim=0).contiguous()
+        b = torch.cat([c.bias.detach().float() for c in convs], dim=0).contiguous()
+        Cout, Cin, KH, KW = w.shape
+        n_pad = n_pad or (Cout + 31) // 32 * 32
+        cin_pad = cin_pad or Cin
+        hi = torch.empty((n_pad, KH * KW * cin_pad), device=w.device, dtype=torch.bfloat16)
+        lo = torch.empty_like(hi) if split else None
+        L.call("as_pack_conv_weight_bf16", w.data_ptr(), hi.data_ptr(), L.ptr(lo), Cout, Cin, KH, KW, n_pad, cin_pad,
+               L.stream_ptr())
+        bias = torch.zeros((n_pad,), device=w.device, dtype=torch.float32)
+        bias[:Cout].copy_(b)
+    hit = dict(key=key, hi=hi, lo=lo, bias=bias, n=n_pad, cin=cin_pad, k=KH)
+    st[name] = hit
+    return hit
+
+
+def _small_weights(ub):
+    """fp32 weights consumed on CUDA cores: convd1 [64][49] and DispHead.conv2 as [9][256]."""
+    st = _state(ub)["w"]
+    e, dh = ub.encoder, ub.disp_head
+    key = tuple((p.data_ptr(), p._version) for p in (e.convd1.weight, e.convd1.bias, dh.conv2.weight, dh.conv2.bias))
+    hit = st.get("small")
+    if hit is not None and hit["key"] == key:
+        return hit
+    with torch.no_grad():
+        wd1 = e.convd1.weight.detach().float().reshape(64, 49).contiguous()
+        bd1 = e.convd1.bias.detach().float().contiguous()
+        w2 = dh.conv2.weight.detach().float()[0].permute(1, 2, 0).reshape(9, -1).contiguous()   # [tap][c]
+        b2 = dh.conv2.bias.detach().float().contiguous()
+    hit = dict(key=key, wd1=wd1, bd1=bd1, w2=w2, b2=b2)
+    st["small"] = hit
+    return hit
+
+
+def _context(ub, idx, inp_i, wzr, wq):
+    """Loop-invariant GRU context with the conv biases folded in: (cz+bz | cr+br) [B,H,W,2Hd], cq+bq [B,H,W,Hd]."""
+    cz, cr, cq = inp_i
+    st = _state(ub)["ctx"]
+    key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in (cz, cr, cq)) + (wzr["key"], wq["key"])
+    hit = st.get(idx)
+    if hit is not None and hit[0] == key and all(r() is t for r, t in zip(hit[3], (cz, cr, cq))):
+        return hit[1], hit[2]
+    B, C, H, W = cz.shape
+    s = L.stream_ptr()
+    zr = torch.empty((B, H, W, 2 * C), device=cz.device, dtype=torch.float32)
+    q = torch.empty((B, H, W, C), device=cz.device, dtype=torch.float32)
+    for t, bias, dst, pitch, off in ((cz, wzr["bias"][:C], zr, 2 * C, 0), (cr, wzr["bias"][C:2 * C], zr, 2 * C, C),
+                                    (cq, wq["bias"][:C], q, C, 0)):
+        t = t.detach().float().contiguous()
+        L.call("as_nchw_to_nhwc_bias", t.data_ptr(), bias.data_ptr(), dst.data_ptr(), B, C, H, W, pitch, off, s)
+    st[idx] = (key, zr, q, tuple(weakref.ref(t) for t in (cz, cr, cq)))
+    return zr, q
+
+
+def _conv(B, H, W, srcs, wt, nsplit, epilogue, out=None, out_coff=0, bias=True, ctx=None, h=None, z=None, out_f32=None,
+          disp=None, w2=None, u=None):
+    d = L.ConvUmmaDesc()
+    d.B, d.H, d.W, d.KH, d.KW, d.Cout = B, H, W, wt["k"], wt["k"], wt["n"]
+    d.num_src = len(srcs)
+    cin = 0
+    for i, pl in enumerate(srcs):
+        d.src[i].hi = pl.hi.data_ptr()
+        d.src[i].lo = L.ptr(pl.lo)
+        d.src[i].channels = pl.shape[3]
+        cin += pl.shape[3]
+    assert cin == wt["cin"], (cin, wt["cin"])
+    d.w_hi = wt["hi"].data_ptr()
+    d.w_lo = L.ptr(wt["lo"])
+    d.nsplit = nsplit
+    d.epilogue = epilogue
+    d.bias = wt["bias"].data_ptr() if bias else None
+    if ctx is not None:
+        d.ctx = ctx.data_ptr()
+        d.ctx_pitch = ctx.shape[3]
+    d.h = L.ptr(h)
+    d.z = L.ptr(z)
+    d.out_f32 = L.ptr(out_f32)
+    if out is not None:
+        d.out_hi = out.hi.data_ptr()
+        d.out_lo = L.ptr(out.lo)
+        d.out_pitch = out.shape[3]
+    d.out_coff = out_coff
+    d.cout_valid = wt["n"]
+    d.disp = L.ptr(disp)
+    d.w2 = L.ptr(w2)
+    d.u = L.ptr(u)
+    L.call("as_conv2d_umma", d, L.stream_ptr())
+
+
+def _planes_of(ub, h_f32, split):
+    """hi/lo planes of a hidden state: reuse what the previous call produced, else split now."""
+    cache = _state(ub)["planes"]
+    hit = cache.get(h_f32.data_ptr())
+    # valid while the tensor we produced is still alive (its memory cannot have been recycled), untouched
+    # (views share the version counter) and of the same extent
+    if (hit is not None and hit[0]() is not None and hit[2] == h_f32._version and hit[1].shape == tuple(h_f32.shape)
+            and (hit[1].lo is not None) == split):
+        return hit[1]
+    pl = _Planes(h_f32.shape, h_f32.device, split)
+    L.call("as_split_f32", h_f32.data_ptr(), pl.hi.data_ptr(), L.ptr(pl.lo), h_f32.numel(), L.stream_ptr())
+    return pl
+
+
+def _remember(ub, h_f32, pl):
+    cache = _state(ub)["planes"]
+    if len(cache) > 16:
+        cache.clear()
+    cache[h_f32.data_ptr()] = (weakref.ref(h_f32), pl, h_f32._version)
+
+
+def forward(ub, net, inp, corr=None, disp=None, iter04=True, iter08=True, iter16=True, update=True):
+    from .update import _nhwc_view, get_update_engine
+    if torch.is_grad_enabled() and any(p.requires_grad for p in ub.parameters()):
+        raise NotImplementedError("anystereo_b200.BasicMultiUpdateBlock: backward is not implemented yet; "
+                                  "call under torch.no_grad()")
+    split = get_update_engine() == "bf16x3"
+    nsplit = 3 if split else 1
+    n_layers = ub.args.n_gru_layers
+    dev = net[0].device
+    s = L.stream_ptr
+
+    def pool2x(x):
+        B, H, W, C = x.shape
+        out = _Planes((B, (H + 1) // 2, (W + 1) // 2, C), dev, split)
+        L.call("as_pool2x_nhwc_split", x.data_ptr(), out.hi.data_ptr(), L.ptr(out.lo), B, H, W, C, s())
+        return out
+
+    def interp(x, ref):
+        B, H, W, C = x.shape
+        out = _Planes((B, ref.shape[1], ref.shape[2], C), dev, split)
+        L.call("as_interp_bilinear_nhwc_split", x.data_ptr(), out.hi.data_ptr(), L.ptr(out.lo), B, H, W, ref.shape[1],
+               ref.shape[2], C, s())
+        return out
+
+    def gru(name, g, idx, h, xs):
+        B, H, W, Hd = h.shape
+        cin = Hd + sum(x.shape[3] for x in xs)
+        wzr = _weights(ub, name + ".zr", [g.convz, g.convr], split=split)
+        wq = _weights(ub, name + ".q", [g.convq], split=split)
+        assert wzr["cin"] == cin
+        ctx_zr, ctx_q = _context(ub, idx, inp[idx], wzr, wq)
+        hS = _planes_of(ub, h, split)
+        z = torch.empty_like(h)
+        rh = _Planes(h.shape, dev, split)
+        _conv(B, H, W, [hS] + xs, wzr, nsplit, L.UEPI_GRU_ZR, out=rh, bias=False, ctx=ctx_zr, h=h, z=z)
+        hn = torch.empty_like(h)
+        hnS = _Planes(h.shape, dev, split)
+        _conv(B, H, W, [rh] + xs, wq, nsplit, L.UEPI_GRU_Q, out=hnS, bias=False, ctx=ctx_q, h=h, z=z, out_f32=hn)
+        _remember(ub, hn, hnS)
+        return hn
+
+    with torch.cuda.device(dev):
+        hs = [None if t is None else _nhwc_view(t.detach())[0] for t in net]
+        if iter16:
+            hs[2] = gru("gru16", ub.gru16, 2, hs[2], [pool2x(hs[1])])
+        if iter08:
+            xs = [pool2x(hs[0])]
+            if n_layers > 2:
+                xs.append(interp(hs[2], hs[1]))
+            hs[1] = gru("gru08", ub.gru08, 1, hs[1], xs)
+        if iter04:
+            L.require_cuda(corr, "corr", torch.float32, contiguous=False)
+            L.require_cuda(disp, "disp", torch.float32, contiguous=False)
+            corr = corr.detach().contiguous()
+            disp = disp.detach().contiguous()
+            B, Cc, H, W = corr.shape
+            e = ub.encoder
+            sw = _small_weights(ub)
+            cpad = (Cc + 63) // 64 * 64
+            corrS = _Planes((B, H, W, cpad), dev, split)
+            L.call("as_nchw_to_nhwc_split", corr.data_ptr(), corrS.hi.data_ptr(), L.ptr(corrS.lo), B, Cc, H, W, cpad, s())
+            c1 = _Planes((B, H, W, 64), dev, split)
+            _conv(B, H, W, [corrS], _weights(ub, "convc1", [e.convc1], cin_pad=cpad, split=split), nsplit,
+                  L.UEPI_RELU_SPLIT, out=c1)
+            enc = _Planes((B, H, W, 128), dev, split)
+            _conv(B, H, W, [c1], _weights(ub, "convc2", [e.convc2], split=split), nsplit, L.UEPI_RELU_SPLIT, out=enc)
+            d1 = _Planes((B, H, W, 64), dev, split)
+            L.call("as_convd1_split", disp.data_ptr(), sw["wd1"].data_ptr(), sw["bd1"].data_ptr(), d1.hi.data_ptr(),
+                   L.ptr(d1.lo), B, H, W, 64, 0, s())
+            _conv(B, H, W, [d1], _weights(ub, "convd2", [e.convd2], split=split), nsplit, L.UEPI_RELU_SPLIT, out=enc,
+                  out_coff=64)
+            mo = _Planes((B, H, W, 128), dev, split)
+            _conv(B, H, W, [enc], _weights(ub, "conv", [e.conv], n_pad=128, split=split), nsplit, L.UEPI_MOTION, out=mo,
+                  disp=disp)
+            xs = [mo]
+            if n_layers > 1:
+                xs.append(interp(hs[1], hs[0]))
+            hs[0] = gru("gru04", ub.gru04, 0, hs[0], xs)
+        for i in range(len(net)):
+            if hs[i] is not None:
+                net[i] = hs[i].permute(0, 3, 1, 2)
+        if not update:
+            return net
+        B, H, W, Hd = hs[0].shape
+        sw = _small_weights(ub)
+        u = torch.empty((B, H, W, 9), device=dev, dtype=torch.float32)
+        _conv(B, H, W, [_planes_of(ub, hs[0], split)], _weights(ub, "dh1", [ub.disp_head.conv1], split=split), nsplit,
+              L.UEPI_DISPHEAD, w2=sw["w2"], u=u)
+        delta = torch.empty((B, 1, H, W), device=dev, dtype=torch.float32)
+        L.call("as_disp_delta", u.data_ptr(), sw["b2"].data_ptr(), delta.data_ptr(), B, H, W, s())
+    return net, delta

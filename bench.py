@@ -307,10 +307,10 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--engine", default=os.environ.get("ANYSTEREO_ENGINE", "fp32"), choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--engine", default=os.environ.get("ANYSTEREO_ENGINE", "bf16x3"), choices=["fp32", "bf16x3", "bf16"])
     ap.add_argument("--corr-mode", default=None, choices=[None, "fp32", "bf16x3", "bf16"])
     ap.add_argument("--pairs-per-gpu", type=int, default=8)
     ap.add_argument("--ref-sample-iters", type=int, default=8)

@@ -209,8 +209,71 @@ int as_nchw_to_nhwc(const float* in, float* out, int B, int C, int H, int W, int
                     int out_coff, as_stream_t stream);
 int as_nhwc_to_nchw(const float* in, float* out, int B, int C, int H, int W, int in_pitch,
                     int in_coff, as_stream_t stream);
+/* as as_nchw_to_nhwc with a per-channel bias added: out[n][coff+c] = in[b,c,y,x] + bias[c]
+ * (folds a convolution's bias into the loop-invariant GRU context term) */
+int as_nchw_to_nhwc_bias(const float* in, const float* bias, float* out, int B, int C, int H, int W,
+                         int out_pitch, int out_coff, as_stream_t stream);
 /* y[i] = a[i] + b[i] (disp = disp + delta, continuous_IGEVstereo.py:295) */
 int as_add_f32(const float* a, const float* b, float* y, long long n, as_stream_t stream);
+
+
+/* ------------------------------------------------------------------------------------------
+ * a8-a11 on tensor cores (tcgen05 + TMA).  Activations are pixel-major bf16 planes [B*H*W][C]:
+ * `hi` = round-to-nearest bf16 of the value, `lo` = bf16 of the remainder (fp32-parity mode, nsplit = 3:
+ * hi*hi + hi*lo + lo*hi with fp32 accumulation in TMEM); nsplit = 1 is the single-bf16 fast mode.
+ * Channels per source must be multiples of 64; Cout a multiple of 32, <= 256.
+ * ------------------------------------------------------------------------------------------ */
+#define AS_UEPI_RELU_SPLIT 0 /* relu(acc+bias) -> hi/lo planes at channel offset out_coff               */
+#define AS_UEPI_MOTION 1     /* as above, last channel <- disp  (cat(out, disp), update.py:92)           */
+#define AS_UEPI_GRU_ZR 2     /* z=sigmoid(acc+ctx) -> z fp32; r likewise, r*h -> hi/lo   (update.py:37-39) */
+#define AS_UEPI_GRU_Q 3      /* h'=(1-z)h + z tanh(acc+ctx) -> out_f32 and hi/lo        (update.py:39-40) */
+#define AS_UEPI_DISPHEAD 4   /* u[n][t] = sum_c w2[t][c]*relu(acc+bias)[c]: DispHead.conv2 folded into
+                                conv1's epilogue (update.py:23-24); finish with as_disp_delta           */
+
+typedef struct as_umma_src {
+  const void* hi; /* bf16 [B*H*W][channels] */
+  const void* lo; /* same, or NULL when nsplit == 1 */
+  int channels;
+} as_umma_src;
+
+typedef struct as_conv_umma_desc {
+  int B, H, W, KH, KW; /* 1x1 or 3x3, stride 1, zero padding KH/2 (done by TMA out-of-bounds fill) */
+  int Cout;            /* padded N of the GEMM */
+  int num_src;
+  as_umma_src src[3];
+  const void* w_hi; /* bf16 [Cout][KH*KW*Cin_total], K index = tap*Cin_total + cin (as_pack_conv_weight_bf16) */
+  const void* w_lo;
+  int nsplit, epilogue;
+  const float* bias;   /* [Cout] (RELU_SPLIT, MOTION, DISPHEAD)                                  */
+  const float* ctx;    /* GRU: context + bias, fp32 [N][ctx_pitch]                               */
+  int ctx_pitch;
+  const float* h;      /* GRU: hidden state fp32 [N][Hd]                                         */
+  float* z;            /* GRU_ZR: written, GRU_Q: read; fp32 [N][Hd]                             */
+  float* out_f32;      /* GRU_Q: new hidden state fp32 [N][Hd]                                   */
+  void* out_hi;        /* bf16 planes [N][out_pitch] written at channel offset out_coff          */
+  void* out_lo;
+  int out_pitch, out_coff, cout_valid;
+  const float* disp;   /* MOTION: [N]                                                            */
+  const float* w2;     /* DISPHEAD: conv2 weight as [9][256] fp32                                */
+  float* u;            /* DISPHEAD: [N][9] fp32                                                  */
+} as_conv_umma_desc;
+
+int as_conv2d_umma(const as_conv_umma_desc* desc, as_stream_t stream);
+/* nn.Conv2d weight [Cout][Cin][KH][KW] fp32 -> bf16 hi/lo [n_pad][KH*KW*cin_pad] (zero padded rows/channels) */
+int as_pack_conv_weight_bf16(const float* w_oihw, void* w_hi, void* w_lo, int Cout, int Cin, int KH, int KW,
+                             int n_pad, int cin_pad, as_stream_t stream);
+/* fp32 -> bf16 hi/lo planes (lo may be NULL) */
+int as_split_f32(const float* in, void* hi, void* lo, long long n, as_stream_t stream);
+int as_nchw_to_nhwc_split(const float* in, void* hi, void* lo, int B, int C, int H, int W, int c_pad,
+                          as_stream_t stream);
+int as_pool2x_nhwc_split(const float* in, void* hi, void* lo, int B, int H, int W, int C, as_stream_t stream);
+int as_interp_bilinear_nhwc_split(const float* in, void* hi, void* lo, int B, int Hin, int Win, int Hout,
+                                  int Wout, int C, as_stream_t stream);
+/* BasicMotionEncoder.convd1 (7x7, 1 -> 64, update.py:80,87) + relu -> bf16 planes [N][out_pitch] at out_coff */
+int as_convd1_split(const float* disp, const float* w /*[64][49]*/, const float* bias, void* hi, void* lo,
+                    int B, int H, int W, int out_pitch, int out_coff, as_stream_t stream);
+/* delta[n] = bias2 + sum_t u[n + shift(t)][t]  (zero outside the image): finishes DispHead.conv2 */
+int as_disp_delta(const float* u, const float* bias2, float* delta, int B, int H, int W, as_stream_t stream);
 
 #ifdef __cplusplus
 }

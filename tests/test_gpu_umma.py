@@ -92,3 +92,88 @@ def test_corr_umma_fullsize_property(A):
     for l in range(2):
         assert rel(got.init_corr_pyramid[l], ref.init_corr_pyramid[l]) < 1e-4
     A.set_corr_mode("fp32")
+
+
+# ---------------------------------------------------------------------------------------------------
+# update block on tensor cores
+# ---------------------------------------------------------------------------------------------------
+import types  # noqa: E402
+
+
+def make_block(A, family, seed):
+    cls = A.BasicMultiUpdateBlock if family == "igev" else A.BasicMultiUpdateBlockRAFT
+    args = types.SimpleNamespace(corr_levels=2 if family == "igev" else 4, corr_radius=4, n_gru_layers=3)
+    m = cls(args, hidden_dims=[128, 128, 128])
+    m.load_state_dict(O.make_update_block_params(162 if family == "igev" else 36, seed=seed), strict=True)
+    return m.cuda().eval()
+
+
+@pytest.mark.parametrize("engine,tol", [("bf16x3", 2e-4), ("bf16", 5e-2)])
+@pytest.mark.parametrize("family", ["igev", "raft"])
+def test_update_block_umma_golden(A, golden, family, engine, tol):
+    g = golden("update_block_" + family)
+    c = cases.update_block_case(family)
+    m = make_block(A, family, 11)
+    A.set_update_engine(engine)
+    inp = [[t.cuda() for t in lst] for lst in c["inp"]]
+    with torch.no_grad():
+        net, delta = m([t.cuda() for t in c["net"]], inp, c["corr"].cuda(), c["disp"].cuda())
+        torch.cuda.synchronize()
+        for i in range(3):
+            assert rel(net[i], g["full_net%d" % i]) < tol, i
+        assert rel(delta, g["full_delta"]) < tol
+        net = m([t.cuda() for t in c["net"]], inp, iter16=True, iter08=True, iter04=False, update=False)
+        for i in range(3):
+            assert rel(net[i], g["lowres_net%d" % i]) < tol
+    A.set_update_engine("fp32")
+
+
+@pytest.mark.parametrize("family", ["igev", "raft"])
+def test_iteration_loop_epe_umma(A, golden, family):
+    """fp32-parity tensor-core mode: final disparity within 0.01 px of the reference after equal iterations."""
+    g = golden("loop_" + family)
+    c = cases.loop_case(family)
+    iters = int(g["iters"])
+    m = make_block(A, family, 12 if family == "igev" else 13)
+    A.set_update_engine("bf16x3")
+    A.set_corr_mode("bf16x3")
+    net = [t.cuda() for t in c["net"]]
+    inp = [[t.cuda() for t in lst] for lst in c["inp"]]
+    if family == "igev":
+        disp, net, hist = A.igev_iterations(m, c["f1"].cuda(), c["f2"].cuda(), c["geo"].cuda(), net, inp,
+                                            c["init_disp"].cuda(), iters, keep_all=True)
+    else:
+        disp, net, hist = A.raft_iterations(m, c["f1"].cuda(), c["f2"].cuda(), net, inp, iters, keep_all=True)
+    ref = torch.from_numpy(g["disps"])
+    err = (torch.stack([h.cpu() for h in hist]) - ref).abs()
+    epe = float(err[-1].mean()) * 4
+    A.set_update_engine("fp32")
+    A.set_corr_mode("fp32")
+    assert epe < 0.01, epe
+
+
+def test_update_block_umma_vs_fp32_medium(A):
+    """1/4-KITTI-sized maps with ragged tiles (W not a multiple of 16, H not of 8): tensor-core engine vs the
+    exact-fp32 CUDA-core engine on the GPU."""
+    torch.manual_seed(3)
+    B, H, W = 2, 46, 75
+    m = make_block(A, "igev", 5)
+    sizes = [(H, W), ((H + 1) // 2, (W + 1) // 2), (((H + 1) // 2 + 1) // 2, ((W + 1) // 2 + 1) // 2)]
+    net = [torch.tanh(torch.randn(B, 128, h, w, device="cuda")) for h, w in sizes]
+    inp = [[0.5 * torch.randn(B, 128, h, w, device="cuda") for _ in range(3)] for h, w in sizes]
+    corr = torch.randn(B, 162, H, W, device="cuda")
+    disp = torch.rand(B, 1, H, W, device="cuda") * 20
+    with torch.no_grad():
+        A.set_update_engine("fp32")
+        n32, d32 = m([t.clone() for t in net], inp, corr, disp)
+        A.set_update_engine("bf16x3")
+        n3, d3 = m([t.clone() for t in net], inp, corr, disp)
+        # second call on its own outputs exercises the cached hi/lo planes
+        n3b, d3b = m(list(n3), inp, corr, disp)
+        A.set_update_engine("fp32")
+        n32b, d32b = m(list(n32), inp, corr, disp)
+    for i in range(3):
+        assert rel(n3[i], n32[i]) < 2e-4
+        assert rel(n3b[i], n32b[i]) < 4e-4
+    assert rel(d3, d32) < 2e-4
+    assert rel(d3b, d32b) < 4e-4
