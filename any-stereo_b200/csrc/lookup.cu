@@ -243,111 +243,139 @@ __global__ void corr_lookup_bwd_kernel(LevelSetRW lv, int L, const float* __rest
 // ------------------------------------------------------------------------------------------------
 // IGEV: geometry volume (8 groups) + correlation, fast path G == 8, r == 4
 // ------------------------------------------------------------------------------------------------
-constexpr int kGP = 32;    // pixels per CTA (one 128-byte output line per channel)
-constexpr int kGT = 192;   // threads per CTA (6 warps): 8 x 128-bit loads in flight per thread, <=64 regs
-constexpr int kGSP = 34;   // smem row stride: 4*34 % 32 == 8 -> conflict-free transposing stores
+constexpr int kGP = 64;    // pixels per tile: each output channel is written as 256 contiguous bytes
+constexpr int kGT = 192;   // 6 warps
+constexpr int kGSP = 66;   // smem row stride (floats): 4*66 % 32 == 8 -> conflict-free transposing stores
+#ifndef AS_GEO_MINB
+#define AS_GEO_MINB 2
+#endif
 constexpr int kG = 8, kR = 4, kTaps = 10, kK = 9;
 
+struct GeoTile {
+  int b, p0;
+};
+
+// Persistent, software-pipelined: while tile i is interpolated and written (phase C), the 128-bit window loads
+// of tile i+1 are already in flight in registers and the disparities of tile i+2 are being fetched, so every CTA
+// keeps HBM reads and writes overlapped instead of alternating between a load phase and a store phase.
 template <int L>
-__global__ void __launch_bounds__(kGT, 5) geo_lookup_fwd_kernel(LevelSet geo, int Dg, LevelSet corr,
-                                                             const float* __restrict__ disp,
-                                                             const float* __restrict__ coords,
-                                                             float* __restrict__ out, int HW, int W) {
+__global__ void __launch_bounds__(kGT, AS_GEO_MINB) geo_lookup_fwd_kernel(LevelSet geo, int Dg, LevelSet corr,
+                                                                const float* __restrict__ disp,
+                                                                const float* __restrict__ coords,
+                                                                float* __restrict__ out, int HW, int W,
+                                                                int tiles_per_img, int num_tiles) {
   extern __shared__ __align__(16) float smem[];
   float* s_geo = smem;                                   // [L][kTaps*kG = 80][kGSP]
   float* s_cor = smem + L * kTaps * kG * kGSP;           // [L][16][kGSP]
-  __shared__ int s_tg[L][kGP], s_tc[L][kGP];
-  __shared__ float s_fg[L][kGP], s_fc[L][kGP];
+  __shared__ int s_tg[2][L][kGP], s_tc[2][L][kGP];
+  __shared__ float s_fg[2][L][kGP], s_fc[2][L][kGP];
 
   const int tid = threadIdx.x;
-  const int b = blockIdx.y;
-  const int p0 = blockIdx.x * kGP;
-  const long long nbase = (long long)b * HW;
-
-  if (tid < kGP) {
-    const int p = p0 + tid;
-    float d = 0.f, c = 0.f;
-    if (p < HW) {
-      d = disp[nbase + p];
-      c = coords ? coords[nbase + p] : (float)(p % W);
-    }
-#pragma unroll
-    for (int l = 0; l < L; ++l) {
-      const float sc = level_scale(l);
-      int t0; float f;
-      split_pos(d * sc, kR, t0, f);                 // geometry.py:43  x0 = dx + disp/2^i
-      s_tg[l][tid] = t0; s_fg[l][tid] = f;
-      split_pos(c * sc - d * sc, kR, t0, f);        // geometry.py:52
-      s_tc[l][tid] = t0; s_fc[l][tid] = f;
-    }
-  }
-  __syncthreads();
-
-  // ---- phase 1: window loads.  A warp instruction covers 8 pixels x 4 consecutive 16-byte chunks.
   const int warp = tid >> 5, lane = tid & 31;
   const int pix8 = lane >> 2, q4 = lane & 3;
-  constexpr int kGeoJobs = L * (kGP / 8) * 5;    // (level, pixel-group, chunk-quad): 20 chunks/pixel
-  constexpr int kCorJobs = L * (kGP / 8);        // 4 chunks/pixel
+  constexpr int kGeoJobs = L * (kGP / 8) * 5;    // (level, pixel-group, chunk-quad): 20 chunks of 16 B per pixel
+  constexpr int kCorJobs = L * (kGP / 8);        // 4 chunks per pixel
   constexpr int kJobs = kGeoJobs + kCorJobs;
   constexpr int kWarps = kGT / 32;
   constexpr int kPerWarp = (kJobs + kWarps - 1) / kWarps;
-  float4 v[kPerWarp];
-  int dst[kPerWarp];
-#pragma unroll
-  for (int i = 0; i < kPerWarp; ++i) {
-    const int job = warp + i * kWarps;
-    dst[i] = -1;
-    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (job < kGeoJobs) {
-      const int l = job / ((kGP / 8) * 5);
-      const int rem = job - l * ((kGP / 8) * 5);
-      const int pg = rem / 5, qq = rem - pg * 5;
-      const int pix = pg * 8 + pix8;
-      const int q = qq * 4 + q4;            // chunk 0..19 : tap j = q>>1, groups (q&1)*4..+3
-      const int p = p0 + pix;
-      const int Dl = Dg >> l;
-      const int x1 = s_tg[l][pix] + (q >> 1);
-      dst[i] = (l * kTaps * kG + q * 4) * kGSP + pix;
-      if (p < HW && x1 >= 0 && x1 < Dl)
-        v[i] = as_ldg_stream(reinterpret_cast<const float4*>(geo.ptr[l] + ((nbase + p) * Dl + x1) * kG + (q & 1) * 4));
-    } else if (job < kJobs) {
-      const int cj = job - kGeoJobs;
-      const int l = cj / (kGP / 8);
-      const int pg = cj - l * (kGP / 8);
-      const int pix = pg * 8 + pix8;
-      const int p = p0 + pix;
-      const int c0 = as_floor4(s_tc[l][pix]) * 4 + q4 * 4;
-      dst[i] = -2 - ((l * 16 + q4 * 4) * kGSP + pix);
-      if (p < HW && c0 >= 0 && c0 < corr.pitch[l])
-        v[i] = as_ldg_stream(reinterpret_cast<const float4*>(corr.ptr[l] + (nbase + p) * corr.pitch[l] + c0));
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < kPerWarp; ++i) {
-    if (dst[i] != -1) {
-      float* s = dst[i] >= 0 ? (s_geo + dst[i]) : (s_cor + (-2 - dst[i]));
-      s[0] = v[i].x; s[kGSP] = v[i].y; s[2 * kGSP] = v[i].z; s[3 * kGSP] = v[i].w;
-    }
-  }
-  __syncthreads();
-
-  // ---- phase 2: lane = pixel; kGT/kGP thread groups share the 9*L (group|corr) rows
-  const int pix = tid & (kGP - 1);
-  const int part = tid / kGP;          // 0..5
-  const int p = p0 + pix;
-  if (p >= HW) return;
   constexpr int C = L * (kG + 1) * kK;
-  float* o = out + (long long)b * C * HW + p;
-  for (int row = part; row < L * (kG + 1); row += kGT / kGP) {
-    const int l = row / (kG + 1);
-    const int g = row - l * (kG + 1);
-    {
-      if (g < kG) {
-        const int t0 = s_tg[l][pix];
-        const float f = s_fg[l][pix], omf = 1.0f - f;
+
+  auto tile_of = [&](int t, GeoTile& g) {
+    g.b = t / tiles_per_img;
+    g.p0 = (t - g.b * tiles_per_img) * kGP;
+  };
+  // (0) disparity / coordinate of this thread's pixel in tile t (threads < kGP)
+  auto fetch_dc = [&](int t, float& d, float& c) {
+    d = 0.f; c = 0.f;
+    if (t < num_tiles && tid < kGP) {
+      GeoTile g; tile_of(t, g);
+      const int p = g.p0 + tid;
+      if (p < HW) {
+        d = __ldg(disp + (long long)g.b * HW + p);
+        c = coords ? __ldg(coords + (long long)g.b * HW + p) : (float)(p % W);
+      }
+    }
+  };
+  auto put_params = [&](int buf, float d, float c) {
+    if (tid < kGP) {
+#pragma unroll
+      for (int l = 0; l < L; ++l) {
+        const float sc = level_scale(l);
+        int t0; float f;
+        split_pos(d * sc, kR, t0, f);                 // geometry.py:43  x0 = dx + disp/2^i
+        s_tg[buf][l][tid] = t0; s_fg[buf][l][tid] = f;
+        split_pos(c * sc - d * sc, kR, t0, f);        // geometry.py:52
+        s_tc[buf][l][tid] = t0; s_fc[buf][l][tid] = f;
+      }
+    }
+  };
+  float4 v[kPerWarp];
+  // (B) issue the window loads of tile t (parameters in buffer `buf`); a warp instruction = 8 pixels x 64 B
+  auto issue_loads = [&](int t, int buf) {
+    GeoTile g; tile_of(t, g);
+    const long long nbase = (long long)g.b * HW;
+#pragma unroll
+    for (int i = 0; i < kPerWarp; ++i) {
+      const int job = warp + i * kWarps;
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (job < kGeoJobs) {
+        const int l = job / ((kGP / 8) * 5);
+        const int rem = job - l * ((kGP / 8) * 5);
+        const int pg = rem / 5, qq = rem - pg * 5;
+        const int pix = pg * 8 + pix8;
+        const int q = qq * 4 + q4;            // chunk 0..19 : tap j = q>>1, groups (q&1)*4..+3
+        const int p = g.p0 + pix;
         const int Dl = Dg >> l;
-        const float* w = s_geo + (l * kTaps * kG + g) * kGSP + pix;
-        float* oc = o + (long long)(l * (kG + 1) * kK + g * kK) * HW;
+        const int x1 = s_tg[buf][l][pix] + (q >> 1);
+        if (p < HW && x1 >= 0 && x1 < Dl)
+          v[i] = as_ldg_stream(reinterpret_cast<const float4*>(geo.ptr[l] + ((nbase + p) * Dl + x1) * kG + (q & 1) * 4));
+      } else if (job < kJobs) {
+        const int cj = job - kGeoJobs;
+        const int l = cj / (kGP / 8);
+        const int pix = (cj - l * (kGP / 8)) * 8 + pix8;
+        const int p = g.p0 + pix;
+        const int c0 = as_floor4(s_tc[buf][l][pix]) * 4 + q4 * 4;
+        if (p < HW && c0 >= 0 && c0 < corr.pitch[l])
+          v[i] = as_ldg_stream(reinterpret_cast<const float4*>(corr.ptr[l] + (nbase + p) * corr.pitch[l] + c0));
+      }
+    }
+  };
+  // (A) registers -> transposed shared-memory windows
+  auto stash = [&]() {
+#pragma unroll
+    for (int i = 0; i < kPerWarp; ++i) {
+      const int job = warp + i * kWarps;
+      float* sp = nullptr;
+      if (job < kGeoJobs) {
+        const int l = job / ((kGP / 8) * 5);
+        const int rem = job - l * ((kGP / 8) * 5);
+        const int pg = rem / 5, qq = rem - pg * 5;
+        sp = s_geo + (l * kTaps * kG + (qq * 4 + q4) * 4) * kGSP + pg * 8 + pix8;
+      } else if (job < kJobs) {
+        const int cj = job - kGeoJobs;
+        const int l = cj / (kGP / 8);
+        sp = s_cor + (l * 16 + q4 * 4) * kGSP + (cj - l * (kGP / 8)) * 8 + pix8;
+      }
+      if (sp) { sp[0] = v[i].x; sp[kGSP] = v[i].y; sp[2 * kGSP] = v[i].z; sp[3 * kGSP] = v[i].w; }
+    }
+  };
+  // (C) lane = pixel: interpolate and write every channel of tile t as full lines
+  auto emit = [&](int t, int buf) {
+    GeoTile g; tile_of(t, g);
+    const int pix = tid & (kGP - 1);
+    const int part = tid / kGP;          // 0..2
+    const int p = g.p0 + pix;
+    if (p >= HW) return;
+    float* o = out + (long long)g.b * C * HW + p;
+    for (int row = part; row < L * (kG + 1); row += kGT / kGP) {
+      const int l = row / (kG + 1);
+      const int gi = row - l * (kG + 1);
+      if (gi < kG) {
+        const int t0 = s_tg[buf][l][pix];
+        const float f = s_fg[buf][l][pix], omf = 1.0f - f;
+        const int Dl = Dg >> l;
+        const float* w = s_geo + (l * kTaps * kG + gi) * kGSP + pix;
+        float* oc = o + (long long)(l * (kG + 1) * kK + gi * kK) * HW;
         float prev = (t0 >= 0 && t0 < Dl) ? w[0] : 0.f;
 #pragma unroll
         for (int k = 0; k < kK; ++k) {
@@ -357,8 +385,8 @@ __global__ void __launch_bounds__(kGT, 5) geo_lookup_fwd_kernel(LevelSet geo, in
           prev = cur;
         }
       } else {
-        const int t0 = s_tc[l][pix];
-        const float f = s_fc[l][pix], omf = 1.0f - f;
+        const int t0 = s_tc[buf][l][pix];
+        const float f = s_fc[buf][l][pix], omf = 1.0f - f;
         const int Wl = corr.width[l];
         const int off = t0 - as_floor4(t0) * 4;
         const float* w = s_cor + (l * 16 + off) * kGSP + pix;
@@ -373,6 +401,27 @@ __global__ void __launch_bounds__(kGT, 5) geo_lookup_fwd_kernel(LevelSet geo, in
         }
       }
     }
+  };
+
+  // ---- prologue: parameters + loads of the first tile, disparities of the second
+  int t = blockIdx.x;
+  if (t >= num_tiles) return;
+  float d_nxt, c_nxt;
+  fetch_dc(t, d_nxt, c_nxt);
+  put_params(0, d_nxt, c_nxt);
+  __syncthreads();
+  issue_loads(t, 0);
+  fetch_dc(t + gridDim.x, d_nxt, c_nxt);
+  int buf = 0;
+  for (; t < num_tiles; t += gridDim.x, buf ^= 1) {
+    const int tn = t + gridDim.x;
+    stash();                                  // tile t windows -> smem
+    put_params(buf ^ 1, d_nxt, c_nxt);        // tile t+1 parameters
+    __syncthreads();
+    if (tn < num_tiles) issue_loads(tn, buf ^ 1);          // in flight during emit(t)
+    fetch_dc(tn + gridDim.x, d_nxt, c_nxt);
+    emit(t, buf);
+    __syncthreads();
   }
 }
 
@@ -554,14 +603,25 @@ extern "C" int as_geo_lookup_fwd(const float* const* geo_levels, int G, int Dg, 
   const int HW = H * W;
   cudaStream_t st = as_cu(stream);
   if (G == kG && radius == kR && num_levels <= 4) {
-    dim3 grid(as_ceil_div(HW, kGP), B);
+    const int tiles_per_img = as_ceil_div(HW, kGP);
+    const long long nt = (long long)tiles_per_img * B;
+    if (nt >= (1LL << 31)) return AS_ERR_INDEX_RANGE;
+    const int num_tiles = (int)nt;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const size_t smem = sizeof(float) * num_levels * (kTaps * kG + 16) * kGSP;
 #define AS_LAUNCH_GEO(LV)                                                                                      \
   case LV: {                                                                                                   \
     cudaError_t e = cudaFuncSetAttribute(geo_lookup_fwd_kernel<LV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                          (int)smem);                                                           \
     if (e != cudaSuccess) return (int)e;                                                                       \
-    geo_lookup_fwd_kernel<LV><<<grid, kGT, smem, st>>>(gs, Dg, cs, disp, coords, out, HW, W);                  \
+    int occ = 1;                                                                                               \
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, geo_lookup_fwd_kernel<LV>, kGT, smem);                 \
+    if (occ < 1) occ = 1;                                                                                      \
+    const int grid = num_tiles < occ * sms ? num_tiles : occ * sms; /* persistent: all CTAs resident */        \
+    geo_lookup_fwd_kernel<LV><<<grid, kGT, smem, st>>>(gs, Dg, cs, disp, coords, out, HW, W, tiles_per_img,    \
+                                                       num_tiles);                                              \
   } break;
     switch (num_levels) {
       AS_LAUNCH_GEO(1)

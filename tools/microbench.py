@@ -53,7 +53,14 @@ def main():
     ap.add_argument("--B", type=int, default=8)
     ap.add_argument("--json", default=None)
     ap.add_argument("--update", action="store_true", help="also time the update block")
+    ap.add_argument("--only", default=None, help="comma list of sections: lookup")
+    ap.add_argument("--l2-fetch", type=int, default=0, help="experiment: cudaLimitMaxL2FetchGranularity (32/64/128)")
     a = ap.parse_args()
+    if a.l2_fetch:
+        import ctypes
+        rt = ctypes.CDLL("libcudart.so.12")
+        torch.cuda.init()
+        print("cudaDeviceSetLimit(L2 fetch granularity, %d) ->" % a.l2_fetch, rt.cudaDeviceSetLimit(5, ctypes.c_size_t(a.l2_fetch)))
     torch.manual_seed(0)
     dev = "cuda"
     B, D, H, W, Dg = a.B, 96, 96, 312, 48
@@ -67,10 +74,17 @@ def main():
 
     f1 = torch.randn(B, D, H, W, device=dev)
     f2 = torch.randn(B, D, H, W, device=dev)
+    gwc = A.build_gwc_volume(f1, f2, Dg, 8)
+    if a.only == "lookup":
+        blk = A.Combined_Geo_Encoding_Volume(f1, f2, gwc, num_levels=2, radius=4)
+        coords = torch.arange(W, device=dev, dtype=torch.float32).reshape(1, 1, W, 1).repeat(B, H, 1, 1)
+        d = (torch.rand(B, 1, H, W, device=dev) * Dg).contiguous()
+        med, best = timeit(lambda: blk(d, coords))
+        rec("geo_lookup_uniform", med, best, 1372 * N)
+        return
     # a7 GWC
     med, best = timeit(lambda: A.build_gwc_volume(f1, f2, Dg, 8))
     rec("gwc_build", med, best, 2 * 4 * B * D * H * W + 4 * B * 8 * Dg * H * W)
-    gwc = A.build_gwc_volume(f1, f2, Dg, 8)
     # a1+a2 corr pyramid, per mode
     for mode in ("fp32", "bf16x3", "bf16"):
         try:
@@ -105,6 +119,17 @@ def main():
     g = torch.randn(B, 9, H, W, device=dev)
     med, best = timeit(lambda: A.corr_sampler.backward(vol, x0, g, 4))
     rec("sampler_bwd", med, best, (36 + 4) * N + 4 * N * W)
+    try:   # the reference's own CUDA kernels recompiled for sm_100a: the "kernel to beat"
+        from oracle import ref_sampler
+        rs = ref_sampler.load()
+        if rs is not None:
+            x2 = torch.cat([x0, torch.zeros_like(x0)], 1).contiguous()
+            med, best = timeit(lambda: rs.forward(vol, x2, 4))
+            rec("REFERENCE_sampler_fwd", med, best, 80 * N)
+            med, best = timeit(lambda: rs.backward(vol, x2, g, 4))
+            rec("REFERENCE_sampler_bwd", med, best, (36 + 4) * N + 4 * N * W)
+    except Exception as e:
+        print("reference sampler unavailable:", e)
     # a3 RAFT lookup at config 3 (496x720, L=4), D reduced to keep the build short: only the lookup is timed
     Br, Hr, Wr = 1, 496, 720
     r1 = torch.randn(Br, 64, Hr, Wr, device=dev)
