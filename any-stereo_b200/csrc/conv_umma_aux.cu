@@ -124,42 +124,53 @@ __global__ void pack_weight_bf16_kernel(const float* __restrict__ w, __nv_bfloat
   if (lo) lo[idx] = l;
 }
 
-// 7x7 conv, 1 input channel -> 64, + bias, relu; one thread = one pixel x 8 output channels
+// 7x7 conv, 1 input channel -> 64, + bias, relu.  CTA = 32x8 pixel tile: the (8+6)x(32+6) disparity patch and the
+// 64x49 weights live in shared memory; one thread = one pixel, 4 passes of 16 output channels.  Weight reads are
+// warp-uniform (broadcast), patch reads are lane-consecutive: no bank conflicts.
+constexpr int kD1TX = 32, kD1TY = 8;
 __global__ void __launch_bounds__(256) convd1_split_kernel(const float* __restrict__ disp, const float* __restrict__ w,
                                                            const float* __restrict__ bias, __nv_bfloat16* __restrict__ hi,
-                                                           __nv_bfloat16* __restrict__ lo, int H, int W, int pitch, int coff,
-                                                           long long N) {
-  __shared__ float ws[64 * 49];
+                                                           __nv_bfloat16* __restrict__ lo, int H, int W, int pitch, int coff) {
+  __shared__ __align__(16) float ws[49 * 64];     // [tap][channel]
   __shared__ float bs[64];
-  for (int i = threadIdx.x; i < 64 * 49; i += 256) ws[i] = w[i];
-  if (threadIdx.x < 64) bs[threadIdx.x] = bias[threadIdx.x];
-  __syncthreads();
-  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-  const long long n = idx >> 3;
-  const int cg = (int)(idx & 7) * 8;
-  if (n >= N) return;
+  __shared__ float patch[kD1TY + 6][kD1TX + 6 + 1];
+  const int tid = threadIdx.x;
+  const int b = blockIdx.z, x0 = blockIdx.x * kD1TX, y0 = blockIdx.y * kD1TY;
   const long long HW = (long long)H * W;
-  const int b = (int)(n / HW);
-  const int rem = (int)(n - (long long)b * HW);
-  const int y = rem / W, x = rem - y * W;
-  float acc[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = bs[cg + j];
-  for (int dy = 0; dy < 7; ++dy) {
-    const int yy = y + dy - 3;
-    if (yy < 0 || yy >= H) continue;
-    for (int dx = 0; dx < 7; ++dx) {
-      const int xx = x + dx - 3;
-      if (xx < 0 || xx >= W) continue;
-      const float d = __ldg(disp + (long long)b * HW + (long long)yy * W + xx);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = fmaf(ws[(cg + j) * 49 + dy * 7 + dx], d, acc[j]);
-    }
+  for (int i = tid; i < 64 * 49; i += 256) { const int c = i / 49, t = i - c * 49; ws[t * 64 + c] = w[i]; }
+  if (tid < 64) bs[tid] = bias[tid];
+  for (int i = tid; i < (kD1TY + 6) * (kD1TX + 6); i += 256) {
+    const int r = i / (kD1TX + 6), c = i - r * (kD1TX + 6);
+    const int yy = y0 + r - 3, xx = x0 + c - 3;
+    patch[r][c] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(disp + (long long)b * HW + (long long)yy * W + xx) : 0.f;
   }
-  float4 a = make_float4(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f), fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
-  float4 c = make_float4(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f), fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f));
-  store_split4(a, hi, lo, n * pitch + coff + cg);
-  store_split4(c, hi, lo, n * pitch + coff + cg + 4);
+  __syncthreads();
+  const int tx = tid & 31, ty = tid >> 5;
+  const int x = x0 + tx, y = y0 + ty;
+  if (x >= W || y >= H) return;
+  const long long n = (long long)b * HW + (long long)y * W + x;
+  for (int cg = 0; cg < 64; cg += 16) {
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = bs[cg + j];
+    for (int dy = 0; dy < 7; ++dy) {
+#pragma unroll
+      for (int dx = 0; dx < 7; ++dx) {
+        const float d = patch[ty + dy][tx + dx];
+        const float4* wp = reinterpret_cast<const float4*>(ws + (dy * 7 + dx) * 64 + cg);
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 w4 = wp[j4];
+          acc[4 * j4] = fmaf(w4.x, d, acc[4 * j4]); acc[4 * j4 + 1] = fmaf(w4.y, d, acc[4 * j4 + 1]);
+          acc[4 * j4 + 2] = fmaf(w4.z, d, acc[4 * j4 + 2]); acc[4 * j4 + 3] = fmaf(w4.w, d, acc[4 * j4 + 3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; j += 4)
+      store_split4(make_float4(fmaxf(acc[j], 0.f), fmaxf(acc[j + 1], 0.f), fmaxf(acc[j + 2], 0.f), fmaxf(acc[j + 3], 0.f)),
+                   hi, lo, n * pitch + coff + cg + j);
+  }
 }
 
 __global__ void disp_delta_kernel(const float* __restrict__ u, const float* __restrict__ bias2, float* __restrict__ delta,
@@ -238,9 +249,10 @@ extern "C" int as_convd1_split(const float* disp, const float* w, const float* b
                                int W, int out_pitch, int out_coff, as_stream_t stream) {
   if (!disp || !w || !bias || !hi || B <= 0 || H <= 0 || W <= 0 || out_pitch < out_coff + 64) return AS_ERR_BAD_ARG;
   if ((out_pitch & 3) || (out_coff & 3)) return AS_ERR_ALIGNMENT;
-  const long long N = (long long)B * H * W;
-  convd1_split_kernel<<<(unsigned)as_ceil_div_ll(N * 8, 256), 256, 0, as_cu(stream)>>>(
-      disp, w, bias, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, H, W, out_pitch, out_coff, N);
+  if (B > 65535 || as_ceil_div(H, kD1TY) > 65535) return AS_ERR_UNSUPPORTED;
+  dim3 grid(as_ceil_div(W, kD1TX), as_ceil_div(H, kD1TY), B);
+  convd1_split_kernel<<<grid, 256, 0, as_cu(stream)>>>(disp, w, bias, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, H, W,
+                                                       out_pitch, out_coff);
   AS_RETURN_IF_LAUNCH_FAILED();
   return AS_OK;
 }
