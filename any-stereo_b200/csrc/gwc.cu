@@ -11,7 +11,7 @@ namespace {
 
 constexpr int kDT = 16;  // disparities per thread tile
 
-__global__ void __launch_bounds__(256) gwc_fwd_tiled_kernel(const float* __restrict__ left,
+__global__ void __launch_bounds__(256, 3) gwc_fwd_tiled_kernel(const float* __restrict__ left,
                                                             const float* __restrict__ right,
                                                             float* __restrict__ out, int C, int H, int W,
                                                             int maxdisp, int G, int padl) {

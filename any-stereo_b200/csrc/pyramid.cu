@@ -44,54 +44,69 @@ struct GeoIn {
   const float* ptr[AS_MAX_LEVELS];
 };
 
-// smem: bufA [Dg*G][33] (level 0, then level 2, ...), bufB [(Dg/2)*G][33] (level 1, 3, ...)
+// One CTA = 32 pixels of one image row x one chunk of DC disparities x all G groups.  DC is a multiple of
+// 2^(L-1), so every pooled level of the chunk is computed from the chunk alone.  The chunk is read as G*DC
+// coalesced 128-byte rows (batched 8 deep per warp for memory-level parallelism), transposed through shared
+// memory ([d*G+g][33], conflict-free both ways) and written as one contiguous (DC>>l)*G-float run per pixel and
+// level.  ~25 KB of smem per CTA -> 8 CTAs/SM.
 __global__ void __launch_bounds__(256) geo_pyramid_kernel(const float* __restrict__ geo, GeoOut outs, int G, int Dg,
-                                                          int H, int W, int L) {
+                                                          int H, int W, int L, int DC, int nchunks) {
   extern __shared__ float s[];
-  const int E0 = Dg * G;
-  float* bufA = s;
-  float* bufB = s + (size_t)E0 * kTStride;
+  const int E0 = DC * G;
+  float* cur = s;                                  // [DC*G][33]
+  float* nxt = s + (size_t)E0 * kTStride;          // [(DC/2)*G][33]
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
-  const int x0 = blockIdx.x * kTX, y = blockIdx.y, b = blockIdx.z;
+  const int x0 = blockIdx.x * kTX, y = blockIdx.y;
+  const int b = blockIdx.z / nchunks, ch = blockIdx.z - b * nchunks;
+  const int d0 = ch * DC;
   const int nx = min(kTX, W - x0);
   const long long HW = (long long)H * W;
+  const float* src = geo + (long long)b * G * Dg * HW + (long long)y * W + x0 + lane;
 
-  // load: row (g,d) of 32 consecutive x -> smem row e = d*G+g
-  for (int row = warp; row < E0; row += 8) {
-    const int g = row / Dg, d = row - g * Dg;
-    float v = 0.f;
-    if (lane < nx) v = __ldg(geo + (((long long)b * G + g) * Dg + d) * HW + (long long)y * W + x0 + lane);
-    bufA[(d * G + g) * kTStride + lane] = v;
+  for (int r0 = warp * 8; r0 < E0; r0 += 64) {     // 8 rows per warp per batch
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = r0 + i;
+      const int g = row / DC, dd = row - g * DC;
+      v[i] = (row < E0 && lane < nx && d0 + dd < Dg) ? __ldg(src + ((long long)g * Dg + d0 + dd) * HW) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = r0 + i;
+      if (row < E0) {
+        const int g = row / DC, dd = row - g * DC;
+        cur[(dd * G + g) * kTStride + lane] = v[i];
+      }
+    }
   }
   __syncthreads();
 
-  const long long n0 = ((long long)b * H + y) * W + x0;   // first pixel of the tile
-  float* cur = bufA;
-  float* nxt = bufB;
-  int Dl = Dg;
+  const long long n0 = ((long long)b * H + y) * W + x0;
+  int Dl = Dg, dc = DC, dl0 = d0;                  // level width, chunk extent and chunk origin at level l
   for (int l = 0; l < L; ++l) {
-    const int El = Dl * G;
-    // write level l: per pixel El contiguous floats, pixels contiguous -> one contiguous run
-    float* dst = outs.ptr[l] + n0 * El;
-    const int total = nx * El;
-    for (int i = tid; i < total; i += 256) {
-      const int px = i / El, e = i - px * El;
-      dst[i] = cur[e * kTStride + px];
+    const int valid = min(dc, Dl - dl0);           // disparities of this chunk that exist at level l
+    if (valid > 0) {
+      const int El = valid * G;
+      float* dst = outs.ptr[l] + (n0 * Dl + dl0) * G;
+      const long long pstride = (long long)Dl * G;
+      for (int i = tid; i < nx * El; i += 256) {
+        const int px = i / El, e = i - px * El;
+        dst[px * pstride + e] = cur[e * kTStride + px];
+      }
     }
     if (l + 1 < L) {
-      const int Dn = Dl >> 1;
-      const int En = Dn * G;
+      const int dn = dc >> 1;
+      const int En = dn * G;
       for (int i = tid; i < En * kTX; i += 256) {
-        const int e = i / kTX, px = i - e * kTX;       // lanes over px: conflict-free
+        const int e = i / kTX, px = i - e * kTX;
         const int d2 = e / G, g = e - d2 * G;
-        const float a = cur[((2 * d2) * G + g) * kTStride + px];
-        const float c = cur[((2 * d2 + 1) * G + g) * kTStride + px];
-        nxt[e * kTStride + px] = (a + c) * 0.5f;
+        nxt[e * kTStride + px] = (cur[((2 * d2) * G + g) * kTStride + px] + cur[((2 * d2 + 1) * G + g) * kTStride + px]) * 0.5f;
       }
       __syncthreads();
       float* t = cur; cur = nxt; nxt = t;
-      Dl = Dn;
+      Dl >>= 1; dc = dn; dl0 >>= 1;
     }
   }
 }
@@ -168,12 +183,16 @@ extern "C" int as_geo_pyramid_build(const float* geo, int B, int G, int Dg, int 
     if (!levels[l]) return AS_ERR_BAD_ARG;
     o.ptr[l] = levels[l];
   }
-  const size_t smem = sizeof(float) * kTStride * ((size_t)Dg * G + (size_t)(Dg / 2) * G);
+  int DC = 16;
+  while (DC < (1 << (num_levels - 1))) DC <<= 1;
+  const int nchunks = as_ceil_div(Dg, DC);
+  if ((long long)B * nchunks > 65535) return AS_ERR_UNSUPPORTED;
+  const size_t smem = sizeof(float) * kTStride * ((size_t)DC * G + (size_t)(DC / 2) * G);
   if (smem > 220 * 1024) return AS_ERR_UNSUPPORTED;
   cudaError_t e = cudaFuncSetAttribute(geo_pyramid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  dim3 grid(as_ceil_div(W, kTX), H, B);
-  geo_pyramid_kernel<<<grid, 256, smem, as_cu(stream)>>>(geo, o, G, Dg, H, W, num_levels);
+  dim3 grid(as_ceil_div(W, kTX), H, B * nchunks);
+  geo_pyramid_kernel<<<grid, 256, smem, as_cu(stream)>>>(geo, o, G, Dg, H, W, num_levels, DC, nchunks);
   AS_RETURN_IF_LAUNCH_FAILED();
   return AS_OK;
 }

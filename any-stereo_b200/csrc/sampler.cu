@@ -113,6 +113,67 @@ __global__ void __launch_bounds__(256) sampler_bwd_kernel(const float* __restric
   }
 }
 
+// fp32, W2 % 4 == 0: one warp writes 8 consecutive volume rows.  The 8 sample positions and the 8 x (2r+1)
+// output gradients are fetched first in two batched rounds (two DRAM latencies per 8 rows instead of per row),
+// then every row is written with 128-bit streaming stores: window values where they fall, zeros elsewhere.
+constexpr int kBwdRows = 8;
+__global__ void __launch_bounds__(256) sampler_bwd_f32v_kernel(const float* __restrict__ coords, long long coords_bstride,
+                                                               const float* __restrict__ gout, float* __restrict__ gvol,
+                                                               int HW, int W2, int r, long long total_rows) {
+  __shared__ float sg[8][kBwdRows][33];
+  __shared__ int st0[8][kBwdRows];
+  __shared__ float sf[8][kBwdRows];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long row0 = ((long long)blockIdx.x * 8 + warp) * kBwdRows;
+  if (row0 >= total_rows) return;
+  const int K = 2 * r + 1;
+  if (lane < kBwdRows) {
+    const long long row = row0 + lane;
+    float x0 = 0.f;
+    if (row < total_rows) {
+      const int b = (int)(row / HW);
+      x0 = __ldg(coords + (long long)b * coords_bstride + (row - (long long)b * HW));
+    }
+    const float fl = floorf(x0);
+    st0[warp][lane] = (int)fl - r;
+    sf[warp][lane] = x0 - fl;
+  }
+  for (int idx = lane; idx < kBwdRows * K; idx += 32) {
+    const int rr = idx / K, k = idx - rr * K;
+    const long long row = row0 + rr;
+    float v = 0.f;
+    if (row < total_rows) {
+      const int b = (int)(row / HW);
+      v = __ldg(gout + ((long long)b * K + k) * HW + (row - (long long)b * HW));
+    }
+    sg[warp][rr][k] = v;
+  }
+  __syncwarp();
+  for (int rr = 0; rr < kBwdRows; ++rr) {
+    const long long row = row0 + rr;
+    if (row >= total_rows) break;
+    const int t0 = st0[warp][rr];
+    const float f = sf[warp][rr], omf = 1.0f - f;
+    float* dst = gvol + row * W2;
+    const float* g = sg[warp][rr];
+    for (int x1 = lane * 4; x1 < W2; x1 += 128) {
+      const int j = x1 - t0;
+      float o[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int ju = j + u;                              // tap index, inside the window when 0 <= ju <= K
+        float v = 0.f;
+        if (ju >= 0 && ju <= K) {
+          if (ju > 0) v += g[ju - 1] * f;                  // sampler_kernel.cu:94-95
+          if (ju < K) v += g[ju] * omf;                    // sampler_kernel.cu:97-98
+        }
+        o[u] = v;
+      }
+      as_stg_stream4(reinterpret_cast<float4*>(dst + x1), make_float4(o[0], o[1], o[2], o[3]));
+    }
+  }
+}
+
 template <typename T>
 int launch_fwd(const void* volume, const float* coords, int coords_ch, void* out, int B, int H, int W1,
                int W2, int radius, cudaStream_t st) {
@@ -132,6 +193,14 @@ int launch_bwd(const float* coords, int coords_ch, const void* gout, void* gvol,
                int W2, int radius, cudaStream_t st) {
   const int HW = H * W1;
   const long long rows = (long long)B * HW;
+  if (sizeof(T) == 4 && (W2 & 3) == 0 && as_aligned16(gvol)) {
+    const long long vblocks = as_ceil_div_ll(rows, 8 * kBwdRows);
+    sampler_bwd_f32v_kernel<<<(unsigned)vblocks, 256, 0, st>>>(coords, (long long)coords_ch * HW,
+                                                              static_cast<const float*>(gout),
+                                                              static_cast<float*>(gvol), HW, W2, radius, rows);
+    AS_RETURN_IF_LAUNCH_FAILED();
+    return AS_OK;
+  }
   const long long blocks = as_ceil_div_ll(rows, 8);
   sampler_bwd_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(coords, (long long)coords_ch * HW,
                                                           static_cast<const T*>(gout),

@@ -74,6 +74,26 @@ def main():
 
     f1 = torch.randn(B, D, H, W, device=dev)
     f2 = torch.randn(B, D, H, W, device=dev)
+    if a.only == "calib":
+        # calibration of the box: what plain streaming achieves (same timing harness, L2 flushed)
+        n = 1 << 28                                   # 1 GiB of fp32
+        x = torch.empty(n, device=dev)
+        y = torch.empty(n, device=dev)
+        med, best = timeit(lambda: y.copy_(x))
+        rec("CALIB_copy_1GiB(read+write)", med, best, 8 * n)
+        med, best = timeit(lambda: y.zero_())
+        rec("CALIB_memset_1GiB(write only)", med, best, 4 * n)
+        med, best = timeit(lambda: torch.sum(x))
+        rec("CALIB_sum_1GiB(read only)", med, best, 4 * n)
+        n2 = 75 * (1 << 20)                           # 300 MB: the size of one correlation volume
+        x2 = torch.empty(n2, device=dev); y2 = torch.empty(n2, device=dev)
+        med, best = timeit(lambda: y2.copy_(x2))
+        rec("CALIB_copy_300MB(read+write)", med, best, 8 * n2)
+        med, best = timeit(lambda: y2.zero_())
+        rec("CALIB_memset_300MB(write only)", med, best, 4 * n2)
+        if a.json:
+            json.dump(res, open(a.json, "w"), indent=1)
+        return
     gwc = A.build_gwc_volume(f1, f2, Dg, 8)
     if a.only == "lookup":
         blk = A.Combined_Geo_Encoding_Volume(f1, f2, gwc, num_levels=2, radius=4)
