@@ -54,7 +54,7 @@ class ConvDesc(C.Structure):
         ("src", ConvSrc * AS_MAX_SRC),
         ("weight", _vp), ("bias", _vp), ("epilogue", _i),
         ("out", _vp), ("out_pitch", _i), ("out_coff", _i), ("out_layout", _i),
-        ("ctx", _vp), ("ctx_pitch", _i), ("h", _vp), ("z", _vp),
+        ("ctx", _vp), ("ctx_pitch", _i), ("h", _vp), ("z", _vp), ("save", _vp),
     ]
 
 
@@ -95,6 +95,14 @@ SIGNATURES = {
     "as_interp_bilinear_nhwc_split": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "as_convd1_split": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "as_disp_delta": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "as_pack_conv_weight_dgrad": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "as_conv2d_wgrad_fp32": (_i, [C.POINTER(ConvDesc), _vp, _i, _i, _vp, _vp, _vp]),
+    "as_relu_bwd": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _ll, _i, _vp]),
+    "as_gru_bwd_gates1": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _vp]),
+    "as_gru_bwd_gates2": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _ll, _i, _vp]),
+    "as_add_slice": (_i, [_vp, _i, _i, _vp, _i, _i, _ll, _i, _vp]),
+    "as_pool2x_nhwc_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "as_interp_bilinear_nhwc_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
 }
 
 _lib = None

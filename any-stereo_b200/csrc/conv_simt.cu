@@ -25,6 +25,7 @@ struct ConvParams {
   const float* ctx; int ctx_pitch;
   const float* h;
   float* z;
+  float* save;
 };
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
@@ -119,11 +120,13 @@ __global__ void __launch_bounds__(VT::kThreads) conv_simt_kernel(ConvParams p) {
         } else {
           const int ch = co - Hd;
           p.out[n * p.out_pitch + p.out_coff + ch] = v * __ldg(p.h + n * Hd + ch);   // r*h, update.py:38-39
+          if (p.save) p.save[n * Hd + ch] = v;                                        // r, kept for the backward pass
         }
         continue;
       }
       if (p.epilogue == AS_EPI_GRU_Q) {
         const float q = tanhf(v + __ldg(p.ctx + n * p.ctx_pitch + co));    // update.py:39
+        if (p.save) p.save[n * p.Cout + co] = q;
         const float zz = p.z[n * p.Cout + co];
         const float hh = __ldg(p.h + n * p.Cout + co);
         v = (1.0f - zz) * hh + zz * q;                                      // update.py:40
@@ -281,7 +284,7 @@ extern "C" int as_conv2d_fp32(const as_conv_desc* d, as_stream_t stream) {
   p.Cin = cin;
   p.weight = d->weight; p.bias = d->bias; p.epilogue = d->epilogue;
   p.out = d->out; p.out_pitch = d->out_pitch; p.out_coff = d->out_coff; p.out_layout = d->out_layout;
-  p.ctx = d->ctx; p.ctx_pitch = d->ctx_pitch; p.h = d->h; p.z = d->z;
+  p.ctx = d->ctx; p.ctx_pitch = d->ctx_pitch; p.h = d->h; p.z = d->z; p.save = d->save;
   if (d->epilogue == AS_EPI_GRU_ZR || d->epilogue == AS_EPI_GRU_Q) {
     if (!d->ctx || !d->h || !d->z) return AS_ERR_BAD_ARG;
     if (d->out_layout != AS_LAYOUT_NHWC) return AS_ERR_UNSUPPORTED;

@@ -229,13 +229,16 @@ class BasicMultiUpdateBlock(nn.Module):
 
     # -- forward ----------------------------------------------------------------------------------
     def forward(self, net, inp, corr=None, disp=None, iter04=True, iter08=True, iter16=True, update=True):
+        needs_grad = torch.is_grad_enabled() and (
+            any(p.requires_grad for p in self.parameters()) or any(t.requires_grad for t in net)
+            or any(t.requires_grad for lst in inp for t in lst) or (corr is not None and corr.requires_grad))
+        if needs_grad:
+            # training (config 5): differentiable path on the exact-fp32 kernels, explicit adjoints
+            from . import update_train
+            return update_train.forward(self, net, inp, corr, disp, iter04, iter08, iter16, update)
         if get_update_engine() != "fp32":
             from . import update_umma
             return update_umma.forward(self, net, inp, corr, disp, iter04, iter08, iter16, update)
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            # TODO(round 2): dgrad/wgrad kernels for config 5; inference is what round 1 covers
-            raise NotImplementedError("anystereo_b200.BasicMultiUpdateBlock: backward is not implemented yet; "
-                                      "call under torch.no_grad()")
         for t in net:
             L.require_cuda(t, "net[i]", torch.float32, contiguous=False)
         n_layers = self.args.n_gru_layers

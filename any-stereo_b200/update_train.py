@@ -1,0 +1,376 @@
+"""Differentiable execution of BasicMultiUpdateBlock.forward (training, BASELINE.json config 5).
+
+Forward and backward both run on the library's exact-fp32 CUDA-core kernels (include/anystereo_b200.h,
+section a13-vi).  The reference obtains these gradients from autograd over models/*/update.py:16-136; here the
+adjoint is written out explicitly as one ``torch.autograd.Function`` per update-block call:
+
+  conv data gradient   = the forward implicit-GEMM kernel on dY with flipped/transposed weights
+  conv weight gradient = as_conv2d_wgrad_fp32 (K = pixels, fp32 atomics)
+  GRU gates            = as_gru_bwd_gates1/2 (update.py:37-40), ReLU masks, pool2x / bilinear adjoints
+
+Gradients flow to: every parameter, the hidden states ``net``, the context terms ``inp``, and the lookup
+features ``corr``.  ``disp`` receives none: both model forwards detach it every iteration
+(continuous_IGEVstereo.py:285, prune_raft_stereo.py:277).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+
+NHWC, NCHW = L.LAYOUT_NHWC, L.LAYOUT_NCHW
+
+
+def _s():
+    return L.stream_ptr()
+
+
+def _to_nhwc(t):
+    """[B,C,H,W] (any strides) -> contiguous [B,H,W,C] fp32."""
+    p = t.permute(0, 2, 3, 1)
+    if p.is_contiguous():
+        return p
+    B, C, H, W = t.shape
+    t = t.contiguous()
+    out = torch.empty((B, H, W, C), device=t.device, dtype=torch.float32)
+    L.call("as_nchw_to_nhwc", t.data_ptr(), out.data_ptr(), B, C, H, W, C, 0, _s())
+    return out
+
+
+def _to_nchw(x, C=None, pitch=None, coff=0):
+    """pixel-major [B,H,W,pitch] slice -> [B,C,H,W] contiguous."""
+    B, H, W, P = x.shape
+    C = C or P
+    out = torch.empty((B, C, H, W), device=x.device, dtype=torch.float32)
+    L.call("as_nhwc_to_nchw", x.data_ptr(), out.data_ptr(), B, C, H, W, pitch or P, coff, _s())
+    return out
+
+
+class _Conv:
+    """One convolution (or z|r pair) with its packed forward / data-gradient weights."""
+
+    def __init__(self, convs):
+        with torch.no_grad():
+            self.w = torch.cat([c.weight.detach().float() for c in convs], 0).contiguous()
+            self.b = torch.cat([c.bias.detach().float() for c in convs], 0).contiguous()
+        self.Cout, self.Cin, self.KH, self.KW = self.w.shape
+        self.convs = convs
+        dev = self.w.device
+        self.wf = torch.empty((self.KH * self.KW * self.Cin, self.Cout), device=dev, dtype=torch.float32)
+        L.call("as_pack_conv_weight", self.w.data_ptr(), self.wf.data_ptr(), self.Cout, self.Cin, self.KH, self.KW, _s())
+        self.wd = torch.empty((self.KH * self.KW * self.Cout, self.Cin), device=dev, dtype=torch.float32)
+        L.call("as_pack_conv_weight_dgrad", self.w.data_ptr(), self.wd.data_ptr(), self.Cout, self.Cin, self.KH, self.KW,
+               _s())
+
+    def _desc(self, B, H, W, srcs):
+        d = L.ConvDesc()
+        d.B, d.H, d.W, d.KH, d.KW = B, H, W, self.KH, self.KW
+        d.num_src = len(srcs)
+        for i, (t, ch, pitch, layout) in enumerate(srcs):
+            d.src[i].ptr = t.data_ptr()
+            d.src[i].channels = ch
+            d.src[i].pitch = pitch
+            d.src[i].layout = layout
+        return d
+
+    def fwd(self, B, H, W, srcs, epi, out, out_pitch, out_coff=0, out_layout=NHWC, ctx=None, ctx_pitch=0, h=None, z=None,
+            save=None, bias=True):
+        d = self._desc(B, H, W, srcs)
+        d.Cout = self.Cout
+        d.weight = self.wf.data_ptr()
+        d.bias = self.b.data_ptr() if bias else None
+        d.epilogue = epi
+        d.out = out.data_ptr()
+        d.out_pitch, d.out_coff, d.out_layout = out_pitch, out_coff, out_layout
+        d.ctx, d.ctx_pitch, d.h, d.z, d.save = L.ptr(ctx), ctx_pitch, L.ptr(h), L.ptr(z), L.ptr(save)
+        L.call("as_conv2d_fp32", d, _s())
+
+    def dgrad(self, B, H, W, dy, dy_pitch):
+        """dX [B,H,W,Cin] from dY [.., Cout] (pixel-major, pitch dy_pitch)."""
+        dx = torch.empty((B, H, W, self.Cin), device=dy.device, dtype=torch.float32)
+        d = self._desc(B, H, W, [(dy, self.Cout, dy_pitch, NHWC)])
+        d.Cout = self.Cin
+        d.weight = self.wd.data_ptr()
+        d.bias = None
+        d.epilogue = L.EPI_BIAS
+        d.out = dx.data_ptr()
+        d.out_pitch, d.out_coff, d.out_layout = self.Cin, 0, NHWC
+        L.call("as_conv2d_fp32", d, _s())
+        return dx
+
+    def wgrad(self, B, H, W, srcs, dy, dy_pitch):
+        """(dW [Cout,Cin,KH,KW], db [Cout]) for this call."""
+        dw = torch.zeros_like(self.w)
+        db = torch.zeros_like(self.b)
+        d = self._desc(B, H, W, srcs)
+        L.call("as_conv2d_wgrad_fp32", d, dy.data_ptr(), dy_pitch, self.Cout, dw.data_ptr(), db.data_ptr(), _s())
+        L.launch_count += 1
+        return dw, db
+
+
+def _src(t):
+    return (t, t.shape[3], t.shape[3], NHWC)
+
+
+class UpdateBlockFn(torch.autograd.Function):
+    """forward(ub, flags, *tensors) with tensors = net[0..n) + flat(inp) + [corr, disp] + parameters."""
+
+    @staticmethod
+    def forward(ctx, ub, flags, n_net, has_corr, *tensors):
+        iter04, iter08, iter16, update = flags
+        n_layers = ub.args.n_gru_layers
+        net = list(tensors[:n_net])
+        inp = [list(tensors[n_net + 3 * i:n_net + 3 * i + 3]) for i in range(n_net)]
+        k = n_net + 3 * n_net
+        corr = disp = None
+        if has_corr:
+            corr, disp = tensors[k], tensors[k + 1]
+            k += 2
+        dev = net[0].device
+        e, dh = ub.encoder, ub.disp_head
+        C = {
+            "convc1": _Conv([e.convc1]), "convc2": _Conv([e.convc2]), "convd1": _Conv([e.convd1]),
+            "convd2": _Conv([e.convd2]), "conv": _Conv([e.conv]), "dh1": _Conv([dh.conv1]), "dh2": _Conv([dh.conv2]),
+        }
+        for name in ("gru04", "gru08", "gru16"):
+            g = getattr(ub, name)
+            C[name + ".zr"] = _Conv([g.convz, g.convr])
+            C[name + ".q"] = _Conv([g.convq])
+        tape = {"C": C, "flags": flags, "n_net": n_net, "has_corr": has_corr, "gru": {}}
+        hs = [_to_nhwc(t.detach().float()) for t in net]
+
+        def context(i):
+            cz, cr, cq = inp[i]
+            B, Cc, H, W = cz.shape
+            zr = torch.empty((B, H, W, 2 * Cc), device=dev, dtype=torch.float32)
+            q = torch.empty((B, H, W, Cc), device=dev, dtype=torch.float32)
+            for t, dst, pitch, off in ((cz, zr, 2 * Cc, 0), (cr, zr, 2 * Cc, Cc), (cq, q, Cc, 0)):
+                t = t.detach().float().contiguous()
+                L.call("as_nchw_to_nhwc", t.data_ptr(), dst.data_ptr(), B, Cc, H, W, pitch, off, _s())
+            return zr, q
+
+        def pool2x(x):
+            B, H, W, Cc = x.shape
+            out = torch.empty((B, (H + 1) // 2, (W + 1) // 2, Cc), device=dev, dtype=torch.float32)
+            L.call("as_pool2x_nhwc", x.data_ptr(), out.data_ptr(), B, H, W, Cc, _s())
+            return out
+
+        def interp(x, ref):
+            B, H, W, Cc = x.shape
+            out = torch.empty((B, ref.shape[1], ref.shape[2], Cc), device=dev, dtype=torch.float32)
+            L.call("as_interp_bilinear_nhwc", x.data_ptr(), out.data_ptr(), B, H, W, ref.shape[1], ref.shape[2], Cc, _s())
+            return out
+
+        def gru(name, i, h, xs):
+            B, H, W, Hd = h.shape
+            czr, cq = context(i)
+            z, rh, r, q, hn = (torch.empty_like(h) for _ in range(5))
+            srcs_x = [_src(x) for x in xs]
+            C[name + ".zr"].fwd(B, H, W, [_src(h)] + srcs_x, L.EPI_GRU_ZR, rh, Hd, ctx=czr, ctx_pitch=2 * Hd, h=h, z=z, save=r)
+            C[name + ".q"].fwd(B, H, W, [_src(rh)] + srcs_x, L.EPI_GRU_Q, hn, Hd, ctx=cq, ctx_pitch=Hd, h=h, z=z, save=q)
+            tape["gru"][name] = dict(h=h, xs=xs, z=z, r=r, q=q, rh=rh)
+            return hn
+
+        if iter16:
+            tape["p08"] = hs[1]
+            hs[2] = gru("gru16", 2, hs[2], [pool2x(hs[1])])
+        if iter08:
+            xs = [pool2x(hs[0])]
+            if n_layers > 2:
+                tape["i16_src"] = hs[2]
+                xs.append(interp(hs[2], hs[1]))
+            hs[1] = gru("gru08", 1, hs[1], xs)
+        if iter04:
+            corr_c = corr.detach().float().contiguous()
+            disp_c = disp.detach().float().contiguous()
+            B, Cc, H, W = corr_c.shape
+            corr_n = _to_nhwc(corr_c)                                   # wgrad reads pixel-major
+            c1 = torch.empty((B, H, W, 64), device=dev, dtype=torch.float32)
+            C["convc1"].fwd(B, H, W, [_src(corr_n)], L.EPI_BIAS_RELU, c1, 64)
+            cd = torch.empty((B, H, W, 128), device=dev, dtype=torch.float32)
+            C["convc2"].fwd(B, H, W, [_src(c1)], L.EPI_BIAS_RELU, cd, 128, 0)
+            d1 = torch.empty((B, H, W, 64), device=dev, dtype=torch.float32)
+            disp_n = disp_c.view(B, H, W, 1)
+            C["convd1"].fwd(B, H, W, [_src(disp_n)], L.EPI_BIAS_RELU, d1, 64)
+            C["convd2"].fwd(B, H, W, [_src(d1)], L.EPI_BIAS_RELU, cd, 128, 64)
+            mo = torch.empty((B, H, W, 128), device=dev, dtype=torch.float32)
+            C["conv"].fwd(B, H, W, [_src(cd)], L.EPI_BIAS_RELU, mo, 128, 0)
+            L.call("as_nchw_to_nhwc", disp_c.data_ptr(), mo.data_ptr(), B, 1, H, W, 128, 127, _s())
+            tape["enc"] = dict(corr=corr_n, c1=c1, cd=cd, d1=d1, disp=disp_n, mo=mo)
+            xs = [mo]
+            if n_layers > 1:
+                tape["i08_src"] = hs[1]
+                xs.append(interp(hs[1], hs[0]))
+            hs[0] = gru("gru04", 0, hs[0], xs)
+        outs = [h.permute(0, 3, 1, 2) for h in hs]
+        if update:
+            B, H, W, Hd = hs[0].shape
+            t = torch.empty((B, H, W, 256), device=dev, dtype=torch.float32)
+            C["dh1"].fwd(B, H, W, [_src(hs[0])], L.EPI_BIAS_RELU, t, 256)
+            delta = torch.empty((B, 1, H, W), device=dev, dtype=torch.float32)
+            C["dh2"].fwd(B, H, W, [_src(t)], L.EPI_BIAS, delta, 1, 0, out_layout=NCHW)
+            tape["head"] = dict(h=hs[0], t=t)
+            outs.append(delta)
+        tape["shapes"] = [tuple(h.shape) for h in hs]
+        ctx.tape = tape
+        ctx.ub = ub
+        ctx.n_params = len(tensors) - k
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        tape, ub = ctx.tape, ctx.ub
+        C = tape["C"]
+        iter04, iter08, iter16, update = tape["flags"]
+        n_net, has_corr = tape["n_net"], tape["has_corr"]
+        n_layers = ub.args.n_gru_layers
+        dev = gouts[0].device if gouts[0] is not None else next(g.device for g in gouts if g is not None)
+        pgrads = {}                                          # id(parameter) -> grad
+
+        def acc_param(conv, dw, db):
+            off = 0
+            for c in conv.convs:
+                n = c.weight.shape[0]
+                pgrads[id(c.weight)] = dw[off:off + n]
+                pgrads[id(c.bias)] = db[off:off + n]
+                off += n
+
+        # incoming gradients as pixel-major fp32 (zeros where autograd passed None)
+        dh = []
+        for i, shp in enumerate(tape["shapes"]):
+            g = gouts[i]
+            dh.append(torch.zeros(shp, device=dev, dtype=torch.float32) if g is None
+                      else _to_nhwc(g.float()).clone())
+        d_inp = [[None, None, None] for _ in range(n_net)]
+        d_corr = None
+
+        def relu_bwd(dy, dy_coff, y, y_coff, Cc):
+            B, H, W, _ = y.shape
+            dx = torch.empty((B, H, W, Cc), device=dev, dtype=torch.float32)
+            L.call("as_relu_bwd", dy.data_ptr(), dy.shape[3], dy_coff, y.data_ptr(), y.shape[3], y_coff, dx.data_ptr(), Cc, 0,
+                   B * H * W, Cc, _s())
+            return dx
+
+        def gru_bwd(name, i, dhn):
+            """returns (dh_in, [dx per source])"""
+            sv = tape["gru"][name]
+            h, xs, z, r, q, rh = sv["h"], sv["xs"], sv["z"], sv["r"], sv["q"], sv["rh"]
+            B, H, W, Hd = h.shape
+            N = B * H * W
+            dq = torch.empty_like(h)
+            dzr = torch.empty((B, H, W, 2 * Hd), device=dev, dtype=torch.float32)
+            dhin = torch.zeros_like(h)
+            L.call("as_gru_bwd_gates1", dhn.data_ptr(), z.data_ptr(), q.data_ptr(), h.data_ptr(), dq.data_ptr(), dzr.data_ptr(),
+                   dhin.data_ptr(), N, Hd, _s())
+            cq_, czr_ = C[name + ".q"], C[name + ".zr"]
+            srcs_x = [_src(x) for x in xs]
+            acc_param(cq_, *cq_.wgrad(B, H, W, [_src(rh)] + srcs_x, dq, Hd))
+            din_q = cq_.dgrad(B, H, W, dq, Hd)                                  # [.., Hd + Cx]
+            cin = din_q.shape[3]
+            L.call("as_gru_bwd_gates2", din_q.data_ptr(), cin, h.data_ptr(), r.data_ptr(), dzr.data_ptr(), dhin.data_ptr(),
+                   N, Hd, _s())
+            acc_param(czr_, *czr_.wgrad(B, H, W, [_src(h)] + srcs_x, dzr, 2 * Hd))
+            din_zr = czr_.dgrad(B, H, W, dzr, 2 * Hd)
+            L.call("as_add_slice", din_zr.data_ptr(), cin, 0, dhin.data_ptr(), Hd, 0, N, Hd, _s())
+            # x gradients: sum of both paths, then slice per source
+            L.call("as_add_slice", din_zr.data_ptr(), cin, Hd, din_q.data_ptr(), cin, Hd, N, cin - Hd, _s())
+            dxs, off = [], Hd
+            for x in xs:
+                cx = x.shape[3]
+                dx = torch.zeros((B, H, W, cx), device=dev, dtype=torch.float32)
+                L.call("as_add_slice", din_q.data_ptr(), cin, off, dx.data_ptr(), cx, 0, N, cx, _s())
+                dxs.append(dx)
+                off += cx
+            # context gradients (cz, cr, cq), back to [B,C,H,W]
+            d_inp[i] = [_to_nchw(dzr, Hd, 2 * Hd, 0), _to_nchw(dzr, Hd, 2 * Hd, Hd), _to_nchw(dq, Hd, Hd, 0)]
+            return dhin, dxs
+
+        def pool_bwd(dy, like):
+            B, H, W, Cc = like.shape
+            L.call("as_pool2x_nhwc_bwd", dy.data_ptr(), like.data_ptr(), B, H, W, Cc, _s())
+
+        def interp_bwd(dy, acc):
+            B, H, W, Cc = acc.shape
+            L.call("as_interp_bilinear_nhwc_bwd", dy.data_ptr(), acc.data_ptr(), B, H, W, dy.shape[1], dy.shape[2], Cc, _s())
+
+        # ---- disparity head
+        if update:
+            hd = tape["head"]
+            h, t = hd["h"], hd["t"]
+            B, H, W, Hd = h.shape
+            gd = gouts[n_net]
+            if gd is not None:
+                gd = gd.float().contiguous().view(B, H, W, 1)
+                acc_param(C["dh2"], *C["dh2"].wgrad(B, H, W, [_src(t)], gd, 1))
+                dt = C["dh2"].dgrad(B, H, W, gd, 1)
+                dpre = relu_bwd(dt, 0, t, 0, 256)
+                acc_param(C["dh1"], *C["dh1"].wgrad(B, H, W, [_src(h)], dpre, 256))
+                dhh = C["dh1"].dgrad(B, H, W, dpre, 256)
+                L.call("as_add_slice", dhh.data_ptr(), Hd, 0, dh[0].data_ptr(), Hd, 0, B * H * W, Hd, _s())
+
+        # ---- gru04 + motion encoder
+        g0 = dh[0]
+        if iter04:
+            dhin, dxs = gru_bwd("gru04", 0, dh[0])
+            g0 = dhin
+            en = tape["enc"]
+            B, H, W, _ = en["mo"].shape
+            N = B * H * W
+            dmo = dxs[0]
+            if n_layers > 1:
+                interp_bwd(dxs[1], dh[1])                       # into the NEW h08 gradient
+            dpre = relu_bwd(dmo, 0, en["mo"], 0, 127)
+            acc_param(C["conv"], *C["conv"].wgrad(B, H, W, [_src(en["cd"])], dpre, 127))
+            dcd = C["conv"].dgrad(B, H, W, dpre, 127)           # [..,128]
+            dp_c2 = relu_bwd(dcd, 0, en["cd"], 0, 64)
+            acc_param(C["convc2"], *C["convc2"].wgrad(B, H, W, [_src(en["c1"])], dp_c2, 64))
+            dc1 = C["convc2"].dgrad(B, H, W, dp_c2, 64)
+            dp_d2 = relu_bwd(dcd, 64, en["cd"], 64, 64)
+            acc_param(C["convd2"], *C["convd2"].wgrad(B, H, W, [_src(en["d1"])], dp_d2, 64))
+            dd1 = C["convd2"].dgrad(B, H, W, dp_d2, 64)
+            dp_d1 = relu_bwd(dd1, 0, en["d1"], 0, 64)
+            acc_param(C["convd1"], *C["convd1"].wgrad(B, H, W, [_src(en["disp"])], dp_d1, 64))
+            dp_c1 = relu_bwd(dc1, 0, en["c1"], 0, 64)
+            acc_param(C["convc1"], *C["convc1"].wgrad(B, H, W, [_src(en["corr"])], dp_c1, 64))
+            d_corr = _to_nchw(C["convc1"].dgrad(B, H, W, dp_c1, 64))
+        # ---- gru08
+        g1 = dh[1]
+        if iter08:
+            dhin, dxs = gru_bwd("gru08", 1, dh[1])
+            g1 = dhin
+            pool_bwd(dxs[0], g0)                                # pool2x(old h04)
+            if n_layers > 2:
+                interp_bwd(dxs[1], dh[2])                       # interp(new h16)
+        # ---- gru16
+        g2 = dh[2] if n_net > 2 else None
+        if iter16:
+            dhin, dxs = gru_bwd("gru16", 2, dh[2])
+            g2 = dhin
+            pool_bwd(dxs[0], g1)                                # pool2x(old h08)
+        gnet = [g0, g1, g2][:n_net]
+        grads = [None, None, None, None]                       # ub, flags, n_net, has_corr
+        grads += [g.permute(0, 3, 1, 2) for g in gnet]
+        for i in range(n_net):
+            grads += d_inp[i]
+        if has_corr:
+            grads += [d_corr, None]
+        for p in ub.parameters():
+            grads.append(pgrads.get(id(p)))
+        return tuple(grads)
+
+
+def forward(ub, net, inp, corr, disp, iter04, iter08, iter16, update):
+    n_net = len(net)
+    has_corr = corr is not None
+    flat = list(net)
+    for i in range(n_net):
+        flat += list(inp[i])
+    if has_corr:
+        flat += [corr, disp]
+    flat += list(ub.parameters())
+    outs = UpdateBlockFn.apply(ub, (iter04, iter08, iter16, update), n_net, has_corr, *flat)
+    for i in range(n_net):
+        net[i] = outs[i]
+    if not update:
+        return net
+    return net, outs[n_net]

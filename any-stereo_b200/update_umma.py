@@ -158,9 +158,6 @@ def _remember(ub, h_f32, pl):
 
 def forward(ub, net, inp, corr=None, disp=None, iter04=True, iter08=True, iter16=True, update=True):
     from .update import _nhwc_view, get_update_engine
-    if torch.is_grad_enabled() and any(p.requires_grad for p in ub.parameters()):
-        raise NotImplementedError("anystereo_b200.BasicMultiUpdateBlock: backward is not implemented yet; "
-                                  "call under torch.no_grad()")
     split = get_update_engine() == "bf16x3"
     nsplit = 3 if split else 1
     n_layers = ub.args.n_gru_layers

@@ -191,6 +191,7 @@ typedef struct as_conv_desc {
   int ctx_pitch;
   const float* h;       /* hidden state [N][Hd]                                                    */
   float* z;             /* ZR: written ; Q: read                                                   */
+  float* save;          /* optional (training): ZR stores r [N][Hd], Q stores q [N][Hd]; NULL otherwise */
 } as_conv_desc;
 
 /* nn.Conv2d weight [Cout][Cin][KH][KW] (update.py:29-31,78-82) -> GEMM operand [KH*KW][Cin][Cout];
@@ -274,6 +275,35 @@ int as_convd1_split(const float* disp, const float* w /*[64][49]*/, const float*
                     int B, int H, int W, int out_pitch, int out_coff, as_stream_t stream);
 /* delta[n] = bias2 + sum_t u[n + shift(t)][t]  (zero outside the image): finishes DispHead.conv2 */
 int as_disp_delta(const float* u, const float* bias2, float* delta, int B, int H, int W, as_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a13-vi  adjoints of the update block (training, config 5), exact fp32 on CUDA cores.
+ * All tensors pixel-major fp32.  "acc" outputs are accumulated into (+=): zero them first.
+ * ------------------------------------------------------------------------------------------ */
+/* weights for the data gradient: [Cout][Cin][KH][KW] -> [KH*KW (flipped)][Cout][Cin]; then
+ * dX = as_conv2d_fp32(src = dY with Cout channels, weight = this, Cout := Cin, no bias)        */
+int as_pack_conv_weight_dgrad(const float* w_oihw, float* w_packed, int Cout, int Cin, int KH, int KW,
+                              as_stream_t stream);
+/* dW[co][ci][ky][kx] += sum_n dY[n][co] * X[n + shift(ky,kx)][ci] ;  db[co] += sum_n dY[n][co] (db may be NULL).
+ * X is the concatenation of the descriptor's sources (desc->src, num_src, B/H/W/KH/KW); other fields ignored. */
+int as_conv2d_wgrad_fp32(const as_conv_desc* desc, const float* dy, int dy_pitch, int Cout, float* dw_acc,
+                         float* db_acc, as_stream_t stream);
+/* dx = dy * (y > 0) over n elements with channel pitches (relu of update.py:85-91,23) */
+int as_relu_bwd(const float* dy, int dy_pitch, int dy_coff, const float* y, int y_pitch, int y_coff, float* dx,
+                int dx_pitch, int dx_coff, long long N, int C, as_stream_t stream);
+/* GRU gate adjoints (update.py:37-40), Hd channels per pixel:
+ *  step 1: dq_pre = dh'*z*(1-q^2) ; dzr_pre[:, :Hd] = dh'*(q-h)*z*(1-z) ; dh_acc += dh'*(1-z)
+ *  step 2: dzr_pre[:, Hd:] = d(rh)*h*r*(1-r) ; dh_acc += d(rh)*r                                */
+int as_gru_bwd_gates1(const float* dhn, const float* z, const float* q, const float* h, float* dq_pre,
+                      float* dzr_pre, float* dh_acc, long long N, int Hd, as_stream_t stream);
+int as_gru_bwd_gates2(const float* drh, int drh_pitch, const float* h, const float* r, float* dzr_pre,
+                      float* dh_acc, long long N, int Hd, as_stream_t stream);
+/* dst[n][dcoff + c] += src[n][scoff + c] */
+int as_add_slice(const float* src, int spitch, int scoff, float* dst, int dpitch, int dcoff, long long N, int C,
+                 as_stream_t stream);
+int as_pool2x_nhwc_bwd(const float* dy, float* dx_acc, int B, int H, int W, int C, as_stream_t stream);
+int as_interp_bilinear_nhwc_bwd(const float* dy, float* dx_acc, int B, int Hin, int Win, int Hout, int Wout,
+                                int C, as_stream_t stream);
 
 #ifdef __cplusplus
 }
