@@ -1,0 +1,96 @@
+"""BASELINE.json config 5 structure: one training step of the IGEV hot path on synthetic 320x736 crops
+(80x184 at 1/4), `--batch` pairs per GPU, `--iters` unrolled iterations, sequence loss, gradient all-reduce
+over NCCL (one process per GPU, launched with torchrun), AdamW on the update block.
+
+Everything between the backbone outputs and the low-resolution disparities runs on this library's kernels
+(forward and backward); backbones / hourglass / LIIF are outside the path, so their outputs are synthetic
+leaf tensors that receive gradients.  Prints one JSON line with the step time (max over ranks)."""
+import argparse
+import json
+import os
+import sys
+import types
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import anystereo_b200 as A  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--iters", type=int, default=16)       # train_iters, train_continuous_IGEV.py:297
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--h", type=int, default=80)
+    ap.add_argument("--w", type=int, default=184)
+    a = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    A.set_update_engine("fp32")
+    A.set_corr_mode("fp32")
+    torch.manual_seed(0)                                    # identical replicas
+    args = types.SimpleNamespace(corr_levels=2, corr_radius=4, n_gru_layers=3)
+    block = A.BasicMultiUpdateBlock(args, hidden_dims=[128, 128, 128]).to(dev).train()
+    opt = torch.optim.AdamW(block.parameters(), lr=2e-4, weight_decay=1e-5, eps=1e-8)   # train_continuous_IGEV.py:127
+    B, H, W = a.batch, a.h, a.w
+    g = torch.Generator(device="cpu").manual_seed(100 + rank)   # each rank its own pairs
+    sizes = [(H, W), (H // 2, W // 2), (H // 4, W // 4)]
+
+    def leaf(*shape, scale=1.0):
+        return (torch.randn(*shape, generator=g) * scale).to(dev).requires_grad_(True)
+
+    f1, f2 = leaf(B, 96, H, W), leaf(B, 96, H, W)
+    geo = leaf(B, 8, 48, H, W)
+    net0 = [torch.tanh(torch.randn(B, 128, h, w, generator=g)).to(dev).requires_grad_(True) for h, w in sizes]
+    inp = [[leaf(B, 128, h, w, scale=0.5) for _ in range(3)] for h, w in sizes]
+    init_disp = (torch.rand(B, 1, H, W, generator=g) * 40).to(dev)
+    gt = (torch.rand(B, 1, H, W, generator=g) * 48).to(dev)
+    coords = torch.arange(W, device=dev, dtype=torch.float32).reshape(1, 1, W, 1).repeat(B, H, 1, 1)
+    times, losses, gnorms = [], [], []
+    for step in range(a.steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        opt.zero_grad(set_to_none=True)
+        fn = A.Combined_Geo_Encoding_Volume(f1, f2, geo, num_levels=2, radius=4)
+        net, disp, loss = list(net0), init_disp, 0.0
+        for it in range(a.iters):
+            disp = disp.detach()
+            feat = fn(disp, coords)
+            net, delta = block(net, inp, feat, disp)
+            disp = disp + delta
+            loss = loss + 0.9 ** (a.iters - 1 - it) * (disp - gt).abs().mean()
+        loss.backward()
+        A.allreduce_gradients(list(block.parameters()))
+        gn = torch.nn.utils.clip_grad_norm_(block.parameters(), 1.0)       # train_continuous_IGEV.py:234
+        opt.step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        times.append(float(ms))
+        losses.append(float(loss.detach()))
+        gnorms.append(float(gn))
+    if rank == 0:
+        print(json.dumps({"config": "IGEV hot-path training step, %dx%d (1/4: %dx%d), batch %d/GPU, %d iters, fp32 CUDA-core kernels"
+                                    % (4 * H, 4 * W, H, W, B, a.iters),
+                          "n_gpus": world, "ms_per_step": times, "pairs_per_s": world * B / (times[-1] / 1e3),
+                          "loss": losses, "grad_norm_after_allreduce": gnorms,
+                          "peak_mem_GB": torch.cuda.max_memory_allocated() / 2 ** 30}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
