@@ -12,12 +12,15 @@
 //   warps 4-7 epilogue: tcgen05.ld -> gates (sigmoid / r*h / tanh / GRU blend / relu / disparity-head dot)
 //   -> per-pixel contiguous stores (fp32 state and/or bf16 hi/lo planes for the next convolution).
 // Two 256-column TMEM accumulators let the epilogue of tile i overlap the MMAs of tile i+1.
+// Operand reuse: for a 3x3 kernel the producer loads ONE (TH+2)-row patch per (dx, channel chunk); the three dy taps
+// are 1024-byte-aligned row offsets into that patch (TW*128 B = one or two swizzle atoms), i.e. three UMMA descriptors
+// over the same shared memory.  L2->smem traffic of the activations drops from 9 to 3.75 tile loads per chunk.
+#include <cstdlib>
 #include "umma.cuh"
 
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kAPlane = 128 * 128;      // one [128 px x 64 ch] bf16 tile
 constexpr int kMaxStages = 4;
 constexpr int kW2Floats = 9 * 256;
 constexpr int kSmemBudget = 227 * 1024;
@@ -32,7 +35,8 @@ struct ConvMaps {
 struct ConvUmmaParams {
   int B, H, W, TW, TH, tiles_x, tiles_y, num_tiles;
   int KH, KW, num_src, src_ch[3], cin_total;
-  int N, nsplit, nstages, stage_bytes, epilogue;
+  int N, nsplit, epilogue;
+  int a_plane, a_stage, b_stage, nstA, nstB;   // bytes of one A patch plane / A stage (hi+lo) / B stage; ring depths
   const float* bias; const float* ctx; int ctx_pitch; const float* h; float* z;
   float* out_f32; __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; int out_pitch, out_coff, cout_valid;
   const float* disp; const float* w2; float* u;
@@ -70,21 +74,32 @@ __device__ __forceinline__ void store_split32(const float* v, __nv_bfloat16* hi,
   }
 }
 
+// CS = thread-block cluster size.  The CTAs of a cluster walk their tiles in lockstep over the same (tap, chunk)
+// sequence, so the weight tile of every K-block is the same for all of them: each CTA fetches 1/CS of it and
+// TMA-multicasts the slice into every CTA's ring slot (L2->smem weight traffic / CS).  A ring slot may be
+// overwritten only when ALL CTAs have consumed it: every MMA warp commits "slot free" to the whole cluster.
+template <int CS>
 __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_constant__ ConvMaps maps,
                                                                 const ConvUmmaParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* stages = smem;
-  float* w2s = reinterpret_cast<float*>(smem + p.nstages * p.stage_bytes);
+  uint8_t* a_ring = smem;
+  uint8_t* b_ring = smem + p.nstA * p.a_stage;
+  float* w2s = reinterpret_cast<float*>(b_ring + p.nstB * p.b_stage);
   uint64_t* bars = reinterpret_cast<uint64_t*>(w2s + kW2Floats);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + kMaxStages;
-  uint64_t* tfull = bars + 2 * kMaxStages;
+  uint64_t* fullA = bars;
+  uint64_t* emptyA = bars + kMaxStages;
+  uint64_t* fullB = bars + 2 * kMaxStages;
+  uint64_t* emptyB = bars + 3 * kMaxStages;
+  uint64_t* tfull = bars + 4 * kMaxStages;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b_bytes = p.N * 128;
+  const uint32_t crank = CS > 1 ? umma::cluster_ctarank() : 0u;
+  constexpr uint16_t kAllCtas = (uint16_t)((1u << CS) - 1u);
+  const int niter = (p.num_tiles + (int)gridDim.x - 1) / (int)gridDim.x;   // identical for every CTA of a cluster
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.num_src; ++s) {
@@ -95,7 +110,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     if (p.nsplit == 3) umma::prefetch_tmap(&maps.b_lo);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < p.nstages; ++s) { umma::mbar_init(&full[s], 1); umma::mbar_init(&empty[s], 1); }
+    for (int s = 0; s < kMaxStages; ++s) {
+      umma::mbar_init(&fullA[s], 1); umma::mbar_init(&emptyA[s], 1);
+      umma::mbar_init(&fullB[s], 1); umma::mbar_init(&emptyB[s], CS);
+    }
     for (int a = 0; a < 2; ++a) { umma::mbar_init(&tfull[a], 1); umma::mbar_init(&tempty[a], 4); }
     umma::fence_barrier_init();
   }
@@ -108,39 +126,54 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   }
   umma::tc_fence_before();
   __syncthreads();
+  if (CS > 1) umma::cluster_sync_all();          // peers' barriers are initialised before any multicast can land
   umma::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int taps = p.KH * p.KW;
   const int chunks = p.cin_total >> 6;           // 64-channel chunks per tap
-  const int nkb = taps * chunks;
+  const int ngroups = p.KW * chunks;             // A patches per tile; each feeds KH taps
   const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int dy_bytes = p.TW * 128;               // row offset of one dy step inside a patch (multiple of 1024)
 
   if (warp == 0) {
     if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      const uint32_t tx = (uint32_t)(kAPlane + b_bytes) * (p.nsplit == 3 ? 2u : 1u);
+      int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
+      const uint32_t txA = (uint32_t)p.a_plane * (p.nsplit == 3 ? 2u : 1u);
+      const uint32_t txB = (uint32_t)b_bytes * (p.nsplit == 3 ? 2u : 1u);
       const int ph = p.KH >> 1, pw = p.KW >> 1;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int itn = 0; itn < niter; ++itn) {
+        int tile = blockIdx.x + itn * gridDim.x;
+        if (tile >= p.num_tiles) tile = 0;       // padding iteration: keeps the cluster in lockstep, result discarded
         const int b = tile / tiles_per_img;
         const int r = tile - b * tiles_per_img;
         const int ty = r / p.tiles_x, txi = r - ty * p.tiles_x;
         const int x0 = txi * p.TW, y0 = ty * p.TH;
-        for (int tap = 0; tap < taps; ++tap) {
-          const int dy = tap / p.KW - ph, dx = tap - (tap / p.KW) * p.KW - pw;
+        for (int kx = 0; kx < p.KW; ++kx) {
           int coff = 0;
           for (int s = 0; s < p.num_src; ++s) {
             for (int c0 = 0; c0 < p.src_ch[s]; c0 += 64) {
-              umma::mbar_wait(&empty[stage], phase ^ 1);
-              uint8_t* st = stages + stage * p.stage_bytes;
-              umma::mbar_expect_tx(&full[stage], tx);
-              const int kcoord = tap * p.cin_total + coff + c0;
-              umma::tma_load_4d(st, &maps.a_hi[s], &full[stage], c0, x0 + dx, y0 + dy, b);
-              umma::tma_load_2d(st + 2 * kAPlane, &maps.b_hi, &full[stage], kcoord, 0);
-              if (p.nsplit == 3) {
-                umma::tma_load_4d(st + kAPlane, &maps.a_lo[s], &full[stage], c0, x0 + dx, y0 + dy, b);
-                umma::tma_load_2d(st + 2 * kAPlane + b_bytes, &maps.b_lo, &full[stage], kcoord, 0);
+              umma::mbar_wait(&emptyA[sa], pha ^ 1);
+              uint8_t* sta = a_ring + sa * p.a_stage;
+              umma::mbar_expect_tx(&fullA[sa], txA);
+              umma::tma_load_4d(sta, &maps.a_hi[s], &fullA[sa], c0, x0 + kx - pw, y0 - ph, b);
+              if (p.nsplit == 3) umma::tma_load_4d(sta + p.a_plane, &maps.a_lo[s], &fullA[sa], c0, x0 + kx - pw, y0 - ph, b);
+              if (++sa == p.nstA) { sa = 0; pha ^= 1; }
+              for (int ky = 0; ky < p.KH; ++ky) {
+                umma::mbar_wait(&emptyB[sb], phb ^ 1);
+                uint8_t* stb = b_ring + sb * p.b_stage;
+                umma::mbar_expect_tx(&fullB[sb], txB);
+                const int kcoord = (ky * p.KW + kx) * p.cin_total + coff + c0;
+                if (CS == 1) {
+                  umma::tma_load_2d(stb, &maps.b_hi, &fullB[sb], kcoord, 0);
+                  if (p.nsplit == 3) umma::tma_load_2d(stb + b_bytes, &maps.b_lo, &fullB[sb], kcoord, 0);
+                } else {                         // my 1/CS slice of the weight rows, multicast to the whole cluster
+                  const int rows = p.N / CS;
+                  const int soff = (int)crank * rows * 128;
+                  umma::tma_load_2d_mc(stb + soff, &maps.b_hi, &fullB[sb], kcoord, (int)crank * rows, kAllCtas);
+                  if (p.nsplit == 3)
+                    umma::tma_load_2d_mc(stb + b_bytes + soff, &maps.b_lo, &fullB[sb], kcoord, (int)crank * rows, kAllCtas);
+                }
+                if (++sb == p.nstB) { sb = 0; phb ^= 1; }
               }
-              if (++stage == p.nstages) { stage = 0; phase ^= 1; }
             }
             coff += p.src_ch[s];
           }
@@ -150,33 +183,40 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
+      int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
       const uint32_t idesc = umma::idesc_bf16_f32(128, p.N);
-      int it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      for (int it = 0; it < niter; ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
         umma::mbar_wait(&tempty[acc], acc_phase ^ 1);
         umma::tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)acc * 256u;
-        for (int kb = 0; kb < nkb; ++kb) {
-          umma::mbar_wait(&full[stage], phase);
-          umma::tc_fence_after();
-          const uint32_t st = umma::smem_u32(stages + stage * p.stage_bytes);
-          const uint32_t a_hi = st, a_lo = st + kAPlane, b_hi = st + 2 * kAPlane, b_lo = b_hi + b_bytes;
+        uint32_t accumulate = 0;
+        for (int g = 0; g < ngroups; ++g) {
+          umma::mbar_wait(&fullA[sa], pha);
+          const uint32_t sta = umma::smem_u32(a_ring + sa * p.a_stage);
+          for (int ky = 0; ky < p.KH; ++ky) {
+            umma::mbar_wait(&fullB[sb], phb);
+            umma::tc_fence_after();
+            const uint32_t a_hi = sta + (uint32_t)(ky * dy_bytes), a_lo = a_hi + (uint32_t)p.a_plane;
+            const uint32_t b_hi = umma::smem_u32(b_ring + sb * p.b_stage), b_lo = b_hi + (uint32_t)b_bytes;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t ko = (uint32_t)k * 32u;
-            const uint64_t dah = umma::smem_desc_k_sw128(a_hi + ko), dbh = umma::smem_desc_k_sw128(b_hi + ko);
-            umma::mma_bf16_ss(tmem_d, dah, dbh, idesc, (kb | k) != 0);
-            if (p.nsplit == 3) {
-              const uint64_t dal = umma::smem_desc_k_sw128(a_lo + ko), dbl = umma::smem_desc_k_sw128(b_lo + ko);
-              umma::mma_bf16_ss(tmem_d, dah, dbl, idesc, 1u);
-              umma::mma_bf16_ss(tmem_d, dal, dbh, idesc, 1u);
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t ko = (uint32_t)k * 32u;
+              const uint64_t dah = umma::smem_desc_k_sw128(a_hi + ko), dbh = umma::smem_desc_k_sw128(b_hi + ko);
+              umma::mma_bf16_ss(tmem_d, dah, dbh, idesc, accumulate);
+              accumulate = 1u;
+              if (p.nsplit == 3) {
+                const uint64_t dal = umma::smem_desc_k_sw128(a_lo + ko), dbl = umma::smem_desc_k_sw128(b_lo + ko);
+                umma::mma_bf16_ss(tmem_d, dah, dbl, idesc, 1u);
+                umma::mma_bf16_ss(tmem_d, dal, dbh, idesc, 1u);
+              }
             }
+            if (CS == 1) umma::mma_commit(&emptyB[sb]); else umma::mma_commit_mc(&emptyB[sb], kAllCtas);
+            if (++sb == p.nstB) { sb = 0; phb ^= 1; }
           }
-          umma::mma_commit(&empty[stage]);
-          if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+          umma::mma_commit(&emptyA[sa]);
+          if (++sa == p.nstA) { sa = 0; pha ^= 1; }
         }
         umma::mma_commit(&tfull[acc]);
       }
@@ -186,13 +226,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     const int q = warp - 4;
     const int m = q * 32 + lane;                 // accumulator row == TMEM lane == pixel within the patch
     const int py = m / p.TW, px = m - py * p.TW;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int it = 0; it < niter; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const bool real_tile = tile < p.num_tiles;
       const int b = tile / tiles_per_img;
       const int r = tile - b * tiles_per_img;
       const int ty = r / p.tiles_x, txi = r - ty * p.tiles_x;
       const int x = txi * p.TW + px, y = ty * p.TH + py;
-      const bool valid = (x < p.W) && (y < p.H);
+      const bool valid = real_tile && (x < p.W) && (y < p.H);
       const long long n = ((long long)b * p.H + y) * p.W + x;
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
@@ -283,7 +324,41 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   }
   umma::tc_fence_before();
   __syncthreads();
+  if (CS > 1) umma::cluster_sync_all();          // nobody exits while a peer may still multicast into its smem
   if (warp == 2) umma::tmem_dealloc(tmem_base, 512);
+}
+
+template <int CS>
+int launch_conv(const ConvMaps& maps, const ConvUmmaParams& p, int sms, int smem, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return (int)e;
+  int grid = p.num_tiles < sms ? p.num_tiles : sms;
+  grid = (grid / CS) * CS;
+  if (grid < CS) grid = CS;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<CS>, maps, p);
+  if (e != cudaSuccess) return (int)e;
+  AS_RETURN_IF_LAUNCH_FAILED();
+  return AS_OK;
+}
+
+// AS_CONV_CLUSTER=1|2|4.  Default 1: measured on B200 (profiles/), weight multicast across a cluster is correct but
+// SLOWER with the current 64-wide K blocks -- N = 256 leaves room for only two weight stages and the cross-CTA
+// "slot free" round trip no longer hides behind one stage of MMAs.  Kept as a tuning knob for a deeper ring.
+int cluster_size_override() {
+  const char* v = getenv("AS_CONV_CLUSTER");
+  if (!v) return 1;
+  const int c = atoi(v);
+  return (c == 1 || c == 2 || c == 4) ? c : 1;
 }
 
 }  // namespace
@@ -312,11 +387,16 @@ extern "C" int as_conv2d_umma(const as_conv_umma_desc* d, as_stream_t stream) {
   }
   p.cin_total = cin;
   p.N = d->Cout; p.nsplit = d->nsplit; p.epilogue = d->epilogue;
-  p.stage_bytes = 2 * kAPlane + 2 * p.N * 128;
+  p.a_plane = (p.TH + d->KH - 1) * p.TW * 128;          // (TH+2)-row patch for 3x3, the tile itself for 1x1
+  p.a_stage = 2 * p.a_plane;
+  p.b_stage = 2 * p.N * 128;
   const int fixed = 1024 + kW2Floats * 4 + 256;
-  p.nstages = (kSmemBudget - fixed) / p.stage_bytes;
-  if (p.nstages > kMaxStages) p.nstages = kMaxStages;
-  if (p.nstages < 2) return AS_ERR_UNSUPPORTED;
+  // ring depths: B is consumed KH times faster than A; give B at least 2 (3 if it fits) stages, A 2
+  p.nstA = 2;
+  p.nstB = (kSmemBudget - fixed - p.nstA * p.a_stage) / p.b_stage;
+  if (p.nstB > kMaxStages) p.nstB = kMaxStages;
+  if (p.nstB >= 4 && p.nstA * p.a_stage + 4 * p.b_stage + p.a_stage + fixed <= kSmemBudget) p.nstA = 3;
+  if (p.nstB < 2) return AS_ERR_UNSUPPORTED;
   p.bias = d->bias; p.ctx = d->ctx; p.ctx_pitch = d->ctx_pitch; p.h = d->h; p.z = d->z;
   p.out_f32 = d->out_f32; p.out_hi = (__nv_bfloat16*)d->out_hi; p.out_lo = (__nv_bfloat16*)d->out_lo;
   p.out_pitch = d->out_pitch; p.out_coff = d->out_coff; p.cout_valid = d->cout_valid;
@@ -347,7 +427,7 @@ extern "C" int as_conv2d_umma(const as_conv_umma_desc* d, as_stream_t stream) {
     const uint64_t C = (uint64_t)d->src[s].channels;
     const uint64_t dims[4] = {C, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
     const uint64_t str[3] = {C * 2, (uint64_t)d->W * C * 2, (uint64_t)d->H * d->W * C * 2};
-    const uint32_t box[4] = {64u, (uint32_t)p.TW, (uint32_t)p.TH, 1u};
+    const uint32_t box[4] = {64u, (uint32_t)p.TW, (uint32_t)(p.TH + d->KH - 1), 1u};
     if ((rc = umma::make_tmap_bf16(&maps.a_hi[s], d->src[s].hi, 4, dims, str, box)) != AS_OK) return rc;
     if (d->nsplit == 3) {
       if ((rc = umma::make_tmap_bf16(&maps.a_lo[s], d->src[s].lo, 4, dims, str, box)) != AS_OK) return rc;
@@ -371,11 +451,25 @@ extern "C" int as_conv2d_umma(const as_conv_umma_desc* d, as_stream_t stream) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int smem = fixed + p.nstages * p.stage_bytes;
-  cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e != cudaSuccess) return (int)e;
-  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
-  conv_umma_kernel<<<grid, kThreads, smem, as_cu(stream)>>>(maps, p);
-  AS_RETURN_IF_LAUNCH_FAILED();
-  return AS_OK;
+  const int smem = fixed + p.nstA * p.a_stage + p.nstB * p.b_stage;
+  int cs = cluster_size_override();
+  while (cs > 1 && (p.num_tiles < 2 * cs || (p.N / cs) % 8 != 0)) cs >>= 1;   // tiny layers: no point in clustering
+  // the weight tensor map's box is one CTA's slice of the rows
+  if (cs > 1) {
+    const uint64_t Kt = (uint64_t)d->KH * d->KW * cin;
+    const uint64_t dims[2] = {Kt, (uint64_t)p.N};
+    const uint64_t str[1] = {Kt * 2};
+    const uint32_t box[2] = {64u, (uint32_t)(p.N / cs)};
+    if ((rc = umma::make_tmap_bf16(&maps.b_hi, d->w_hi, 2, dims, str, box)) != AS_OK) return rc;
+    if (d->nsplit == 3) {
+      if ((rc = umma::make_tmap_bf16(&maps.b_lo, d->w_lo, 2, dims, str, box)) != AS_OK) return rc;
+    } else {
+      maps.b_lo = maps.b_hi;
+    }
+  }
+  switch (cs) {
+    case 4: return launch_conv<4>(maps, p, sms, smem, as_cu(stream));
+    case 2: return launch_conv<2>(maps, p, sms, smem, as_cu(stream));
+    default: return launch_conv<1>(maps, p, sms, smem, as_cu(stream));
+  }
 }

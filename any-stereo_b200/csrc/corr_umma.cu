@@ -9,7 +9,8 @@
 //                                3 MMAs per K-step in split mode: hi*hi + hi*lo + lo*hi)
 //       warp 2   TMEM allocator (512 columns = 2 accumulator buffers, so the epilogue of tile i overlaps
 //                                the MMAs of tile i+1 -- the kernel is store-bound)
-//       warps4-7 epilogue       (tcgen05.ld -> registers -> pairwise pooling for every level ->
+//       warps4-11 epilogue      two groups of 4 warps, one per TMEM accumulator buffer, so two tiles drain
+//                                concurrently (tcgen05.ld -> registers -> pairwise pooling for every level ->
 //                                shared-memory transpose -> 128-bit row-contiguous global stores)
 // The volume is written exactly once; pooled levels never re-read level 0 from HBM.
 #include "umma.cuh"
@@ -19,11 +20,11 @@ namespace {
 constexpr int kBM = 128;
 constexpr int kBK = 64;
 constexpr int kStages = 2;
-constexpr int kThreads = 256;
-constexpr int kMaxBN = 192;
+constexpr int kThreads = 384;
+constexpr int kMaxBN = 160;
 constexpr int kStageBytes = 2 * (kBM * 128) + 2 * (kMaxBN * 128);   // A hi/lo + B hi/lo
 constexpr int kStgStride = 68;                                      // floats per epilogue staging row
-constexpr int kStgBytes = 4 * 32 * kStgStride * 4;
+constexpr int kStgBytes = 8 * 32 * kStgStride * 4;
 constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kStgBytes + 256;
 constexpr int kMaxPoolLevels = 6;                                   // 32 columns pool down to 1
 
@@ -34,38 +35,52 @@ struct CorrUmmaParams {
   int pitch[AS_MAX_LEVELS];
 };
 
-// fp32 NCHW -> bf16 hi/lo, K-major [BH][W][Dp]; one CTA = 32 pixels of one row, all channels
+// fp32 NCHW -> bf16 hi/lo, K-major [BH][W][Dp].  One CTA = 64 pixels of one image row x 64 channels: 16 coalesced
+// loads per thread are issued back to back (memory-level parallelism), transposed through shared memory, and each
+// pixel's 64 channels leave as one 128-byte line per plane (8 lanes x 16 B).
 __global__ void __launch_bounds__(256) split_transpose_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi,
                                                               __nv_bfloat16* __restrict__ lo, int D, int Dp, int H,
                                                               int W) {
-  __shared__ float t[64][33];
+  __shared__ float t[64][65];
   const int by = blockIdx.y, b = by / H, y = by - b * H;
-  const int x0 = blockIdx.x * 32;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int x0 = blockIdx.x * 64, d0 = blockIdx.z * 64;
+  const int tid = threadIdx.x;
   const long long HW = (long long)H * W;
-  for (int d0 = 0; d0 < Dp; d0 += 64) {
+  const float* src = in + ((long long)b * D) * HW + (long long)y * W;
+  float v[16];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int dd = warp + 8 * i, d = d0 + dd, x = x0 + lane;
-      t[dd][lane] = (d < D && x < W) ? __ldg(in + ((long long)b * D + d) * HW + (long long)y * W + x) : 0.f;
-    }
-    __syncthreads();
+  for (int i = 0; i < 16; ++i) {
+    const int e = tid + 256 * i;
+    const int dd = e >> 6, xx = e & 63;
+    const int d = d0 + dd, x = x0 + xx;
+    v[i] = (d < D && x < W) ? __ldg(src + (long long)d * HW + x) : 0.f;
+  }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int xx = warp + 8 * i, x = x0 + xx;
-      if (x < W) {
-        const float v0 = t[2 * lane][xx], v1 = t[2 * lane + 1][xx];
-        const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
-        const long long o = ((long long)by * W + x) * Dp + d0 + 2 * lane;
-        *reinterpret_cast<__nv_bfloat162*>(hi + o) = __halves2bfloat162(h0, h1);
-        if (lo) {
-          const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0));
-          const __nv_bfloat16 l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
-          *reinterpret_cast<__nv_bfloat162*>(lo + o) = __halves2bfloat162(l0, l1);
-        }
-      }
+  for (int i = 0; i < 16; ++i) {
+    const int e = tid + 256 * i;
+    t[e >> 6][e & 63] = v[i];
+  }
+  __syncthreads();
+  const int c = tid & 7;                 // 8-channel chunk
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int xx = (tid >> 3) + 32 * i;
+    const int x = x0 + xx;
+    if (x >= W) continue;
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float a0 = t[8 * c + 2 * j][xx], a1 = t[8 * c + 2 * j + 1][xx];
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(a0), h1 = __float2bfloat16_rn(a1);
+      __nv_bfloat162 hh = __halves2bfloat162(h0, h1);
+      __nv_bfloat162 ll = __halves2bfloat162(__float2bfloat16_rn(a0 - __bfloat162float(h0)),
+                                             __float2bfloat16_rn(a1 - __bfloat162float(h1)));
+      h[j] = *reinterpret_cast<uint32_t*>(&hh);
+      l[j] = *reinterpret_cast<uint32_t*>(&ll);
     }
-    __syncthreads();
+    const long long o = ((long long)by * W + x) * Dp + d0 + 8 * c;
+    *reinterpret_cast<uint4*>(hi + o) = make_uint4(h[0], h[1], h[2], h[3]);
+    if (lo) *reinterpret_cast<uint4*>(lo + o) = make_uint4(l[0], l[1], l[2], l[3]);
   }
 }
 
@@ -211,11 +226,13 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     }
     __syncwarp();
   } else if (warp >= 4) {
-    const int q = warp - 4;                          // TMEM lane quarter == warp % 4
-    float* stg = stg_all + q * 32 * kStgStride;
+    const int q = warp & 3;                          // TMEM lane quarter == warp % 4
+    const int group = (warp - 4) >> 2;               // which accumulator buffer this warp drains
+    float* stg = stg_all + (warp - 4) * 32 * kStgStride;
     float* mine = stg + lane * kStgStride;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      if ((it & 1) != group) continue;
       int by, mt, nt;
       decode_tile(tile, p, by, mt, nt);
       const int acc = it & 1;
@@ -291,9 +308,9 @@ int as_corr_umma_launch(const float* f1, const float* f2, int B, int D, int H, i
   __nv_bfloat16* lo1 = split ? reinterpret_cast<__nv_bfloat16*>(w + s1 + s2) : nullptr;
   __nv_bfloat16* lo2 = split ? reinterpret_cast<__nv_bfloat16*>(w + 2 * s1 + s2) : nullptr;
 
-  split_transpose_kernel<<<dim3(as_ceil_div(W1, 32), BH), 256, 0, st>>>(f1, hi1, lo1, D, Dp, H, W1);
+  split_transpose_kernel<<<dim3(as_ceil_div(W1, 64), BH, Dp / 64), 256, 0, st>>>(f1, hi1, lo1, D, Dp, H, W1);
   AS_RETURN_IF_LAUNCH_FAILED();
-  split_transpose_kernel<<<dim3(as_ceil_div(W2, 32), BH), 256, 0, st>>>(f2, hi2, lo2, D, Dp, H, W2);
+  split_transpose_kernel<<<dim3(as_ceil_div(W2, 64), BH, Dp / 64), 256, 0, st>>>(f2, hi2, lo2, D, Dp, H, W2);
   AS_RETURN_IF_LAUNCH_FAILED();
 
   CorrUmmaParams p{};

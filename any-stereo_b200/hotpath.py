@@ -95,6 +95,9 @@ class HotLoopGraph:
             for _ in range(2):   # warm-up: fills the weight/context caches outside capture
                 self._run()
         torch.cuda.current_stream().wait_stream(s)
+        # the loop-invariant context / hi-lo plane caches were filled by the warm-up: drop them so the conversion
+        # kernels are part of the captured graph and follow the static buffers on every replay
+        update_block.reset_caches()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.out_disp, self.out_net = self._run()

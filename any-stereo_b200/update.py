@@ -148,6 +148,14 @@ class BasicMultiUpdateBlock(nn.Module):
         self._ctx_cache = {}
 
     # -- caches ---------------------------------------------------------------------------------
+    def reset_caches(self):
+        """Forget the loop-invariant context conversions and cached hi/lo planes (weights stay packed)."""
+        self._ctx_cache.clear()
+        st = self.__dict__.get("_umma_state")
+        if st is not None:
+            st["ctx"].clear()
+            st["planes"].clear()
+
     def _pk(self, name, convs):
         if name not in self._packed:
             self._packed[name] = _PackedConv()

@@ -97,7 +97,7 @@ def main():
         save("update_block_" + fam, **arrs)
 
     # ---- whole iterative loop (reference classes driven exactly like the model forward) ---
-    ITERS = 12
+    ITERS = 32
     c = cases.loop_case("igev")
     args = ref_loader.update_block_args("igev")
     mod = R.IGEVUpdateBlock(args, hidden_dims=[128, 128, 128]).eval()

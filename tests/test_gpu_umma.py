@@ -177,3 +177,63 @@ def test_update_block_umma_vs_fp32_medium(A):
         assert rel(n3b[i], n32b[i]) < 4e-4
     assert rel(d3, d32) < 2e-4
     assert rel(d3b, d32b) < 4e-4
+
+
+def test_hot_loop_cuda_graph(A):
+    """The whole IGEV hot-path step (volume build + iterations) captured in a CUDA graph replays to the same
+    result as eager execution, and follows new inputs loaded into its static buffers."""
+    c = cases.loop_case("igev", seed=55, B=1, H=16, W=24)
+    m = make_block(A, "igev", 7)
+    A.set_update_engine("bf16x3")
+    A.set_corr_mode("bf16x3")
+    dev = "cuda"
+    args = [c["f1"].to(dev), c["f2"].to(dev), c["geo"].to(dev), [t.to(dev) for t in c["net"]],
+            [[t.to(dev) for t in l] for l in c["inp"]], c["init_disp"].to(dev)]
+    eager, _ = A.igev_iterations(m, *args, 4)
+    g = A.HotLoopGraph(m, *args, 4)
+    d1, _ = g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(d1, eager)
+    # new inputs through the static buffers
+    c2 = cases.loop_case("igev", seed=56, B=1, H=16, W=24)
+    args2 = [c2["f1"].to(dev), c2["f2"].to(dev), c2["geo"].to(dev), [t.to(dev) for t in c2["net"]],
+             [[t.to(dev) for t in l] for l in c2["inp"]], c2["init_disp"].to(dev)]
+    eager2, _ = A.igev_iterations(m, *args2, 4)
+    g.load(*args2)
+    d2, _ = g.replay()
+    torch.cuda.synchronize()
+    A.set_update_engine("fp32")
+    A.set_corr_mode("fp32")
+    assert torch.equal(d2, eager2)
+
+
+def test_raft_fullsize_config1(A):
+    """BASELINE config 1 shapes (320x736 -> 80x184, D=256, L=4): tensor-core pyramid + fused lookup against the
+    exact-fp32 CUDA-core path, and integer-disparity lookups are exact gathers."""
+    torch.manual_seed(2)
+    B, D, H, W = 1, 256, 80, 184
+    f1 = torch.randn(B, D, H, W, device="cuda") / 4
+    f2 = torch.randn(B, D, H, W, device="cuda") / 4
+    A.set_corr_mode("fp32")
+    ref = A.CorrBlock1D(f1, f2, num_levels=4, radius=4)
+    A.set_corr_mode("bf16x3")
+    got = A.CorrBlock1D(f1, f2, num_levels=4, radius=4)
+    A.set_corr_mode("fp32")
+    for l in range(4):
+        assert rel(got.init_corr_pyramid[l], ref.init_corr_pyramid[l]) < 1e-4
+    coords = O.pixel_coords(B, H, W).cuda()
+    disp = torch.randint(0, 60, (B, 1, H, W), device="cuda").float()
+    out = ref(disp, coords)
+    N = B * H * W
+    for l in range(4):
+        Wl = W >> l
+        lvl = ref.init_corr_pyramid[l].reshape(N, Wl)
+        x = (coords.reshape(N, 1) - disp.reshape(N, 1)) / 2 ** l
+        fl = torch.floor(x)
+        fr = (x - fl)
+        idx = fl.long() + torch.arange(-4, 6, device="cuda").view(1, 10)
+        ok = (idx >= 0) & (idx < Wl)
+        g = torch.gather(lvl, 1, idx.clamp(0, Wl - 1)) * ok
+        want = g[:, :9] * (1 - fr) + g[:, 1:] * fr
+        have = out[:, 9 * l:9 * l + 9].permute(0, 2, 3, 1).reshape(N, 9)
+        assert float((have - want).abs().max()) <= 2e-6 * max(1.0, float(want.abs().max()))

@@ -74,6 +74,24 @@ def main():
 
     f1 = torch.randn(B, D, H, W, device=dev)
     f2 = torch.randn(B, D, H, W, device=dev)
+    if a.only == "corr3":
+        # all-pairs correlation GEMM at BASELINE config 3 (Middlebury-F 1984x2880 -> 496x720, D=256, 4 levels)
+        Br, Dr, Hr, Wr = 1, 256, 496, 720
+        r1 = torch.randn(Br, Dr, Hr, Wr, device=dev)
+        r2 = torch.randn(Br, Dr, Hr, Wr, device=dev)
+        flops = 2.0 * Br * Hr * Wr * Wr * Dr
+        byts = 2 * 4 * Br * Dr * Hr * Wr + 4 * Br * Hr * Wr * Wr * (1 + 0.5 + 0.25 + 0.125)
+        for mode in ("fp32", "bf16x3", "bf16"):
+            A.set_corr_mode(mode)
+            med, best = timeit(lambda: A.geometry._build_corr_levels(r1, r2, 4), reps=10)
+            rec("corr_build_c3_" + mode, med, best, byts)
+            res["corr_build_c3_" + mode]["TFLOPs_logical"] = round(flops / med / 1e6, 1)
+            res["corr_build_c3_" + mode]["TFLOPs_issued"] = round(flops * (3 if mode == "bf16x3" else 1) / med / 1e6, 1)
+            print("   ", res["corr_build_c3_" + mode])
+        A.set_corr_mode("fp32")
+        if a.json:
+            json.dump(res, open(a.json, "w"), indent=1)
+        return
     if a.only == "calib":
         # calibration of the box: what plain streaming achieves (same timing harness, L2 flushed)
         n = 1 << 28                                   # 1 GiB of fp32
