@@ -237,3 +237,26 @@ def test_raft_fullsize_config1(A):
         want = g[:, :9] * (1 - fr) + g[:, 1:] * fr
         have = out[:, 9 * l:9 * l + 9].permute(0, 2, 3, 1).reshape(N, 9)
         assert float((have - want).abs().max()) <= 2e-6 * max(1.0, float(want.abs().max()))
+
+
+def test_config3_middlebury_full_res_smoke(A):
+    """BASELINE config 3: 1984x2880 -> 496x720, RAFT family, 4-level pyramid (1.9 GB).  Two iterations of the hot
+    path on the tensor-core engines; the fp32 CUDA-core engine must agree on the first iteration's update."""
+    torch.manual_seed(4)
+    B, D, H, W = 1, 256, 496, 720
+    dev = "cuda"
+    f1 = torch.randn(B, D, H, W, device=dev) / 8
+    f2 = torch.randn(B, D, H, W, device=dev) / 8
+    m = make_block(A, "raft", 21)
+    sizes = [(H, W), (H // 2, W // 2), (H // 4, W // 4)]
+    net = [torch.tanh(torch.randn(B, 128, h, w, device=dev)) for h, w in sizes]
+    inp = [[0.5 * torch.randn(B, 128, h, w, device=dev) for _ in range(3)] for h, w in sizes]
+    A.set_update_engine("bf16x3")
+    A.set_corr_mode("bf16x3")
+    disp, net2, hist = A.raft_iterations(m, f1, f2, [t.clone() for t in net], inp, 2, keep_all=True)
+    A.set_update_engine("fp32")
+    disp32, _, hist32 = A.raft_iterations(m, f1, f2, [t.clone() for t in net], inp, 1, keep_all=True)
+    A.set_corr_mode("fp32")
+    torch.cuda.synchronize()
+    assert tuple(disp.shape) == (B, 1, H, W) and bool(torch.isfinite(disp).all())
+    assert float((hist[0] - hist32[0]).abs().max()) < 2e-4 * max(1.0, float(hist32[0].abs().max()))
