@@ -40,12 +40,31 @@ def test_header_symbols_exported(A):
     assert b"alignment" in lib.as_error_string(-4)
 
 
-def test_conv_desc_layout_matches_header(A):
+def test_struct_layouts_match_header(A, tmp_path):
+    """ctypes mirrors of the descriptor structs agree with what a C compiler makes of include/anystereo_b200.h."""
     import ctypes
-    d = A._lib.ConvDesc
-    assert ctypes.sizeof(A._lib.ConvSrc) == 24
-    assert d.src.offset == 32 and d.weight.offset == 32 + 4 * 24
-    assert ctypes.sizeof(d) == 208
+    import subprocess
+    src = tmp_path / "layout.c"
+    src.write_text(r"""
+#include <stdio.h>
+#include <stddef.h>
+#include "anystereo_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu\n", sizeof(as_conv_src), sizeof(as_conv_desc), offsetof(as_conv_desc, src),
+         offsetof(as_conv_desc, weight), offsetof(as_conv_desc, out), offsetof(as_conv_desc, save));
+  printf("%zu %zu %zu %zu %zu %zu\n", sizeof(as_umma_src), sizeof(as_conv_umma_desc), offsetof(as_conv_umma_desc, src),
+         offsetof(as_conv_umma_desc, w_hi), offsetof(as_conv_umma_desc, out_hi), offsetof(as_conv_umma_desc, u));
+  return 0;
+}
+""")
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)]).decode().split()
+    c = [int(x) for x in out]
+    L = A._lib
+    d, u = L.ConvDesc, L.ConvUmmaDesc
+    assert c[:6] == [ctypes.sizeof(L.ConvSrc), ctypes.sizeof(d), d.src.offset, d.weight.offset, d.out.offset, d.save.offset]
+    assert c[6:] == [ctypes.sizeof(L.UmmaSrc), ctypes.sizeof(u), u.src.offset, u.w_hi.offset, u.out_hi.offset, u.u.offset]
 
 
 def test_argument_errors_without_gpu(A):
