@@ -74,11 +74,14 @@ __device__ __forceinline__ void store_split32(const float* v, __nv_bfloat16* hi,
   }
 }
 
-// CS = thread-block cluster size.  The CTAs of a cluster walk their tiles in lockstep over the same (tap, chunk)
-// sequence, so the weight tile of every K-block is the same for all of them: each CTA fetches 1/CS of it and
-// TMA-multicasts the slice into every CTA's ring slot (L2->smem weight traffic / CS).  A ring slot may be
-// overwritten only when ALL CTAs have consumed it: every MMA warp commits "slot free" to the whole cluster.
-template <int CS>
+// TWO = CTA-pair mode (tcgen05 cta_group::2).  The SS-mode MMA is bound by shared-memory READ bandwidth (per K-step it
+// reads 128 x 32 B of A and N x 32 B of B; at N = 256 that is 96 B/clk of the 128 B/clk port before the TMA fills are
+// counted), so two CTAs of a cluster pair up: each loads its own 128-pixel patch and HALF of the weight rows, the
+// leader issues M = 256 MMAs that read A from both SMs and half of B from each, and each CTA drains its own 128
+// accumulator lanes.  Per SM the B reads and the B ring footprint halve (4 weight stages instead of 2).
+//   full barriers live in the leader (both producers arm them remotely, TMA credits them with cta_group::2),
+//   "slot free" / "accumulator ready" are multicast commits to both CTAs, "accumulator drained" arrives remotely.
+template <bool TWO>
 __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_constant__ ConvMaps maps,
                                                                 const ConvUmmaParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -96,10 +99,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b_bytes = p.N * 128;
-  const uint32_t crank = CS > 1 ? umma::cluster_ctarank() : 0u;
-  constexpr uint16_t kAllCtas = (uint16_t)((1u << CS) - 1u);
-  const int niter = (p.num_tiles + (int)gridDim.x - 1) / (int)gridDim.x;   // identical for every CTA of a cluster
+  const uint32_t crank = TWO ? umma::cluster_ctarank() : 0u;
+  const bool leader = crank == 0;
+  const int nb_rows = TWO ? p.N / 2 : p.N;       // weight rows held by this CTA
+  const int b_bytes = nb_rows * 128;             // one weight plane of a stage
+  const int niter = (p.num_tiles + (int)gridDim.x - 1) / (int)gridDim.x;   // identical for both CTAs of a pair
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.num_src; ++s) {
@@ -111,22 +115,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kMaxStages; ++s) {
-      umma::mbar_init(&fullA[s], 1); umma::mbar_init(&emptyA[s], 1);
-      umma::mbar_init(&fullB[s], 1); umma::mbar_init(&emptyB[s], CS);
+      umma::mbar_init(&fullA[s], TWO ? 2 : 1); umma::mbar_init(&emptyA[s], 1);
+      umma::mbar_init(&fullB[s], TWO ? 2 : 1); umma::mbar_init(&emptyB[s], 1);
     }
-    for (int a = 0; a < 2; ++a) { umma::mbar_init(&tfull[a], 1); umma::mbar_init(&tempty[a], 4); }
+    for (int a = 0; a < 2; ++a) { umma::mbar_init(&tfull[a], 1); umma::mbar_init(&tempty[a], TWO ? 8 : 4); }
     umma::fence_barrier_init();
   }
   if (warp == 2) {
-    umma::tmem_alloc(tmem_slot, 512);
-    umma::tmem_relinquish();
+    if (TWO) { umma::tmem_alloc_2sm(tmem_slot, 512); umma::tmem_relinquish_2sm(); }
+    else { umma::tmem_alloc(tmem_slot, 512); umma::tmem_relinquish(); }
   }
   if (p.epilogue == AS_UEPI_DISPHEAD) {
     for (int i = threadIdx.x; i < kW2Floats; i += kThreads) w2s[i] = p.w2[i];
   }
   umma::tc_fence_before();
   __syncthreads();
-  if (CS > 1) umma::cluster_sync_all();          // peers' barriers are initialised before any multicast can land
+  if (TWO) umma::cluster_sync_all();             // both CTAs' barriers exist before anyone signals them
   umma::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int chunks = p.cin_total >> 6;           // 64-channel chunks per tap
@@ -140,9 +144,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
       const uint32_t txA = (uint32_t)p.a_plane * (p.nsplit == 3 ? 2u : 1u);
       const uint32_t txB = (uint32_t)b_bytes * (p.nsplit == 3 ? 2u : 1u);
       const int ph = p.KH >> 1, pw = p.KW >> 1;
+      const int brow0 = (int)crank * nb_rows;    // first weight row of my half
       for (int itn = 0; itn < niter; ++itn) {
         int tile = blockIdx.x + itn * gridDim.x;
-        if (tile >= p.num_tiles) tile = 0;       // padding iteration: keeps the cluster in lockstep, result discarded
+        if (tile >= p.num_tiles) tile = 0;       // padding iteration: keeps the pair in lockstep, result discarded
         const int b = tile / tiles_per_img;
         const int r = tile - b * tiles_per_img;
         const int ty = r / p.tiles_x, txi = r - ty * p.tiles_x;
@@ -153,24 +158,30 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
             for (int c0 = 0; c0 < p.src_ch[s]; c0 += 64) {
               umma::mbar_wait(&emptyA[sa], pha ^ 1);
               uint8_t* sta = a_ring + sa * p.a_stage;
-              umma::mbar_expect_tx(&fullA[sa], txA);
-              umma::tma_load_4d(sta, &maps.a_hi[s], &fullA[sa], c0, x0 + kx - pw, y0 - ph, b);
-              if (p.nsplit == 3) umma::tma_load_4d(sta + p.a_plane, &maps.a_lo[s], &fullA[sa], c0, x0 + kx - pw, y0 - ph, b);
+              if (!TWO) {
+                umma::mbar_expect_tx(&fullA[sa], txA);
+                umma::tma_load_4d(sta, &maps.a_hi[s], &fullA[sa], c0, x0 + kx - pw, y0 - ph, b);
+                if (p.nsplit == 3) umma::tma_load_4d(sta + p.a_plane, &maps.a_lo[s], &fullA[sa], c0, x0 + kx - pw, y0 - ph, b);
+              } else {
+                const uint32_t bar = umma::mapa(umma::smem_u32(&fullA[sa]), 0);
+                umma::mbar_expect_tx_cluster(bar, txA);
+                umma::tma_load_4d_2sm(sta, &maps.a_hi[s], bar, c0, x0 + kx - pw, y0 - ph, b);
+                if (p.nsplit == 3) umma::tma_load_4d_2sm(sta + p.a_plane, &maps.a_lo[s], bar, c0, x0 + kx - pw, y0 - ph, b);
+              }
               if (++sa == p.nstA) { sa = 0; pha ^= 1; }
               for (int ky = 0; ky < p.KH; ++ky) {
                 umma::mbar_wait(&emptyB[sb], phb ^ 1);
                 uint8_t* stb = b_ring + sb * p.b_stage;
-                umma::mbar_expect_tx(&fullB[sb], txB);
                 const int kcoord = (ky * p.KW + kx) * p.cin_total + coff + c0;
-                if (CS == 1) {
+                if (!TWO) {
+                  umma::mbar_expect_tx(&fullB[sb], txB);
                   umma::tma_load_2d(stb, &maps.b_hi, &fullB[sb], kcoord, 0);
                   if (p.nsplit == 3) umma::tma_load_2d(stb + b_bytes, &maps.b_lo, &fullB[sb], kcoord, 0);
-                } else {                         // my 1/CS slice of the weight rows, multicast to the whole cluster
-                  const int rows = p.N / CS;
-                  const int soff = (int)crank * rows * 128;
-                  umma::tma_load_2d_mc(stb + soff, &maps.b_hi, &fullB[sb], kcoord, (int)crank * rows, kAllCtas);
-                  if (p.nsplit == 3)
-                    umma::tma_load_2d_mc(stb + b_bytes + soff, &maps.b_lo, &fullB[sb], kcoord, (int)crank * rows, kAllCtas);
+                } else {
+                  const uint32_t bar = umma::mapa(umma::smem_u32(&fullB[sb]), 0);
+                  umma::mbar_expect_tx_cluster(bar, txB);
+                  umma::tma_load_2d_2sm(stb, &maps.b_hi, bar, kcoord, brow0);
+                  if (p.nsplit == 3) umma::tma_load_2d_2sm(stb + b_bytes, &maps.b_lo, bar, kcoord, brow0);
                 }
                 if (++sb == p.nstB) { sb = 0; phb ^= 1; }
               }
@@ -182,9 +193,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (lane == 0 && leader) {
       int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
-      const uint32_t idesc = umma::idesc_bf16_f32(128, p.N);
+      const uint32_t idesc = umma::idesc_bf16_f32(TWO ? 256 : 128, p.N);
       for (int it = 0; it < niter; ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
@@ -204,21 +215,27 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
             for (int k = 0; k < 4; ++k) {
               const uint32_t ko = (uint32_t)k * 32u;
               const uint64_t dah = umma::smem_desc_k_sw128(a_hi + ko), dbh = umma::smem_desc_k_sw128(b_hi + ko);
-              umma::mma_bf16_ss(tmem_d, dah, dbh, idesc, accumulate);
+              if (TWO) umma::mma_bf16_ss_2sm(tmem_d, dah, dbh, idesc, accumulate);
+              else umma::mma_bf16_ss(tmem_d, dah, dbh, idesc, accumulate);
               accumulate = 1u;
               if (p.nsplit == 3) {
                 const uint64_t dal = umma::smem_desc_k_sw128(a_lo + ko), dbl = umma::smem_desc_k_sw128(b_lo + ko);
-                umma::mma_bf16_ss(tmem_d, dah, dbl, idesc, 1u);
-                umma::mma_bf16_ss(tmem_d, dal, dbh, idesc, 1u);
+                if (TWO) {
+                  umma::mma_bf16_ss_2sm(tmem_d, dah, dbl, idesc, 1u);
+                  umma::mma_bf16_ss_2sm(tmem_d, dal, dbh, idesc, 1u);
+                } else {
+                  umma::mma_bf16_ss(tmem_d, dah, dbl, idesc, 1u);
+                  umma::mma_bf16_ss(tmem_d, dal, dbh, idesc, 1u);
+                }
               }
             }
-            if (CS == 1) umma::mma_commit(&emptyB[sb]); else umma::mma_commit_mc(&emptyB[sb], kAllCtas);
+            if (TWO) umma::mma_commit_2sm(&emptyB[sb], 3); else umma::mma_commit(&emptyB[sb]);
             if (++sb == p.nstB) { sb = 0; phb ^= 1; }
           }
-          umma::mma_commit(&emptyA[sa]);
+          if (TWO) umma::mma_commit_2sm(&emptyA[sa], 3); else umma::mma_commit(&emptyA[sa]);
           if (++sa == p.nstA) { sa = 0; pha ^= 1; }
         }
-        umma::mma_commit(&tfull[acc]);
+        if (TWO) umma::mma_commit_2sm(&tfull[acc], 3); else umma::mma_commit(&tfull[acc]);
       }
     }
     __syncwarp();
@@ -319,19 +336,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
       }
       umma::tc_fence_before();
       __syncwarp();
-      if (lane == 0) umma::mbar_arrive(&tempty[acc]);
+      if (lane == 0) {
+        if (TWO) umma::mbar_arrive_cluster(umma::mapa(umma::smem_u32(&tempty[acc]), 0));   // the leader issues the MMAs
+        else umma::mbar_arrive(&tempty[acc]);
+      }
     }
   }
   umma::tc_fence_before();
   __syncthreads();
-  if (CS > 1) umma::cluster_sync_all();          // nobody exits while a peer may still multicast into its smem
-  if (warp == 2) umma::tmem_dealloc(tmem_base, 512);
+  if (TWO) umma::cluster_sync_all();             // nobody exits while the pair may still signal / read its smem
+  if (warp == 2) {
+    if (TWO) umma::tmem_dealloc_2sm(tmem_base, 512); else umma::tmem_dealloc(tmem_base, 512);
+  }
 }
 
-template <int CS>
+template <bool TWO>
 int launch_conv(const ConvMaps& maps, const ConvUmmaParams& p, int sms, int smem, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return (int)e;
+  constexpr int CS = TWO ? 2 : 1;
   int grid = p.num_tiles < sms ? p.num_tiles : sms;
   grid = (grid / CS) * CS;
   if (grid < CS) grid = CS;
@@ -345,20 +368,16 @@ int launch_conv(const ConvMaps& maps, const ConvUmmaParams& p, int sms, int smem
   attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<CS>, maps, p);
+  e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<TWO>, maps, p);
   if (e != cudaSuccess) return (int)e;
   AS_RETURN_IF_LAUNCH_FAILED();
   return AS_OK;
 }
 
-// AS_CONV_CLUSTER=1|2|4.  Default 1: measured on B200 (profiles/), weight multicast across a cluster is correct but
-// SLOWER with the current 64-wide K blocks -- N = 256 leaves room for only two weight stages and the cross-CTA
-// "slot free" round trip no longer hides behind one stage of MMAs.  Kept as a tuning knob for a deeper ring.
-int cluster_size_override() {
-  const char* v = getenv("AS_CONV_CLUSTER");
-  if (!v) return 1;
-  const int c = atoi(v);
-  return (c == 1 || c == 2 || c == 4) ? c : 1;
+// AS_CONV_2CTA=0|1 selects the CTA-pair (cta_group::2) kernel; default on.
+bool two_cta_enabled() {
+  const char* v = getenv("AS_CONV_2CTA");
+  return !(v && v[0] == '0');
 }
 
 }  // namespace
@@ -387,9 +406,10 @@ extern "C" int as_conv2d_umma(const as_conv_umma_desc* d, as_stream_t stream) {
   }
   p.cin_total = cin;
   p.N = d->Cout; p.nsplit = d->nsplit; p.epilogue = d->epilogue;
+  const bool two = two_cta_enabled() && p.num_tiles >= 4 && (p.N % 32) == 0;
   p.a_plane = (p.TH + d->KH - 1) * p.TW * 128;          // (TH+2)-row patch for 3x3, the tile itself for 1x1
   p.a_stage = 2 * p.a_plane;
-  p.b_stage = 2 * p.N * 128;
+  p.b_stage = 2 * (two ? p.N / 2 : p.N) * 128;           // CTA-pair mode: each CTA holds half of the weight rows
   const int fixed = 1024 + kW2Floats * 4 + 256;
   // ring depths: B is consumed KH times faster than A; give B at least 2 (3 if it fits) stages, A 2
   p.nstA = 2;
@@ -452,24 +472,18 @@ extern "C" int as_conv2d_umma(const as_conv_umma_desc* d, as_stream_t stream) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int smem = fixed + p.nstA * p.a_stage + p.nstB * p.b_stage;
-  int cs = cluster_size_override();
-  while (cs > 1 && (p.num_tiles < 2 * cs || (p.N / cs) % 8 != 0)) cs >>= 1;   // tiny layers: no point in clustering
-  // the weight tensor map's box is one CTA's slice of the rows
-  if (cs > 1) {
+  if (two) {   // the weight tensor map's box is one CTA's half of the rows
     const uint64_t Kt = (uint64_t)d->KH * d->KW * cin;
     const uint64_t dims[2] = {Kt, (uint64_t)p.N};
     const uint64_t str[1] = {Kt * 2};
-    const uint32_t box[2] = {64u, (uint32_t)(p.N / cs)};
+    const uint32_t box[2] = {64u, (uint32_t)(p.N / 2)};
     if ((rc = umma::make_tmap_bf16(&maps.b_hi, d->w_hi, 2, dims, str, box)) != AS_OK) return rc;
     if (d->nsplit == 3) {
       if ((rc = umma::make_tmap_bf16(&maps.b_lo, d->w_lo, 2, dims, str, box)) != AS_OK) return rc;
     } else {
       maps.b_lo = maps.b_hi;
     }
+    return launch_conv<true>(maps, p, sms, smem, as_cu(stream));
   }
-  switch (cs) {
-    case 4: return launch_conv<4>(maps, p, sms, smem, as_cu(stream));
-    case 2: return launch_conv<2>(maps, p, sms, smem, as_cu(stream));
-    default: return launch_conv<1>(maps, p, sms, smem, as_cu(stream));
-  }
+  return launch_conv<false>(maps, p, sms, smem, as_cu(stream));
 }
