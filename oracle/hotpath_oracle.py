@@ -104,7 +104,7 @@ def lookup_rows_exact(rows: torch.Tensor, x: torch.Tensor, radius: int) -> torch
     """
     N, C, W = rows.shape
     t0, f = tap_indices(x, radius)
-    k = torch.arange(2 * radius + 2, dtype=torch.int64)
+    k = torch.arange(2 * radius + 2, dtype=torch.int64, device=rows.device)
     idx = t0.to(torch.int64)[:, None] + k[None, :]                 # [N,2r+2]
     ok = (idx >= 0) & (idx < W)
     g = torch.gather(rows, 2, idx.clamp(0, W - 1)[:, None, :].expand(N, C, -1))
@@ -122,7 +122,7 @@ def lookup_rows_gridsample(rows: torch.Tensor, x: torch.Tensor, radius: int) -> 
     rows [N,C,W], x [N] -> [N,C,2r+1].
     """
     N, C, W = rows.shape
-    taps = torch.linspace(-radius, radius, 2 * radius + 1).view(1, 1, -1, 1)
+    taps = torch.linspace(-radius, radius, 2 * radius + 1, device=rows.device).view(1, 1, -1, 1)
     xs = taps + x.reshape(N, 1, 1, 1)
     ys = torch.zeros_like(xs)
     grid = torch.cat([2 * xs / (W - 1) - 1, ys], dim=-1)           # [N,1,2r+1,2]
@@ -301,9 +301,9 @@ def update_block(p, net, inp, corr=None, disp=None, iter04=True, iter08=True, it
 # a12  loop glue
 # --------------------------------------------------------------------------------------
 
-def pixel_coords(B, H, W):
+def pixel_coords(B, H, W, device=None):
     """coords[b,y,x,0] = x as float (continuous_IGEVstereo.py:280, prune_raft_stereo.py:272)."""
-    return torch.arange(W).float().reshape(1, 1, W, 1).repeat(B, H, 1, 1)
+    return torch.arange(W, device=device).float().reshape(1, 1, W, 1).repeat(B, H, 1, 1)
 
 
 def igev_iterations(p, fmap1, fmap2, geo_volume, net, inp, init_disp, iters,
@@ -313,7 +313,7 @@ def igev_iterations(p, fmap1, fmap2, geo_volume, net, inp, init_disp, iters,
     B, _, H, W = fmap1.shape
     cp = corr_pyramid(all_pairs_corr(fmap1.float(), fmap2.float()), num_levels)
     gp = geo_pyramid(geo_volume.float(), num_levels)
-    coords = pixel_coords(B, H, W)
+    coords = pixel_coords(B, H, W, fmap1.device)
     disp = init_disp
     hist = []
     for _ in range(iters):
@@ -330,7 +330,7 @@ def raft_iterations(p, fmap1, fmap2, net, inp, iters, radius=4, num_levels=4, ex
     """prune_raft_stereo.py:267-286 (disp starts at zero, :274)."""
     B, _, H, W = fmap1.shape
     cp = corr_pyramid(all_pairs_corr(fmap1.float(), fmap2.float()), num_levels)
-    coords = pixel_coords(B, H, W)
+    coords = pixel_coords(B, H, W, fmap1.device)
     disp = fmap1.new_zeros(B, 1, H, W)
     hist = []
     for _ in range(iters):
