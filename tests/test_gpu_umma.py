@@ -260,3 +260,49 @@ def test_config3_middlebury_full_res_smoke(A):
     torch.cuda.synchronize()
     assert tuple(disp.shape) == (B, 1, H, W) and bool(torch.isfinite(disp).all())
     assert float((hist[0] - hist32[0]).abs().max()) < 2e-4 * max(1.0, float(hist32[0].abs().max()))
+
+
+@pytest.mark.parametrize("engine", ["fp32", "bf16x3"])
+def test_model_level_raft_epe(A, golden, engine):
+    """Drop-in at the model level: the tensors the real reference RAFT model feeds into its hot path (captured on
+    CPU, tests/golden/make_model_golden.py) replayed through our operators for the same 32 iterations give the
+    reference model's low-resolution disparity to within 0.01 px (x4 = full-resolution pixels)."""
+    g = golden("model_raft_boundary")
+    net = [torch.from_numpy(g["net%d" % i]).cuda() for i in range(3)]
+    inp = [[torch.from_numpy(g["inp%d_%d" % (i, j)]).cuda() for j in range(3)] for i in range(3)]
+    args = types.SimpleNamespace(corr_levels=4, corr_radius=4, n_gru_layers=3)
+    m = A.BasicMultiUpdateBlockRAFT(args, hidden_dims=[128, 128, 128])
+    m.load_state_dict(O.make_update_block_params(36, seed=77), strict=True)
+    m = m.cuda().eval()
+    A.set_update_engine(engine)
+    A.set_corr_mode(engine)
+    disp, _ = A.raft_iterations(m, torch.from_numpy(g["f1"]).cuda(), torch.from_numpy(g["f2"]).cuda(), net, inp,
+                                int(g["iters"]))
+    A.set_update_engine("fp32")
+    A.set_corr_mode("fp32")
+    epe = float((disp.cpu() - torch.from_numpy(g["disp_lowres"])).abs().mean()) * 4
+    assert epe < 0.01, epe
+
+
+@pytest.mark.parametrize("engine", ["fp32", "bf16x3"])
+def test_model_level_igev_epe(A, golden, engine):
+    """IGEV family at the model level: build_gwc_volume on the real model's matching features, then the combined
+    volume + 32 iterations from the real model's boundary tensors -> within 0.01 px of the reference model."""
+    g = golden("model_igev_boundary")
+    net = [torch.from_numpy(g["net%d" % i]).cuda() for i in range(3)]
+    inp = [[torch.from_numpy(g["inp%d_%d" % (i, j)]).cuda() for j in range(3)] for i in range(3)]
+    f1, f2 = torch.from_numpy(g["f1"]).cuda(), torch.from_numpy(g["f2"]).cuda()
+    gwc = A.build_gwc_volume(f1, f2, 48, 8)
+    assert rel(gwc, g["gwc"]) < 1e-5
+    args = types.SimpleNamespace(corr_levels=2, corr_radius=4, n_gru_layers=3)
+    m = A.BasicMultiUpdateBlock(args, hidden_dims=[128, 128, 128])
+    m.load_state_dict(O.make_update_block_params(162, seed=78), strict=True)
+    m = m.cuda().eval()
+    A.set_update_engine(engine)
+    A.set_corr_mode(engine)
+    disp, _ = A.igev_iterations(m, f1, f2, torch.from_numpy(g["geo"]).cuda(), net, inp,
+                                torch.from_numpy(g["init_disp"]).cuda(), int(g["iters"]))
+    A.set_update_engine("fp32")
+    A.set_corr_mode("fp32")
+    epe = float((disp.cpu() - torch.from_numpy(g["disp_lowres"])).abs().mean()) * 4
+    assert epe < 0.01, epe

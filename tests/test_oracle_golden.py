@@ -164,3 +164,35 @@ def test_adjoints(golden):
     dL, dR = O.gwc_volume_bwd(torch.from_numpy(g["gwc_cot"]), gc["left"], gc["right"], gc["groups"])
     assert rel(dL, g["gwc_gL"]) < 1e-5
     assert rel(dR, g["gwc_gR"]) < 1e-5
+
+
+def _model_case(golden):
+    g = golden("model_raft_boundary")
+    net = [torch.from_numpy(g["net%d" % i]) for i in range(3)]
+    inp = [[torch.from_numpy(g["inp%d_%d" % (i, j)]) for j in range(3)] for i in range(3)]
+    return g, torch.from_numpy(g["f1"]), torch.from_numpy(g["f2"]), net, inp
+
+
+def test_model_level_raft(golden):
+    """Oracle loop fed with the tensors the REAL reference model graph passes into the hot path reproduces the
+    low-res disparity that model computed (tests/golden/make_model_golden.py)."""
+    g, f1, f2, net, inp = _model_case(golden)
+    p = O.make_update_block_params(36, seed=77)
+    disp, _ = O.raft_iterations(p, f1, f2, net, inp, int(g["iters"]))
+    err = (disp - torch.from_numpy(g["disp_lowres"])).abs()
+    assert float(err.mean()) * 4 < 1e-3
+
+
+def test_model_level_igev(golden):
+    """Same at the IGEV family: tensors captured inside the real continuous_IGEVStereo graph (timm backbone replaced
+    by a shape-identical torchvision MobileNetV2, off the hot path)."""
+    g = golden("model_igev_boundary")
+    net = [torch.from_numpy(g["net%d" % i]) for i in range(3)]
+    inp = [[torch.from_numpy(g["inp%d_%d" % (i, j)]) for j in range(3)] for i in range(3)]
+    f1, f2 = torch.from_numpy(g["f1"]), torch.from_numpy(g["f2"])
+    assert np.array_equal(O.gwc_volume(f1, f2, 48, 8).numpy(), g["gwc"])
+    p = O.make_update_block_params(162, seed=78)
+    disp, _ = O.igev_iterations(p, f1, f2, torch.from_numpy(g["geo"]), net, inp, torch.from_numpy(g["init_disp"]),
+                                int(g["iters"]))
+    err = (disp - torch.from_numpy(g["disp_lowres"])).abs()
+    assert float(err.mean()) * 4 < 1e-3
