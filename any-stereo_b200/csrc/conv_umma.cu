@@ -391,8 +391,15 @@ extern "C" int as_conv2d_umma(const as_conv_umma_desc* d, as_stream_t stream) {
   if (d->nsplit == 3 && !d->w_lo) return AS_ERR_BAD_ARG;
   ConvUmmaParams p{};
   p.B = d->B; p.H = d->H; p.W = d->W; p.KH = d->KH; p.KW = d->KW;
-  p.TW = 16; p.TH = 8;
-  if (d->W <= 8) { p.TW = 8; p.TH = 16; }
+  // 128-pixel patch 16 (x) x 8 (y).  Measured on B200 at 312x96: the 8x16 orientation tiles the image exactly (2.5 %
+  // fewer MMAs, smaller halo) but runs 2.5 % SLOWER (shorter TMA rows), so 16x8 stays the default.
+  {
+    p.TW = 16; p.TH = 8;
+    if (d->W <= 8) { p.TW = 8; p.TH = 16; }
+    const char* force = getenv("AS_CONV_TILE");       // tuning knob: "16x8" | "8x16"
+    if (force && force[0] == '1' && d->W > 8) { p.TW = 16; p.TH = 8; }
+    if (force && force[0] == '8') { p.TW = 8; p.TH = 16; }
+  }
   p.tiles_x = as_ceil_div(d->W, p.TW); p.tiles_y = as_ceil_div(d->H, p.TH);
   p.num_tiles = p.tiles_x * p.tiles_y * d->B;
   p.num_src = d->num_src;

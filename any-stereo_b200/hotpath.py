@@ -27,7 +27,7 @@ def _add(a, b):
 
 
 def _iterate(lookup, update_block, net_list, inp_list, disp, coords, iters, slow_fast_gru=False, keep_all=False,
-             lookup_events=None):
+             lookup_events=None, update_events=None):
     n_layers = update_block.args.n_gru_layers
     hist = []
     net_list = list(net_list)
@@ -46,7 +46,14 @@ def _iterate(lookup, update_block, net_list, inp_list, disp, coords, iters, slow
             net_list = update_block(net_list, inp_list, iter16=True, iter08=False, iter04=False, update=False)
         if n_layers >= 2 and slow_fast_gru:
             net_list = update_block(net_list, inp_list, iter16=n_layers == 3, iter08=True, iter04=False, update=False)
+        if update_events is not None:
+            u0 = torch.cuda.Event(enable_timing=True)
+            u1 = torch.cuda.Event(enable_timing=True)
+            u0.record()
         net_list, delta = update_block(net_list, inp_list, feat, disp, iter16=n_layers == 3, iter08=n_layers >= 2)
+        if update_events is not None:
+            u1.record()
+            update_events.append((u0, u1))
         disp = _add(disp, delta)
         if keep_all:
             hist.append(disp)
@@ -56,14 +63,14 @@ def _iterate(lookup, update_block, net_list, inp_list, disp, coords, iters, slow
 @torch.no_grad()
 def igev_iterations(update_block: BasicMultiUpdateBlock, match_left, match_right, geo_encoding_volume, net_list,
                     inp_list, init_disp, iters, radius=4, num_levels=2, slow_fast_gru=False, keep_all=False,
-                    lookup_events=None):
+                    lookup_events=None, update_events=None):
     """Build the combined volume, then ``iters`` x {lookup -> update -> disp += delta}."""
     geo_fn = Combined_Geo_Encoding_Volume(match_left.float(), match_right.float(), geo_encoding_volume.float(),
                                           radius=radius, num_levels=num_levels)
     B, _, H, W = match_left.shape
     coords = pixel_coords(B, H, W, match_left.device)
     return _iterate(geo_fn, update_block, net_list, inp_list, init_disp, coords, iters, slow_fast_gru, keep_all,
-                    lookup_events)
+                    lookup_events, update_events)
 
 
 @torch.no_grad()

@@ -202,10 +202,10 @@ def run_ours(args):
     host_out = torch.empty(B, 1, H4, W4).pin_memory()
     L = A._lib
 
-    def step(d, events=None):
+    def step(d, events=None, uevents=None):
         geo = A.build_gwc_volume(d["ml"], d["mr"], GEO_D, GROUPS)
         disp, net = A.igev_iterations(block, d["ml"], d["mr"], geo, d["net"], d["inp"], d["disp"], ITERS,
-                                      radius=4, num_levels=2, lookup_events=events)
+                                      radius=4, num_levels=2, lookup_events=events, update_events=uevents)
         return disp
 
     # e2e: every step copies ITS inputs from pinned host memory and reads its result back.  Two device staging
@@ -271,13 +271,14 @@ def run_ours(args):
         sampler = ClockSampler(local) if rank == 0 else None
         if sampler:
             sampler.start()
-        events = []
+        events, uevents = [], []
         l0 = L.launch_count
-        ms = timed(lambda: step(dd, events), args.steps)
+        ms = timed(lambda: step(dd, events, uevents), args.steps)
         launches = L.launch_count - l0
         clocks = sampler.stop() if sampler else None
         torch.cuda.synchronize()
         look_us = [a.elapsed_time(b) * 1e3 for a, b in events]
+        upd_us = [a.elapsed_time(b) * 1e3 for a, b in uevents]
         for _ in range(2):
             e2e_step()
         ms_e2e = timed(e2e_step, args.steps)
@@ -299,6 +300,17 @@ def run_ours(args):
             traffic = json.load(f).get("geo_lookup_fwd_bytes_per_launch")
     except Exception:
         pass
+    # second roofline: the update block (tensor-bound).  FLOPs per SURVEY.md 8(d); in the bf16x3 mode every MAC is
+    # issued 3 times, so "issued" is what the tensor pipe executes; peak = measured sustained cuBLAS bf16.
+    upd_avg_us = sum(upd_us) / max(len(upd_us), 1)
+    upd_flops = 2.0 * (n_pix * (1847488 + 64 * 162) + n_pix / 4 * 1327104 + n_pix / 16 * 884736)
+    issued = upd_flops * (3 if args.engine == "bf16x3" else 1)
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            tpeak = float(json.load(f)["bf16_tflops_sustained"])
+        tpeak_src = "measured sustained (MEASURED_PEAKS.json)"
+    except Exception:
+        tpeak, tpeak_src = 1400.0, "fallback (B200_PROFILING.md sustained)"
     cpu = cpu_reference_sample(sample_iters=args.ref_sample_iters) if not args.no_cpu_baseline else None
     line = {
         "metric": "pairs/s @384x1248, 32 iters", "value": value, "unit": "pairs/s", "n_gpus": world,
@@ -319,6 +331,11 @@ def run_ours(args):
                      "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": LOOKUP_BYTES_PER_PIXEL * n_pix,
                      "avg_launch_us": look_avg_us, "launches_timed": len(look_us)},
+        "roofline_update_block": None if args.engine == "fp32" else {
+            "kernels": "conv_umma_kernel (tcgen05, 11 launches) + 9 small kernels per iteration", "bound": "tensor",
+            "achieved": issued / (upd_avg_us * 1e-6) / 1e12, "peak": tpeak, "unit": "TFLOP/s", "frac": issued / (upd_avg_us * 1e-6) / 1e12 / tpeak,
+            "logical_tflops": upd_flops / (upd_avg_us * 1e-6) / 1e12, "mma_issue_factor": 3 if args.engine == "bf16x3" else 1,
+            "avg_us_per_iteration": upd_avg_us, "peak_source": tpeak_src},
         "cpu_baseline": None if cpu is None else {"value": cpu["pairs_per_s"], "unit": "pairs/s", "cores": cpu["cores"],
                                                   "kind": "port", "sample": cpu["sample"]},
         "clocks": clocks,
