@@ -84,22 +84,27 @@ def raft_iterations(update_block: BasicMultiUpdateBlock, match_left, match_right
 
 
 class HotLoopGraph:
-    """CUDA-graph replay of one IGEV hot-path step (volume build + all iterations) on static buffers.
+    """CUDA-graph replay of one hot-path step (volume build + all iterations) on static buffers.
 
-    The per-iteration work is ~20 short launches; at small shapes the loop is launch-bound, so the whole
-    step is captured once and replayed (no tracing compiler involved: the graph records exactly the
-    library's kernels)."""
+    The per-iteration work is ~20 launches; at small shapes (config 1: one 320x736 pair) the loop is launch-bound, so
+    the whole step is captured once and replayed (no tracing compiler involved: the graph records exactly the
+    library's kernels).  ``geo_volume`` / ``init_disp`` given -> IGEV family, else RAFT family."""
 
-    def __init__(self, update_block, match_left, match_right, geo_volume, net_list, inp_list, init_disp, iters,
-                 radius=4, num_levels=2):
-        self.static_in = dict(ml=match_left.clone(), mr=match_right.clone(), geo=geo_volume.clone(),
+    def __init__(self, update_block, match_left, match_right, geo_volume=None, net_list=None, inp_list=None,
+                 init_disp=None, iters=32, radius=4, num_levels=None):
+        self.igev = geo_volume is not None
+        if num_levels is None:
+            num_levels = 2 if self.igev else 4
+        self.static_in = dict(ml=match_left.clone(), mr=match_right.clone(),
+                              geo=geo_volume.clone() if self.igev else None,
                               net=[t.clone() for t in net_list],
-                              inp=[[t.clone() for t in lst] for lst in inp_list], disp=init_disp.clone())
+                              inp=[[t.clone() for t in lst] for lst in inp_list],
+                              disp=init_disp.clone() if init_disp is not None else None)
         self.args = (update_block, iters, radius, num_levels)
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
-            for _ in range(2):   # warm-up: fills the weight/context caches outside capture
+            for _ in range(2):   # warm-up: packs the weights outside capture
                 self._run()
         torch.cuda.current_stream().wait_stream(s)
         # the loop-invariant context / hi-lo plane caches were filled by the warm-up: drop them so the conversion
@@ -112,20 +117,23 @@ class HotLoopGraph:
     def _run(self):
         ub, iters, radius, num_levels = self.args
         si = self.static_in
-        return igev_iterations(ub, si["ml"], si["mr"], si["geo"], si["net"], si["inp"], si["disp"], iters,
-                               radius=radius, num_levels=num_levels)
+        if self.igev:
+            return igev_iterations(ub, si["ml"], si["mr"], si["geo"], si["net"], si["inp"], si["disp"], iters,
+                                   radius=radius, num_levels=num_levels)
+        return raft_iterations(ub, si["ml"], si["mr"], si["net"], si["inp"], iters, radius=radius, num_levels=num_levels)
 
-    def load(self, match_left, match_right, geo_volume, net_list, inp_list, init_disp):
+    def load(self, match_left, match_right, geo_volume=None, net_list=None, inp_list=None, init_disp=None):
         si = self.static_in
         si["ml"].copy_(match_left, non_blocking=True)
         si["mr"].copy_(match_right, non_blocking=True)
-        si["geo"].copy_(geo_volume, non_blocking=True)
+        if self.igev:
+            si["geo"].copy_(geo_volume, non_blocking=True)
+            si["disp"].copy_(init_disp, non_blocking=True)
         for d, s in zip(si["net"], net_list):
             d.copy_(s, non_blocking=True)
         for dl, sl in zip(si["inp"], inp_list):
             for d, s in zip(dl, sl):
                 d.copy_(s, non_blocking=True)
-        si["disp"].copy_(init_disp, non_blocking=True)
 
     def replay(self):
         self.graph.replay()

@@ -283,6 +283,43 @@ def run_ours(args):
             e2e_step()
         ms_e2e = timed(e2e_step, args.steps)
 
+    # the other BASELINE.json configs that run the same path (parity-test cases; reported for context, rank 0, N=1)
+    other = {}
+    if rank == 0 and world == 1 and not args.no_other_configs:
+        with torch.no_grad():
+            rblock = A.BasicMultiUpdateBlockRAFT(types.SimpleNamespace(corr_levels=4, corr_radius=4, n_gru_layers=3),
+                                                 hidden_dims=[128, 128, 128]).to(dev).eval()
+            for name, (rb, rh, rw) in {"config1_raft_320x736_b1": (1, 80, 184), "config3_raft_1984x2880_b1": (1, 496, 720)}.items():
+                g = torch.Generator(device="cpu").manual_seed(7)
+                rs = [(rh, rw), (rh // 2, rw // 2), (rh // 4, rw // 4)]
+                rf1 = (torch.randn(rb, 256, rh, rw, generator=g) / 4).to(dev)
+                rf2 = (torch.randn(rb, 256, rh, rw, generator=g) / 4).to(dev)
+                rnet = [torch.tanh(torch.randn(rb, 128, h_, w_, generator=g)).to(dev) for h_, w_ in rs]
+                rinp = [[torch.relu(torch.randn(rb, 128, h_, w_, generator=g)).to(dev) for _ in range(3)] for h_, w_ in rs]
+                for _ in range(2):
+                    A.raft_iterations(rblock, rf1, rf2, rnet, rinp, ITERS)
+                torch.cuda.synchronize()
+                r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                r0.record()
+                for _ in range(3):
+                    A.raft_iterations(rblock, rf1, rf2, rnet, rinp, ITERS)
+                r1.record()
+                torch.cuda.synchronize()
+                rms = r0.elapsed_time(r1) / 3
+                other[name] = {"ms_per_pair": rms / rb, "pairs_per_s": rb / (rms / 1e3), "iters": ITERS, "corr_levels": 4}
+                # same step replayed from a CUDA graph (launch-bound at small shapes)
+                hg = A.HotLoopGraph(rblock, rf1, rf2, net_list=rnet, inp_list=rinp, iters=ITERS)
+                hg.replay()
+                torch.cuda.synchronize()
+                r0.record()
+                for _ in range(3):
+                    hg.replay()
+                r1.record()
+                torch.cuda.synchronize()
+                gms = r0.elapsed_time(r1) / 3
+                other[name]["cuda_graph_ms_per_pair"] = gms / rb
+                other[name]["cuda_graph_pairs_per_s"] = rb / (gms / 1e3)
+                del hg, rf1, rf2, rnet, rinp
     pairs = world * B * args.steps
     value = pairs / (ms / 1e3)
     e2e_value = pairs / (ms_e2e / 1e3)
@@ -339,6 +376,7 @@ def run_ours(args):
         "cpu_baseline": None if cpu is None else {"value": cpu["pairs_per_s"], "unit": "pairs/s", "cores": cpu["cores"],
                                                   "kind": "port", "sample": cpu["sample"]},
         "clocks": clocks,
+        "other_configs": other,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -356,6 +394,7 @@ def main():
     ap.add_argument("--pairs-per-gpu", type=int, default=8)
     ap.add_argument("--ref-sample-iters", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -190,7 +190,7 @@ def test_hot_loop_cuda_graph(A):
     args = [c["f1"].to(dev), c["f2"].to(dev), c["geo"].to(dev), [t.to(dev) for t in c["net"]],
             [[t.to(dev) for t in l] for l in c["inp"]], c["init_disp"].to(dev)]
     eager, _ = A.igev_iterations(m, *args, 4)
-    g = A.HotLoopGraph(m, *args, 4)
+    g = A.HotLoopGraph(m, args[0], args[1], args[2], args[3], args[4], args[5], iters=4)
     d1, _ = g.replay()
     torch.cuda.synchronize()
     assert torch.equal(d1, eager)
