@@ -13,6 +13,7 @@ Everything computes in hand-written CUDA kernels behind the C ABI of include/any
 """
 from . import _lib
 from . import corr_sampler
+from . import update_umma
 from .geometry import CorrBlock1D, Combined_Geo_Encoding_Volume, set_corr_mode, get_corr_mode
 from .submodule import build_gwc_volume
 from .update import (BasicMultiUpdateBlock, BasicMultiUpdateBlockRAFT, BasicMotionEncoder, ConvGRU, DispHead,

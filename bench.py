@@ -191,6 +191,8 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     A.set_update_engine(args.engine)
+    if args.overlap:
+        A.update_umma.set_encoder_overlap(True)
     A.set_corr_mode(args.corr_mode or ("fp32" if args.engine == "fp32" else args.engine))
     B = args.pairs_per_gpu
     torch.manual_seed(0)
@@ -395,6 +397,7 @@ def main():
     ap.add_argument("--ref-sample-iters", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true")
+    ap.add_argument("--overlap", action="store_true", help="motion encoder on a side stream (A/B knob, default off)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
