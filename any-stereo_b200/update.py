@@ -248,10 +248,11 @@ class BasicMultiUpdateBlock(nn.Module):
             from . import update_umma
             return update_umma.forward(self, net, inp, corr, disp, iter04, iter08, iter16, update)
         for t in net:
-            L.require_cuda(t, "net[i]", torch.float32, contiguous=False)
+            L.require_cuda(t, "net[i]", contiguous=False)
         n_layers = self.args.n_gru_layers
         with torch.cuda.device(net[0].device):
-            hs = [None if t is None else _nhwc_view(t.detach())[0] for t in net]
+            # half inputs (the reference runs this block under autocast when mixed_precision is on) are widened
+            hs = [None if t is None else _nhwc_view(t.detach().float())[0] for t in net]
             if iter16:
                 hs[2] = self._gru("gru16", self.gru16, 2, hs[2], inp[2], [self._pool2x(hs[1])])
             if iter08:
@@ -260,10 +261,10 @@ class BasicMultiUpdateBlock(nn.Module):
                     xs.append(self._interp(hs[2], hs[1]))
                 hs[1] = self._gru("gru08", self.gru08, 1, hs[1], inp[1], xs)
             if iter04:
-                L.require_cuda(corr, "corr", torch.float32, contiguous=False)
-                L.require_cuda(disp, "disp", torch.float32, contiguous=False)
-                corr = corr.detach().contiguous()
-                disp = disp.detach().contiguous()
+                L.require_cuda(corr, "corr", contiguous=False)
+                L.require_cuda(disp, "disp", contiguous=False)
+                corr = corr.detach().float().contiguous()
+                disp = disp.detach().float().contiguous()
                 xs = [self._encoder(disp, corr)]
                 if n_layers > 1:
                     xs.append(self._interp(hs[1], hs[0]))

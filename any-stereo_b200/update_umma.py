@@ -239,13 +239,13 @@ def forward(ub, net, inp, corr=None, disp=None, iter04=True, iter08=True, iter16
         return mo
 
     with torch.cuda.device(dev):
-        hs = [None if t is None else _nhwc_view(t.detach())[0] for t in net]
+        hs = [None if t is None else _nhwc_view(t.detach().float())[0] for t in net]
         enc_job = None
         if iter04:
-            L.require_cuda(corr, "corr", torch.float32, contiguous=False)
-            L.require_cuda(disp, "disp", torch.float32, contiguous=False)
-            corr = corr.detach().contiguous()
-            disp = disp.detach().contiguous()
+            L.require_cuda(corr, "corr", contiguous=False)
+            L.require_cuda(disp, "disp", contiguous=False)
+            corr = corr.detach().float().contiguous()
+            disp = disp.detach().float().contiguous()
             if _OVERLAP["on"] and (iter16 or iter08):
                 # The motion encoder depends only on (corr, disp); the 1/16 and 1/8 GRUs launch 120-470 tiles on 148
                 # SMs.  Fork it onto a side stream so its CTAs fill the SMs those small grids leave idle; joined by an

@@ -306,3 +306,34 @@ def test_model_level_igev_epe(A, golden, engine):
     A.set_corr_mode("fp32")
     epe = float((disp.cpu() - torch.from_numpy(g["disp_lowres"])).abs().mean()) * 4
     assert epe < 0.01, epe
+
+
+@pytest.mark.parametrize("engine,tol", [("fp32", 1e-4), ("bf16x3", 3e-4)])
+@pytest.mark.parametrize("n_layers", [1, 2])
+def test_update_block_fewer_gru_layers(A, engine, tol, n_layers):
+    """n_gru_layers = 1 / 2 variants of BasicMultiUpdateBlock (update.py:111-112,121-130) and half-precision inputs."""
+    import torch.nn as nn
+    torch.manual_seed(n_layers)
+    B, H, W = 1, 12, 20
+    args = types.SimpleNamespace(corr_levels=2, corr_radius=4, n_gru_layers=n_layers)
+    m = A.BasicMultiUpdateBlock(args, hidden_dims=[128, 128, 128]).cuda().eval()
+    p = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    sizes = [(H, W), (H // 2, W // 2), (H // 4, W // 4)][:n_layers]
+    net = [torch.tanh(torch.randn(B, 128, h, w)) for h, w in sizes]
+    inp = [[0.5 * torch.randn(B, 128, h, w) for _ in range(3)] for h, w in sizes]
+    corr = torch.randn(B, 162, H, W)
+    disp = torch.rand(B, 1, H, W) * 10
+    ref_net, ref_delta = O.update_block(p, net, inp, corr, disp, iter16=n_layers == 3, iter08=n_layers >= 2,
+                                        n_gru_layers=n_layers)
+    A.set_update_engine(engine)
+    with torch.no_grad():
+        got_net, got_delta = m([t.cuda() for t in net], [[t.cuda() for t in l] for l in inp], corr.cuda(), disp.cuda(),
+                               iter16=n_layers == 3, iter08=n_layers >= 2)
+        for i in range(n_layers):
+            assert rel(got_net[i], ref_net[i]) < tol
+        assert rel(got_delta, ref_delta) < tol
+        if engine == "fp32":   # half inputs are accepted and widened
+            h_net, h_delta = m([t.cuda().half() for t in net], [[t.cuda() for t in l] for l in inp], corr.cuda().half(),
+                               disp.cuda(), iter16=n_layers == 3, iter08=n_layers >= 2)
+            assert rel(h_delta, ref_delta) < 2e-2
+    A.set_update_engine("fp32")
