@@ -18,7 +18,7 @@ from .geometry import CorrBlock1D, Combined_Geo_Encoding_Volume, set_corr_mode, 
 from .submodule import build_gwc_volume
 from .update import (BasicMultiUpdateBlock, BasicMultiUpdateBlockRAFT, BasicMotionEncoder, ConvGRU, DispHead,
                      set_update_engine, get_update_engine)
-from .hotpath import igev_iterations, raft_iterations, install_into_reference, HotLoopGraph
+from .hotpath import igev_iterations, raft_iterations, install_into_reference, HotLoopGraph, set_lookup_fusion
 from .parallel import shard_pairs, allreduce_gradients
 
 __all__ = [

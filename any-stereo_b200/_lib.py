@@ -76,6 +76,8 @@ SIGNATURES = {
     "as_corr_lookup_bwd": (_i, [_pp, _ip, _ip, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "as_geo_lookup_fwd": (_i, [_pp, _i, _i, _pp, _ip, _ip, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "as_geo_lookup_bwd": (_i, [_pp, _i, _i, _pp, _ip, _ip, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "as_geo_lookup_convc1": (_i, [_pp, _i, _i, _pp, _ip, _ip, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i,
+                                  _vp]),
     "as_lookup_taps": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "as_gwc_build_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "as_gwc_build_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),

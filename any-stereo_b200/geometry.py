@@ -300,7 +300,69 @@ class Combined_Geo_Encoding_Volume:
         return _geo_lookup(self._geo_bufs, self._G, self._Dg, self._corr_bufs, self._widths, self._pitches,
                            self.radius, disp, coords)
 
+    def deferred(self, disp, coords):
+        """The same lookup, not yet run: hand the result to BasicMultiUpdateBlock.forward as `corr` and the
+        tensor-core engines fuse it with BasicMotionEncoder.convc1, so the 162-channel tensor never
+        reaches HBM.  Engines / shapes without the fused kernel call .materialize() and behave as before."""
+        disp, coords = _check_disp_coords(disp, coords)
+        return DeferredGeoLookup(self, disp, coords)
+
     @staticmethod
     def corr(fmap1, fmap2):
         """coreContinuous_IGEV/geometry.py:63-72."""
         return CorrBlock1D.corr(fmap1, fmap2)
+
+
+class DeferredGeoLookup:
+    """(volume, disp, coords) of one Combined_Geo_Encoding_Volume.__call__ (geometry.py:34-60), evaluated by its consumer."""
+
+    def __init__(self, vol, disp, coords):
+        self.vol, self.disp, self.coords = vol, disp, coords
+        B, _, H, W = disp.shape
+        self.shape = (B, vol.num_levels * (vol._G + 1) * (2 * vol.radius + 1), H, W)
+        self.device = disp.device
+        self.events = None          # bench.py: list collecting (start, end) CUDA events around the fused kernel
+
+    @property
+    def fusable(self):
+        v = self.vol
+        needs_grad = torch.is_grad_enabled() and any(b.requires_grad for b in list(v._geo_bufs) + list(v._corr_bufs))
+        return v._G == 8 and v.radius == 4 and v.num_levels in (1, 2) and not needs_grad
+
+    def materialize(self):
+        return self.vol(self.disp, self.coords)
+
+    @staticmethod
+    def pack_convc1_weight(weight, split=True):
+        """convc1.weight [64, L*81, 1, 1] -> bf16 hi/lo [64][192] in the K order of the fused kernel:
+        channel (level l, group g, tap k) at K = l*96 + g*10 + k (g == 8: correlation taps); pads are zero."""
+        w = weight.detach().float().reshape(weight.shape[0], -1)
+        Cout, Cin = w.shape
+        if Cout != 64 or Cin not in (81, 162):
+            raise RuntimeError("fused lookup+convc1 needs convc1: 81|162 -> 64 channels")
+        c = torch.arange(Cin, device=w.device)
+        kidx = (c // 81) * 96 + ((c % 81) // 9) * 10 + (c % 9)
+        wp = torch.zeros((Cout, 192), device=w.device, dtype=torch.float32)
+        wp[:, kidx] = w
+        hi = torch.empty((Cout, 192), device=w.device, dtype=torch.bfloat16)
+        lo = torch.empty_like(hi) if split else None
+        with torch.cuda.device(w.device):
+            L.call("as_pack_conv_weight_bf16", wp.data_ptr(), hi.data_ptr(), L.ptr(lo), Cout, 192, 1, 1, Cout, 192,
+                   L.stream_ptr())
+        return hi, lo
+
+    def convc1_planes(self, w_hi, w_lo, bias, out_hi, out_lo):
+        """relu(convc1(lookup)) as bf16 planes [B,H,W,64] (update.py:78,85 applied to geometry.py:34-60)."""
+        v = self.vol
+        B, _, H, W = self.disp.shape
+        with torch.cuda.device(self.device):
+            if self.events is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            L.call("as_geo_lookup_convc1", L.ptr_array(v._geo_bufs), v._G, v._Dg, L.ptr_array(v._corr_bufs),
+                   L.int_array(v._widths), L.int_array(v._pitches), v.num_levels, self.disp.data_ptr(),
+                   L.ptr(self.coords), w_hi.data_ptr(), L.ptr(w_lo), bias.data_ptr(), 3 if w_lo is not None else 1,
+                   out_hi.data_ptr(), L.ptr(out_lo), B, H, W, v.radius, L.stream_ptr())
+            if self.events is not None:
+                e1.record()
+                self.events.append((e0, e1))

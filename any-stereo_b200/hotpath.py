@@ -10,7 +10,7 @@ import torch
 from . import _lib as L
 from .geometry import CorrBlock1D, Combined_Geo_Encoding_Volume
 from .submodule import build_gwc_volume
-from .update import BasicMultiUpdateBlock
+from .update import BasicMultiUpdateBlock, get_update_engine
 
 
 def pixel_coords(B, H, W, device):
@@ -26,14 +26,27 @@ def _add(a, b):
     return y
 
 
+_FUSION = {"on": True}
+
+
+def set_lookup_fusion(on: bool) -> bool:
+    """Fuse the IGEV lookup with BasicMotionEncoder.convc1 inside igev_iterations (tensor-core engines only)."""
+    prev = _FUSION["on"]
+    _FUSION["on"] = bool(on)
+    return prev
+
+
 def _iterate(lookup, update_block, net_list, inp_list, disp, coords, iters, slow_fast_gru=False, keep_all=False,
-             lookup_events=None, update_events=None):
+             lookup_events=None, update_events=None, fused_lookup=None):
     n_layers = update_block.args.n_gru_layers
     hist = []
     net_list = list(net_list)
     for _ in range(iters):
         disp = disp.detach()
-        if lookup_events is not None:      # bench.py: CUDA events around the lookup launch, on its stream
+        if fused_lookup is not None:       # lookup evaluated inside the update block, fused with convc1 (8(f)-1)
+            feat = fused_lookup(disp, coords)
+            feat.events = lookup_events
+        elif lookup_events is not None:    # bench.py: CUDA events around the lookup launch, on its stream
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -69,8 +82,9 @@ def igev_iterations(update_block: BasicMultiUpdateBlock, match_left, match_right
                                           radius=radius, num_levels=num_levels)
     B, _, H, W = match_left.shape
     coords = pixel_coords(B, H, W, match_left.device)
+    fused = geo_fn.deferred if _FUSION["on"] and get_update_engine() != "fp32" else None
     return _iterate(geo_fn, update_block, net_list, inp_list, init_disp, coords, iters, slow_fast_gru, keep_all,
-                    lookup_events, update_events)
+                    lookup_events, update_events, fused_lookup=fused)
 
 
 @torch.no_grad()
@@ -156,7 +170,7 @@ def install_into_reference(ref_igev_module=None, ref_raft_module=None):
 
 def adopt_update_block(ref_update_block, family="igev"):
     """Build our update block around the SAME nn.Parameter objects as a reference BasicMultiUpdateBlock."""
-    from .update import BasicMultiUpdateBlockRAFT
+    from .update import BasicMultiUpdateBlock, BasicMultiUpdateBlockRAFT
     cls = BasicMultiUpdateBlock if family == "igev" else BasicMultiUpdateBlockRAFT
     hd = [ref_update_block.gru16.convz.out_channels, ref_update_block.gru08.convz.out_channels,
           ref_update_block.gru04.convz.out_channels]

@@ -237,6 +237,9 @@ class BasicMultiUpdateBlock(nn.Module):
 
     # -- forward ----------------------------------------------------------------------------------
     def forward(self, net, inp, corr=None, disp=None, iter04=True, iter08=True, iter16=True, update=True):
+        deferred = corr is not None and not torch.is_tensor(corr)     # geometry.DeferredGeoLookup
+        if deferred and (get_update_engine() == "fp32" or torch.is_grad_enabled()):
+            corr, deferred = corr.materialize(), False
         needs_grad = torch.is_grad_enabled() and (
             any(p.requires_grad for p in self.parameters()) or any(t.requires_grad for t in net)
             or any(t.requires_grad for lst in inp for t in lst) or (corr is not None and corr.requires_grad))

@@ -18,6 +18,7 @@ import weakref
 import torch
 
 from . import _lib as L
+from .geometry import DeferredGeoLookup
 
 
 _OVERLAP = {"on": False}
@@ -80,6 +81,22 @@ def _weights(ub, name, convs, n_pad=None, cin_pad=None, split=True):
         bias[:Cout].copy_(b)
     hit = dict(key=key, hi=hi, lo=lo, bias=bias, n=n_pad, cin=cin_pad, k=KH)
     st[name] = hit
+    return hit
+
+
+def _fused_c1_weights(ub, split):
+    """convc1 weights in the K order of the fused lookup kernel (geometry.DeferredGeoLookup.pack_convc1_weight)."""
+    st = _state(ub)["w"]
+    c = ub.encoder.convc1
+    key = (split, c.weight.data_ptr(), c.weight._version, c.bias.data_ptr(), c.bias._version)
+    hit = st.get("convc1.fused")
+    if hit is not None and hit["key"] == key:
+        return hit
+    with torch.no_grad():
+        hi, lo = DeferredGeoLookup.pack_convc1_weight(c.weight, split)
+        bias = c.bias.detach().float().contiguous()
+    hit = dict(key=key, hi=hi, lo=lo, bias=bias)
+    st["convc1.fused"] = hit
     return hit
 
 
@@ -221,11 +238,15 @@ def forward(ub, net, inp, corr=None, disp=None, iter04=True, iter08=True, iter16
         e = ub.encoder
         sw = _small_weights(ub)
         cpad = (Cc + 63) // 64 * 64
-        corrS = _Planes((B, H, W, cpad), dev, split)
-        L.call("as_nchw_to_nhwc_split", corr.data_ptr(), corrS.hi.data_ptr(), L.ptr(corrS.lo), B, Cc, H, W, cpad, s())
         c1 = _Planes((B, H, W, 64), dev, split)
-        _conv(B, H, W, [corrS], _weights(ub, "convc1", [e.convc1], cin_pad=cpad, split=split), nsplit,
-              L.UEPI_RELU_SPLIT, out=c1)
+        if isinstance(corr, DeferredGeoLookup):      # lookup + convc1 + ReLU in one kernel, features stay on chip
+            wf = _fused_c1_weights(ub, split)
+            corr.convc1_planes(wf["hi"], wf["lo"], wf["bias"], c1.hi, c1.lo)
+        else:
+            wc1 = _weights(ub, "convc1", [e.convc1], cin_pad=cpad, split=split)
+            corrS = _Planes((B, H, W, cpad), dev, split)
+            L.call("as_nchw_to_nhwc_split", corr.data_ptr(), corrS.hi.data_ptr(), L.ptr(corrS.lo), B, Cc, H, W, cpad, s())
+            _conv(B, H, W, [corrS], wc1, nsplit, L.UEPI_RELU_SPLIT, out=c1)
         enc = _Planes((B, H, W, 128), dev, split)
         _conv(B, H, W, [c1], _weights(ub, "convc2", [e.convc2], split=split), nsplit, L.UEPI_RELU_SPLIT, out=enc)
         d1 = _Planes((B, H, W, 64), dev, split)
@@ -242,9 +263,13 @@ def forward(ub, net, inp, corr=None, disp=None, iter04=True, iter08=True, iter16
         hs = [None if t is None else _nhwc_view(t.detach().float())[0] for t in net]
         enc_job = None
         if iter04:
-            L.require_cuda(corr, "corr", contiguous=False)
+            if isinstance(corr, DeferredGeoLookup):
+                if not corr.fusable or ub.encoder.convc1.out_channels != 64:
+                    corr = corr.materialize()
+            if not isinstance(corr, DeferredGeoLookup):
+                L.require_cuda(corr, "corr", contiguous=False)
+                corr = corr.detach().float().contiguous()
             L.require_cuda(disp, "disp", contiguous=False)
-            corr = corr.detach().float().contiguous()
             disp = disp.detach().float().contiguous()
             if _OVERLAP["on"] and (iter16 or iter08):
                 # The motion encoder depends only on (corr, disp); the 1/16 and 1/8 GRUs launch 120-470 tiles on 148

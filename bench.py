@@ -27,6 +27,8 @@ sys.path.insert(0, ROOT)
 
 H4, W4, FEAT_D, GEO_D, GROUPS, ITERS = 96, 312, 96, 48, 8, 32     # 384x1248 at 1/4 resolution
 LOOKUP_BYTES_PER_PIXEL = 1372                                      # IGEV L=2, r=4, G=8
+# fused lookup+convc1: the same 724 B of windows + 4 B disp read, 64 bf16 hi(+lo) channels written
+FUSED_BYTES_PER_PIXEL = {"bf16x3": 728 + 256, "bf16": 728 + 128}
 
 
 def load_peaks():
@@ -193,6 +195,7 @@ def run_ours(args):
     A.set_update_engine(args.engine)
     if args.overlap:
         A.update_umma.set_encoder_overlap(True)
+    A.set_lookup_fusion(not args.no_fusion)
     A.set_corr_mode(args.corr_mode or ("fp32" if args.engine == "fp32" else args.engine))
     B = args.pairs_per_gpu
     torch.manual_seed(0)
@@ -332,11 +335,16 @@ def run_ours(args):
     peak, peak_src = load_peaks()
     n_pix = B * H4 * W4
     look_avg_us = sum(look_us) / max(len(look_us), 1)
-    achieved = LOOKUP_BYTES_PER_PIXEL * n_pix / (look_avg_us * 1e-6) / 1e9
+    fused = (not args.no_fusion) and args.engine != "fp32"
+    look_bpp = FUSED_BYTES_PER_PIXEL[args.engine] if fused else LOOKUP_BYTES_PER_PIXEL
+    look_kernel = ("geo_lookup_convc1_kernel<2> (Combined_Geo_Encoding_Volume.__call__ fused with "
+                   "BasicMotionEncoder.convc1+ReLU)" if fused else
+                   "geo_lookup_fwd_kernel<2> (Combined_Geo_Encoding_Volume.__call__)")
+    achieved = look_bpp * n_pix / (look_avg_us * 1e-6) / 1e9
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            traffic = json.load(f).get("geo_lookup_fwd_bytes_per_launch")
+            traffic = json.load(f).get("geo_lookup_convc1_bytes_per_launch" if fused else "geo_lookup_fwd_bytes_per_launch")
     except Exception:
         pass
     # second roofline: the update block (tensor-bound).  FLOPs per SURVEY.md 8(d); in the bf16x3 mode every MAC is
@@ -360,18 +368,19 @@ def run_ours(args):
         "config": {"workload": "coreContinuous_IGEV hot path (BASELINE configs[1]): 384x1248 -> 96x312 @1/4, "
                                "batch %d pairs/GPU, 32 iters, corr_levels=2, radius=4" % B,
                    "pairs_per_gpu": B, "iters": ITERS, "engine": args.engine, "corr_mode": A.get_corr_mode(),
+                   "lookup_fused_with_convc1": fused,
                    "parallelism": "pairs sharded across ranks, no data-path collective",
                    "l2": "working set per step (~1 GB of pyramids + 155 MB lookup output per iteration) exceeds the 126 MB L2; no explicit flush"},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": host_bytes(hh),
                 "d2h_bytes_per_step": 4 * B * H4 * W4, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
-        "roofline": {"kernel": "geo_lookup_fwd_kernel<2> (Combined_Geo_Encoding_Volume.__call__)", "bound": "hbm",
+        "roofline": {"kernel": look_kernel, "bound": "hbm",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": LOOKUP_BYTES_PER_PIXEL * n_pix,
+                     "algorithmic_bytes_per_launch": look_bpp * n_pix, "algorithmic_bytes_per_pixel": look_bpp,
                      "avg_launch_us": look_avg_us, "launches_timed": len(look_us)},
         "roofline_update_block": None if args.engine == "fp32" else {
-            "kernels": "conv_umma_kernel (tcgen05, 11 launches) + 9 small kernels per iteration", "bound": "tensor",
+            "kernels": "conv_umma_kernel (tcgen05) + small kernels per iteration" + (" + the fused lookup/convc1 kernel" if fused else ""), "bound": "tensor",
             "achieved": issued / (upd_avg_us * 1e-6) / 1e12, "peak": tpeak, "unit": "TFLOP/s", "frac": issued / (upd_avg_us * 1e-6) / 1e12 / tpeak,
             "logical_tflops": upd_flops / (upd_avg_us * 1e-6) / 1e12, "mma_issue_factor": 3 if args.engine == "bf16x3" else 1,
             "avg_us_per_iteration": upd_avg_us, "peak_source": tpeak_src},
@@ -397,6 +406,7 @@ def main():
     ap.add_argument("--ref-sample-iters", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true")
+    ap.add_argument("--no-fusion", action="store_true", help="materialise the 162-channel lookup tensor (A/B knob)")
     ap.add_argument("--overlap", action="store_true", help="motion encoder on a side stream (A/B knob, default off)")
     args = ap.parse_args()
     if args.impl == "reference":

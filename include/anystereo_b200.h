@@ -134,6 +134,17 @@ int as_geo_lookup_bwd(float* const* g_geo_levels, int G, int Dg,
                       float* const* g_corr_levels, const int* corr_widths, const int* corr_pitches,
                       int num_levels, const float* disp, const float* coords, const float* g_out,
                       int B, int H, int W, int radius, as_stream_t stream);
+/* the lookup above fused with its only consumer, BasicMotionEncoder.convc1 (1x1, L*(G+1)*9 -> 64)
+ * + ReLU (models/coreContinuous_IGEV/update.py:78,85).  The lookup tensor never reaches HBM: features are produced
+ * into the shared-memory operand tiles of a tcgen05 MMA.  G must be 8, radius 4, num_levels 1 or 2.
+ * w_hi/w_lo: bf16 [64][192] with channel (level l, group g, tap k; g == 8: correlation taps) at
+ * K = l*96 + g*10 + k and zeros elsewhere (as_pack_conv_weight_bf16 of the permuted matrix); bias fp32 [64];
+ * out_hi/out_lo: bf16 planes [B*H*W][64] = relu(convc1(lookup)); nsplit 3 (bf16x3) or 1 (w_lo/out_lo NULL). */
+int as_geo_lookup_convc1(const float* const* geo_levels, int G, int Dg,
+                         const float* const* corr_levels, const int* corr_widths, const int* corr_pitches,
+                         int num_levels, const float* disp, const float* coords,
+                         const void* w_hi, const void* w_lo, const float* bias, int nsplit,
+                         void* out_hi, void* out_lo, int B, int H, int W, int radius, as_stream_t stream);
 /* index-parity probe: integer base tap (floor(x)-r) and fractional weight per pixel for one level.
  * kind 0 = geo position disp/2^l, kind 1 = corr position (coords-disp)/2^l. */
 int as_lookup_taps(const float* disp, const float* coords, int B, int H, int W, int radius,

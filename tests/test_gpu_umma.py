@@ -337,3 +337,87 @@ def test_update_block_fewer_gru_layers(A, engine, tol, n_layers):
                                disp.cuda(), iter16=n_layers == 3, iter08=n_layers >= 2)
             assert rel(h_delta, ref_delta) < 2e-2
     A.set_update_engine("fp32")
+
+
+@pytest.mark.parametrize("engine,tol", [("bf16x3", 1e-4), ("bf16", 2e-2)])
+@pytest.mark.parametrize("shape", [(2, 5, 23, 16, 2), (1, 16, 24, 48, 2), (1, 7, 150, 24, 1), (3, 9, 40, 20, 2)])
+def test_fused_lookup_convc1_vs_oracle(A, engine, tol, shape):
+    """lookup fused with BasicMotionEncoder.convc1 + ReLU on the tensor cores against
+    relu(conv1x1(oracle lookup)); ragged 128-pixel tiles, out-of-range disparities, 1 and 2 levels."""
+    B, H, W, Dg, Lv = shape
+    c = cases.igev_geo_case(seed=31 + H, B=B, D=16, H=H, W=W, Dg=Dg)
+    rng = np.random.RandomState(W)
+    disp = torch.from_numpy(rng.uniform(-6, Dg + 6, (B, 1, H, W)).astype("float32"))
+    disp[0, 0, 0, :3] = torch.tensor([0.0, Dg - 1.0, 3.0])          # integer positions: frac == 0
+    coords = torch.arange(W).float().reshape(1, 1, W, 1).repeat(B, H, 1, 1)
+    w = torch.from_numpy(rng.standard_normal((64, Lv * 81, 1, 1)).astype("float32")) * 0.2
+    b = torch.from_numpy(rng.standard_normal(64).astype("float32")) * 0.1
+    feat = O.geo_lookup(O.geo_pyramid(c["geo"], Lv), O.corr_pyramid(O.all_pairs_corr(c["f1"], c["f2"]), Lv), disp, coords,
+                        4, exact=True)
+    ref = torch.relu(torch.nn.functional.conv2d(feat.double(), w.double(), b.double())).float()
+    A.set_corr_mode("fp32")
+    vol = A.Combined_Geo_Encoding_Volume(c["f1"].cuda(), c["f2"].cuda(), c["geo"].cuda(), num_levels=Lv, radius=4)
+    split = engine == "bf16x3"
+    w_hi, w_lo = A.geometry.DeferredGeoLookup.pack_convc1_weight(w.cuda(), split)
+    out_hi = torch.full((B, H, W, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+    out_lo = torch.full_like(out_hi, float("nan")) if split else None
+    d = vol.deferred(disp.cuda(), coords.cuda())
+    assert d.fusable and d.shape == (B, Lv * 81, H, W)
+    d.convc1_planes(w_hi, w_lo, b.cuda(), out_hi, out_lo)
+    torch.cuda.synchronize()
+    got = out_hi.float() + (out_lo.float() if split else 0)
+    assert rel(got.permute(0, 3, 1, 2), ref) < tol
+    # coords=None means the default pixel grid
+    out2 = torch.empty_like(out_hi)
+    vol.deferred(disp.cuda(), None).convc1_planes(w_hi, w_lo, b.cuda(), out2, torch.empty_like(out_hi) if split else None)
+    torch.cuda.synchronize()
+    assert torch.equal(out2, out_hi)
+
+
+@pytest.mark.parametrize("engine", ["bf16x3", "bf16"])
+def test_fused_lookup_matches_unfused_loop(A, engine):
+    """igev_iterations with the lookup fused into the update block == the same loop with the 162-channel tensor
+    materialised (identical arithmetic: fp32 interpolation, same bf16 split, same K order on the MMA)."""
+    c = cases.loop_case("igev", seed=77, B=2, H=19, W=45)
+    m = make_block(A, "igev", 9)
+    A.set_update_engine(engine)
+    A.set_corr_mode("bf16x3")
+    args = [c["f1"].cuda(), c["f2"].cuda(), c["geo"].cuda(), [t.cuda() for t in c["net"]],
+            [[t.cuda() for t in l] for l in c["inp"]], c["init_disp"].cuda()]
+    prev = A.set_lookup_fusion(True)
+    for on in (False, True):                        # both paths pack their weights / fill the context caches
+        A.set_lookup_fusion(on)
+        A.igev_iterations(m, *args, 1)
+    n0 = A._lib.launch_count
+    d_f, net_f = A.igev_iterations(m, *args, 6)
+    n1 = A._lib.launch_count
+    A.set_lookup_fusion(False)
+    d_u, net_u = A.igev_iterations(m, *args, 6)
+    n2 = A._lib.launch_count
+    A.set_lookup_fusion(prev)
+    A.set_update_engine("fp32")
+    A.set_corr_mode("fp32")
+    assert (n2 - n1) - (n1 - n0) >= 6, (n0, n1, n2)         # at least one launch fewer per iteration
+    tol = 1e-5 if engine == "bf16x3" else 2e-3       # K order differs: fp32 accumulation order, amplified by 6 GRU steps
+    assert rel(d_f, d_u) < tol
+    for a, b in zip(net_f, net_u):
+        assert rel(a, b) < tol
+
+
+def test_fused_lookup_falls_back(A):
+    """Deferred lookups are materialised by the exact-fp32 engine and by unsupported shapes (G != 8)."""
+    c = cases.loop_case("igev", seed=78, B=1, H=8, W=20)
+    m = make_block(A, "igev", 9)
+    args = [c["f1"].cuda(), c["f2"].cuda(), c["geo"].cuda()]
+    vol = A.Combined_Geo_Encoding_Volume(*args, num_levels=2, radius=4)
+    disp = c["init_disp"].cuda()
+    net = [t.cuda() for t in c["net"]]
+    inp = [[t.cuda() for t in l] for l in c["inp"]]
+    with torch.no_grad():
+        A.set_update_engine("fp32")
+        n_a, d_a = m(list(net), inp, vol.deferred(disp, None), disp)
+        n_b, d_b = m(list(net), inp, vol(disp, None), disp)
+    assert torch.equal(d_a, d_b)
+    rc = A._lib.lib().as_geo_lookup_convc1(None, 4, 8, None, None, None, 2, None, None, None, None, None, 3, None, None,
+                                           1, 1, 1, 4, None)
+    assert rc == -1          # AS_ERR_BAD_ARG

@@ -48,6 +48,19 @@ def timeit(fn, reps=20, warm=3, flush=True):
     return ts[len(ts) // 2], ts[0]
 
 
+def fused_lookup_bench(blk, d, coords, rec, N):
+    """8(f)-1: lookup + convc1 + ReLU in one kernel; algorithmic bytes 728 read + 256 written per pixel (bf16x3)."""
+    B, _, H, W = d.shape
+    for split in (True, False):
+        w_hi, w_lo = A.geometry.DeferredGeoLookup.pack_convc1_weight(torch.randn(64, 162, 1, 1, device="cuda") * 0.1, split)
+        bias = torch.randn(64, device="cuda")
+        o_hi = torch.empty(B, H, W, 64, device="cuda", dtype=torch.bfloat16)
+        o_lo = torch.empty_like(o_hi) if split else None
+        dl = blk.deferred(d, coords)
+        med, best = timeit(lambda: dl.convc1_planes(w_hi, w_lo, bias, o_hi, o_lo))
+        rec("geo_lookup_convc1_fused_" + ("bf16x3" if split else "bf16"), med, best, (728 + (256 if split else 128)) * N)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--B", type=int, default=8)
@@ -119,6 +132,7 @@ def main():
         d = (torch.rand(B, 1, H, W, device=dev) * Dg).contiguous()
         med, best = timeit(lambda: blk(d, coords))
         rec("geo_lookup_uniform", med, best, 1372 * N)
+        fused_lookup_bench(blk, d, coords, rec, N)
         return
     # a7 GWC
     med, best = timeit(lambda: A.build_gwc_volume(f1, f2, Dg, 8))
