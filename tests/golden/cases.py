@@ -83,3 +83,29 @@ def loop_case(family, seed=7, B=1, H=16, W=24, hidden=128):
         case["geo"] = _t(rng.standard_normal((B, 8, 12, H, W)))
         case["init_disp"] = _t(rng.uniform(0, 11, size=(B, 1, H, W)))
     return case
+
+
+def liif_case(n_in=2, seed=21, B=2, h=6, w=10, scale=2.5, extra_q=77):
+    """Inputs of continuous_IGEVStereo.upsample_disp (multi-scale branch): feature maps at 1/4 (stem_4x ++ hidden,
+    176 ch), 1/2 (32 ch) and, for agg_type type2, 1/1 (8 ch); query coordinates = the full output grid at `scale`
+    plus random points (incl. exact +-1 borders); disparity at 1/4."""
+    rng = np.random.RandomState(seed + n_in)
+    x4 = _t(rng.standard_normal((B, 176, h, w)))
+    x2 = _t(rng.standard_normal((B, 32, 2 * h, 2 * w)))
+    x1 = _t(rng.standard_normal((B, 8, 4 * h, 4 * w)))
+    x4[0, :, 1, 2] = 0.0                                     # an all-zero feature vector: normalisation eps path
+    feats = [x4, x2] if n_in == 2 else [x1, x2, x4]           # continuous_IGEVstereo.py:214-217 ordering
+    H, W = int(h * 4 * scale), int(w * 4 * scale)
+    ry, rx = 1.0 / H, 1.0 / W
+    ys = -1 + ry + 2 * ry * np.arange(H)
+    xs = -1 + rx + 2 * rx * np.arange(W)
+    grid = np.stack(np.meshgrid(ys, xs, indexing="ij"), -1).reshape(-1, 2)
+    rnd = rng.uniform(-1, 1, size=(extra_q, 2))
+    rnd[:4] = [[-1, -1], [1, 1], [-1, 1], [0.0, 0.0]]
+    coords = np.concatenate([grid, rnd], 0).astype("float32")
+    coords = _t(np.broadcast_to(coords, (B,) + coords.shape).copy())
+    coords[1] = coords[1].flip(0)                             # different query order per batch element
+    disp = _t(rng.uniform(0, 12, size=(B, 1, h, w)))
+    sc = _t(np.full((B,), scale))
+    in_dim = sum(f.shape[1] + 8 + 2 for f in feats)
+    return dict(feats=feats, coords=coords, disp=disp, scale=sc, in_dim=in_dim, n_in=n_in)

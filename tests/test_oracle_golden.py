@@ -196,3 +196,27 @@ def test_model_level_igev(golden):
                                 int(g["iters"]))
     err = (disp - torch.from_numpy(g["disp_lowres"])).abs()
     assert float(err.mean()) * 4 < 1e-3
+
+
+# ---- LIIF arbitrary-scale upsampler ---------------------------------------------
+@pytest.mark.parametrize("n_in", [2, 3])
+def test_liif_oracle_vs_reference(golden, n_in):
+    from oracle import liif_oracle as LO
+    g = golden("liif_upsample")
+    c = cases.liif_case(n_in)
+    t = "n%d_" % n_in
+    params = LO.make_liif_params(c["in_dim"], seed=40 + n_in)
+    aff = LO.isu_affinity(c["feats"][0])
+    assert aff.shape == g[t + "affinity0"].shape
+    assert rel(aff, g[t + "affinity0"]) < 2e-6
+    assert float(aff.min()) >= 0.0
+    q, r = LO.liif_query(LO.structure_feature(c["feats"][-1]), c["coords"])
+    # nearest-pixel index math is bit-exact: the gathered features are copies, rel_coord is the same fp32 arithmetic
+    assert np.array_equal(q[:, :, :4].numpy(), g[t + "qfeat_last_head"])
+    assert np.array_equal(r.numpy(), g[t + "rel_last"])
+    logits = LO.liif_logits(params, c["feats"], c["coords"])
+    assert logits.shape == g[t + "logits"].shape
+    assert rel(logits, g[t + "logits"]) < 1e-5
+    up = LO.upsample_disp_multiscale(params, c["disp"], c["feats"], c["coords"], c["scale"])
+    assert up.shape == g[t + "up_disp"].shape
+    assert rel(up, g[t + "up_disp"]) < 1e-5
