@@ -20,6 +20,8 @@ from .update import (BasicMultiUpdateBlock, BasicMultiUpdateBlockRAFT, BasicMoti
                      set_update_engine, get_update_engine)
 from .hotpath import igev_iterations, raft_iterations, install_into_reference, HotLoopGraph, set_lookup_fusion
 from .parallel import shard_pairs, allreduce_gradients
+from . import liif
+from .liif import liif_out_multi_scale_Training, context_upsample_multiscale_train, upsample_disp
 
 __all__ = [
     "CorrBlock1D", "Combined_Geo_Encoding_Volume", "build_gwc_volume", "corr_sampler",

@@ -18,7 +18,7 @@ DTYPE_F32, DTYPE_F16, DTYPE_F64 = 0, 1, 2
 CORR_FP32_SIMT, CORR_BF16X3, CORR_BF16 = 0, 1, 2
 LAYOUT_NHWC, LAYOUT_NCHW = 0, 1
 EPI_BIAS, EPI_BIAS_RELU, EPI_GRU_ZR, EPI_GRU_Q = 0, 1, 2, 3
-UEPI_RELU_SPLIT, UEPI_MOTION, UEPI_GRU_ZR, UEPI_GRU_Q, UEPI_DISPHEAD = 0, 1, 2, 3, 4
+UEPI_RELU_SPLIT, UEPI_MOTION, UEPI_GRU_ZR, UEPI_GRU_Q, UEPI_DISPHEAD, UEPI_LINEAR_F32 = 0, 1, 2, 3, 4, 5
 
 _vp = C.c_void_p
 _i = C.c_int
@@ -45,6 +45,17 @@ class ConvUmmaDesc(C.Structure):
         ("out_f32", _vp), ("out_hi", _vp), ("out_lo", _vp),
         ("out_pitch", _i), ("out_coff", _i), ("cout_valid", _i),
         ("disp", _vp), ("w2", _vp), ("u", _vp),
+    ]
+
+
+class LiifQueryDesc(C.Structure):
+    _fields_ = [
+        ("n_in", _i), ("P", _vp * 3), ("h", _i * 3), ("w", _i * 3),
+        ("coords", _vp), ("B", _i), ("Q", _i), ("wc", _vp),
+        ("w2_hi", _vp), ("w2_lo", _vp), ("w3_hi", _vp), ("w3_lo", _vp), ("w4_hi", _vp), ("w4_lo", _vp),
+        ("b2", _vp), ("b3", _vp), ("b4", _vp), ("nsplit", _i),
+        ("disp", _vp), ("disp_scale", _vp), ("hd", _i), ("wd", _i),
+        ("logits", _vp), ("out", _vp),
     ]
 
 
@@ -78,6 +89,9 @@ SIGNATURES = {
     "as_geo_lookup_bwd": (_i, [_pp, _i, _i, _pp, _ip, _ip, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "as_geo_lookup_convc1": (_i, [_pp, _i, _i, _pp, _ip, _ip, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i,
                                   _vp]),
+    "as_isu_affinity": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp]),
+    "as_liif_query": (_i, [C.POINTER(LiifQueryDesc), _vp]),
+    "as_context_upsample_multiscale": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "as_lookup_taps": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "as_gwc_build_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "as_gwc_build_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),

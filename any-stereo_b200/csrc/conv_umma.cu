@@ -317,6 +317,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
               u[t] = fmaf(w4.x, y0, fmaf(w4.y, y1, fmaf(w4.z, y2, fmaf(w4.w, y3, u[t]))));
             }
           }
+        } else if (p.epilogue == AS_UEPI_LINEAR_F32) {       // plain (1x1) linear map, fp32 NHWC out (LIIF first layer)
+          float* op = p.out_f32 + n * p.N + c0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
+            *reinterpret_cast<float4*>(op + j) = make_float4(v[j] + b4.x, v[j + 1] + b4.y, v[j + 2] + b4.z, v[j + 3] + b4.w);
+          }
         } else {                                             // relu(conv + bias) [+ disp in the last channel]
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -443,6 +451,9 @@ extern "C" int as_conv2d_umma(const as_conv_umma_desc* d, as_stream_t stream) {
       break;
     case AS_UEPI_DISPHEAD:
       if (!d->bias || !d->w2 || !d->u || d->Cout != 256) return AS_ERR_BAD_ARG;
+      break;
+    case AS_UEPI_LINEAR_F32:
+      if (!d->out_f32) return AS_ERR_BAD_ARG;
       break;
     default: return AS_ERR_UNSUPPORTED;
   }

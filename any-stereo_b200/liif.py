@@ -1,0 +1,233 @@
+"""Arbitrary-scale (LIIF) disparity upsampler that follows the iterative loop -- SURVEY.md 8(f) rank 2.
+
+Mirrors the reference's objects for its training-default configuration
+(models/coreContinuous_IGEV/liif.py:575-678 ``liif_out_multi_scale_Training`` with ``unfold_similarity`` "with_ISU" /
+"with_v2ISU", ``pos_dim=0``, no cell decoding, no local ensemble, no quarter sampling;
+submodule.py:357-372 ``context_upsample_multiscale_train``; continuous_IGEVstereo.py:192-237 ``upsample_disp``):
+same class / function names, constructor arguments, parameter names (``imnet.layers.{0,2,4,6}``) and tensor layouts,
+so a reference state_dict loads unchanged.  Other reference variants raise NotImplementedError.
+
+B200-first restructuring (csrc/liif_umma.cu): the first Linear commutes with the nearest-neighbour gather, so it runs
+as a 1x1 tensor-core convolution at the SOURCE resolution; the per-query kernel gathers 128-channel rows, adds the
+relative-coordinate terms and chains layers 2..4 as tcgen05 MMAs with activations kept on chip, fused with softmax
+and the 3x3 context upsample.  There is no CPU / PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from .update import get_update_engine
+
+
+class MLP(nn.Module):
+    """liif.py:9-25 -- container for the parameters (names match the reference); evaluated by the CUDA kernels."""
+
+    def __init__(self, in_dim, out_dim, hidden_list):
+        super().__init__()
+        layers = []
+        lastv = in_dim
+        for hidden in hidden_list:
+            layers.append(nn.Linear(lastv, hidden))
+            layers.append(nn.ReLU())
+            lastv = hidden
+        layers.append(nn.Linear(lastv, out_dim))
+        self.layers = nn.Sequential(*layers)
+
+
+def _split_mode():
+    eng = get_update_engine()
+    return eng != "bf16"          # "fp32" and "bf16x3" both mean fp32 parity here (split bf16, fp32 accumulate)
+
+
+def _pack_linear(w, n_pad=None, split=True):
+    """nn.Linear weight [out][in] -> bf16 hi/lo [n_pad][in] for the K-major B operand."""
+    w = w.detach().float().contiguous()
+    out_f, in_f = w.shape
+    n_pad = n_pad or out_f
+    hi = torch.empty((n_pad, in_f), device=w.device, dtype=torch.bfloat16)
+    lo = torch.empty_like(hi) if split else None
+    L.call("as_pack_conv_weight_bf16", w.data_ptr(), hi.data_ptr(), L.ptr(lo), out_f, in_f, 1, 1, n_pad, in_f, L.stream_ptr())
+    return hi, lo
+
+
+def isu_affinity(feature):
+    """AffinityFeature.forward (liif.py:434-449) for the 3x3 / dilation-1 window: [B,C,H,W] -> [B,8,H,W]."""
+    L.require_cuda(feature, "feature", torch.float32, contiguous=False)
+    x = feature.detach().contiguous()
+    B, Cc, H, W = x.shape
+    out = torch.empty((B, 8, H, W), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        L.call("as_isu_affinity", x.data_ptr(), B, Cc, H, W, out.data_ptr(), None, None, 0, 0, L.stream_ptr())
+    return out
+
+
+class StructureFeature(nn.Module):
+    """liif.py:451-572, "with_ISU" / "with_v2ISU" branches: cat([x, affinity])."""
+
+    def __init__(self, affinity_settings, unfold, input_chanels=None):
+        super().__init__()
+        if unfold not in ("with_ISU", "with_v2ISU"):
+            raise NotImplementedError("StructureFeature variant %r is outside the built hot path" % (unfold,))
+        if (affinity_settings["win_w"], affinity_settings["win_h"]) != (3, 3) or affinity_settings["dilation"][0] != 1:
+            raise NotImplementedError("only the 3x3 / dilation-1 affinity window is built")
+        self.unfold = unfold
+
+    def forward(self, x):
+        return torch.cat([x, isu_affinity(x)], dim=1)
+
+
+class liif_out_multi_scale_Training(nn.Module):
+    """liif.py:575-678.  forward(feats, coord, scale) -> logits [B, 9, Q]."""
+
+    def __init__(self, pos_dim=24, encoder_dim=256, mlphidden_list=[128, 64, 64], pos_enconding=False,
+                 pos_enconding_new=False, local_ensemble=False, decode_cell=False, unfold=False, affinity_settings=None,
+                 quater_nearest=None, require_grad=True, number_input=3, chanels=0):
+        super().__init__()
+        if pos_dim != 0 or pos_enconding or pos_enconding_new or local_ensemble or decode_cell or quater_nearest is not None:
+            raise NotImplementedError("only pos_dim=0 without positional / cell encoding, ensemble or quarter sampling is built")
+        if list(mlphidden_list) != [128, 64, 64]:
+            raise NotImplementedError("the fused MLP kernel is built for hidden sizes [128, 64, 64]")
+        if unfold not in ("with_ISU", "with_v2ISU"):
+            raise NotImplementedError("unfold_similarity %r is outside the built hot path" % (unfold,))
+        if number_input not in (2, 3) or len(chanels) != number_input:
+            raise NotImplementedError("2 or 3 input feature maps")
+        self.unfold = unfold
+        self.pos_dim = 2
+        self.outputdim = 9
+        self.number_input = number_input
+        self.chanels = list(chanels)
+        in_c = affinity_settings["win_h"] * affinity_settings["win_w"] - 1
+        self.to_sf_l2 = nn.ModuleList(StructureFeature(affinity_settings, unfold, input_chanels=i) for i in chanels)
+        imnet_in_dim = encoder_dim + in_c * number_input + self.pos_dim * number_input
+        assert encoder_dim == sum(chanels)
+        self.imnet = MLP(imnet_in_dim, self.outputdim, hidden_list=mlphidden_list)
+        self._cache = None
+
+    # ---- weights in the layouts the kernels consume, cached per parameter version ------------------
+    def _weights(self, split):
+        lin = [m for m in self.imnet.layers if isinstance(m, nn.Linear)]
+        key = (split,) + tuple((p.data_ptr(), p._version) for m in lin for p in (m.weight, m.bias))
+        if self._cache is not None and self._cache["key"] == key:
+            return self._cache
+        with torch.no_grad():
+            w1 = lin[0].weight.detach().float()                       # [128][sum_i (C_i + 8 + 2)]
+            dev = w1.device
+            per_map = []
+            wc = [lin[0].bias.detach().float()]
+            col = 0
+            for Cc in self.chanels:
+                c_off = (Cc + 7) // 8 * 8                              # affinity channels start 16-byte aligned
+                c_pad = (c_off + 8 + 63) // 64 * 64
+                wp = torch.zeros((128, c_pad), device=dev)
+                wp[:, :Cc] = w1[:, col:col + Cc]
+                wp[:, c_off:c_off + 8] = w1[:, col + Cc:col + Cc + 8]
+                hi, lo = _pack_linear(wp, split=split)
+                per_map.append(dict(hi=hi, lo=lo, n=128, cin=c_pad, k=1, bias=None, c_off=c_off, c_pad=c_pad))
+                wc.append(w1[:, col + Cc + 8])                         # rel_coord y column
+                wc.append(w1[:, col + Cc + 9])                         # rel_coord x column
+                col += Cc + 10
+            assert col == w1.shape[1]
+            w2 = _pack_linear(lin[1].weight, split=split)
+            w3 = _pack_linear(lin[2].weight, split=split)
+            w4 = _pack_linear(lin[3].weight, n_pad=16, split=split)
+            b4 = torch.zeros(16, device=dev)
+            b4[:9] = lin[3].bias.detach().float()
+            self._cache = dict(key=key, per_map=per_map, wc=torch.stack(wc).contiguous(), w2=w2, w3=w3, w4=w4,
+                               b2=lin[1].bias.detach().float().contiguous(), b3=lin[2].bias.detach().float().contiguous(), b4=b4)
+        return self._cache
+
+    def _first_layer_maps(self, feats, wts, split):
+        """P_i = W1_i . cat([feat_i, affinity_i]) at the source resolution: fp32 [B,h_i,w_i,128]."""
+        from .update_umma import _Planes, _conv
+        out = []
+        for f, wm in zip(feats, wts["per_map"]):
+            L.require_cuda(f, "feats[i]", contiguous=False)
+            x = f.detach().float().contiguous()
+            B, Cc, H, W = x.shape
+            pl = _Planes((B, H, W, wm["c_pad"]), x.device, split)
+            s = L.stream_ptr()
+            L.call("as_nchw_to_nhwc_split", x.data_ptr(), pl.hi.data_ptr(), L.ptr(pl.lo), B, Cc, H, W, wm["c_pad"], s)
+            L.call("as_isu_affinity", x.data_ptr(), B, Cc, H, W, None, pl.hi.data_ptr(), L.ptr(pl.lo), wm["c_pad"], wm["c_off"], s)
+            P = torch.empty((B, H, W, 128), device=x.device, dtype=torch.float32)
+            _conv(B, H, W, [pl], wm, 3 if split else 1, L.UEPI_LINEAR_F32, bias=False, out_f32=P)
+            out.append(P)
+        return out
+
+    def _query(self, feats, coord, disp=None, disp_scale=None, want_logits=True):
+        if len(feats) != self.number_input:
+            raise RuntimeError("expected %d feature maps" % self.number_input)
+        L.require_cuda(coord, "coord", torch.float32, contiguous=False)
+        coord = coord.detach().contiguous()
+        B, Q, _ = coord.shape
+        dev = coord.device
+        split = _split_mode()
+        with torch.cuda.device(dev), torch.no_grad():
+            wts = self._weights(split)
+            P = self._first_layer_maps(feats, wts, split)
+            d = L.LiifQueryDesc()
+            d.n_in = len(P)
+            for i, p in enumerate(P):
+                d.P[i] = p.data_ptr()
+                d.h[i], d.w[i] = p.shape[1], p.shape[2]
+            d.coords = coord.data_ptr()
+            d.B, d.Q = B, Q
+            d.wc = wts["wc"].data_ptr()
+            d.w2_hi, d.w2_lo = wts["w2"][0].data_ptr(), L.ptr(wts["w2"][1])
+            d.w3_hi, d.w3_lo = wts["w3"][0].data_ptr(), L.ptr(wts["w3"][1])
+            d.w4_hi, d.w4_lo = wts["w4"][0].data_ptr(), L.ptr(wts["w4"][1])
+            d.b2, d.b3, d.b4 = wts["b2"].data_ptr(), wts["b3"].data_ptr(), wts["b4"].data_ptr()
+            d.nsplit = 3 if split else 1
+            logits = torch.empty((B, 9, Q), device=dev, dtype=torch.float32) if want_logits else None
+            out = None
+            if disp is not None:
+                L.require_cuda(disp, "disp", torch.float32, contiguous=False)
+                disp = disp.detach().contiguous()
+                d.disp = disp.data_ptr()
+                d.hd, d.wd = disp.shape[-2], disp.shape[-1]
+                if disp_scale is not None:
+                    disp_scale = disp_scale.detach().float().contiguous()
+                    d.disp_scale = disp_scale.data_ptr()
+                out = torch.empty((B, Q), device=dev, dtype=torch.float32)
+                d.out = out.data_ptr()
+            d.logits = L.ptr(logits)
+            L.call("as_liif_query", C.byref(d), L.stream_ptr())
+        return logits, out
+
+    def forward(self, feats, coord, scale=None):
+        return self._query(feats, coord)[0]
+
+    def upsample(self, feats, coord, disp_low, disp_scale=None):
+        """Fused tail of continuous_IGEVStereo.upsample_disp: softmax(logits) applied to the 3x3 neighbourhood of
+        ``disp_low * disp_scale[b]`` -> [B, Q]; the logits never reach HBM."""
+        return self._query(feats, coord, disp=disp_low, disp_scale=disp_scale, want_logits=False)[1]
+
+
+def context_upsample_multiscale_train(disp_low, up_weights, hr_coord):
+    """submodule.py:357-372: [B,1,h,w], [B,9,Q] (already soft-maxed), [B,Q,2] -> [B,Q]."""
+    L.require_cuda(disp_low, "disp_low", torch.float32, contiguous=False)
+    L.require_cuda(up_weights, "up_weights", torch.float32, contiguous=False)
+    L.require_cuda(hr_coord, "hr_coord", torch.float32, contiguous=False)
+    B, _, h, w = disp_low.shape
+    Q = hr_coord.shape[1]
+    d, u, c = disp_low.detach().contiguous(), up_weights.detach().contiguous(), hr_coord.detach().contiguous()
+    out = torch.empty((B, Q), device=d.device, dtype=torch.float32)
+    with torch.cuda.device(d.device):
+        L.call("as_context_upsample_multiscale", d.data_ptr(), u.data_ptr(), c.data_ptr(), out.data_ptr(), B, h, w, Q,
+               L.stream_ptr())
+    return out
+
+
+def upsample_disp(liif_up, disp, hidden_layer, stem_4x, stem_2x, stem_1x=None, hr_coord=None, scale=None):
+    """continuous_IGEVStereo.upsample_disp, multi_training branch without disparity_norm
+    (continuous_IGEVstereo.py:192-237) -> [B, 1, Q]."""
+    x = torch.cat((stem_4x, hidden_layer), 1)
+    feats = [x, stem_2x] if stem_1x is None else [stem_1x, stem_2x, x]
+    B = disp.shape[0]
+    sc = torch.as_tensor(scale, device=disp.device, dtype=torch.float32).reshape(-1)
+    if sc.numel() == 1:
+        sc = sc.expand(B)
+    return liif_up.upsample(feats, hr_coord, disp, 4.0 * sc).unsqueeze(1)

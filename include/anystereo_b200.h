@@ -241,6 +241,7 @@ int as_add_f32(const float* a, const float* b, float* y, long long n, as_stream_
 #define AS_UEPI_GRU_Q 3      /* h'=(1-z)h + z tanh(acc+ctx) -> out_f32 and hi/lo        (update.py:39-40) */
 #define AS_UEPI_DISPHEAD 4   /* u[n][t] = sum_c w2[t][c]*relu(acc+bias)[c]: DispHead.conv2 folded into
                                 conv1's epilogue (update.py:23-24); finish with as_disp_delta           */
+#define AS_UEPI_LINEAR_F32 5 /* out_f32[n][c] = acc (+ bias if given): plain linear map, fp32 NHWC out      */
 
 typedef struct as_umma_src {
   const void* hi; /* bf16 [B*H*W][channels] */
@@ -315,6 +316,49 @@ int as_add_slice(const float* src, int spitch, int scoff, float* dst, int dpitch
 int as_pool2x_nhwc_bwd(const float* dy, float* dx_acc, int B, int H, int W, int C, as_stream_t stream);
 int as_interp_bilinear_nhwc_bwd(const float* dy, float* dx_acc, int B, int Hin, int Win, int Hout, int Wout,
                                 int C, as_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * SURVEY 8(f)-2  arbitrary-scale (LIIF) disparity upsampler after the loop
+ * (models/coreContinuous_IGEV/liif.py:575-678 liif_out_multi_scale_Training with
+ *  unfold "with_ISU"/"with_v2ISU", pos_dim 0, no cell decoding / local ensemble / quarter sampling;
+ *  submodule.py:357-372 context_upsample_multiscale_train; continuous_IGEVstereo.py:192-237).
+ * ------------------------------------------------------------------------------------------ */
+/* AffinityFeature.forward (liif.py:434-449), 3x3 window, dilation 1: cosine similarity with the 8 neighbours,
+ * clipped at 0.  feat fp32 NCHW [B,C,H,W].  aff: fp32 NCHW [B,8,H,W] or NULL.  hi/lo: bf16 planes [B*H*W][c_pad];
+ * the 8 affinities are written at channel c_off (multiple of 8) -- i.e. StructureFeature's cat([x, affinity])
+ * when the planes already hold x in channels [0, C) (as_nchw_to_nhwc_split).  hi NULL = fp32 output only. */
+int as_isu_affinity(const float* feat, int B, int C, int H, int W, float* aff, void* hi, void* lo, int c_pad,
+                    int c_off, as_stream_t stream);
+
+/* Per-query part of the upsampler.  The first Linear of the MLP is applied at the SOURCE resolution beforehand
+ * (it commutes with the nearest-neighbour gather): P[i] = W1[:, cols of input i] . cat([feat_i, affinity_i]),
+ * fp32 [B,h_i,w_i,128] (as_conv2d_umma 1x1 with AS_UEPI_LINEAR_F32).  Per query q = coords[b][q] = (y, x) in [-1,1]:
+ *   z1 = relu(wc[0] + sum_i P[i][nearest pixel] + sum_i (wc[1+2i]*rel_y_i + wc[2+2i]*rel_x_i))   (liif.py:108-137)
+ *   logits = W4 relu(W3 relu(W2 z1 + b2) + b3) + b4                                          (MLP 128-64-64-9)
+ *   out = sum_k softmax(logits)_k * (disp*disp_scale[b]) at the 3x3 neighbourhood of the nearest low-res pixel.
+ * w2 [64][128], w3 [64][64], w4 [16][64] (rows 9..15 zero): bf16 hi/lo from as_pack_conv_weight_bf16; b4 padded to 16.
+ * logits [B,9,Q] and/or out [B,Q] (either may be NULL).  nsplit 3 = fp32 parity (split bf16), 1 = bf16. */
+typedef struct as_liif_query_desc {
+  int n_in;            /* 1..3 feature maps                                          */
+  const float* P[3];
+  int h[3], w[3];
+  const float* coords; /* [B][Q][2]                                                  */
+  int B, Q;
+  const float* wc;     /* [1 + 2*n_in][128]: b1, then W1's relative-coordinate columns */
+  const void *w2_hi, *w2_lo, *w3_hi, *w3_lo, *w4_hi, *w4_lo;
+  const float *b2, *b3, *b4;
+  int nsplit;
+  const float* disp;       /* [B][hd][wd] low-resolution disparity (needed for `out`) */
+  const float* disp_scale; /* [B] multiplier (4*scale) or NULL                        */
+  int hd, wd;
+  float* logits;
+  float* out;
+} as_liif_query_desc;
+int as_liif_query(const as_liif_query_desc* desc, as_stream_t stream);
+
+/* context_upsample_multiscale_train (submodule.py:357-372) with caller-supplied weights up_weights [B,9,Q]. */
+int as_context_upsample_multiscale(const float* disp_low, const float* up_weights, const float* hr_coord, float* out,
+                                   int B, int h, int w, int Q, as_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -54,6 +54,8 @@ int main(void) {
          offsetof(as_conv_desc, weight), offsetof(as_conv_desc, out), offsetof(as_conv_desc, save));
   printf("%zu %zu %zu %zu %zu %zu\n", sizeof(as_umma_src), sizeof(as_conv_umma_desc), offsetof(as_conv_umma_desc, src),
          offsetof(as_conv_umma_desc, w_hi), offsetof(as_conv_umma_desc, out_hi), offsetof(as_conv_umma_desc, u));
+  printf("%zu %zu %zu %zu %zu %zu\n", sizeof(as_liif_query_desc), offsetof(as_liif_query_desc, P), offsetof(as_liif_query_desc, coords),
+         offsetof(as_liif_query_desc, w2_hi), offsetof(as_liif_query_desc, disp), offsetof(as_liif_query_desc, out));
   return 0;
 }
 """)
@@ -64,7 +66,9 @@ int main(void) {
     L = A._lib
     d, u = L.ConvDesc, L.ConvUmmaDesc
     assert c[:6] == [ctypes.sizeof(L.ConvSrc), ctypes.sizeof(d), d.src.offset, d.weight.offset, d.out.offset, d.save.offset]
-    assert c[6:] == [ctypes.sizeof(L.UmmaSrc), ctypes.sizeof(u), u.src.offset, u.w_hi.offset, u.out_hi.offset, u.u.offset]
+    assert c[6:12] == [ctypes.sizeof(L.UmmaSrc), ctypes.sizeof(u), u.src.offset, u.w_hi.offset, u.out_hi.offset, u.u.offset]
+    q = L.LiifQueryDesc
+    assert c[12:] == [ctypes.sizeof(q), q.P.offset, q.coords.offset, q.w2_hi.offset, q.disp.offset, q.out.offset]
 
 
 def test_argument_errors_without_gpu(A):
@@ -73,6 +77,9 @@ def test_argument_errors_without_gpu(A):
     assert lib.as_sampler_fwd(None, None, 1, None, 1, 1, 1, 1, 4, 0, None) == -1
     assert lib.as_gwc_build_fwd(None, None, None, 1, 8, 1, 1, 4, 8, None) == -1
     assert lib.as_pool1d_halve(None, None, 1, 4, 4, 2, None) == -1
+    assert lib.as_isu_affinity(None, 1, 8, 4, 4, None, None, None, 0, 0, None) == -1
+    assert lib.as_liif_query(None, None) == -1
+    assert lib.as_context_upsample_multiscale(None, None, None, None, 1, 2, 2, 4, None) == -1
     assert lib.as_corr1d_workspace_bytes(1, 8, 2, 4, 4, 0) == 0
     with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
         A.corr_sampler.forward(torch.zeros(1, 2, 3, 4), torch.zeros(1, 1, 2, 3), 4)

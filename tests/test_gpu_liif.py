@@ -1,0 +1,109 @@
+"""GPU parity of the LIIF arbitrary-scale upsampler against the committed reference outputs
+(tests/golden/liif_upsample.npz) and the oracle.  Tolerance: 1e-4 relative to max|ref| in the fp32-parity mode
+(split bf16 on the tensor cores), 2e-2 in the single-bf16 mode; nearest-pixel index math bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+from oracle import liif_oracle as LO
+
+pytestmark = pytest.mark.gpu
+
+AFF = {"win_w": 3, "win_h": 3, "dilation": [1, 2, 4, 8]}
+
+
+def rel(a, b):
+    a = torch.as_tensor(a).detach().double().cpu()
+    b = torch.as_tensor(b).detach().double().cpu()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+@pytest.fixture(scope="module")
+def A():
+    import anystereo_b200 as a
+    yield a
+    a.set_update_engine("fp32")
+
+
+def make_module(A, c, seed):
+    chanels = [f.shape[1] for f in c["feats"]]
+    m = A.liif_out_multi_scale_Training(encoder_dim=sum(chanels), mlphidden_list=[128, 64, 64], pos_dim=0,
+                                        unfold="with_v2ISU", affinity_settings=AFF, number_input=c["n_in"], chanels=chanels)
+    m.load_state_dict(LO.make_liif_params(c["in_dim"], seed=seed), strict=True)
+    return m.cuda().eval()
+
+
+@pytest.mark.parametrize("shape", [(2, 176, 6, 10), (1, 32, 33, 47), (3, 8, 16, 16), (1, 5, 1, 1), (1, 40, 17, 2)])
+def test_isu_affinity_vs_oracle(A, shape):
+    rng = np.random.RandomState(shape[1])
+    x = torch.from_numpy(rng.standard_normal(shape).astype("float32"))
+    if shape[2] > 2:
+        x[0, :, 1, 1] = 0.0                                   # zero vector: F.normalize eps path
+    ref = LO.isu_affinity(x)
+    got = A.liif.isu_affinity(x.cuda())
+    torch.cuda.synchronize()
+    assert got.shape == ref.shape
+    assert float((got.cpu() - ref).abs().max()) < 2e-6
+    assert float(got.min()) >= 0.0
+
+
+def test_isu_affinity_golden(A, golden):
+    g = golden("liif_upsample")
+    c = cases.liif_case(2)
+    got = A.liif.isu_affinity(c["feats"][0].cuda())
+    assert float((got.cpu() - torch.from_numpy(g["n2_affinity0"])).abs().max()) < 2e-6
+
+
+@pytest.mark.parametrize("engine,tol", [("bf16x3", 1e-4), ("bf16", 2e-2)])
+@pytest.mark.parametrize("n_in", [2, 3])
+def test_liif_logits_and_upsample_golden(A, golden, n_in, engine, tol):
+    g = golden("liif_upsample")
+    c = cases.liif_case(n_in)
+    m = make_module(A, c, 40 + n_in)
+    A.set_update_engine(engine)
+    feats = [f.cuda() for f in c["feats"]]
+    logits = m(feats, c["coords"].cuda(), c["scale"].cuda())
+    up = m.upsample(feats, c["coords"].cuda(), c["disp"].cuda(), 4.0 * c["scale"].cuda())
+    torch.cuda.synchronize()
+    A.set_update_engine("fp32")
+    t = "n%d_" % n_in
+    assert tuple(logits.shape) == g[t + "logits"].shape
+    assert rel(logits, g[t + "logits"]) < tol
+    assert rel(up.unsqueeze(1), g[t + "up_disp"]) < tol
+    # the two-step API (softmax outside, context_upsample_multiscale_train) agrees with the fused tail
+    d = c["disp"].cuda() * 4.0 * c["scale"].cuda().view(-1, 1, 1, 1)
+    up2 = A.context_upsample_multiscale_train(d, torch.softmax(logits, 1), c["coords"].cuda())
+    assert rel(up2, up) < 1e-5
+
+
+def test_upsample_disp_matches_oracle_ragged(A):
+    """continuous_IGEVStereo.upsample_disp call shape: x = cat(stem_4x, hidden); Q not a multiple of the 64-query tile,
+    per-sample scales, fp32-parity engine."""
+    rng = np.random.RandomState(5)
+    B, h, w, Q = 2, 9, 13, 1000
+    stem4 = torch.from_numpy(rng.standard_normal((B, 48, h, w)).astype("float32"))
+    hid = torch.from_numpy(np.tanh(rng.standard_normal((B, 128, h, w))).astype("float32"))
+    stem2 = torch.from_numpy(rng.standard_normal((B, 32, 2 * h, 2 * w)).astype("float32"))
+    coords = torch.from_numpy(rng.uniform(-1, 1, (B, Q, 2)).astype("float32"))
+    disp = torch.from_numpy(rng.uniform(0, 30, (B, 1, h, w)).astype("float32"))
+    scale = torch.tensor([2.5, 3.7])
+    c = dict(feats=[torch.cat([stem4, hid], 1), stem2], n_in=2, in_dim=228)
+    m = make_module(A, c, 3)
+    A.set_update_engine("bf16x3")
+    got = A.upsample_disp(m, disp.cuda(), hid.cuda(), stem4.cuda(), stem2.cuda(), None, hr_coord=coords.cuda(), scale=scale.cuda())
+    torch.cuda.synchronize()
+    A.set_update_engine("fp32")
+    ref = LO.upsample_disp_multiscale(LO.make_liif_params(228, seed=3), disp, c["feats"], coords, scale)
+    assert tuple(got.shape) == (B, 1, Q)
+    assert rel(got, ref) < 1e-4
+
+
+def test_liif_unsupported_variants_raise(A):
+    with pytest.raises(NotImplementedError):
+        A.liif_out_multi_scale_Training(encoder_dim=208, pos_dim=24, unfold="with_v2ISU", affinity_settings=AFF,
+                                        number_input=2, chanels=[176, 32])
+    with pytest.raises(NotImplementedError):
+        A.liif_out_multi_scale_Training(encoder_dim=208, pos_dim=0, unfold="with_Dila_ISU", affinity_settings=AFF,
+                                        number_input=2, chanels=[176, 32])
