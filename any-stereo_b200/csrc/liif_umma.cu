@@ -107,16 +107,17 @@ __device__ __forceinline__ float rel_coord(float c, int i, int n, float c0, floa
   return __fmul_rn(__fadd_rn(c, -q), (float)n);
 }
 
-constexpr int kQT = 64;                        // queries per tile (rows 64..127 of the M = 128 MMAs are don't-care)
-constexpr int kQThreads = 256;
-constexpr int kBlk = kQT * 128;                // one [64 rows x 64 K] bf16 block
+constexpr int kQT = 128;                       // queries per tile == UMMA M
+constexpr int kGroups = 2;                     // independent tile pipelines per CTA sharing the resident weights
+constexpr int kGroupThreads = 256;
+constexpr int kQThreads = kGroups * kGroupThreads;
+constexpr int kBlk = kQT * 128;                // one [128 rows x 64 K] bf16 block
 constexpr int kH1 = 128, kH2 = 64, kH3 = 64, kOutPad = 16, kOut = 9;
-constexpr int kWcStride = 144;                 // 4 parts x 36 floats: bank-staggered
-// smem: activations (hi: 2 blocks, lo: 2 blocks) | W2 hi,lo (2 blocks of 64 rows each) | W3 hi,lo | W4 hi,lo | Wc | bars
+// smem: per group activations (hi: 2 blocks, lo: 2 blocks) | W2 hi,lo (2 blocks of 64 rows) | W3 hi,lo | W4 hi,lo | Wc | bars
 constexpr int kActBytes = 4 * kBlk;
 constexpr int kW2Bytes = 2 * 2 * kH2 * 128, kW3Bytes = 2 * kH3 * 128, kW4Bytes = 2 * kOutPad * 128;
-constexpr int kWcBytes = 7 * kWcStride * 4;
-constexpr int kQSmem = 1024 + kActBytes + kW2Bytes + kW3Bytes + kW4Bytes + kWcBytes + 64;
+constexpr int kWcBytes = 7 * kH1 * 4;
+constexpr int kQSmem = 1024 + kGroups * kActBytes + kW2Bytes + kW3Bytes + kW4Bytes + kWcBytes + 64;
 
 struct QueryArgs {
   const float* P[3];                           // fp32 [B][h_i][w_i][128]
@@ -139,15 +140,32 @@ __device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
-// K-major, 128B-swizzled operand tile: block kb (64 K values) is 8 KB, row r at r*128, 16-byte chunks XORed with r & 7
-__device__ __forceinline__ void put_pair(uint32_t a_hi, uint32_t lo_off, int row, int k, float v0, float v1, bool split) {
+// K-major, 128B-swizzled operand tile: block kb (64 K values) is 16 KB, row r at r*128, 16-byte chunks XORed with r & 7
+// four consecutive K values (k multiple of 4) of one row as one 8-byte store per plane
+__device__ __forceinline__ void put_quad(uint32_t a_hi, uint32_t lo_off, int row, int k, float v0, float v1, float v2, float v3,
+                                         bool split) {
   const uint32_t addr = a_hi + ((uint32_t)(k >> 6) * kBlk) + row * 128 + ((((uint32_t)(k & 63) << 1)) ^ ((uint32_t)(row & 7) << 4));
-  const uint32_t h = cvt_bf16x2(v0, v1);
-  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(h) : "memory");
+  const uint32_t h0 = cvt_bf16x2(v0, v1), h1 = cvt_bf16x2(v2, v3);
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(h0), "r"(h1) : "memory");
   if (split) {
-    const uint32_t l = cvt_bf16x2(v0 - __uint_as_float(h << 16), v1 - __uint_as_float(h & 0xFFFF0000u));
-    asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr + lo_off), "r"(l) : "memory");
+    const uint32_t l0 = cvt_bf16x2(v0 - __uint_as_float(h0 << 16), v1 - __uint_as_float(h0 & 0xFFFF0000u));
+    const uint32_t l1 = cvt_bf16x2(v2 - __uint_as_float(h1 << 16), v3 - __uint_as_float(h1 & 0xFFFF0000u));
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr + lo_off), "r"(l0), "r"(l1) : "memory");
   }
+}
+
+// eight consecutive K values (k multiple of 8) of one row: a whole 16-byte swizzle chunk per plane
+__device__ __forceinline__ void put_oct(uint32_t a_hi, uint32_t lo_off, int row, int k, const float (&v)[8], bool split) {
+  const uint32_t addr = a_hi + ((uint32_t)(k >> 6) * kBlk) + row * 128 + ((((uint32_t)(k & 63) << 1)) ^ ((uint32_t)(row & 7) << 4));
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    h[i] = cvt_bf16x2(v[2 * i], v[2 * i + 1]);
+    l[i] = cvt_bf16x2(v[2 * i] - __uint_as_float(h[i] << 16), v[2 * i + 1] - __uint_as_float(h[i] & 0xFFFF0000u));
+  }
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+  if (split)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr + lo_off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
 }
 
 __device__ __forceinline__ void issue_layer(uint32_t acc, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, int kblocks,
@@ -169,14 +187,18 @@ __device__ __forceinline__ void issue_layer(uint32_t acc, uint32_t a_hi, uint32_
   }
 }
 
-__global__ void __launch_bounds__(kQThreads, 2)
+__device__ __forceinline__ void group_sync(int group) {      // named barrier over the 256 threads of one pipeline
+  asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(kGroupThreads) : "memory");
+}
+
+__global__ void __launch_bounds__(kQThreads, 1)
 liif_query_kernel(const __grid_constant__ CUtensorMap tW2h, const __grid_constant__ CUtensorMap tW2l,
                   const __grid_constant__ CUtensorMap tW3h, const __grid_constant__ CUtensorMap tW3l,
                   const __grid_constant__ CUtensorMap tW4h, const __grid_constant__ CUtensorMap tW4l, const QueryArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* act = smem;                                   // hi blocks 0,1 | lo blocks 0,1
-  uint8_t* w2h = act + kActBytes;
+  uint8_t* act0 = smem;                                  // per group: hi blocks 0,1 | lo blocks 0,1
+  uint8_t* w2h = act0 + kGroups * kActBytes;
   uint8_t* w2l = w2h + kW2Bytes / 2;
   uint8_t* w3h = w2h + kW2Bytes;
   uint8_t* w3l = w3h + kW3Bytes / 2;
@@ -185,35 +207,33 @@ liif_query_kernel(const __grid_constant__ CUtensorMap tW2h, const __grid_constan
   float* wc_s = reinterpret_cast<float*>(w4h + kW4Bytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(wc_s) + kWcBytes);
   uint64_t* w_full = bars;
-  uint64_t* mma_done = bars + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  uint64_t* mma_done = bars + 1;                         // [kGroups]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + kGroups);
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int group = warp >> 3, gtid = tid - group * kGroupThreads, gwarp = warp & 7;
   const bool split = a.nsplit == 3;
   const uint32_t lo_off = 2 * kBlk;
 
   if (tid == 0) {
     umma::prefetch_tmap(&tW2h);
     umma::mbar_init(w_full, 1);
-    umma::mbar_init(mma_done, 1);
+    for (int g = 0; g < kGroups; ++g) umma::mbar_init(mma_done + g, 1);
     umma::fence_barrier_init();
   }
   if (warp == 1) {
-    umma::tmem_alloc(tmem_slot, 128);
+    umma::tmem_alloc(tmem_slot, 128 * kGroups);
     umma::tmem_relinquish();
   }
-  for (int i = tid; i < kActBytes / 16; i += kQThreads) reinterpret_cast<uint4*>(act)[i] = make_uint4(0, 0, 0, 0);
-  // b1 and the relative-coordinate columns of W1, bank-staggered per 32-channel part
+  // b1 and the relative-coordinate columns of W1
   for (int i = tid; i < (1 + 2 * a.n_in) * kH1; i += kQThreads) {
-    const int j = i / kH1, ch = i - j * kH1;
-    wc_s[j * kWcStride + (ch >> 5) * 36 + (ch & 31)] = __ldg(a.wc + i);
+    wc_s[i] = __ldg(a.wc + i);
   }
-  umma::fence_proxy_async();
   umma::tc_fence_before();
   __syncthreads();
   umma::tc_fence_after();
-  const uint32_t tmem_d = *tmem_slot;
+  const uint32_t tmem_d = *tmem_slot + (uint32_t)(group * 128);
   if (tid == 0) {                                        // resident weights of layers 2..4
     const uint32_t bytes = (uint32_t)(kW2Bytes + kW3Bytes + kW4Bytes) / (split ? 1u : 2u);
     umma::mbar_expect_tx(w_full, bytes);
@@ -226,115 +246,115 @@ liif_query_kernel(const __grid_constant__ CUtensorMap tW2h, const __grid_constan
     umma::tma_load_2d(w4h, &tW4h, w_full, 0, 0);
     if (split) umma::tma_load_2d(w4l, &tW4l, w_full, 0, 0);
   }
-  const uint32_t act_s = umma::smem_u32(act);
+  const uint32_t act_s = umma::smem_u32(act0 + group * kActBytes);
+  uint64_t* done = mma_done + group;
   uint32_t phase = 0;
   bool weights_ready = false;
 
-  for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
-    const int b = t / a.tiles_per_b;
-    const int q0 = (t - b * a.tiles_per_b) * kQT;
-    // ---- layer 1 (gathered): z1 = relu(b1 + sum_i P_i[pix_i] + Wc . rel)  -> operand tile, K = 128
-    {
-      const int r = tid >> 2, part = tid & 3;
-      const int gq = q0 + r;
-      const bool valid = gq < a.Q;
-      float z[32];
-      const float* wrow = wc_s + part * 36;
+  // relu(acc + bias) of a hidden layer -> K = 64 operand tile of the next one; warps w and w+4 share a TMEM lane quarter
+  auto hidden_epilogue = [&](uint32_t col0, const float* bias) {
+    const int q = gwarp & 3, half = gwarp >> 2;
+    float v[32];
+    umma::tmem_ld_32x32(tmem_d + col0 + (uint32_t)(half * 32) + ((uint32_t)(q * 32) << 16), v);
+    umma::tmem_ld_wait();
+    const int row = q * 32 + lane;
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 b4 = *reinterpret_cast<const float4*>(wrow + j);
-        z[j] = b4.x; z[j + 1] = b4.y; z[j + 2] = b4.z; z[j + 3] = b4.w;
-      }
-      float cy = 0.f, cx = 0.f;
-      if (valid) {
-        const float2 c2 = __ldg(reinterpret_cast<const float2*>(a.coords + ((long long)b * a.Q + gq) * 2));
-        cy = c2.x; cx = c2.y;
-      }
+    for (int j = 0; j < 32; j += 8) {                    // one 16-byte chunk (8 channels) per store: conflict-free across rows
+      const int c = half * 32 + j;
+      float y[8];
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        if (i < a.n_in) {
-          const int iy = nearest_index(cy, a.h[i]), ix = nearest_index(cx, a.w[i]);
-          const float ry = rel_coord(cy, iy, a.h[i], a.cy0[i], a.cy1[i]);
-          const float rx = rel_coord(cx, ix, a.w[i], a.cx0[i], a.cx1[i]);
-          const float4* prow = reinterpret_cast<const float4*>(a.P[i] + (((long long)b * a.h[i] + iy) * a.w[i] + ix) * kH1 + part * 32);
-          const float* wy = wc_s + (1 + 2 * i) * kWcStride + part * 36;
-          const float* wx = wy + kWcStride;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 p4 = __ldg(prow + (j >> 2));
-            const float4 y4 = *reinterpret_cast<const float4*>(wy + j);
-            const float4 x4 = *reinterpret_cast<const float4*>(wx + j);
-            z[j] += p4.x + y4.x * ry + x4.x * rx;
-            z[j + 1] += p4.y + y4.y * ry + x4.y * rx;
-            z[j + 2] += p4.z + y4.z * ry + x4.z * rx;
-            z[j + 3] += p4.w + y4.w * ry + x4.w * rx;
-          }
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 32; j += 2)
-        put_pair(act_s, lo_off, r, part * 32 + j, valid ? fmaxf(z[j], 0.f) : 0.f, valid ? fmaxf(z[j + 1], 0.f) : 0.f, split);
+      for (int i = 0; i < 8; ++i) y[i] = fmaxf(v[j + i] + __ldg(bias + c + i), 0.f);
+      put_oct(act_s, lo_off, row, c, y, split);
     }
+    umma::tc_fence_before();
     umma::fence_proxy_async();
-    __syncthreads();
-    // ---- layer 2: [64 x 128] . W2^T -> TMEM columns [0, 64)
-    if (tid == 0) {
+    group_sync(group);
+  };
+  auto run_layer = [&](uint32_t acc_col, uint32_t b_hi, uint32_t b_lo, int kblocks, int b_blk_bytes, int n) {
+    if (gtid == 0) {
       if (!weights_ready) umma::mbar_wait(w_full, 0);
       umma::tc_fence_after();
-      issue_layer(tmem_d, act_s, act_s + lo_off, umma::smem_u32(w2h), umma::smem_u32(w2l), 2, kH2 * 128,
-                  umma::idesc_bf16_f32(128, kH2), split);
-      umma::mma_commit(mma_done);
+      issue_layer(tmem_d + acc_col, act_s, act_s + lo_off, b_hi, b_lo, kblocks, b_blk_bytes, umma::idesc_bf16_f32(128, n), split);
+      umma::mma_commit(done);
     }
     weights_ready = true;
-    umma::mbar_wait(mma_done, phase);
+    umma::mbar_wait(done, phase);
     phase ^= 1;
     umma::tc_fence_after();
-    // epilogue 2 / 3: relu(acc + bias) -> operand tile of the next layer (K = 64); warps 0,1,4,5 own TMEM lanes 0..63
-    auto hidden_epilogue = [&](uint32_t col0, const float* bias) {
-      if ((warp & 3) < 2) {
-        const int q = warp & 3, half = warp >> 2;
-        float v[32];
-        umma::tmem_ld_32x32(tmem_d + col0 + (uint32_t)(half * 32) + ((uint32_t)(q * 32) << 16), v);
-        umma::tmem_ld_wait();
-        const int row = q * 32 + lane;
+  };
+
+  // this lane's 4 channels of b1 and of the relative-coordinate columns of W1 (layer-1 mapping: lane = channel quad)
+  const float4 bias4 = *reinterpret_cast<const float4*>(wc_s + lane * 4);
+  float4 wy4[3], wx4[3];
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const int c = half * 32 + j;
-          put_pair(act_s, lo_off, row, c, fmaxf(v[j] + __ldg(bias + c), 0.f), fmaxf(v[j + 1] + __ldg(bias + c + 1), 0.f), split);
+  for (int i = 0; i < 3; ++i) {
+    wy4[i] = wx4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < a.n_in) {
+      wy4[i] = *reinterpret_cast<const float4*>(wc_s + (1 + 2 * i) * kH1 + lane * 4);
+      wx4[i] = *reinterpret_cast<const float4*>(wc_s + (2 + 2 * i) * kH1 + lane * 4);
+    }
+  }
+
+  for (int t = blockIdx.x * kGroups + group; t < a.num_tiles; t += gridDim.x * kGroups) {
+    const int b = t / a.tiles_per_b;
+    const int q0 = (t - b * a.tiles_per_b) * kQT;
+    // ---- layer 1 (gathered): z1 = relu(b1 + sum_i P_i[pix_i] + Wc . rel)  -> operand tile, K = 128.
+    // One warp per query, lane = 4 consecutive channels: the 512-byte P rows are read fully coalesced, the lane's
+    // slice of b1 / Wc lives in registers, and the row of the operand tile is written as 8-byte pieces.
+    {
+      // lanes 0..15 each resolve one of the warp's 16 queries (nearest pixels, relative coordinates)
+      const int my_q = q0 + gwarp * 16 + (lane & 15);
+      float cy = 0.f, cx = 0.f;
+      if (my_q < a.Q) {
+        const float2 c2 = __ldg(reinterpret_cast<const float2*>(a.coords + ((long long)b * a.Q + my_q) * 2));
+        cy = c2.x; cx = c2.y;
+      }
+      long long off[3];
+      float ry[3], rx[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        off[i] = 0; ry[i] = 0.f; rx[i] = 0.f;
+        if (i < a.n_in) {
+          const int iy = nearest_index(cy, a.h[i]), ix = nearest_index(cx, a.w[i]);
+          ry[i] = rel_coord(cy, iy, a.h[i], a.cy0[i], a.cy1[i]);
+          rx[i] = rel_coord(cx, ix, a.w[i], a.cx0[i], a.cx1[i]);
+          off[i] = (((long long)b * a.h[i] + iy) * a.w[i] + ix) * (kH1 / 4);       // in float4 units
         }
       }
-      umma::tc_fence_before();
-      umma::fence_proxy_async();
-      __syncthreads();
-    };
+#pragma unroll 4
+      for (int j = 0; j < 16; ++j) {
+        const int row = gwarp * 16 + j;
+        const bool valid = q0 + row < a.Q;
+        float4 z = bias4;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          if (i < a.n_in) {
+            const long long o = __shfl_sync(0xffffffffu, off[i], j);
+            const float qy = __shfl_sync(0xffffffffu, ry[i], j), qx = __shfl_sync(0xffffffffu, rx[i], j);
+            const float4 p4 = __ldg(reinterpret_cast<const float4*>(a.P[i]) + o + lane);
+            z.x += p4.x + wy4[i].x * qy + wx4[i].x * qx;
+            z.y += p4.y + wy4[i].y * qy + wx4[i].y * qx;
+            z.z += p4.z + wy4[i].z * qy + wx4[i].z * qx;
+            z.w += p4.w + wy4[i].w * qy + wx4[i].w * qx;
+          }
+        }
+        if (!valid) z = make_float4(0.f, 0.f, 0.f, 0.f);
+        put_quad(act_s, lo_off, row, lane * 4, fmaxf(z.x, 0.f), fmaxf(z.y, 0.f), fmaxf(z.z, 0.f), fmaxf(z.w, 0.f), split);
+      }
+    }
+    umma::fence_proxy_async();
+    group_sync(group);
+    run_layer(0, umma::smem_u32(w2h), umma::smem_u32(w2l), 2, kH2 * 128, kH2);         // [128 x 128] . W2^T -> cols [0, 64)
     hidden_epilogue(0, a.b2);
-    // ---- layer 3: [64 x 64] . W3^T -> TMEM columns [64, 128)
-    if (tid == 0) {
-      umma::tc_fence_after();
-      issue_layer(tmem_d + 64, act_s, act_s + lo_off, umma::smem_u32(w3h), umma::smem_u32(w3l), 1, kH3 * 128,
-                  umma::idesc_bf16_f32(128, kH3), split);
-      umma::mma_commit(mma_done);
-    }
-    umma::mbar_wait(mma_done, phase);
-    phase ^= 1;
-    umma::tc_fence_after();
+    run_layer(64, umma::smem_u32(w3h), umma::smem_u32(w3l), 1, kH3 * 128, kH3);        // [128 x 64] . W3^T -> cols [64, 128)
     hidden_epilogue(64, a.b3);
-    // ---- layer 4: [64 x 64] . W4^T -> TMEM columns [0, 16)
-    if (tid == 0) {
-      umma::tc_fence_after();
-      issue_layer(tmem_d, act_s, act_s + lo_off, umma::smem_u32(w4h), umma::smem_u32(w4l), 1, kOutPad * 128,
-                  umma::idesc_bf16_f32(128, kOutPad), split);
-      umma::mma_commit(mma_done);
-    }
-    umma::mbar_wait(mma_done, phase);
-    phase ^= 1;
-    umma::tc_fence_after();
+    run_layer(0, umma::smem_u32(w4h), umma::smem_u32(w4l), 1, kOutPad * 128, kOutPad); // [128 x 64] . W4^T -> cols [0, 16)
     // ---- final epilogue: logits -> softmax -> 3x3 context upsample of the low-res disparity
-    if (warp < 2) {
+    if (gwarp < 4) {
       float v[32];
-      umma::tmem_ld_32x32(tmem_d + ((uint32_t)(warp * 32) << 16), v);
+      umma::tmem_ld_32x32(tmem_d + ((uint32_t)(gwarp * 32) << 16), v);
       umma::tmem_ld_wait();
-      const int gq = q0 + warp * 32 + lane;
+      const int gq = q0 + gwarp * 32 + lane;
       if (gq < a.Q) {
         float lg[kOut], m = -3.0e38f;
 #pragma unroll
@@ -365,12 +385,12 @@ liif_query_kernel(const __grid_constant__ CUtensorMap tW2h, const __grid_constan
       }
     }
     umma::tc_fence_before();
-    __syncthreads();
+    group_sync(group);
   }
   if (tid == 0 && !weights_ready) umma::mbar_wait(w_full, 0);
   umma::tc_fence_before();
   __syncthreads();
-  if (warp == 1) umma::tmem_dealloc(tmem_d, 128);
+  if (warp == 1) umma::tmem_dealloc(*tmem_slot, 128 * kGroups);
 }
 
 // standalone context_upsample_multiscale_train (submodule.py:357-372) for callers that supply their own weights
@@ -454,7 +474,8 @@ extern "C" int as_liif_query(const as_liif_query_desc* d, as_stream_t stream) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaError_t e = cudaFuncSetAttribute(liif_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kQSmem);
   if (e != cudaSuccess) return (int)e;
-  const int grid = nt < 2LL * sms ? (int)nt : 2 * sms;
+  const long long want = (nt + kGroups - 1) / kGroups;
+  const int grid = want < sms ? (int)want : sms;
   liif_query_kernel<<<grid, kQThreads, kQSmem, as_cu(stream)>>>(m[0], m[1], m[2], m[3], m[4], m[5], a);
   AS_RETURN_IF_LAUNCH_FAILED();
   return AS_OK;

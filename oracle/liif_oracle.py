@@ -21,11 +21,11 @@ from typing import Dict, List, Sequence
 import torch
 
 
-def make_coord_axis(n: int) -> torch.Tensor:
+def make_coord_axis(n: int, device=None) -> torch.Tensor:
     """Pixel-centre coordinates of an axis with n samples in [-1, 1]  (make_coord :32-45: v0 + r + 2r*i, r = 1/n,
     evaluated exactly like the reference: python-double scalars applied to an fp32 arange)."""
     r = (1 - (-1)) / (2 * n)
-    return -1 + r + (2 * r) * torch.arange(n).float()
+    return -1 + r + (2 * r) * torch.arange(n, device=device).float()
 
 
 def nearest_index(c: torch.Tensor, n: int) -> torch.Tensor:
@@ -42,7 +42,7 @@ def isu_affinity(x: torch.Tensor) -> torch.Tensor:
     order (row-major 3x3) with the centre removed."""
     B, C, H, W = x.shape
     n = x / x.norm(dim=1, keepdim=True).clamp_min(1e-12)           # F.normalize(p=2, dim=1)
-    p = torch.zeros(B, C, H + 2, W + 2, dtype=x.dtype)
+    p = torch.zeros(B, C, H + 2, W + 2, dtype=x.dtype, device=x.device)
     p[:, :, 1:H + 1, 1:W + 1] = n
     out = []
     for dy in range(3):
@@ -65,10 +65,10 @@ def liif_query(feat: torch.Tensor, coords: torch.Tensor):
     B, C, h, w = feat.shape
     iy = nearest_index(coords[:, :, 0], h)
     ix = nearest_index(coords[:, :, 1], w)
-    bidx = torch.arange(B).view(B, 1).expand_as(iy)
+    bidx = torch.arange(B, device=feat.device).view(B, 1).expand_as(iy)
     q_feat = feat[bidx, :, iy, ix]                                 # [B,Q,C]
-    qy = make_coord_axis(h)[iy]
-    qx = make_coord_axis(w)[ix]
+    qy = make_coord_axis(h, feat.device)[iy]
+    qx = make_coord_axis(w, feat.device)[ix]
     rel = torch.stack([(coords[:, :, 0].float() - qy) * h, (coords[:, :, 1].float() - qx) * w], dim=-1)
     return q_feat, rel
 
@@ -100,10 +100,10 @@ def context_upsample_multiscale(disp_low: torch.Tensor, up_weights: torch.Tensor
     B, _, h, w = disp_low.shape
     iy = nearest_index(hr_coord[:, :, 0], h)
     ix = nearest_index(hr_coord[:, :, 1], w)
-    p = torch.zeros(B, h + 2, w + 2, dtype=disp_low.dtype)
+    p = torch.zeros(B, h + 2, w + 2, dtype=disp_low.dtype, device=disp_low.device)
     p[:, 1:h + 1, 1:w + 1] = disp_low[:, 0]
-    bidx = torch.arange(B).view(B, 1).expand_as(iy)
-    out = torch.zeros(B, hr_coord.shape[1], dtype=disp_low.dtype)
+    bidx = torch.arange(B, device=disp_low.device).view(B, 1).expand_as(iy)
+    out = torch.zeros(B, hr_coord.shape[1], dtype=disp_low.dtype, device=disp_low.device)
     k = 0
     for dy in range(3):
         for dx in range(3):
