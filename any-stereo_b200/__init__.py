@@ -18,7 +18,8 @@ from .geometry import CorrBlock1D, Combined_Geo_Encoding_Volume, set_corr_mode, 
 from .submodule import build_gwc_volume
 from .update import (BasicMultiUpdateBlock, BasicMultiUpdateBlockRAFT, BasicMotionEncoder, ConvGRU, DispHead,
                      set_update_engine, get_update_engine)
-from .hotpath import igev_iterations, raft_iterations, install_into_reference, HotLoopGraph, set_lookup_fusion
+from .hotpath import (igev_iterations, raft_iterations, install_into_reference, HotLoopGraph, set_lookup_fusion,
+                      adopt_update_block, adopt_liif_up)
 from .parallel import shard_pairs, allreduce_gradients
 from . import liif
 from .liif import liif_out_multi_scale_Training, context_upsample_multiscale_train, upsample_disp

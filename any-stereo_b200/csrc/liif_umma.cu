@@ -107,11 +107,15 @@ __device__ __forceinline__ float rel_coord(float c, int i, int n, float c0, floa
   return __fmul_rn(__fadd_rn(c, -q), (float)n);
 }
 
-constexpr int kQT = 128;                       // queries per tile == UMMA M
-constexpr int kGroups = 2;                     // independent tile pipelines per CTA sharing the resident weights
-constexpr int kGroupThreads = 256;
+#ifndef AS_LIIF_QT
+#define AS_LIIF_QT 128
+#endif
+constexpr int kQT = AS_LIIF_QT;                // queries per tile: 128 (= UMMA M) or 64 (rows 64..127 are don't-care)
+constexpr int kGroups = 256 / kQT;             // independent tile pipelines per CTA sharing the resident weights
+constexpr int kGroupThreads = 2 * kQT;         // 16 queries per warp in layer 1
 constexpr int kQThreads = kGroups * kGroupThreads;
-constexpr int kBlk = kQT * 128;                // one [128 rows x 64 K] bf16 block
+constexpr int kBlk = kQT * 128;                // one [kQT rows x 64 K] bf16 block (the M = 128 MMA over-reads into the
+                                               // next block / the weights when kQT = 64: lanes 64..127 of TMEM are never read)
 constexpr int kH1 = 128, kH2 = 64, kH3 = 64, kOutPad = 16, kOut = 9;
 // smem: per group activations (hi: 2 blocks, lo: 2 blocks) | W2 hi,lo (2 blocks of 64 rows) | W3 hi,lo | W4 hi,lo | Wc | bars
 constexpr int kActBytes = 4 * kBlk;
@@ -212,7 +216,8 @@ liif_query_kernel(const __grid_constant__ CUtensorMap tW2h, const __grid_constan
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  const int group = warp >> 3, gtid = tid - group * kGroupThreads, gwarp = warp & 7;
+  constexpr int kGroupWarps = kGroupThreads / 32;
+  const int group = warp / kGroupWarps, gtid = tid - group * kGroupThreads, gwarp = warp - group * kGroupWarps;
   const bool split = a.nsplit == 3;
   const uint32_t lo_off = 2 * kBlk;
 
@@ -251,20 +256,27 @@ liif_query_kernel(const __grid_constant__ CUtensorMap tW2h, const __grid_constan
   uint32_t phase = 0;
   bool weights_ready = false;
 
-  // relu(acc + bias) of a hidden layer -> K = 64 operand tile of the next one; warps w and w+4 share a TMEM lane quarter
+  // relu(acc + bias) of a hidden layer -> K = 64 operand tile of the next one.  A warp reads the TMEM lane quarter
+  // (warp % 4); with 128-query tiles warps w and w+4 split the 64 columns, with 64-query tiles warps 0,1 take all 64.
   auto hidden_epilogue = [&](uint32_t col0, const float* bias) {
-    const int q = gwarp & 3, half = gwarp >> 2;
-    float v[32];
-    umma::tmem_ld_32x32(tmem_d + col0 + (uint32_t)(half * 32) + ((uint32_t)(q * 32) << 16), v);
-    umma::tmem_ld_wait();
-    const int row = q * 32 + lane;
+    const int q = gwarp & 3;
+    const int half0 = kQT == 128 ? (gwarp >> 2) : 0, nhalf = kQT == 128 ? 1 : 2;
+    if (q * 32 < kQT) {
+      const int row = q * 32 + lane;
+      for (int hh = 0; hh < nhalf; ++hh) {
+        const int half = half0 + hh;
+        float v[32];
+        umma::tmem_ld_32x32(tmem_d + col0 + (uint32_t)(half * 32) + ((uint32_t)(q * 32) << 16), v);
+        umma::tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 32; j += 8) {                    // one 16-byte chunk (8 channels) per store: conflict-free across rows
-      const int c = half * 32 + j;
-      float y[8];
+        for (int j = 0; j < 32; j += 8) {                // one 16-byte chunk (8 channels) per store: conflict-free across rows
+          const int c = half * 32 + j;
+          float y[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) y[i] = fmaxf(v[j + i] + __ldg(bias + c + i), 0.f);
-      put_oct(act_s, lo_off, row, c, y, split);
+          for (int i = 0; i < 8; ++i) y[i] = fmaxf(v[j + i] + __ldg(bias + c + i), 0.f);
+          put_oct(act_s, lo_off, row, c, y, split);
+        }
+      }
     }
     umma::tc_fence_before();
     umma::fence_proxy_async();
@@ -295,6 +307,18 @@ liif_query_kernel(const __grid_constant__ CUtensorMap tW2h, const __grid_constan
     }
   }
 
+  // lanes 0..15 of a warp own one query each of the warp's 16 (lanes 16..31 mirror them)
+  auto load_coords = [&](int tile) {
+    float2 c = make_float2(0.f, 0.f);
+    if (tile < a.num_tiles) {
+      const int tb = tile / a.tiles_per_b;
+      const int q = (tile - tb * a.tiles_per_b) * kQT + gwarp * 16 + (lane & 15);
+      if (q < a.Q) c = __ldg(reinterpret_cast<const float2*>(a.coords + ((long long)tb * a.Q + q) * 2));
+    }
+    return c;
+  };
+  float2 next_c = load_coords(blockIdx.x * kGroups + group);
+
   for (int t = blockIdx.x * kGroups + group; t < a.num_tiles; t += gridDim.x * kGroups) {
     const int b = t / a.tiles_per_b;
     const int q0 = (t - b * a.tiles_per_b) * kQT;
@@ -303,12 +327,8 @@ liif_query_kernel(const __grid_constant__ CUtensorMap tW2h, const __grid_constan
     // slice of b1 / Wc lives in registers, and the row of the operand tile is written as 8-byte pieces.
     {
       // lanes 0..15 each resolve one of the warp's 16 queries (nearest pixels, relative coordinates)
-      const int my_q = q0 + gwarp * 16 + (lane & 15);
-      float cy = 0.f, cx = 0.f;
-      if (my_q < a.Q) {
-        const float2 c2 = __ldg(reinterpret_cast<const float2*>(a.coords + ((long long)b * a.Q + my_q) * 2));
-        cy = c2.x; cx = c2.y;
-      }
+      const float cy = next_c.x, cx = next_c.y;          // fetched while the previous tile was in its MMA phases
+      next_c = load_coords(t + gridDim.x * kGroups);
       long long off[3];
       float ry[3], rx[3];
 #pragma unroll
@@ -321,7 +341,7 @@ liif_query_kernel(const __grid_constant__ CUtensorMap tW2h, const __grid_constan
           off[i] = (((long long)b * a.h[i] + iy) * a.w[i] + ix) * (kH1 / 4);       // in float4 units
         }
       }
-#pragma unroll 4
+#pragma unroll 8
       for (int j = 0; j < 16; ++j) {
         const int row = gwarp * 16 + j;
         const bool valid = q0 + row < a.Q;
@@ -350,7 +370,7 @@ liif_query_kernel(const __grid_constant__ CUtensorMap tW2h, const __grid_constan
     hidden_epilogue(64, a.b3);
     run_layer(0, umma::smem_u32(w4h), umma::smem_u32(w4l), 1, kOutPad * 128, kOutPad); // [128 x 64] . W4^T -> cols [0, 16)
     // ---- final epilogue: logits -> softmax -> 3x3 context upsample of the low-res disparity
-    if (gwarp < 4) {
+    if (gwarp * 32 < kQT) {
       float v[32];
       umma::tmem_ld_32x32(tmem_d + ((uint32_t)(gwarp * 32) << 16), v);
       umma::tmem_ld_wait();

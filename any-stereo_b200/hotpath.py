@@ -158,12 +158,16 @@ def install_into_reference(ref_igev_module=None, ref_raft_module=None):
     """Rebind the names the reference's model graphs resolve at call time:
 
         models.coreContinuous_IGEV.continuous_IGEVstereo.{Combined_Geo_Encoding_Volume, build_gwc_volume}
+        models.coreContinuous_IGEV.continuous_IGEVstereo.context_upsample_multiscale_train
         models.corePrune_RAFT.prune_raft_stereo.CorrBlock1D
 
-    ``model.update_block`` is swapped per model instance with ``adopt_update_block``."""
+    ``model.update_block`` / ``model.liif_up`` are swapped per model instance with ``adopt_update_block`` /
+    ``adopt_liif_up``."""
     if ref_igev_module is not None:
         ref_igev_module.Combined_Geo_Encoding_Volume = Combined_Geo_Encoding_Volume
         ref_igev_module.build_gwc_volume = build_gwc_volume
+        from .liif import context_upsample_multiscale_train      # SURVEY 8(f)-2, continuous_IGEVstereo.py:219
+        ref_igev_module.context_upsample_multiscale_train = context_upsample_multiscale_train
     if ref_raft_module is not None:
         ref_raft_module.CorrBlock1D = CorrBlock1D
 
@@ -187,3 +191,22 @@ def adopt_update_block(ref_update_block, family="igev"):
             mod = getattr(mod, p)
         mod._parameters[parts[-1]] = ref_params[name]
     return ours.to(next(ref_update_block.parameters()).device)
+
+
+def adopt_liif_up(ref_liif_up, chanels):
+    """Our liif_out_multi_scale_Training around the parameters of a reference one (model.liif_up);
+    ``chanels`` = channel counts of the feature maps in call order (continuous_IGEVstereo.py:120-163)."""
+    from .liif import liif_out_multi_scale_Training
+    aff = {"win_w": 3, "win_h": 3, "dilation": [1, 2, 4, 8]}
+    ours = liif_out_multi_scale_Training(encoder_dim=sum(chanels), mlphidden_list=[128, 64, 64], pos_dim=0,
+                                         unfold=ref_liif_up.unfold, affinity_settings=aff, number_input=len(chanels),
+                                         chanels=list(chanels))
+    ours.load_state_dict(ref_liif_up.state_dict(), strict=True)
+    ref_params = dict(ref_liif_up.named_parameters())
+    for name, _ in list(ours.named_parameters()):
+        mod = ours
+        parts = name.split(".")
+        for p in parts[:-1]:
+            mod = getattr(mod, p)
+        mod._parameters[parts[-1]] = ref_params[name]
+    return ours.to(next(ref_liif_up.parameters()).device)

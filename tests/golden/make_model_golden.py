@@ -164,6 +164,27 @@ def main_igev():
     with torch.no_grad():
         model(img1, img2, iters=ITERS, test_mode=True, hr_coord=make_coord([Hi, Wi])[None], scale=torch.tensor([[1.0]]))
     final = disp_track["d"] + state["delta"]           # continuous_IGEVstereo.py:295 for the last iteration
+    # ---- the arbitrary-scale upsampler at the end of the same model graph, x2.5 query grid ----
+    up_cap = {}
+    orig_up = model.upsample_disp
+
+    def spy_up(disp, hidden, stem_4x, stem_2x, stem_1x, hr_coord=None, scale=1):
+        out_ = orig_up(disp, hidden, stem_4x, stem_2x, stem_1x, hr_coord=hr_coord.clone(), scale=scale)
+        up_cap.update(disp=disp.detach().clone(), hidden=hidden.detach().clone(), stem4=stem_4x.detach().clone(),
+                      stem2=stem_2x.detach().clone(), out=out_.detach().clone())
+        return out_
+
+    model.upsample_disp = spy_up
+    Ho, Wo = int(Hi * 2.5), int(Wi * 2.5)
+    with torch.no_grad():
+        model(img1, img2, iters=4, test_mode=True, hr_coord=make_coord([Ho, Wo])[None], scale=torch.tensor([[2.5]]))
+    up = {"disp": up_cap["disp"], "hidden": up_cap["hidden"], "stem4": up_cap["stem4"], "stem2": up_cap["stem2"],
+          "up_disp": up_cap["out"], "out_hw": np.asarray([Ho, Wo]), "scale": np.asarray([2.5], dtype="float32")}
+    for k, v in model.liif_up.state_dict().items():
+        up["liif." + k] = v
+    path = os.path.join(HERE, "model_igev_upsample.npz")
+    np.savez_compressed(path, **{k: (v.numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in up.items()})
+    print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024), "up_disp", tuple(up_cap["out"].shape))
     cis.Combined_Geo_Encoding_Volume = orig_geo
     cis.build_gwc_volume = orig_gwc
     out = {"f1": captured["f1"], "f2": captured["f2"], "geo": captured["geo"], "gwc": captured["gwc"],

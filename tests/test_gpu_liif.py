@@ -107,3 +107,24 @@ def test_liif_unsupported_variants_raise(A):
     with pytest.raises(NotImplementedError):
         A.liif_out_multi_scale_Training(encoder_dim=208, pos_dim=0, unfold="with_Dila_ISU", affinity_settings=AFF,
                                         number_input=2, chanels=[176, 32])
+
+
+@pytest.mark.parametrize("engine,tol", [("bf16x3", 1e-4), ("bf16", 2e-2)])
+def test_model_level_igev_upsample(A, golden, engine, tol):
+    """Inputs and output captured inside the reference's continuous_IGEVStereo.forward (x2.5 query grid)."""
+    g = golden("model_igev_upsample")
+    params = {k[5:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("liif.")}
+    m = A.liif_out_multi_scale_Training(encoder_dim=208, mlphidden_list=[128, 64, 64], pos_dim=0, unfold="with_v2ISU",
+                                        affinity_settings=AFF, number_input=2, chanels=[176, 32])
+    m.load_state_dict(params, strict=True)
+    m = m.cuda().eval()
+    Ho, Wo = [int(v) for v in g["out_hw"]]
+    coords = torch.stack(torch.meshgrid(LO.make_coord_axis(Ho), LO.make_coord_axis(Wo), indexing="ij"), -1).reshape(1, -1, 2)
+    A.set_update_engine(engine)
+    t = lambda k: torch.from_numpy(g[k]).cuda()   # noqa: E731
+    up = A.upsample_disp(m, t("disp"), t("hidden"), t("stem4"), t("stem2"), None, hr_coord=coords.cuda(), scale=t("scale"))
+    torch.cuda.synchronize()
+    A.set_update_engine("fp32")
+    assert rel(up, g["up_disp"]) < tol
+    # mean absolute error in pixels of the full-resolution disparity
+    assert float((up.cpu() - torch.from_numpy(g["up_disp"])).abs().mean()) < (0.01 if engine == "bf16x3" else 0.1)

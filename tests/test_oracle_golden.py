@@ -220,3 +220,18 @@ def test_liif_oracle_vs_reference(golden, n_in):
     up = LO.upsample_disp_multiscale(params, c["disp"], c["feats"], c["coords"], c["scale"])
     assert up.shape == g[t + "up_disp"].shape
     assert rel(up, g[t + "up_disp"]) < 1e-5
+
+
+def test_liif_oracle_vs_model_graph(golden):
+    """The upsampler restatement against the output of the reference's own model graph
+    (continuous_IGEVStereo.forward -> upsample_disp at a x2.5 query grid, tests/golden/make_model_golden.py)."""
+    from oracle import liif_oracle as LO
+    g = golden("model_igev_upsample")
+    params = {k[5:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("liif.")}
+    Ho, Wo = [int(v) for v in g["out_hw"]]
+    coords = torch.stack(torch.meshgrid(LO.make_coord_axis(Ho), LO.make_coord_axis(Wo), indexing="ij"), -1).reshape(1, -1, 2)
+    x = torch.cat([torch.from_numpy(g["stem4"]), torch.from_numpy(g["hidden"])], 1)
+    up = LO.upsample_disp_multiscale(params, torch.from_numpy(g["disp"]), [x, torch.from_numpy(g["stem2"])], coords,
+                                     torch.from_numpy(g["scale"]))
+    assert up.shape == g["up_disp"].shape
+    assert rel(up, g["up_disp"]) < 1e-5
