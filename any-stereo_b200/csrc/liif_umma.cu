@@ -21,11 +21,12 @@ namespace {
 constexpr int kIsuT = 16;                      // interior tile edge
 constexpr int kIsuH = kIsuT + 2;               // with halo
 constexpr int kIsuThreads = 352;               // >= 18*18
+constexpr int kIsuCh = 8;                      // channel planes staged per barrier pair
 
 __global__ void __launch_bounds__(kIsuThreads)
 isu_affinity_kernel(const float* __restrict__ feat, float* __restrict__ aff, __nv_bfloat16* __restrict__ hi,
                     __nv_bfloat16* __restrict__ lo, int C, int H, int W, int c_pad, int c_off) {
-  __shared__ float tile[kIsuH][kIsuH + 1];
+  __shared__ float tile[kIsuCh][kIsuH][kIsuH + 1];
   __shared__ float nrm[kIsuH][kIsuH + 1];
   const int b = blockIdx.z, y0 = blockIdx.y * kIsuT, x0 = blockIdx.x * kIsuT;
   const int t = threadIdx.x;
@@ -34,25 +35,36 @@ isu_affinity_kernel(const float* __restrict__ feat, float* __restrict__ aff, __n
   const int y = y0 - 1 + hy, x = x0 - 1 + hx;
   const bool in_img = in_halo && y >= 0 && y < H && x >= 0 && x < W;
   const bool interior = in_halo && hy >= 1 && hy <= kIsuT && hx >= 1 && hx <= kIsuT && y < H && x < W;
-  const float* src = feat + (long long)b * C * H * W + (long long)y * W + x;
+  const long long HW = (long long)H * W;
+  const float* src = feat + (long long)b * C * HW + (long long)y * W + x;
   float n2 = 0.f, dot[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) dot[k] = 0.f;
-  for (int c = 0; c < C; ++c) {
-    const float v = in_img ? __ldg(src + (long long)c * H * W) : 0.f;
-    if (in_halo) tile[hy][hx] = v;
-    n2 = fmaf(v, v, n2);
+  for (int c0 = 0; c0 < C; c0 += kIsuCh) {                   // kIsuCh channel planes per barrier pair
+    float v[kIsuCh];
+#pragma unroll
+    for (int j = 0; j < kIsuCh; ++j) {
+      v[j] = (in_img && c0 + j < C) ? __ldg(src + (long long)(c0 + j) * HW) : 0.f;
+      n2 = fmaf(v[j], v[j], n2);
+    }
+    if (in_halo) {
+#pragma unroll
+      for (int j = 0; j < kIsuCh; ++j) tile[j][hy][hx] = v[j];
+    }
     __syncthreads();
     if (interior) {
-      int k = 0;
 #pragma unroll
-      for (int dy = -1; dy <= 1; ++dy)
+      for (int j = 0; j < kIsuCh; ++j) {
+        int k = 0;
 #pragma unroll
-        for (int dx = -1; dx <= 1; ++dx) {
-          if (dy == 0 && dx == 0) continue;
-          dot[k] = fmaf(v, tile[hy + dy][hx + dx], dot[k]);
-          ++k;
-        }
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+          for (int dx = -1; dx <= 1; ++dx) {
+            if (dy == 0 && dx == 0) continue;
+            dot[k] = fmaf(v[j], tile[j][hy + dy][hx + dx], dot[k]);
+            ++k;
+          }
+      }
     }
     __syncthreads();
   }
