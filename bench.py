@@ -325,6 +325,38 @@ def run_ours(args):
                 other[name]["cuda_graph_ms_per_pair"] = gms / rb
                 other[name]["cuda_graph_pairs_per_s"] = rb / (gms / 1e3)
                 del hg, rf1, rf2, rnet, rinp
+            # config 4: arbitrary-scale disparity query after the loop, one 384x1248 pair per call
+            aff = {"win_w": 3, "win_h": 3, "dilation": [1, 2, 4, 8]}
+            liif = A.liif_out_multi_scale_Training(encoder_dim=208, mlphidden_list=[128, 64, 64], pos_dim=0,
+                                                   unfold="with_v2ISU", affinity_settings=aff, number_input=2,
+                                                   chanels=[176, 32]).to(dev).eval()
+            g = torch.Generator(device="cpu").manual_seed(11)
+            stem4 = torch.randn(1, 48, H4, W4, generator=g).to(dev)
+            hid = torch.tanh(torch.randn(1, 128, H4, W4, generator=g)).to(dev)
+            stem2 = torch.randn(1, 32, 2 * H4, 2 * W4, generator=g).to(dev)
+            dlow = (torch.rand(1, 1, H4, W4, generator=g) * GEO_D).to(dev)
+            loop_ms_per_pair = ms / args.steps / B
+            for scale in (2.5, 3.7):
+                Ho, Wo = int(H4 * 4 * scale), int(W4 * 4 * scale)
+                ys = -1 + 1.0 / Ho + (2.0 / Ho) * torch.arange(Ho, device=dev).float()
+                xs = -1 + 1.0 / Wo + (2.0 / Wo) * torch.arange(Wo, device=dev).float()
+                hr = torch.stack(torch.meshgrid(ys, xs, indexing="ij"), -1).reshape(1, -1, 2).contiguous()
+                sc = torch.full((1,), scale, device=dev)
+                for _ in range(2):
+                    A.upsample_disp(liif, dlow, hid, stem4, stem2, None, hr_coord=hr, scale=sc)
+                torch.cuda.synchronize()
+                r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                r0.record()
+                for _ in range(5):
+                    A.upsample_disp(liif, dlow, hid, stem4, stem2, None, hr_coord=hr, scale=sc)
+                r1.record()
+                torch.cuda.synchronize()
+                ums = r0.elapsed_time(r1) / 5
+                other["config4_igev_query_x%.1f" % scale] = {
+                    "queries_per_pair": int(hr.shape[1]), "upsampler_ms_per_pair": ums,
+                    "Mqueries_per_s": hr.shape[1] / ums / 1e3,
+                    "loop_plus_upsampler_pairs_per_s": 1e3 / (loop_ms_per_pair + ums)}
+                del hr
     pairs = world * B * args.steps
     value = pairs / (ms / 1e3)
     e2e_value = pairs / (ms_e2e / 1e3)

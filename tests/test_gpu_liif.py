@@ -128,3 +128,30 @@ def test_model_level_igev_upsample(A, golden, engine, tol):
     assert rel(up, g["up_disp"]) < tol
     # mean absolute error in pixels of the full-resolution disparity
     assert float((up.cpu() - torch.from_numpy(g["up_disp"])).abs().mean()) < (0.01 if engine == "bf16x3" else 0.1)
+
+
+def test_liif_fullsize_config4_vs_torch_same_gpu(A):
+    """BASELINE config 4 size: one 384x1248 pair queried on the x2.5 grid (3.0 M queries) against the oracle's
+    arithmetic run by torch on the same GPU (strict fp32); also the 64-bit indexing / ragged last tile at full size."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(1)
+    dev = "cuda"
+    h, w, scale = 96, 312, 2.5
+    stem4 = torch.randn(1, 48, h, w, device=dev)
+    hid = torch.tanh(torch.randn(1, 128, h, w, device=dev))
+    stem2 = torch.randn(1, 32, 2 * h, 2 * w, device=dev)
+    disp = torch.rand(1, 1, h, w, device=dev) * 48
+    H, W = int(h * 4 * scale), int(w * 4 * scale)
+    coords = torch.stack(torch.meshgrid(LO.make_coord_axis(H, dev), LO.make_coord_axis(W, dev), indexing="ij"), -1).reshape(1, -1, 2)
+    coords = coords[:, :-37].contiguous()                   # Q not a multiple of the 128-query tile
+    params = LO.make_liif_params(228, seed=9)
+    c = dict(feats=[torch.cat([stem4, hid], 1), stem2], n_in=2, in_dim=228)
+    m = make_module(A, c, 9)
+    sc = torch.tensor([scale], device=dev)
+    A.set_update_engine("bf16x3")
+    got = A.upsample_disp(m, disp, hid, stem4, stem2, None, hr_coord=coords, scale=sc)
+    A.set_update_engine("fp32")
+    ref = LO.upsample_disp_multiscale({k: v.to(dev) for k, v in params.items()}, disp, c["feats"], coords, sc)
+    torch.cuda.synchronize()
+    assert rel(got, ref) < 1e-4
+    assert float((got - ref).abs().mean()) < 1e-3          # pixels of full-resolution disparity

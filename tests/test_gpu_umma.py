@@ -421,3 +421,31 @@ def test_fused_lookup_falls_back(A):
     rc = A._lib.lib().as_geo_lookup_convc1(None, 4, 8, None, None, None, 2, None, None, None, None, None, 3, None, None,
                                            1, 1, 1, 4, None)
     assert rc == -1          # AS_ERR_BAD_ARG
+
+
+def test_fused_lookup_fullsize_config2(A):
+    """Config-2 size (8 x 96x312, Dg=48): the fused lookup+convc1 kernel against the unfused kernels
+    (lookup -> bf16 split -> 1x1 tcgen05 conv), same arithmetic up to the K order of the fp32 accumulation."""
+    torch.manual_seed(2)
+    dev = "cuda"
+    B, D, H, W, Dg = 8, 96, 96, 312, 48
+    f1 = torch.randn(B, D, H, W, device=dev) * 0.2
+    f2 = torch.randn(B, D, H, W, device=dev) * 0.2
+    geo = torch.randn(B, 8, Dg, H, W, device=dev)
+    A.set_corr_mode("bf16x3")
+    A.set_update_engine("bf16x3")
+    vol = A.Combined_Geo_Encoding_Volume(f1, f2, geo, num_levels=2, radius=4)
+    disp = (torch.rand(B, 1, H, W, device=dev) * (Dg + 8) - 4).contiguous()
+    m = make_block(A, "igev", 4)
+    from anystereo_b200 import update_umma as U
+    wf = U._fused_c1_weights(m, True)
+    out_hi = torch.empty(B, H, W, 64, device=dev, dtype=torch.bfloat16)
+    out_lo = torch.empty_like(out_hi)
+    vol.deferred(disp, None).convc1_planes(wf["hi"], wf["lo"], wf["bias"], out_hi, out_lo)
+    feat = vol(disp, None)
+    ref = torch.relu(torch.nn.functional.conv2d(feat.double(), m.encoder.convc1.weight.double(), m.encoder.convc1.bias.double()))
+    torch.cuda.synchronize()
+    A.set_corr_mode("fp32")
+    A.set_update_engine("fp32")
+    got = (out_hi.float() + out_lo.float()).permute(0, 3, 1, 2)
+    assert rel(got, ref.float()) < 1e-4
