@@ -15,7 +15,7 @@ from . import _lib
 from . import corr_sampler
 from . import update_umma
 from .geometry import CorrBlock1D, Combined_Geo_Encoding_Volume, set_corr_mode, get_corr_mode
-from .submodule import build_gwc_volume
+from .submodule import build_gwc_volume, disparity_regression, init_disparity
 from .update import (BasicMultiUpdateBlock, BasicMultiUpdateBlockRAFT, BasicMotionEncoder, ConvGRU, DispHead,
                      set_update_engine, get_update_engine)
 from .hotpath import (igev_iterations, raft_iterations, install_into_reference, HotLoopGraph, set_lookup_fusion,

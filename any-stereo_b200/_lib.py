@@ -92,6 +92,8 @@ SIGNATURES = {
     "as_isu_affinity": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp]),
     "as_liif_query": (_i, [C.POINTER(LiifQueryDesc), _vp]),
     "as_context_upsample_multiscale": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "as_init_disparity": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "as_disparity_regression": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "as_lookup_taps": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "as_gwc_build_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "as_gwc_build_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),

@@ -56,3 +56,37 @@ def build_gwc_volume(refimg_fea, targetimg_fea, maxdisp, num_groups):
     else:
         vol = _gwc_fwd(left, right, int(maxdisp), int(num_groups))
     return vol if dt == torch.float32 else vol.to(dt)
+
+
+def disparity_regression(x, maxdisp):
+    """submodule.py:321-325: sum_d x[:, d] * d  -> [B,1,H,W]."""
+    assert len(x.shape) == 4
+    L.require_cuda(x, "x", torch.float32, contiguous=False)
+    if x.shape[1] != maxdisp:
+        raise RuntimeError("x must have maxdisp channels")
+    x = x.detach().contiguous()
+    B, D, H, W = x.shape
+    out = torch.empty((B, 1, H, W), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        L.call("as_disparity_regression", x.data_ptr(), out.data_ptr(), B, D, H, W, L.stream_ptr())
+    return out
+
+
+def init_disparity(geo_encoding_volume, classifier_weight, maxdisp=None, return_prob=False):
+    """The initial-disparity head in one kernel (continuous_IGEVstereo.py:267-268):
+        prob = F.softmax(classifier(geo_encoding_volume).squeeze(1), dim=1); init_disp = disparity_regression(prob, D)
+    with ``classifier = nn.Conv3d(G, 1, 3, 1, 1, bias=False)``.  -> init_disp [B,1,H,W] (and prob [B,D,H,W])."""
+    L.require_cuda(geo_encoding_volume, "geo_encoding_volume", torch.float32, contiguous=False)
+    L.require_cuda(classifier_weight, "classifier_weight", torch.float32, contiguous=False)
+    g = geo_encoding_volume.detach().contiguous()
+    w = classifier_weight.detach().contiguous()
+    B, G, D, H, W = g.shape
+    if tuple(w.shape) != (1, G, 3, 3, 3):
+        raise RuntimeError("classifier weight must be [1,G,3,3,3]")
+    if maxdisp is not None and maxdisp != D:
+        raise RuntimeError("geo_encoding_volume must have maxdisp disparity planes")
+    disp = torch.empty((B, 1, H, W), device=g.device, dtype=torch.float32)
+    prob = torch.empty((B, D, H, W), device=g.device, dtype=torch.float32) if return_prob else None
+    with torch.cuda.device(g.device):
+        L.call("as_init_disparity", g.data_ptr(), w.data_ptr(), disp.data_ptr(), L.ptr(prob), B, G, D, H, W, L.stream_ptr())
+    return (disp, prob) if return_prob else disp

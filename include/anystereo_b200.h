@@ -360,6 +360,17 @@ int as_liif_query(const as_liif_query_desc* desc, as_stream_t stream);
 int as_context_upsample_multiscale(const float* disp_low, const float* up_weights, const float* hr_coord, float* out,
                                    int B, int h, int w, int Q, as_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * SURVEY 8(f)-3 (first half)  initial-disparity head before the loop
+ * (continuous_IGEVstereo.py:267-268: softmax over D of Conv3d(G->1, 3x3x3, pad 1, no bias)(geo_encoding_volume),
+ *  then disparity_regression, submodule.py:321-325), fused: cost and probability volumes stay on chip.
+ * geo fp32 [B,G,D,H,W]; weight fp32 [1,G,3,3,3]; disp_out [B,1,H,W]; prob_out [B,D,H,W] or NULL.  D <= 64.
+ * ------------------------------------------------------------------------------------------ */
+int as_init_disparity(const float* geo, const float* weight, float* disp_out, float* prob_out,
+                      int B, int G, int D, int H, int W, as_stream_t stream);
+/* disparity_regression (submodule.py:321-325): out[b,0,y,x] = sum_d prob[b,d,y,x] * d */
+int as_disparity_regression(const float* prob, float* out, int B, int D, int H, int W, as_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -438,3 +438,28 @@ def make_update_block_params(cor_planes: int, seed: int = 0, hidden: int = 128,
         p[name + ".weight"] = torch.from_numpy(rng.uniform(-bound, bound, size=shp).astype("float32"))
         p[name + ".bias"] = torch.from_numpy(rng.uniform(-bound, bound, size=(shp[0],)).astype("float32"))
     return p
+
+
+# --------------------------------------------------------------------------------------
+# SURVEY 8(f)-3 (first half)  initial-disparity head before the loop
+# --------------------------------------------------------------------------------------
+def disparity_regression(x: torch.Tensor, maxdisp: int) -> torch.Tensor:
+    """submodule.py:321-325."""
+    d = torch.arange(0, maxdisp, dtype=x.dtype, device=x.device).view(1, maxdisp, 1, 1)
+    return torch.sum(x * d, 1, keepdim=True)
+
+
+def init_disparity(geo_volume: torch.Tensor, classifier_weight: torch.Tensor):
+    """continuous_IGEVstereo.py:267-268 with classifier = nn.Conv3d(G,1,3,1,1,bias=False) (:176), written as explicit
+    shifted sums (no conv3d call).  -> (init_disp [B,1,H,W], prob [B,D,H,W])."""
+    B, G, D, H, W = geo_volume.shape
+    p = torch.zeros(B, G, D + 2, H + 2, W + 2, dtype=geo_volume.dtype, device=geo_volume.device)
+    p[:, :, 1:D + 1, 1:H + 1, 1:W + 1] = geo_volume
+    cost = torch.zeros(B, D, H, W, dtype=geo_volume.dtype, device=geo_volume.device)
+    for kd in range(3):
+        for kh in range(3):
+            for kw in range(3):
+                wv = classifier_weight[0, :, kd, kh, kw].view(1, G, 1, 1, 1)
+                cost = cost + (p[:, :, kd:kd + D, kh:kh + H, kw:kw + W] * wv).sum(1)
+    prob = torch.softmax(cost, dim=1)
+    return disparity_regression(prob, D), prob

@@ -109,3 +109,8 @@ def liif_case(n_in=2, seed=21, B=2, h=6, w=10, scale=2.5, extra_q=77):
     sc = _t(np.full((B,), scale))
     in_dim = sum(f.shape[1] + 8 + 2 for f in feats)
     return dict(feats=feats, coords=coords, disp=disp, scale=sc, in_dim=in_dim, n_in=n_in)
+
+
+def init_disp_case(seed=31, B=2, G=8, D=12, H=5, W=37):
+    rng = np.random.RandomState(seed)
+    return dict(geo=_t(rng.standard_normal((B, G, D, H, W)) * 2.0), weight=_t(rng.standard_normal((1, G, 3, 3, 3)) * 0.2))

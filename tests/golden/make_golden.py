@@ -76,6 +76,14 @@ def main():
         arrs[name] = R.build_gwc_volume(g["left"], g["right"], g["maxdisp"], g["groups"])
     save("gwc_volume", **arrs)
 
+    # ---- initial-disparity head: the reference's classifier Conv3d + softmax + regression ----
+    from models.coreContinuous_IGEV.submodule import disparity_regression
+    c = cases.init_disp_case()
+    classifier = torch.nn.Conv3d(8, 1, 3, 1, 1, bias=False)          # continuous_IGEVstereo.py:176
+    classifier.weight.data.copy_(c["weight"])
+    prob = torch.nn.functional.softmax(classifier(c["geo"]).squeeze(1), dim=1)     # :267
+    save("init_disparity", prob=prob, init_disp=disparity_regression(prob, c["geo"].shape[2]))
+
     # ---- update block (both families, all flag combinations the models use) -------------
     for fam, cls in (("igev", R.IGEVUpdateBlock), ("raft", R.RAFTUpdateBlock)):
         c = cases.update_block_case(fam)

@@ -359,3 +359,45 @@ def test_fullsize_properties_igev(A):
     x0 = (coords.reshape(B, 1, H, W) - d2).contiguous()
     smp, = A.corr_sampler.forward(blk.init_corr_pyramid[0].reshape(B, H, W, W).contiguous(), x0, 4)
     assert rel(smp, blk(d2, coords)[:, 72:81]) < 1e-6
+
+
+# ---- initial-disparity head (classifier Conv3d + softmax + disparity_regression) ----
+def test_init_disparity_golden(A, golden):
+    g = golden("init_disparity")
+    c = cases.init_disp_case()
+    disp, prob = A.init_disparity(c["geo"].cuda(), c["weight"].cuda(), return_prob=True)
+    torch.cuda.synchronize()
+    assert tuple(disp.shape) == g["init_disp"].shape and tuple(prob.shape) == g["prob"].shape
+    assert float((prob.cpu() - torch.from_numpy(g["prob"])).abs().max()) < 5e-6
+    assert float((disp.cpu() - torch.from_numpy(g["init_disp"])).abs().max()) < 1e-4 * float(np.abs(g["init_disp"]).max())
+    d2 = A.disparity_regression(torch.from_numpy(g["prob"]).cuda(), 12)
+    assert float((d2.cpu() - torch.from_numpy(g["init_disp"])).abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(1, 8, 48, 7, 70), (2, 8, 17, 3, 33), (1, 4, 64, 2, 5), (1, 8, 1, 4, 4)])
+def test_init_disparity_vs_oracle(A, shape):
+    B, G, D, H, W = shape
+    rng = np.random.RandomState(D + W)
+    geo = torch.from_numpy(rng.standard_normal(shape).astype("float32")) * 3
+    w = torch.from_numpy(rng.standard_normal((1, G, 3, 3, 3)).astype("float32")) * 0.2
+    ref_d, ref_p = O.init_disparity(geo, w)
+    disp, prob = A.init_disparity(geo.cuda(), w.cuda(), return_prob=True)
+    torch.cuda.synchronize()
+    assert float((prob.cpu() - ref_p).abs().max()) < 5e-6
+    assert float((disp.cpu() - ref_d).abs().max()) < 1e-4 * max(1.0, float(ref_d.abs().max()))
+    only = A.init_disparity(geo.cuda(), w.cuda())
+    assert torch.equal(only, disp)
+    with pytest.raises(RuntimeError):
+        A.init_disparity(geo.cuda(), w.cuda()[:, :, :2])
+
+
+def test_init_disparity_fullsize_config2(A):
+    """8 x [8,48,96,312] (368 MB): against torch conv3d + softmax on the same GPU (strict fp32)."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(4)
+    geo = torch.randn(8, 8, 48, 96, 312, device="cuda")
+    w = torch.randn(1, 8, 3, 3, 3, device="cuda") * 0.2
+    disp = A.init_disparity(geo, w)
+    ref = O.disparity_regression(torch.softmax(torch.nn.functional.conv3d(geo, w, padding=1).squeeze(1), dim=1), 48)
+    torch.cuda.synchronize()
+    assert float((disp - ref).abs().max()) < 2e-3           # disparities up to 47; 1e-4 relative

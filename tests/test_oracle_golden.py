@@ -235,3 +235,13 @@ def test_liif_oracle_vs_model_graph(golden):
                                      torch.from_numpy(g["scale"]))
     assert up.shape == g["up_disp"].shape
     assert rel(up, g["up_disp"]) < 1e-5
+
+
+def test_init_disparity_oracle_vs_reference(golden):
+    """classifier Conv3d + softmax + disparity_regression (continuous_IGEVstereo.py:267-268)."""
+    g = golden("init_disparity")
+    c = cases.init_disp_case()
+    disp, prob = O.init_disparity(c["geo"], c["weight"])
+    assert rel(prob, g["prob"]) < 1e-5
+    assert rel(disp, g["init_disp"]) < 1e-5
+    assert np.array_equal(O.disparity_regression(torch.from_numpy(g["prob"]), 12).numpy(), g["init_disp"])

@@ -126,6 +126,21 @@ def main():
             json.dump(res, open(a.json, "w"), indent=1)
         return
     gwc = A.build_gwc_volume(f1, f2, Dg, 8)
+    if a.only == "initdisp":
+        # classifier Conv3d + softmax + disparity_regression fused; bytes = geo read once + disp written
+        geo = torch.randn(B, 8, Dg, H, W, device=dev)
+        wcl = torch.randn(1, 8, 3, 3, 3, device=dev) * 0.2
+        med, best = timeit(lambda: A.init_disparity(geo, wcl))
+        rec("init_disparity_fused", med, best, 4 * B * 8 * Dg * H * W + 4 * N)
+        torch.backends.cudnn.allow_tf32 = False
+        def ref():
+            p = torch.softmax(torch.nn.functional.conv3d(geo, wcl, padding=1).squeeze(1), dim=1)
+            return (p * torch.arange(Dg, device=dev).view(1, Dg, 1, 1)).sum(1, keepdim=True)
+        med, best = timeit(ref)
+        rec("TORCH_same_gpu_conv3d_softmax_regression", med, best, 4 * B * 8 * Dg * H * W + 4 * N)
+        if a.json:
+            json.dump(res, open(a.json, "w"), indent=1)
+        return
     if a.only == "lookup":
         blk = A.Combined_Geo_Encoding_Volume(f1, f2, gwc, num_levels=2, radius=4)
         coords = torch.arange(W, device=dev, dtype=torch.float32).reshape(1, 1, W, 1).repeat(B, H, 1, 1)
