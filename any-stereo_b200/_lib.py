@@ -94,6 +94,7 @@ SIGNATURES = {
     "as_context_upsample_multiscale": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "as_init_disparity": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "as_disparity_regression": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "as_convd1_umma": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "as_lookup_taps": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "as_gwc_build_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "as_gwc_build_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),

@@ -13,6 +13,7 @@ in TMEM) -- fp32-parity mode; engine "bf16": hi planes only -- fast mode, report
 """
 from __future__ import annotations
 
+import os
 import weakref
 
 import torch
@@ -97,6 +98,27 @@ def _fused_c1_weights(ub, split):
         bias = c.bias.detach().float().contiguous()
     hit = dict(key=key, hi=hi, lo=lo, bias=bias)
     st["convc1.fused"] = hit
+    return hit
+
+
+_CONVD1_SIMT = os.environ.get("AS_CONVD1_SIMT", "0") == "1"     # A/B knob: CUDA-core convd1 kernel
+
+
+def _convd1_weights(ub, split):
+    """convd1.weight [64,1,7,7] as the K-major [64][64] (49 taps + zero pad) bf16 hi/lo operand."""
+    st = _state(ub)["w"]
+    c = ub.encoder.convd1
+    key = (split, c.weight.data_ptr(), c.weight._version)
+    hit = st.get("convd1.umma")
+    if hit is not None and hit["key"] == key:
+        return hit
+    with torch.no_grad():
+        w = c.weight.detach().float().reshape(64, 49).contiguous()
+        hi = torch.empty((64, 64), device=w.device, dtype=torch.bfloat16)
+        lo = torch.empty_like(hi) if split else None
+        L.call("as_pack_conv_weight_bf16", w.data_ptr(), hi.data_ptr(), L.ptr(lo), 64, 49, 1, 1, 64, 64, L.stream_ptr())
+    hit = dict(key=key, hi=hi, lo=lo)
+    st["convd1.umma"] = hit
     return hit
 
 
@@ -250,8 +272,13 @@ def forward(ub, net, inp, corr=None, disp=None, iter04=True, iter08=True, iter16
         enc = _Planes((B, H, W, 128), dev, split)
         _conv(B, H, W, [c1], _weights(ub, "convc2", [e.convc2], split=split), nsplit, L.UEPI_RELU_SPLIT, out=enc)
         d1 = _Planes((B, H, W, 64), dev, split)
-        L.call("as_convd1_split", disp.data_ptr(), sw["wd1"].data_ptr(), sw["bd1"].data_ptr(), d1.hi.data_ptr(),
-               L.ptr(d1.lo), B, H, W, 64, 0, s())
+        if _CONVD1_SIMT:
+            L.call("as_convd1_split", disp.data_ptr(), sw["wd1"].data_ptr(), sw["bd1"].data_ptr(), d1.hi.data_ptr(),
+                   L.ptr(d1.lo), B, H, W, 64, 0, s())
+        else:                                            # 49 taps as one K = 64 row per pixel on the tensor cores
+            wd = _convd1_weights(ub, split)
+            L.call("as_convd1_umma", disp.data_ptr(), wd["hi"].data_ptr(), L.ptr(wd["lo"]), sw["bd1"].data_ptr(),
+                   d1.hi.data_ptr(), L.ptr(d1.lo), B, H, W, 64, 0, nsplit, s())
         _conv(B, H, W, [d1], _weights(ub, "convd2", [e.convd2], split=split), nsplit, L.UEPI_RELU_SPLIT, out=enc,
               out_coff=64)
         mo = _Planes((B, H, W, 128), dev, split)

@@ -285,6 +285,11 @@ int as_interp_bilinear_nhwc_split(const float* in, void* hi, void* lo, int B, in
 /* BasicMotionEncoder.convd1 (7x7, 1 -> 64, update.py:80,87) + relu -> bf16 planes [N][out_pitch] at out_coff */
 int as_convd1_split(const float* disp, const float* w /*[64][49]*/, const float* bias, void* hi, void* lo,
                     int B, int H, int W, int out_pitch, int out_coff, as_stream_t stream);
+/* the same convolution on the tensor cores: im2col rows (49 taps padded to K = 64) built in shared memory, one
+ * tcgen05 MMA group per 128-pixel tile.  w_hi/w_lo = as_pack_conv_weight_bf16(convd1.weight viewed as [64][49][1][1],
+ * n_pad 64, cin_pad 64).  nsplit 3 (fp32 parity) or 1. */
+int as_convd1_umma(const float* disp, const void* w_hi, const void* w_lo, const float* bias, void* out_hi, void* out_lo,
+                   int B, int H, int W, int out_pitch, int out_coff, int nsplit, as_stream_t stream);
 /* delta[n] = bias2 + sum_t u[n + shift(t)][t]  (zero outside the image): finishes DispHead.conv2 */
 int as_disp_delta(const float* u, const float* bias2, float* delta, int B, int H, int W, as_stream_t stream);
 
