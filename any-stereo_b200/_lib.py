@@ -95,6 +95,8 @@ SIGNATURES = {
     "as_init_disparity": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "as_disparity_regression": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "as_convd1_umma": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "as_set_operand_format": (_i, [_i]),
+    "as_get_operand_format": (_i, []),
     "as_lookup_taps": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "as_gwc_build_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "as_gwc_build_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
@@ -143,6 +145,36 @@ def lib():
             fn.argtypes = args
         _lib = L
     return _lib
+
+
+FMT_BF16, FMT_F16 = 0, 1
+_operand_format = FMT_BF16
+
+
+def operand_format() -> int:
+    return _operand_format
+
+
+def set_operand_format(fmt: int):
+    """16-bit operand format of the tensor-core kernels (process-wide, see as_set_operand_format)."""
+    global _operand_format
+    if fmt != _operand_format:
+        check(lib().as_set_operand_format(fmt), "as_set_operand_format")
+        _operand_format = fmt
+
+
+class operand_format_scope:
+    """Run a block with a given operand format and restore the previous one."""
+
+    def __init__(self, fmt):
+        self.fmt = fmt
+
+    def __enter__(self):
+        self.prev = _operand_format
+        set_operand_format(self.fmt)
+
+    def __exit__(self, *exc):
+        set_operand_format(self.prev)
 
 
 def check(rc: int, what: str = ""):

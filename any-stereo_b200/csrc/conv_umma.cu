@@ -40,35 +40,26 @@ struct ConvUmmaParams {
   const float* bias; const float* ctx; int ctx_pitch; const float* h; float* z;
   float* out_f32; __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; int out_pitch, out_coff, cout_valid;
   const float* disp; const float* w2; float* u;
+  bool f16;                                   // operand planes / weights are IEEE half instead of bf16
 };
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
-__device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
-  __nv_bfloat162 t = __halves2bfloat162(a, b);
-  return *reinterpret_cast<uint32_t*>(&t);
-}
-
-// 8 floats -> 8 bf16 hi (+ 8 bf16 lo = x - hi)
-__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
+// 8 floats -> 8 16-bit hi (+ 8 lo = x - hi)
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo, bool f16) {
   uint32_t h[4], l[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
-    h[i] = pack_bf16(h0, h1);
-    l[i] = pack_bf16(__float2bfloat16_rn(v[2 * i] - __bfloat162float(h0)),
-                     __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(h1)));
-  }
+  for (int i = 0; i < 4; ++i) as_split2(v[2 * i], v[2 * i + 1], h[i], l[i], f16);
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 // store 32 consecutive channels of one pixel as bf16 hi (/lo) planes
-__device__ __forceinline__ void store_split32(const float* v, __nv_bfloat16* hi, __nv_bfloat16* lo, long long off) {
+__device__ __forceinline__ void store_split32(const float* v, __nv_bfloat16* hi, __nv_bfloat16* lo, long long off, bool f16) {
 #pragma unroll
   for (int j = 0; j < 32; j += 8) {
     uint4 h, l;
-    split8(v + j, h, l);
+    split8(v + j, h, l, f16);
     *reinterpret_cast<uint4*>(hi + off + j) = h;
     if (lo) *reinterpret_cast<uint4*>(lo + off + j) = l;
   }
@@ -195,7 +186,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   } else if (warp == 1) {
     if (lane == 0 && leader) {
       int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
-      const uint32_t idesc = umma::idesc_bf16_f32(TWO ? 256 : 128, p.N);
+      const uint32_t idesc = umma::idesc_16_f32(TWO ? 256 : 128, p.N, p.f16);
       for (int it = 0; it < niter; ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
@@ -285,7 +276,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
               const float4 h4 = __ldg(reinterpret_cast<const float4*>(hp + j));
               v[j] *= h4.x; v[j + 1] *= h4.y; v[j + 2] *= h4.z; v[j + 3] *= h4.w;
             }
-            store_split32(v, p.out_hi, p.out_lo, n * p.out_pitch + p.out_coff + (c0 - Hd));
+            store_split32(v, p.out_hi, p.out_lo, n * p.out_pitch + p.out_coff + (c0 - Hd), p.f16);
           }
         } else if (p.epilogue == AS_UEPI_GRU_Q) {            // h' = (1-z) h + z tanh(convq + cq)   update.py:39-40
           const float* cx = p.ctx + n * p.ctx_pitch + c0;
@@ -304,7 +295,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
           float* op = p.out_f32 + n * p.N + c0;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          store_split32(v, p.out_hi, p.out_lo, n * p.out_pitch + p.out_coff + c0);
+          store_split32(v, p.out_hi, p.out_lo, n * p.out_pitch + p.out_coff + c0, p.f16);
         } else if (p.epilogue == AS_UEPI_DISPHEAD) {         // relu(conv1) dotted with conv2's 9 taps  update.py:23-24
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -333,7 +324,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
             v[j + 2] = fmaxf(v[j + 2] + b4.z, 0.f); v[j + 3] = fmaxf(v[j + 3] + b4.w, 0.f);
           }
           if (p.epilogue == AS_UEPI_MOTION && c0 + 32 == p.N) v[31] = __ldg(p.disp + n);   // cat(out, disp) update.py:92
-          store_split32(v, p.out_hi, p.out_lo, n * p.out_pitch + p.out_coff + c0);
+          store_split32(v, p.out_hi, p.out_lo, n * p.out_pitch + p.out_coff + c0, p.f16);
         }
         }
         __syncwarp();     // reconverge before the next warp-aligned tcgen05.ld
@@ -421,6 +412,7 @@ extern "C" int as_conv2d_umma(const as_conv_umma_desc* d, as_stream_t stream) {
   }
   p.cin_total = cin;
   p.N = d->Cout; p.nsplit = d->nsplit; p.epilogue = d->epilogue;
+  p.f16 = as_operand_f16_internal() != 0;
   const bool two = two_cta_enabled() && p.num_tiles >= 4 && (p.N % 32) == 0;
   p.a_plane = (p.TH + d->KH - 1) * p.TW * 128;          // (TH+2)-row patch for 3x3, the tile itself for 1x1
   p.a_stage = 2 * p.a_plane;

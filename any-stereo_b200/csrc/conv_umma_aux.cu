@@ -7,35 +7,24 @@
 
 namespace {
 
-__device__ __forceinline__ void split1(float v, __nv_bfloat16& h, __nv_bfloat16& l) {
-  h = __float2bfloat16_rn(v);
-  l = __float2bfloat16_rn(v - __bfloat162float(h));
-}
-
-__device__ __forceinline__ void store_split4(float4 v, __nv_bfloat16* hi, __nv_bfloat16* lo, long long off) {
-  __nv_bfloat16 h[4], l[4];
-  split1(v.x, h[0], l[0]); split1(v.y, h[1], l[1]); split1(v.z, h[2], l[2]); split1(v.w, h[3], l[3]);
-  __nv_bfloat162 a = __halves2bfloat162(h[0], h[1]), b = __halves2bfloat162(h[2], h[3]);
-  uint2 pk;
-  pk.x = *reinterpret_cast<uint32_t*>(&a); pk.y = *reinterpret_cast<uint32_t*>(&b);
-  *reinterpret_cast<uint2*>(hi + off) = pk;
-  if (lo) {
-    a = __halves2bfloat162(l[0], l[1]); b = __halves2bfloat162(l[2], l[3]);
-    pk.x = *reinterpret_cast<uint32_t*>(&a); pk.y = *reinterpret_cast<uint32_t*>(&b);
-    *reinterpret_cast<uint2*>(lo + off) = pk;
-  }
+__device__ __forceinline__ void store_split4(float4 v, __nv_bfloat16* hi, __nv_bfloat16* lo, long long off, bool f16) {
+  uint2 h, l;
+  as_split2(v.x, v.y, h.x, l.x, f16);
+  as_split2(v.z, v.w, h.y, l.y, f16);
+  *reinterpret_cast<uint2*>(hi + off) = h;
+  if (lo) *reinterpret_cast<uint2*>(lo + off) = l;
 }
 
 __global__ void split_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                             long long n4) {
+                             long long n4, bool f16) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
-  store_split4(__ldg(reinterpret_cast<const float4*>(in) + i), hi, lo, i * 4);
+  store_split4(__ldg(reinterpret_cast<const float4*>(in) + i), hi, lo, i * 4, f16);
 }
 
 // [B,C,HW] fp32 -> [B*HW][Cp] bf16 hi/lo, channels >= C zero-filled
 __global__ void __launch_bounds__(256) nchw_to_nhwc_split_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi,
-                                                                 __nv_bfloat16* __restrict__ lo, int C, long long HW, int Cp) {
+                                                                 __nv_bfloat16* __restrict__ lo, int C, long long HW, int Cp, bool f16) {
   __shared__ float t[32][33];
   const int b = blockIdx.z;
   const long long p0 = (long long)blockIdx.x * 32;
@@ -53,11 +42,11 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_split_kernel(const float* __
   const long long pp = p0 + pr;
   if (pp < HW && c0 + cq < Cp)
     store_split4(make_float4(t[cq][pr], t[cq + 1][pr], t[cq + 2][pr], t[cq + 3][pr]), hi, lo,
-                 ((long long)b * HW + pp) * Cp + c0 + cq);
+                 ((long long)b * HW + pp) * Cp + c0 + cq, f16);
 }
 
 __global__ void pool2x_split_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                                    int H, int W, int Ho, int Wo, int C4, long long total) {
+                                    int H, int W, int Ho, int Wo, int C4, long long total, bool f16) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int c4 = (int)(idx % C4);
@@ -79,11 +68,11 @@ __global__ void pool2x_split_kernel(const float* __restrict__ in, __nv_bfloat16*
     }
   }
   const float inv = 1.0f / 9.0f;
-  store_split4(make_float4(s.x * inv, s.y * inv, s.z * inv, s.w * inv), hi, lo, idx * 4);
+  store_split4(make_float4(s.x * inv, s.y * inv, s.z * inv, s.w * inv), hi, lo, idx * 4, f16);
 }
 
 __global__ void interp_split_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                                    int Hi, int Wi, int Ho, int Wo, int C4, float sy, float sx, long long total) {
+                                    int Hi, int Wi, int Ho, int Wo, int C4, float sy, float sx, long long total, bool f16) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int c4 = (int)(idx % C4);
@@ -103,12 +92,12 @@ __global__ void interp_split_kernel(const float* __restrict__ in, __nv_bfloat16*
   o.y = hy * (hx * v00.y + lx * v01.y) + ly * (hx * v10.y + lx * v11.y);
   o.z = hy * (hx * v00.z + lx * v01.z) + ly * (hx * v10.z + lx * v11.z);
   o.w = hy * (hx * v00.w + lx * v01.w) + ly * (hx * v10.w + lx * v11.w);
-  store_split4(o, hi, lo, idx * 4);
+  store_split4(o, hi, lo, idx * 4, f16);
 }
 
 __global__ void pack_weight_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi,
                                         __nv_bfloat16* __restrict__ lo, int Cout, int Cin, int T, int n_pad, int cin_pad,
-                                        long long total) {
+                                        long long total, bool f16) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   // idx = (n * T + tap) * cin_pad + c
@@ -118,10 +107,10 @@ __global__ void pack_weight_bf16_kernel(const float* __restrict__ w, __nv_bfloat
   const int n = (int)(r / T);
   float v = 0.f;
   if (n < Cout && c < Cin) v = w[((long long)n * Cin + c) * T + tap];
-  __nv_bfloat16 h, l;
-  split1(v, h, l);
-  hi[idx] = h;
-  if (lo) lo[idx] = l;
+  uint32_t h, l;
+  as_split2(v, 0.f, h, l, f16);
+  reinterpret_cast<unsigned short*>(hi)[idx] = (unsigned short)(h & 0xFFFFu);
+  if (lo) reinterpret_cast<unsigned short*>(lo)[idx] = (unsigned short)(l & 0xFFFFu);
 }
 
 // 7x7 conv, 1 input channel -> 64, + bias, relu.  CTA = 32x8 pixel tile: the (8+6)x(32+6) disparity patch and the
@@ -130,7 +119,7 @@ __global__ void pack_weight_bf16_kernel(const float* __restrict__ w, __nv_bfloat
 constexpr int kD1TX = 32, kD1TY = 8;
 __global__ void __launch_bounds__(256) convd1_split_kernel(const float* __restrict__ disp, const float* __restrict__ w,
                                                            const float* __restrict__ bias, __nv_bfloat16* __restrict__ hi,
-                                                           __nv_bfloat16* __restrict__ lo, int H, int W, int pitch, int coff) {
+                                                           __nv_bfloat16* __restrict__ lo, int H, int W, int pitch, int coff, bool f16) {
   __shared__ __align__(16) float ws[49 * 64];     // [tap][channel]
   __shared__ float bs[64];
   __shared__ float patch[kD1TY + 6][kD1TX + 6 + 2];
@@ -183,7 +172,7 @@ __global__ void __launch_bounds__(256) convd1_split_kernel(const float* __restri
     for (int j = 0; j < 16; j += 4)
       store_split4(make_float4(fmaxf(acc[px][j], 0.f), fmaxf(acc[px][j + 1], 0.f), fmaxf(acc[px][j + 2], 0.f),
                                fmaxf(acc[px][j + 3], 0.f)),
-                   hi, lo, n * pitch + coff + cg + j);
+                   hi, lo, n * pitch + coff + cg + j, f16);
   }
 }
 
@@ -209,7 +198,7 @@ __global__ void disp_delta_kernel(const float* __restrict__ u, const float* __re
 extern "C" int as_split_f32(const float* in, void* hi, void* lo, long long n, as_stream_t stream) {
   if (!in || !hi || n <= 0) return AS_ERR_BAD_ARG;
   if ((n & 3) || !as_aligned16(in)) return AS_ERR_ALIGNMENT;
-  split_kernel<<<(unsigned)as_ceil_div_ll(n / 4, 256), 256, 0, as_cu(stream)>>>(in, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n / 4);
+  split_kernel<<<(unsigned)as_ceil_div_ll(n / 4, 256), 256, 0, as_cu(stream)>>>(in, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n / 4, as_operand_f16_internal() != 0);
   AS_RETURN_IF_LAUNCH_FAILED();
   return AS_OK;
 }
@@ -220,7 +209,7 @@ extern "C" int as_nchw_to_nhwc_split(const float* in, void* hi, void* lo, int B,
   if ((c_pad & 31) || B > 65535) return AS_ERR_UNSUPPORTED;
   const long long HW = (long long)H * W;
   dim3 grid((unsigned)as_ceil_div_ll(HW, 32), c_pad / 32, B);
-  nchw_to_nhwc_split_kernel<<<grid, 256, 0, as_cu(stream)>>>(in, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, C, HW, c_pad);
+  nchw_to_nhwc_split_kernel<<<grid, 256, 0, as_cu(stream)>>>(in, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, C, HW, c_pad, as_operand_f16_internal() != 0);
   AS_RETURN_IF_LAUNCH_FAILED();
   return AS_OK;
 }
@@ -231,7 +220,7 @@ extern "C" int as_pool2x_nhwc_split(const float* in, void* hi, void* lo, int B, 
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
   const long long total = (long long)B * Ho * Wo * (C / 4);
   pool2x_split_kernel<<<(unsigned)as_ceil_div_ll(total, 256), 256, 0, as_cu(stream)>>>(
-      in, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, H, W, Ho, Wo, C / 4, total);
+      in, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, H, W, Ho, Wo, C / 4, total, as_operand_f16_internal() != 0);
   AS_RETURN_IF_LAUNCH_FAILED();
   return AS_OK;
 }
@@ -244,7 +233,7 @@ extern "C" int as_interp_bilinear_nhwc_split(const float* in, void* hi, void* lo
   const float sx = Wout > 1 ? (float)(Win - 1) / (float)(Wout - 1) : 0.f;
   const long long total = (long long)B * Hout * Wout * (C / 4);
   interp_split_kernel<<<(unsigned)as_ceil_div_ll(total, 256), 256, 0, as_cu(stream)>>>(
-      in, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, Hin, Win, Hout, Wout, C / 4, sy, sx, total);
+      in, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, Hin, Win, Hout, Wout, C / 4, sy, sx, total, as_operand_f16_internal() != 0);
   AS_RETURN_IF_LAUNCH_FAILED();
   return AS_OK;
 }
@@ -254,7 +243,7 @@ extern "C" int as_pack_conv_weight_bf16(const float* w_oihw, void* w_hi, void* w
   if (!w_oihw || !w_hi || Cout <= 0 || Cin <= 0 || KH <= 0 || KW <= 0 || n_pad < Cout || cin_pad < Cin) return AS_ERR_BAD_ARG;
   const long long total = (long long)n_pad * KH * KW * cin_pad;
   pack_weight_bf16_kernel<<<(unsigned)as_ceil_div_ll(total, 256), 256, 0, as_cu(stream)>>>(
-      w_oihw, (__nv_bfloat16*)w_hi, (__nv_bfloat16*)w_lo, Cout, Cin, KH * KW, n_pad, cin_pad, total);
+      w_oihw, (__nv_bfloat16*)w_hi, (__nv_bfloat16*)w_lo, Cout, Cin, KH * KW, n_pad, cin_pad, total, as_operand_f16_internal() != 0);
   AS_RETURN_IF_LAUNCH_FAILED();
   return AS_OK;
 }
@@ -266,7 +255,7 @@ extern "C" int as_convd1_split(const float* disp, const float* w, const float* b
   if (B > 65535 || as_ceil_div(H, kD1TY) > 65535) return AS_ERR_UNSUPPORTED;
   dim3 grid(as_ceil_div(W, kD1TX), as_ceil_div(H, kD1TY), B);
   convd1_split_kernel<<<grid, 256, 0, as_cu(stream)>>>(disp, w, bias, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, H, W,
-                                                       out_pitch, out_coff);
+                                                       out_pitch, out_coff, as_operand_f16_internal() != 0);
   AS_RETURN_IF_LAUNCH_FAILED();
   return AS_OK;
 }

@@ -19,13 +19,12 @@ __device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
   return r;
 }
 
-__device__ __forceinline__ void put_oct(uint32_t a_hi, uint32_t lo_off, int row, int k, const float (&v)[8], bool split) {
+__device__ __forceinline__ void put_oct(uint32_t a_hi, uint32_t lo_off, int row, int k, const float (&v)[8], bool split, bool f16) {
   const uint32_t addr = a_hi + row * 128 + ((((uint32_t)(k & 63) << 1)) ^ ((uint32_t)(row & 7) << 4));
   uint32_t h[4], l[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    h[i] = cvt_bf16x2(v[2 * i], v[2 * i + 1]);
-    l[i] = cvt_bf16x2(v[2 * i] - __uint_as_float(h[i] << 16), v[2 * i + 1] - __uint_as_float(h[i] & 0xFFFF0000u));
+    as_split2(v[2 * i], v[2 * i + 1], h[i], l[i], f16);
   }
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
   if (split)
@@ -36,7 +35,7 @@ __global__ void __launch_bounds__(kThreads, 3)
 convd1_umma_kernel(const __grid_constant__ CUtensorMap tWh, const __grid_constant__ CUtensorMap tWl,
                    const float* __restrict__ disp, const float* __restrict__ bias, __nv_bfloat16* __restrict__ out_hi,
                    __nv_bfloat16* __restrict__ out_lo, int H, int W, int tiles_x, int tiles_y, int num_tiles, int pitch,
-                   int coff, int nsplit) {
+                   int coff, int nsplit, bool f16) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* act = smem;                                   // hi | lo
@@ -98,7 +97,7 @@ convd1_umma_kernel(const __grid_constant__ CUtensorMap tWh, const __grid_constan
           const int ky = tap / 7, kx = tap - ky * 7;
           v[i] = tap < 49 ? patch[(py + ky) * PW + px + kx] : 0.f;
         }
-        put_oct(act_s, kBlk, row, half * 32 + o * 8, v, split);
+        put_oct(act_s, kBlk, row, half * 32 + o * 8, v, split, f16);
       }
     }
     umma::fence_proxy_async();
@@ -106,7 +105,7 @@ convd1_umma_kernel(const __grid_constant__ CUtensorMap tWh, const __grid_constan
     if (tid == 0) {
       if (!weights_ready) umma::mbar_wait(w_full, 0);
       umma::tc_fence_after();
-      const uint32_t idesc = umma::idesc_bf16_f32(128, 64);
+      const uint32_t idesc = umma::idesc_16_f32(128, 64, f16);
       const uint32_t bh = umma::smem_u32(wh), bl = umma::smem_u32(wl);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -140,8 +139,7 @@ convd1_umma_kernel(const __grid_constant__ CUtensorMap tWh, const __grid_constan
           for (int i = 0; i < 4; ++i) {
             const float y0f = fmaxf(v[j + 2 * i] + __ldg(bias + half * 32 + j + 2 * i), 0.f);
             const float y1f = fmaxf(v[j + 2 * i + 1] + __ldg(bias + half * 32 + j + 2 * i + 1), 0.f);
-            h[i] = cvt_bf16x2(y0f, y1f);
-            l[i] = cvt_bf16x2(y0f - __uint_as_float(h[i] << 16), y1f - __uint_as_float(h[i] & 0xFFFF0000u));
+            as_split2(y0f, y1f, h[i], l[i], f16);
           }
           *reinterpret_cast<uint4*>(out_hi + o + j) = make_uint4(h[0], h[1], h[2], h[3]);
           if (out_lo) *reinterpret_cast<uint4*>(out_lo + o + j) = make_uint4(l[0], l[1], l[2], l[3]);
@@ -186,7 +184,8 @@ extern "C" int as_convd1_umma(const float* disp, const void* w_hi, const void* w
   if (e != cudaSuccess) return (int)e;
   const int grid = nt < 3LL * sms ? (int)nt : 3 * sms;
   convd1_umma_kernel<<<grid, kThreads, kSmem, as_cu(stream)>>>(tWh, tWl, disp, bias, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo,
-                                                               H, W, tiles_x, tiles_y, (int)nt, out_pitch, out_coff, nsplit);
+                                                               H, W, tiles_x, tiles_y, (int)nt, out_pitch, out_coff, nsplit,
+                                                               as_operand_f16_internal() != 0);
   AS_RETURN_IF_LAUNCH_FAILED();
   return AS_OK;
 }

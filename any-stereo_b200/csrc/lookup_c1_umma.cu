@@ -69,12 +69,13 @@ __device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
 // r*128 and XORs the 16-byte chunk bits [4,7) with r & 7 (the 128B swizzle the MMA descriptor expects).
 __device__ __forceinline__ uint32_t k_offset(int kidx) { return ((uint32_t)(kidx >> 6) << 13) | ((uint32_t)(kidx & 63) << 1); }
 
+template <bool kF16>
 __device__ __forceinline__ void put_pair(uint32_t row_addr, uint32_t r7s, uint32_t koff, float v0, float v1, bool split) {
   const uint32_t addr = row_addr + (koff ^ r7s);
-  const uint32_t h = cvt_bf16x2(v0, v1);
+  const uint32_t h = as_cvt16x2(v0, v1, kF16);
   asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(h) : "memory");
   if (split) {
-    const uint32_t l = cvt_bf16x2(v0 - __uint_as_float(h << 16), v1 - __uint_as_float(h & 0xFFFF0000u));
+    const uint32_t l = as_cvt16x2(v0 - as_widen_lo16(h, kF16), v1 - as_widen_hi16(h, kF16), kF16);
     asm volatile("st.shared.b32 [%0+%2], %1;" ::"r"(addr), "r"(l), "n"(3 * kABlock) : "memory");
   }
 }
@@ -177,7 +178,7 @@ __device__ __forceinline__ void prefetch_windows(const C1Levels& lv, int Dg, con
   if (lo < hi && off < (long long)hi * (kG * 4)) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + off));
 }
 
-template <int L>
+template <int L, bool kF16>
 __device__ __forceinline__ void emit_features(const Taps<L>& t, uint32_t a_s, int row, int g, bool split) {
   const uint32_t row_addr = a_s + row * 128, r7s = (uint32_t)(row & 7) << 4;
 #pragma unroll
@@ -188,7 +189,7 @@ __device__ __forceinline__ void emit_features(const Taps<L>& t, uint32_t a_s, in
     for (int k = 0; k < kK; ++k) v[k] = t.wg[l][k] * omf + t.wg[l][k + 1] * f;
     v[kK] = 0.f;
 #pragma unroll
-    for (int k = 0; k < kTaps; k += 2) put_pair(row_addr, r7s, k_offset(l * 96 + g * kTaps + k), v[k], v[k + 1], split);
+    for (int k = 0; k < kTaps; k += 2) put_pair<kF16>(row_addr, r7s, k_offset(l * 96 + g * kTaps + k), v[k], v[k + 1], split);
   }
   if (g < L) {
     const float omf = 1.0f - t.fc;
@@ -197,7 +198,7 @@ __device__ __forceinline__ void emit_features(const Taps<L>& t, uint32_t a_s, in
     for (int k = 0; k < kK; ++k) v[k] = t.wc[k] * omf + t.wc[k + 1] * t.fc;
     v[kK] = 0.f;
 #pragma unroll
-    for (int k = 0; k < kTaps; k += 2) put_pair(row_addr, r7s, k_offset(g * 96 + kG * kTaps + k), v[k], v[k + 1], split);
+    for (int k = 0; k < kTaps; k += 2) put_pair<kF16>(row_addr, r7s, k_offset(g * 96 + kG * kTaps + k), v[k], v[k + 1], split);
   }
 }
 
@@ -206,7 +207,7 @@ __device__ __forceinline__ void wait_backoff(uint64_t* bar, uint32_t parity) {
   while (!umma::mbar_try_wait(bar, parity)) __nanosleep(100);
 }
 
-template <int L>
+template <int L, bool kF16>
 __global__ void __launch_bounds__(kThreads, 1)
 geo_lookup_convc1_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
                          const C1Levels lv, int Dg, const float* __restrict__ disp, const float* __restrict__ coords,
@@ -287,13 +288,13 @@ geo_lookup_convc1_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __gri
       for (int i = 0; i < 4; ++i) pn[i] = load_pixel(disp, coords, tn.nbase, tn.p0 + i * 16, HW, W, tn.valid);
       load_taps<L>(bufB, lv, Dg, px[1], g);
       umma::mbar_wait(a_empty + grp, (k & 1) ^ 1);     // the MMAs of this stage's previous tile have read it
-      emit_features<L>(bufA, a_s, prow, g, split);
+      emit_features<L, kF16>(bufA, a_s, prow, g, split);
       load_taps<L>(bufA, lv, Dg, px[2], g);
-      emit_features<L>(bufB, a_s, 16 + prow, g, split);
+      emit_features<L, kF16>(bufB, a_s, 16 + prow, g, split);
       load_taps<L>(bufB, lv, Dg, px[3], g);
-      emit_features<L>(bufA, a_s, 32 + prow, g, split);
+      emit_features<L, kF16>(bufA, a_s, 32 + prow, g, split);
       load_taps<L>(bufA, lv, Dg, pn[0], g);
-      emit_features<L>(bufB, a_s, 48 + prow, g, split);
+      emit_features<L, kF16>(bufB, a_s, 48 + prow, g, split);
       umma::fence_proxy_async();                       // generic-proxy smem writes -> visible to the tensor-core proxy
       umma::mbar_arrive(a_full + grp);
 #pragma unroll
@@ -308,7 +309,7 @@ geo_lookup_convc1_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __gri
         if (split) umma::tma_load_2d(b_lo + kb * kBBlock, &tmW_lo, w_full, kb * 64, 0);
       }
       umma::mbar_wait(w_full, 0);
-      const uint32_t idesc = umma::idesc_bf16_f32(128, kNOut);
+      const uint32_t idesc = umma::idesc_16_f32(128, kNOut, kF16);
       const uint32_t bh = umma::smem_u32(b_hi), bl = umma::smem_u32(b_lo);
       int used[kNG];                                   // tiles already issued per group
 #pragma unroll
@@ -397,8 +398,7 @@ geo_lookup_convc1_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __gri
               const int ch = hf * 32 + jj + 2 * i;
               const float y0 = fmaxf(v[hf][jj + 2 * i] + __ldg(bias + ch), 0.f);
               const float y1 = fmaxf(v[hf][jj + 2 * i + 1] + __ldg(bias + ch + 1), 0.f);
-              h[i] = cvt_bf16x2(y0, y1);
-              l[i] = cvt_bf16x2(y0 - __uint_as_float(h[i] << 16), y1 - __uint_as_float(h[i] & 0xFFFF0000u));
+              as_split2(y0, y1, h[i], l[i], kF16);
             }
             *reinterpret_cast<uint4*>(out_hi + o + hf * 32 + jj) = make_uint4(h[0], h[1], h[2], h[3]);
             if (out_lo) *reinterpret_cast<uint4*>(out_lo + o + hf * 32 + jj) = make_uint4(l[0], l[1], l[2], l[3]);
@@ -449,17 +449,21 @@ extern "C" int as_geo_lookup_convc1(const float* const* geo_levels, int G, int D
   const int grid = nt < sms ? (int)nt : sms;
   cudaStream_t st = as_cu(stream);
   cudaError_t e;
+  const bool f16 = as_operand_f16_internal() != 0;
+#define AS_C1_LAUNCH(LV, F)                                                                                              \
+  do {                                                                                                                   \
+    e = cudaFuncSetAttribute(geo_lookup_convc1_kernel<LV, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);       \
+    if (e != cudaSuccess) return (int)e;                                                                                 \
+    geo_lookup_convc1_kernel<LV, F><<<grid, kThreads, kSmem, st>>>(tW_hi, tW_lo, lv, Dg, disp, coords, bias,             \
+                                                                   (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, HW, W, \
+                                                                   tiles_per_img, (int)nt, nsplit);                      \
+  } while (0)
   if (num_levels == 2) {
-    e = cudaFuncSetAttribute(geo_lookup_convc1_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-    if (e != cudaSuccess) return (int)e;
-    geo_lookup_convc1_kernel<2><<<grid, kThreads, kSmem, st>>>(tW_hi, tW_lo, lv, Dg, disp, coords, bias, (__nv_bfloat16*)out_hi,
-                                                               (__nv_bfloat16*)out_lo, HW, W, tiles_per_img, (int)nt, nsplit);
+    if (f16) AS_C1_LAUNCH(2, true); else AS_C1_LAUNCH(2, false);
   } else {
-    e = cudaFuncSetAttribute(geo_lookup_convc1_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-    if (e != cudaSuccess) return (int)e;
-    geo_lookup_convc1_kernel<1><<<grid, kThreads, kSmem, st>>>(tW_hi, tW_lo, lv, Dg, disp, coords, bias, (__nv_bfloat16*)out_hi,
-                                                               (__nv_bfloat16*)out_lo, HW, W, tiles_per_img, (int)nt, nsplit);
+    if (f16) AS_C1_LAUNCH(1, true); else AS_C1_LAUNCH(1, false);
   }
+#undef AS_C1_LAUNCH
   AS_RETURN_IF_LAUNCH_FAILED();
   return AS_OK;
 }

@@ -218,6 +218,11 @@ __device__ __forceinline__ uint64_t smem_desc_k_sw128(uint32_t smem_addr_bytes) 
   return d;
 }
 // kind::f16 instruction descriptor: bf16 x bf16 -> fp32, both operands K-major
+// same with IEEE-half operands (format code 0) when f16 is set
+__host__ __device__ __forceinline__ uint32_t idesc_16_f32(int M, int N, bool f16) {
+  const uint32_t fmt = f16 ? 0u : 1u;
+  return (1u << 4) /*D=f32*/ | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 __host__ __device__ __forceinline__ uint32_t idesc_bf16_f32(int M, int N) {
   return (1u << 4) /*D=f32*/ | (1u << 7) /*A=bf16*/ | (1u << 10) /*B=bf16*/ | ((uint32_t)(N >> 3) << 17) |
          ((uint32_t)(M >> 4) << 24);

@@ -165,7 +165,8 @@ class liif_out_multi_scale_Training(nn.Module):
         B, Q, _ = coord.shape
         dev = coord.device
         split = _split_mode()
-        with torch.cuda.device(dev), torch.no_grad():
+        # the upsampler's kernels are built for bf16 operands (split = fp32 parity): pin the format for their duration
+        with torch.cuda.device(dev), torch.no_grad(), L.operand_format_scope(L.FMT_BF16):
             wts = self._weights(split)
             P = self._first_layer_maps(feats, wts, split)
             d = L.LiifQueryDesc()

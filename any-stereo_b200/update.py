@@ -28,8 +28,11 @@ _ENGINE = {"engine": "fp32"}
 
 
 def set_update_engine(engine: str):
-    if engine not in ("fp32", "bf16x3", "bf16"):
-        raise ValueError("engine must be fp32, bf16x3 or bf16")
+    if engine not in ("fp32", "bf16x3", "bf16", "fp16"):
+        raise ValueError("engine must be fp32, bf16x3, bf16 or fp16")
+    # "fp16": single-MMA fast mode with IEEE-half operands (11-bit mantissas) -- the analogue of the reference's
+    # autocast mixed precision (continuous_IGEVstereo.py:287); every other engine uses bf16 bit patterns
+    L.set_operand_format(L.FMT_F16 if engine == "fp16" else L.FMT_BF16)
     _ENGINE["engine"] = engine
 
 

@@ -45,10 +45,11 @@ def _side_stream(dev):
 
 class _Planes:
     """bf16 hi (+lo) planes of a pixel-major activation [B,H,W,C]."""
-    __slots__ = ("hi", "lo", "shape")
+    __slots__ = ("hi", "lo", "shape", "fmt")
 
     def __init__(self, shape, device, split):
         self.shape = tuple(shape)
+        self.fmt = L.operand_format()          # bf16 or IEEE half bit patterns (stored in bfloat16-typed tensors)
         self.hi = torch.empty(shape, device=device, dtype=torch.bfloat16)
         self.lo = torch.empty(shape, device=device, dtype=torch.bfloat16) if split else None
 
@@ -64,7 +65,7 @@ def _state(ub):
 def _weights(ub, name, convs, n_pad=None, cin_pad=None, split=True):
     """bf16 hi/lo GEMM weights [n_pad][taps*cin_pad] + padded fp32 bias, cached per parameter version."""
     st = _state(ub)["w"]
-    key = (split,) + tuple((c.weight.data_ptr(), c.weight._version, c.bias.data_ptr(), c.bias._version) for c in convs)
+    key = (split, L.operand_format()) + tuple((c.weight.data_ptr(), c.weight._version, c.bias.data_ptr(), c.bias._version) for c in convs)
     hit = st.get(name)
     if hit is not None and hit["key"] == key:
         return hit
@@ -89,7 +90,7 @@ def _fused_c1_weights(ub, split):
     """convc1 weights in the K order of the fused lookup kernel (geometry.DeferredGeoLookup.pack_convc1_weight)."""
     st = _state(ub)["w"]
     c = ub.encoder.convc1
-    key = (split, c.weight.data_ptr(), c.weight._version, c.bias.data_ptr(), c.bias._version)
+    key = (split, L.operand_format(), c.weight.data_ptr(), c.weight._version, c.bias.data_ptr(), c.bias._version)
     hit = st.get("convc1.fused")
     if hit is not None and hit["key"] == key:
         return hit
@@ -108,7 +109,7 @@ def _convd1_weights(ub, split):
     """convd1.weight [64,1,7,7] as the K-major [64][64] (49 taps + zero pad) bf16 hi/lo operand."""
     st = _state(ub)["w"]
     c = ub.encoder.convd1
-    key = (split, c.weight.data_ptr(), c.weight._version)
+    key = (split, L.operand_format(), c.weight.data_ptr(), c.weight._version)
     hit = st.get("convd1.umma")
     if hit is not None and hit["key"] == key:
         return hit
@@ -202,7 +203,7 @@ def _planes_of(ub, h_f32, split):
     # valid while the tensor we produced is still alive (its memory cannot have been recycled), untouched
     # (views share the version counter) and of the same extent
     if (hit is not None and hit[0]() is not None and hit[2] == h_f32._version and hit[1].shape == tuple(h_f32.shape)
-            and (hit[1].lo is not None) == split):
+            and (hit[1].lo is not None) == split and hit[1].fmt == L.operand_format()):
         return hit[1]
     pl = _Planes(h_f32.shape, h_f32.device, split)
     L.call("as_split_f32", h_f32.data_ptr(), pl.hi.data_ptr(), L.ptr(pl.lo), h_f32.numel(), L.stream_ptr())

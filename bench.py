@@ -28,7 +28,7 @@ sys.path.insert(0, ROOT)
 H4, W4, FEAT_D, GEO_D, GROUPS, ITERS = 96, 312, 96, 48, 8, 32     # 384x1248 at 1/4 resolution
 LOOKUP_BYTES_PER_PIXEL = 1372                                      # IGEV L=2, r=4, G=8
 # fused lookup+convc1: the same 724 B of windows + 4 B disp read, 64 bf16 hi(+lo) channels written
-FUSED_BYTES_PER_PIXEL = {"bf16x3": 728 + 256, "bf16": 728 + 128}
+FUSED_BYTES_PER_PIXEL = {"bf16x3": 728 + 256, "bf16": 728 + 128, "fp16": 728 + 128}
 
 
 def load_peaks():
@@ -196,7 +196,7 @@ def run_ours(args):
     if args.overlap:
         A.update_umma.set_encoder_overlap(True)
     A.set_lookup_fusion(not args.no_fusion)
-    A.set_corr_mode(args.corr_mode or ("fp32" if args.engine == "fp32" else args.engine))
+    A.set_corr_mode(args.corr_mode or {"fp32": "fp32", "bf16x3": "bf16x3", "bf16": "bf16", "fp16": "bf16x3"}[args.engine])
     B = args.pairs_per_gpu
     torch.manual_seed(0)
     uargs = types.SimpleNamespace(corr_levels=2, corr_radius=4, n_gru_layers=3)
@@ -395,7 +395,8 @@ def run_ours(args):
         "metric": "pairs/s @384x1248, 32 iters", "value": value, "unit": "pairs/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"fp32": "f32", "bf16x3": "f32 (3x split-bf16 on tcgen05, fp32 accumulate)", "bf16": "bf16"}[args.engine],
+        "dtype": {"fp32": "f32", "bf16x3": "f32 (3x split-bf16 on tcgen05, fp32 accumulate)", "bf16": "bf16",
+                  "fp16": "f16 (IEEE half operands, fp32 accumulate; mixed-precision analogue)"}[args.engine],
         "data": "synthetic",
         "config": {"workload": "coreContinuous_IGEV hot path (BASELINE configs[1]): 384x1248 -> 96x312 @1/4, "
                                "batch %d pairs/GPU, 32 iters, corr_levels=2, radius=4" % B,
@@ -432,7 +433,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--engine", default=os.environ.get("ANYSTEREO_ENGINE", "bf16x3"), choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--engine", default=os.environ.get("ANYSTEREO_ENGINE", "bf16x3"), choices=["fp32", "bf16x3", "bf16", "fp16"])
     ap.add_argument("--corr-mode", default=None, choices=[None, "fp32", "bf16x3", "bf16"])
     ap.add_argument("--pairs-per-gpu", type=int, default=8)
     ap.add_argument("--ref-sample-iters", type=int, default=8)

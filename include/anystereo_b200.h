@@ -272,6 +272,14 @@ typedef struct as_conv_umma_desc {
 } as_conv_umma_desc;
 
 int as_conv2d_umma(const as_conv_umma_desc* desc, as_stream_t stream);
+/* 16-bit operand format of the tensor-core kernels and of every "hi/lo plane" / packed-weight producer below.
+ * AS_FMT_BF16 (default): bf16; with nsplit 3 (hi+lo) this is the fp32-parity mode.  AS_FMT_F16: IEEE half, meant for
+ * nsplit 1 -- the single-MMA fast mode with 11-bit mantissas (the analogue of the reference's autocast mixed
+ * precision, continuous_IGEVstereo.py:287).  Process-wide; planes and weights must be (re)produced after a switch. */
+#define AS_FMT_BF16 0
+#define AS_FMT_F16 1
+int as_set_operand_format(int fmt);
+int as_get_operand_format(void);
 /* nn.Conv2d weight [Cout][Cin][KH][KW] fp32 -> bf16 hi/lo [n_pad][KH*KW*cin_pad] (zero padded rows/channels) */
 int as_pack_conv_weight_bf16(const float* w_oihw, void* w_hi, void* w_lo, int Cout, int Cin, int KH, int KW,
                              int n_pad, int cin_pad, as_stream_t stream);

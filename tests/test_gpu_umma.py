@@ -108,7 +108,7 @@ def make_block(A, family, seed):
     return m.cuda().eval()
 
 
-@pytest.mark.parametrize("engine,tol", [("bf16x3", 2e-4), ("bf16", 5e-2)])
+@pytest.mark.parametrize("engine,tol", [("bf16x3", 2e-4), ("bf16", 5e-2), ("fp16", 6e-3)])
 @pytest.mark.parametrize("family", ["igev", "raft"])
 def test_update_block_umma_golden(A, golden, family, engine, tol):
     g = golden("update_block_" + family)
@@ -128,14 +128,16 @@ def test_update_block_umma_golden(A, golden, family, engine, tol):
     A.set_update_engine("fp32")
 
 
+@pytest.mark.parametrize("engine", ["bf16x3", "fp16"])
 @pytest.mark.parametrize("family", ["igev", "raft"])
-def test_iteration_loop_epe_umma(A, golden, family):
-    """fp32-parity tensor-core mode: final disparity within 0.01 px of the reference after equal iterations."""
+def test_iteration_loop_epe_umma(A, golden, family, engine):
+    """fp32-parity tensor-core mode (and the IEEE-half fast mode): final disparity within 0.01 px of the reference
+    after equal iterations."""
     g = golden("loop_" + family)
     c = cases.loop_case(family)
     iters = int(g["iters"])
     m = make_block(A, family, 12 if family == "igev" else 13)
-    A.set_update_engine("bf16x3")
+    A.set_update_engine(engine)
     A.set_corr_mode("bf16x3")
     net = [t.cuda() for t in c["net"]]
     inp = [[t.cuda() for t in lst] for lst in c["inp"]]
@@ -339,7 +341,7 @@ def test_update_block_fewer_gru_layers(A, engine, tol, n_layers):
     A.set_update_engine("fp32")
 
 
-@pytest.mark.parametrize("engine,tol", [("bf16x3", 1e-4), ("bf16", 2e-2)])
+@pytest.mark.parametrize("engine,tol", [("bf16x3", 1e-4), ("bf16", 2e-2), ("fp16", 3e-3)])
 @pytest.mark.parametrize("shape", [(2, 5, 23, 16, 2), (1, 16, 24, 48, 2), (1, 7, 150, 24, 1), (3, 9, 40, 20, 2)])
 def test_fused_lookup_convc1_vs_oracle(A, engine, tol, shape):
     """lookup fused with BasicMotionEncoder.convc1 + ReLU on the tensor cores against
@@ -356,6 +358,7 @@ def test_fused_lookup_convc1_vs_oracle(A, engine, tol, shape):
                         4, exact=True)
     ref = torch.relu(torch.nn.functional.conv2d(feat.double(), w.double(), b.double())).float()
     A.set_corr_mode("fp32")
+    A.set_update_engine(engine)                       # selects the 16-bit operand format (bf16 / IEEE half)
     vol = A.Combined_Geo_Encoding_Volume(c["f1"].cuda(), c["f2"].cuda(), c["geo"].cuda(), num_levels=Lv, radius=4)
     split = engine == "bf16x3"
     w_hi, w_lo = A.geometry.DeferredGeoLookup.pack_convc1_weight(w.cuda(), split)
@@ -365,13 +368,15 @@ def test_fused_lookup_convc1_vs_oracle(A, engine, tol, shape):
     assert d.fusable and d.shape == (B, Lv * 81, H, W)
     d.convc1_planes(w_hi, w_lo, b.cuda(), out_hi, out_lo)
     torch.cuda.synchronize()
-    got = out_hi.float() + (out_lo.float() if split else 0)
-    assert rel(got.permute(0, 3, 1, 2), ref) < tol
+    widen = (lambda t: t.view(torch.float16).float()) if engine == "fp16" else (lambda t: t.float())
+    got = widen(out_hi) + (widen(out_lo) if split else 0)
     # coords=None means the default pixel grid
     out2 = torch.empty_like(out_hi)
     vol.deferred(disp.cuda(), None).convc1_planes(w_hi, w_lo, b.cuda(), out2, torch.empty_like(out_hi) if split else None)
     torch.cuda.synchronize()
-    assert torch.equal(out2, out_hi)
+    A.set_update_engine("fp32")
+    assert rel(got.permute(0, 3, 1, 2), ref) < tol
+    assert torch.equal(out2.view(torch.int16), out_hi.view(torch.int16))
 
 
 @pytest.mark.parametrize("engine", ["bf16x3", "bf16"])

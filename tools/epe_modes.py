@@ -12,8 +12,8 @@ for fam in ("igev", "raft"):
     m = cls(args, hidden_dims=[128] * 3)
     m.load_state_dict(O.make_update_block_params(162 if fam == "igev" else 36, seed=78 if fam == "igev" else 77), strict=True)
     m = m.cuda().eval()
-    for eng in ("fp32", "bf16x3", "bf16"):
-        A.set_update_engine(eng); A.set_corr_mode(eng)
+    for eng in ("fp32", "bf16x3", "bf16", "fp16"):
+        A.set_update_engine(eng); A.set_corr_mode("bf16x3" if eng == "fp16" else eng)
         if fam == "igev":
             d, _ = A.igev_iterations(m, f1, f2, torch.from_numpy(g["geo"]).cuda(), [t.clone() for t in net], inp, torch.from_numpy(g["init_disp"]).cuda(), int(g["iters"]))
         else:
