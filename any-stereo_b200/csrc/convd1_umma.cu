@@ -13,12 +13,6 @@ constexpr int kBlk = 128 * 128;                  // [128 rows][64 K] bf16
 constexpr int kWBlk = 64 * 128;                  // [64 rows][64 K] bf16
 constexpr int kSmem = 1024 + 2 * kBlk + 2 * kWBlk + (kTH + 6) * (kTW + 6) * 4 + 64;
 
-__device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
-
 __device__ __forceinline__ void put_oct(uint32_t a_hi, uint32_t lo_off, int row, int k, const float (&v)[8], bool split, bool f16) {
   const uint32_t addr = a_hi + row * 128 + ((((uint32_t)(k & 63) << 1)) ^ ((uint32_t)(row & 7) << 4));
   uint32_t h[4], l[4];

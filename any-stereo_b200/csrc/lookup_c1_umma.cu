@@ -16,18 +16,7 @@
 
 namespace {
 
-#ifndef AS_C1_NG
-#define AS_C1_NG 3
-#endif
-#ifndef AS_C1_PREFETCH
-#define AS_C1_PREFETCH 1
-#endif
-constexpr int kNG = AS_C1_NG;              // producer groups == A stages == TMEM accumulators
-#ifndef AS_C1_L2PF
-#define AS_C1_L2PF 0
-#endif
-constexpr bool kL2Prefetch = AS_C1_L2PF;   // prefetch.global.L2 of the group's next tile
-constexpr bool kPrefetch = AS_C1_PREFETCH; // load the next pass's taps before converting the current one
+constexpr int kNG = 3;                     // producer groups == A stages == TMEM accumulators
 constexpr int kGroupThreads = 128;         // 4 warps per producer group
 constexpr int kThreads = kNG * kGroupThreads + 96;   // + 2 epilogue warps + 1 MMA warp
 constexpr int kTile = 64;                  // pixels per tile (rows 64..127 of the M = 128 MMA are don't-care)
@@ -54,13 +43,6 @@ __device__ __forceinline__ void split_pos(float x, int& t0, float& f) {
   t0 = (int)fminf(fmaxf(fl, -1.0e6f), 1.0e6f) - kR;
 }
 __device__ __forceinline__ float level_scale(int l) { return __int_as_float((127 - l) << 23); }
-
-// packed round-to-nearest convert: lo -> bits [0,16), hi -> bits [16,32)  (one F2FP instead of two F2F)
-__device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
 
 // K order of the fused GEMM: channel (level l, group g, tap k) sits at K = l*96 + g*10 + k (g == 8: the correlation taps),
 // i.e. every 9-tap run starts on an even K and is padded to 10, so a lane emits aligned bf16 PAIRS (st.shared.b32);
@@ -158,24 +140,6 @@ __device__ __forceinline__ void load_taps(Taps<L>& t, const C1Levels& lv, int Dg
     const float* row = cbase + n * pitch + t0;
     TapLoader<4>::run(t.wc, row, t0, inside ? (unsigned)Wl : 0u);
   }
-}
-
-// L2 prefetch of the geometry windows of one pixel (the group's NEXT tile): holds no registers, so the DRAM latency of
-// tile j+kNG overlaps the conversion work of tile j.  Lane g covers 128-byte line (g & 3) of level (g >> 2).
-template <int L>
-__device__ __forceinline__ void prefetch_windows(const C1Levels& lv, int Dg, const float* __restrict__ disp, long long nbase,
-                                                 int p, int HW, int g) {
-  const int l = g >> 2;
-  if (p >= HW || l >= L) return;
-  const float d = __ldg(disp + nbase + p);
-  int t0;
-  float f;
-  split_pos(d * level_scale(l), t0, f);
-  const int Dl = Dg >> l;
-  const int lo = max(t0, 0), hi = min(t0 + kTaps, Dl);             // taps [lo, hi) exist
-  const char* row = reinterpret_cast<const char*>((l == 0 ? lv.geo[0] : lv.geo[1]) + (nbase + p) * (long long)Dl * kG);
-  const long long first = ((long long)lo * (kG * 4)) & ~127LL, off = first + (g & 3) * 128;
-  if (lo < hi && off < (long long)hi * (kG * 4)) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + off));
 }
 
 template <int L, bool kF16>
