@@ -46,7 +46,7 @@ int as_operand_f16_internal();
 // two floats -> packed 16-bit pair (lo in bits [0,16)), round to nearest even
 __device__ __forceinline__ uint32_t as_cvt16x2(float lo, float hi, bool f16) {
   uint32_t r;
-  if (f16) asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  if (f16) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }

@@ -454,3 +454,20 @@ def test_fused_lookup_fullsize_config2(A):
     A.set_update_engine("fp32")
     got = (out_hi.float() + out_lo.float()).permute(0, 3, 1, 2)
     assert rel(got, ref.float()) < 1e-4
+
+
+def test_fp16_operand_format_saturates(A):
+    """IEEE-half operand planes clamp to +-65504 instead of overflowing to inf (the fp32 accumulators never see inf)."""
+    L = A._lib
+    x = torch.tensor([1.0e6, -3.0e5, 65504.0, 0.333251953125, -1.5, 0.0, 7.0e-8, 1.0], device="cuda")
+    hi = torch.empty(8, device="cuda", dtype=torch.bfloat16)
+    A.set_update_engine("fp16")
+    assert L.lib().as_get_operand_format() == 1
+    L.call("as_split_f32", x.data_ptr(), hi.data_ptr(), None, 8, L.stream_ptr())
+    torch.cuda.synchronize()
+    A.set_update_engine("fp32")
+    assert L.lib().as_get_operand_format() == 0
+    got = hi.view(torch.float16).float().cpu()
+    ref = x.cpu().clamp(-65504.0, 65504.0).half().float()
+    assert torch.equal(got, ref)
+    assert L.lib().as_set_operand_format(7) == -1
