@@ -353,7 +353,13 @@ liif_query_kernel(const __grid_constant__ CUtensorMap tW2h, const __grid_constan
           off[i] = (((long long)b * a.h[i] + iy) * a.w[i] + ix) * (kH1 / 4);       // in float4 units
         }
       }
-#pragma unroll 8
+      // consecutive queries of a dense grid fall into the same source pixel (4*scale of them per 1/4-res pixel):
+      // a P row is fetched only when the (warp-uniform) row offset changes, otherwise it is reused from registers
+      float4 p4[3];
+      long long held[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { p4[i] = make_float4(0.f, 0.f, 0.f, 0.f); held[i] = -1; }
+#pragma unroll 4
       for (int j = 0; j < 16; ++j) {
         const int row = gwarp * 16 + j;
         const bool valid = q0 + row < a.Q;
@@ -363,11 +369,14 @@ liif_query_kernel(const __grid_constant__ CUtensorMap tW2h, const __grid_constan
           if (i < a.n_in) {
             const long long o = __shfl_sync(0xffffffffu, off[i], j);
             const float qy = __shfl_sync(0xffffffffu, ry[i], j), qx = __shfl_sync(0xffffffffu, rx[i], j);
-            const float4 p4 = __ldg(reinterpret_cast<const float4*>(a.P[i]) + o + lane);
-            z.x += p4.x + wy4[i].x * qy + wx4[i].x * qx;
-            z.y += p4.y + wy4[i].y * qy + wx4[i].y * qx;
-            z.z += p4.z + wy4[i].z * qy + wx4[i].z * qx;
-            z.w += p4.w + wy4[i].w * qy + wx4[i].w * qx;
+            if (o != held[i]) {
+              p4[i] = __ldg(reinterpret_cast<const float4*>(a.P[i]) + o + lane);
+              held[i] = o;
+            }
+            z.x += p4[i].x + wy4[i].x * qy + wx4[i].x * qx;
+            z.y += p4[i].y + wy4[i].y * qy + wx4[i].y * qx;
+            z.z += p4[i].z + wy4[i].z * qy + wx4[i].z * qx;
+            z.w += p4[i].w + wy4[i].w * qy + wx4[i].w * qx;
           }
         }
         if (!valid) z = make_float4(0.f, 0.f, 0.f, 0.f);
