@@ -49,8 +49,12 @@ struct GeoIn {
 // coalesced 128-byte rows (batched 8 deep per warp for memory-level parallelism), transposed through shared
 // memory ([d*G+g][33], conflict-free both ways) and written as one contiguous (DC>>l)*G-float run per pixel and
 // level.  ~25 KB of smem per CTA -> 8 CTAs/SM.
-__global__ void __launch_bounds__(256) geo_pyramid_kernel(const float* __restrict__ geo, GeoOut outs, int G, int Dg,
-                                                          int H, int W, int L, int DC, int nchunks) {
+// GT / DCT > 0: compile-time group count and chunk size (every index division becomes a shift); 0 = runtime values
+template <int GT, int DCT>
+__global__ void __launch_bounds__(256) geo_pyramid_kernel(const float* __restrict__ geo, GeoOut outs, int G_, int Dg,
+                                                          int H, int W, int L, int DC_, int nchunks) {
+  const int G = GT > 0 ? GT : G_;
+  const int DC = DCT > 0 ? DCT : DC_;
   extern __shared__ float s[];
   const int E0 = DC * G;
   float* cur = s;                                  // [DC*G][33]
@@ -91,10 +95,8 @@ __global__ void __launch_bounds__(256) geo_pyramid_kernel(const float* __restric
       const int El = valid * G;
       float* dst = outs.ptr[l] + (n0 * Dl + dl0) * G;
       const long long pstride = (long long)Dl * G;
-      for (int i = tid; i < nx * El; i += 256) {
-        const int px = i / El, e = i - px * El;
-        dst[px * pstride + e] = cur[e * kTStride + px];
-      }
+      for (int px = warp; px < nx; px += 8)          // one warp per pixel record: 128-byte contiguous stores
+        for (int e = lane; e < El; e += 32) dst[px * pstride + e] = cur[e * kTStride + px];
     }
     if (l + 1 < L) {
       const int dn = dc >> 1;
@@ -189,10 +191,17 @@ extern "C" int as_geo_pyramid_build(const float* geo, int B, int G, int Dg, int 
   if ((long long)B * nchunks > 65535) return AS_ERR_UNSUPPORTED;
   const size_t smem = sizeof(float) * kTStride * ((size_t)DC * G + (size_t)(DC / 2) * G);
   if (smem > 220 * 1024) return AS_ERR_UNSUPPORTED;
-  cudaError_t e = cudaFuncSetAttribute(geo_pyramid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
   dim3 grid(as_ceil_div(W, kTX), H, B * nchunks);
-  geo_pyramid_kernel<<<grid, 256, smem, as_cu(stream)>>>(geo, o, G, Dg, H, W, num_levels, DC, nchunks);
+  cudaError_t e;
+  if (G == 8 && DC == 16) {                         // the IGEV shape: constant-folded index arithmetic
+    e = cudaFuncSetAttribute(geo_pyramid_kernel<8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    geo_pyramid_kernel<8, 16><<<grid, 256, smem, as_cu(stream)>>>(geo, o, G, Dg, H, W, num_levels, DC, nchunks);
+  } else {
+    e = cudaFuncSetAttribute(geo_pyramid_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    geo_pyramid_kernel<0, 0><<<grid, 256, smem, as_cu(stream)>>>(geo, o, G, Dg, H, W, num_levels, DC, nchunks);
+  }
   AS_RETURN_IF_LAUNCH_FAILED();
   return AS_OK;
 }
