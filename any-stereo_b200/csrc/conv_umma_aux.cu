@@ -45,15 +45,13 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_split_kernel(const float* __
                  ((long long)b * HW + pp) * Cp + c0 + cq, f16);
 }
 
+// grid = (ceil(Wo*C4 / 256), Ho, B): the row / image indices come from the block, one 32-bit division per thread
 __global__ void pool2x_split_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                                    int H, int W, int Ho, int Wo, int C4, long long total, bool f16) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int c4 = (int)(idx % C4);
-  long long t = idx / C4;
-  const int xo = (int)(t % Wo); t /= Wo;
-  const int yo = (int)(t % Ho);
-  const int b = (int)(t / Ho);
+                                    int H, int W, int Ho, int Wo, int C4, bool f16) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= Wo * C4) return;
+  const int xo = r / C4, c4 = r - xo * C4;
+  const int yo = blockIdx.y, b = blockIdx.z;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
@@ -68,18 +66,16 @@ __global__ void pool2x_split_kernel(const float* __restrict__ in, __nv_bfloat16*
     }
   }
   const float inv = 1.0f / 9.0f;
+  const long long idx = (((long long)b * Ho + yo) * Wo + xo) * C4 + c4;
   store_split4(make_float4(s.x * inv, s.y * inv, s.z * inv, s.w * inv), hi, lo, idx * 4, f16);
 }
 
 __global__ void interp_split_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                                    int Hi, int Wi, int Ho, int Wo, int C4, float sy, float sx, long long total, bool f16) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int c4 = (int)(idx % C4);
-  long long t = idx / C4;
-  const int xo = (int)(t % Wo); t /= Wo;
-  const int yo = (int)(t % Ho);
-  const int b = (int)(t / Ho);
+                                    int Hi, int Wi, int Ho, int Wo, int C4, float sy, float sx, bool f16) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= Wo * C4) return;
+  const int xo = r / C4, c4 = r - xo * C4;
+  const int yo = blockIdx.y, b = blockIdx.z;
   const float fy = sy * yo, fx = sx * xo;
   const int y0 = (int)fy, x0 = (int)fx;
   const int y1 = min(y0 + 1, Hi - 1), x1 = min(x0 + 1, Wi - 1);
@@ -92,6 +88,7 @@ __global__ void interp_split_kernel(const float* __restrict__ in, __nv_bfloat16*
   o.y = hy * (hx * v00.y + lx * v01.y) + ly * (hx * v10.y + lx * v11.y);
   o.z = hy * (hx * v00.z + lx * v01.z) + ly * (hx * v10.z + lx * v11.z);
   o.w = hy * (hx * v00.w + lx * v01.w) + ly * (hx * v10.w + lx * v11.w);
+  const long long idx = (((long long)b * Ho + yo) * Wo + xo) * C4 + c4;
   store_split4(o, hi, lo, idx * 4, f16);
 }
 
@@ -218,9 +215,10 @@ extern "C" int as_pool2x_nhwc_split(const float* in, void* hi, void* lo, int B, 
   if (!in || !hi || B <= 0 || H <= 0 || W <= 0 || C <= 0) return AS_ERR_BAD_ARG;
   if ((C & 3) || !as_aligned16(in)) return AS_ERR_ALIGNMENT;
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
-  const long long total = (long long)B * Ho * Wo * (C / 4);
-  pool2x_split_kernel<<<(unsigned)as_ceil_div_ll(total, 256), 256, 0, as_cu(stream)>>>(
-      in, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, H, W, Ho, Wo, C / 4, total, as_operand_f16_internal() != 0);
+  if (B > 65535 || Ho > 65535 || (long long)Wo * (C / 4) >= (1LL << 31)) return AS_ERR_INDEX_RANGE;
+  dim3 grid(as_ceil_div(Wo * (C / 4), 256), Ho, B);
+  pool2x_split_kernel<<<grid, 256, 0, as_cu(stream)>>>(in, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, H, W, Ho, Wo, C / 4,
+                                                       as_operand_f16_internal() != 0);
   AS_RETURN_IF_LAUNCH_FAILED();
   return AS_OK;
 }
@@ -231,9 +229,10 @@ extern "C" int as_interp_bilinear_nhwc_split(const float* in, void* hi, void* lo
   if ((C & 3) || !as_aligned16(in)) return AS_ERR_ALIGNMENT;
   const float sy = Hout > 1 ? (float)(Hin - 1) / (float)(Hout - 1) : 0.f;
   const float sx = Wout > 1 ? (float)(Win - 1) / (float)(Wout - 1) : 0.f;
-  const long long total = (long long)B * Hout * Wout * (C / 4);
-  interp_split_kernel<<<(unsigned)as_ceil_div_ll(total, 256), 256, 0, as_cu(stream)>>>(
-      in, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, Hin, Win, Hout, Wout, C / 4, sy, sx, total, as_operand_f16_internal() != 0);
+  if (B > 65535 || Hout > 65535 || (long long)Wout * (C / 4) >= (1LL << 31)) return AS_ERR_INDEX_RANGE;
+  dim3 grid(as_ceil_div(Wout * (C / 4), 256), Hout, B);
+  interp_split_kernel<<<grid, 256, 0, as_cu(stream)>>>(in, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, Hin, Win, Hout, Wout, C / 4,
+                                                       sy, sx, as_operand_f16_internal() != 0);
   AS_RETURN_IF_LAUNCH_FAILED();
   return AS_OK;
 }
