@@ -22,11 +22,14 @@ template <> __device__ __forceinline__ __half from_acc<__half, float>(float v) {
 
 constexpr int kPix = 128;  // pixels per CTA
 
-template <typename T>
+// RT > 0: compile-time radius (the models use 4): the staging loop unrolls into independent loads with constant
+// index arithmetic; RT = 0: runtime radius
+template <typename T, int RT>
 __global__ void __launch_bounds__(kPix) sampler_fwd_kernel(const T* __restrict__ vol,
                                                            const float* __restrict__ coords,
                                                            long long coords_bstride, T* __restrict__ out,
-                                                           int HW, int W2, int r) {
+                                                           int HW, int W2, int r_) {
+  const int r = RT > 0 ? RT : r_;
   using A = typename Acc<T>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   A* s_win = reinterpret_cast<A*>(smem_raw);  // [kPix][ntap+1]
@@ -50,6 +53,7 @@ __global__ void __launch_bounds__(kPix) sampler_fwd_kernel(const T* __restrict__
   __syncthreads();
 
   const T* vrow = vol + (long long)b * HW * W2;
+#pragma unroll
   for (int flat = tid; flat < kPix * ntap; flat += kPix) {
     const int pix = flat / ntap;
     const int j = flat - pix * ntap;
@@ -70,6 +74,7 @@ __global__ void __launch_bounds__(kPix) sampler_fwd_kernel(const T* __restrict__
   const A* w = s_win + tid * stride;
   T* o = out + (long long)b * (2 * r + 1) * HW + p;
   A prev = w[0];
+#pragma unroll
   for (int k = 0; k < 2 * r + 1; ++k) {
     const A cur = w[k + 1];
     o[(long long)k * HW] = from_acc<T, A>(prev * omf + cur * f);
@@ -181,9 +186,12 @@ int launch_fwd(const void* volume, const float* coords, int coords_ch, void* out
   const int HW = H * W1;
   dim3 grid(as_ceil_div(HW, kPix), B);
   const size_t smem = sizeof(A) * kPix * (2 * radius + 3);
-  sampler_fwd_kernel<T><<<grid, kPix, smem, st>>>(static_cast<const T*>(volume), coords,
-                                                   (long long)coords_ch * HW, static_cast<T*>(out), HW,
-                                                   W2, radius);
+  if (radius == 4)
+    sampler_fwd_kernel<T, 4><<<grid, kPix, smem, st>>>(static_cast<const T*>(volume), coords,
+                                                        (long long)coords_ch * HW, static_cast<T*>(out), HW, W2, radius);
+  else
+    sampler_fwd_kernel<T, 0><<<grid, kPix, smem, st>>>(static_cast<const T*>(volume), coords,
+                                                        (long long)coords_ch * HW, static_cast<T*>(out), HW, W2, radius);
   AS_RETURN_IF_LAUNCH_FAILED();
   return AS_OK;
 }
