@@ -196,7 +196,19 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries exactly one JSON line: NCCL's version banner (printed on stdout at communicator creation when
+        # NCCL_DEBUG >= VERSION) is sent to stderr by swapping the descriptor around init + the first collective
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     A.set_update_engine(args.engine)
     if args.overlap:
         A.update_umma.set_encoder_overlap(True)
