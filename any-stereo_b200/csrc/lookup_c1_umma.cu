@@ -24,11 +24,16 @@ constexpr int kG = 8, kR = 4, kK = 9, kTaps = 10;
 constexpr int kKPad = 192;                 // 162 channels padded to 3 K-blocks of 64
 constexpr int kNOut = 64;                  // convc1 output channels == UMMA N
 constexpr int kABlock = kTile * 128;       // bytes of one [64 x 64] bf16 K-block
-constexpr int kAStage = 2 * 3 * kABlock;   // hi + lo planes of one tile
 constexpr int kBBlock = kNOut * 128;
+// GEO = true: IGEV (8 geometry groups + correlation, K = 192 = 3 blocks); GEO = false: RAFT CorrBlock1D (correlation rows
+// of up to 6 levels only, K = 10*L <= 64 = 1 block; corePrune_RAFT/geometry.py:24-43 feeding update.py:78,85)
+__host__ __device__ constexpr int k_blocks(bool geo) { return geo ? 3 : 1; }
+__host__ __device__ constexpr int a_stage_bytes(bool geo) { return 2 * k_blocks(geo) * kABlock; }   // hi + lo planes of a tile
 // The M = 128 MMA reads 128 rows per K-block, i.e. 8 KB past each 64-row block: into the next block / stage / the
 // weight tiles, all inside this allocation.  Those rows land in TMEM lanes 64..127, which nobody reads.
-constexpr int kSmem = 1024 + kNG * kAStage + 2 * 3 * kBBlock + 256;
+__host__ __device__ constexpr int smem_bytes(bool geo) {
+  return 1024 + kNG * a_stage_bytes(geo) + 2 * k_blocks(geo) * kBBlock + 256 + (geo ? 0 : kABlock);   // RAFT: slack for the over-read
+}
 
 struct C1Levels {
   const float* geo[4];
@@ -51,14 +56,14 @@ __device__ __forceinline__ float level_scale(int l) { return __int_as_float((127
 // r*128 and XORs the 16-byte chunk bits [4,7) with r & 7 (the 128B swizzle the MMA descriptor expects).
 __device__ __forceinline__ uint32_t k_offset(int kidx) { return ((uint32_t)(kidx >> 6) << 13) | ((uint32_t)(kidx & 63) << 1); }
 
-template <bool kF16>
+template <bool kF16, int LO_OFF>
 __device__ __forceinline__ void put_pair(uint32_t row_addr, uint32_t r7s, uint32_t koff, float v0, float v1, bool split) {
   const uint32_t addr = row_addr + (koff ^ r7s);
   const uint32_t h = as_cvt16x2(v0, v1, kF16);
   asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(h) : "memory");
   if (split) {
     const uint32_t l = as_cvt16x2(v0 - as_widen_lo16(h, kF16), v1 - as_widen_hi16(h, kF16), kF16);
-    asm volatile("st.shared.b32 [%0+%2], %1;" ::"r"(addr), "r"(l), "n"(3 * kABlock) : "memory");
+    asm volatile("st.shared.b32 [%0+%2], %1;" ::"r"(addr), "r"(l), "n"(LO_OFF) : "memory");
   }
 }
 
@@ -111,13 +116,13 @@ __device__ __forceinline__ PixelIn load_pixel(const float* __restrict__ disp, co
   return px;
 }
 
-template <int L>
-__device__ __forceinline__ void load_taps(Taps<L>& t, const C1Levels& lv, int Dg, const PixelIn& px, int g) {
+template <int L, bool GEO>
+__device__ __forceinline__ void load_taps(Taps<GEO ? L : 1>& t, const C1Levels& lv, int Dg, const PixelIn& px, int g) {
   const float d = px.d, c = px.c;
   const bool inside = px.inside;
   const long long n = px.n;
 #pragma unroll
-  for (int l = 0; l < L; ++l) {
+  for (int l = 0; l < (GEO ? L : 0); ++l) {
     const float sc = level_scale(l);
     int t0;
     split_pos(d * sc, t0, t.fg[l]);                                  // geometry.py:43
@@ -142,18 +147,19 @@ __device__ __forceinline__ void load_taps(Taps<L>& t, const C1Levels& lv, int Dg
   }
 }
 
-template <int L, bool kF16>
-__device__ __forceinline__ void emit_features(const Taps<L>& t, uint32_t a_s, int row, int g, bool split) {
+template <int L, bool kF16, bool GEO>
+__device__ __forceinline__ void emit_features(const Taps<GEO ? L : 1>& t, uint32_t a_s, int row, int g, bool split) {
   const uint32_t row_addr = a_s + row * 128, r7s = (uint32_t)(row & 7) << 4;
+  constexpr int kLo = k_blocks(GEO) * kABlock;
 #pragma unroll
-  for (int l = 0; l < L; ++l) {
+  for (int l = 0; l < (GEO ? L : 0); ++l) {
     const float f = t.fg[l], omf = 1.0f - f;
     float v[kTaps];
 #pragma unroll
     for (int k = 0; k < kK; ++k) v[k] = t.wg[l][k] * omf + t.wg[l][k + 1] * f;
     v[kK] = 0.f;
 #pragma unroll
-    for (int k = 0; k < kTaps; k += 2) put_pair<kF16>(row_addr, r7s, k_offset(l * 96 + g * kTaps + k), v[k], v[k + 1], split);
+    for (int k = 0; k < kTaps; k += 2) put_pair<kF16, kLo>(row_addr, r7s, k_offset(l * 96 + g * kTaps + k), v[k], v[k + 1], split);
   }
   if (g < L) {
     const float omf = 1.0f - t.fc;
@@ -162,7 +168,7 @@ __device__ __forceinline__ void emit_features(const Taps<L>& t, uint32_t a_s, in
     for (int k = 0; k < kK; ++k) v[k] = t.wc[k] * omf + t.wc[k + 1] * t.fc;
     v[kK] = 0.f;
 #pragma unroll
-    for (int k = 0; k < kTaps; k += 2) put_pair<kF16>(row_addr, r7s, k_offset(g * 96 + kG * kTaps + k), v[k], v[k + 1], split);
+    for (int k = 0; k < kTaps; k += 2) put_pair<kF16, kLo>(row_addr, r7s, k_offset(GEO ? g * 96 + kG * kTaps + k : g * kTaps + k), v[k], v[k + 1], split);
   }
 }
 
@@ -171,7 +177,7 @@ __device__ __forceinline__ void wait_backoff(uint64_t* bar, uint32_t parity) {
   while (!umma::mbar_try_wait(bar, parity)) __nanosleep(100);
 }
 
-template <int L, bool kF16>
+template <int L, bool kF16, bool GEO>
 __global__ void __launch_bounds__(kThreads, 1)
 geo_lookup_convc1_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
                          const C1Levels lv, int Dg, const float* __restrict__ disp, const float* __restrict__ coords,
@@ -179,10 +185,11 @@ geo_lookup_convc1_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __gri
                          __nv_bfloat16* __restrict__ out_lo, int HW, int W, int tiles_per_img, int num_tiles, int nsplit) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* a_base = smem;                              // kNG stages x (hi[3 blocks] | lo[3 blocks])
+  constexpr int kKB = k_blocks(GEO), kAStage = a_stage_bytes(GEO);
+  uint8_t* a_base = smem;                              // kNG stages x (hi[kKB blocks] | lo[kKB blocks])
   uint8_t* b_hi = smem + kNG * kAStage;
-  uint8_t* b_lo = b_hi + 3 * kBBlock;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(b_lo + 3 * kBBlock);
+  uint8_t* b_lo = b_hi + kKB * kBBlock;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_lo + kKB * kBBlock + (GEO ? 0 : kABlock));
   uint64_t* w_full = bars;                             // weights landed
   uint64_t* a_full = bars + 1;                         // [kNG] producers -> MMA
   uint64_t* a_empty = a_full + kNG;                    // [kNG] MMA done reading the stage -> producers
@@ -210,7 +217,7 @@ geo_lookup_convc1_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __gri
     umma::tmem_alloc(tmem_slot, kNG > 2 ? 256 : 128);
     umma::tmem_relinquish();
   }
-  // zero the A stages once: channels 162..191 are never written again and must read as 0
+  // zero the A stages once: the pad channels are never written again and must read as 0
   for (int i = tid; i < (kNG * kAStage) / 16; i += kThreads) reinterpret_cast<uint4*>(a_base)[i] = make_uint4(0, 0, 0, 0);
   umma::fence_proxy_async();
   umma::tc_fence_before();
@@ -243,22 +250,22 @@ geo_lookup_convc1_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __gri
     PixelIn px[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) px[i] = load_pixel(disp, coords, ta.nbase, ta.p0 + i * 16, HW, W, ta.valid);
-    Taps<L> bufA, bufB;
-    load_taps<L>(bufA, lv, Dg, px[0], g);
+    Taps<GEO ? L : 1> bufA, bufB;
+    load_taps<L, GEO>(bufA, lv, Dg, px[0], g);
     for (int k = 0; k < group_tiles; ++k) {
       const TileAt tn = tile_at(k + 1);
       PixelIn pn[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) pn[i] = load_pixel(disp, coords, tn.nbase, tn.p0 + i * 16, HW, W, tn.valid);
-      load_taps<L>(bufB, lv, Dg, px[1], g);
+      load_taps<L, GEO>(bufB, lv, Dg, px[1], g);
       umma::mbar_wait(a_empty + grp, (k & 1) ^ 1);     // the MMAs of this stage's previous tile have read it
-      emit_features<L, kF16>(bufA, a_s, prow, g, split);
-      load_taps<L>(bufA, lv, Dg, px[2], g);
-      emit_features<L, kF16>(bufB, a_s, 16 + prow, g, split);
-      load_taps<L>(bufB, lv, Dg, px[3], g);
-      emit_features<L, kF16>(bufA, a_s, 32 + prow, g, split);
-      load_taps<L>(bufA, lv, Dg, pn[0], g);
-      emit_features<L, kF16>(bufB, a_s, 48 + prow, g, split);
+      emit_features<L, kF16, GEO>(bufA, a_s, prow, g, split);
+      load_taps<L, GEO>(bufA, lv, Dg, px[2], g);
+      emit_features<L, kF16, GEO>(bufB, a_s, 16 + prow, g, split);
+      load_taps<L, GEO>(bufB, lv, Dg, px[3], g);
+      emit_features<L, kF16, GEO>(bufA, a_s, 32 + prow, g, split);
+      load_taps<L, GEO>(bufA, lv, Dg, pn[0], g);
+      emit_features<L, kF16, GEO>(bufB, a_s, 48 + prow, g, split);
       umma::fence_proxy_async();                       // generic-proxy smem writes -> visible to the tensor-core proxy
       umma::mbar_arrive(a_full + grp);
 #pragma unroll
@@ -267,8 +274,8 @@ geo_lookup_convc1_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __gri
   } else if (warp == kMmaWarp) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      umma::mbar_expect_tx(w_full, (uint32_t)(3 * kBBlock) * (split ? 2u : 1u));     // resident weights
-      for (int kb = 0; kb < 3; ++kb) {
+      umma::mbar_expect_tx(w_full, (uint32_t)(kKB * kBBlock) * (split ? 2u : 1u));     // resident weights
+      for (int kb = 0; kb < kKB; ++kb) {
         umma::tma_load_2d(b_hi + kb * kBBlock, &tmW_hi, w_full, kb * 64, 0);
         if (split) umma::tma_load_2d(b_lo + kb * kBBlock, &tmW_lo, w_full, kb * 64, 0);
       }
@@ -293,11 +300,11 @@ geo_lookup_convc1_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __gri
         ++issued;
         wait_backoff(acc_empty + grp, (use & 1) ^ 1);
         umma::tc_fence_after();
-        const uint32_t ah = umma::smem_u32(a_base + grp * kAStage), al = ah + 3 * kABlock;
+        const uint32_t ah = umma::smem_u32(a_base + grp * kAStage), al = ah + kKB * kABlock;
         const uint32_t acc = tmem_d + (uint32_t)(grp * kNOut);
         uint32_t accumulate = 0;
 #pragma unroll 1
-        for (int kb = 0; kb < 3; ++kb) {
+        for (int kb = 0; kb < kKB; ++kb) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint32_t ko = (uint32_t)k * 32u;
@@ -378,23 +385,23 @@ geo_lookup_convc1_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __gri
 
 }  // namespace
 
-extern "C" int as_geo_lookup_convc1(const float* const* geo_levels, int G, int Dg, const float* const* corr_levels,
-                                    const int* corr_widths, const int* corr_pitches, int num_levels, const float* disp,
-                                    const float* coords, const void* w_hi, const void* w_lo, const float* bias, int nsplit,
-                                    void* out_hi, void* out_lo, int B, int H, int W, int radius, as_stream_t stream) {
-  if (!geo_levels || !corr_levels || !corr_widths || !corr_pitches || !disp || !w_hi || !bias || !out_hi) return AS_ERR_BAD_ARG;
-  if (B <= 0 || H <= 0 || W <= 0 || Dg <= 0) return AS_ERR_BAD_ARG;
-  if (G != kG || radius != kR || num_levels < 1 || num_levels > 2) return AS_ERR_UNSUPPORTED;   // 162 (or 81) channels
+// shared host path of the two entry points
+static int launch_lookup_convc1(bool geo, const float* const* geo_levels, int Dg, const float* const* corr_levels,
+                                const int* corr_widths, const int* corr_pitches, int num_levels, const float* disp,
+                                const float* coords, const void* w_hi, const void* w_lo, const float* bias, int nsplit,
+                                void* out_hi, void* out_lo, int B, int H, int W, as_stream_t stream) {
   if (nsplit != 1 && nsplit != 3) return AS_ERR_BAD_ARG;
   if (nsplit == 3 && (!w_lo || !out_lo)) return AS_ERR_BAD_ARG;
   C1Levels lv{};
   for (int l = 0; l < num_levels; ++l) {
-    if (!geo_levels[l] || !corr_levels[l] || corr_pitches[l] < corr_widths[l]) return AS_ERR_BAD_ARG;
-    lv.geo[l] = geo_levels[l]; lv.corr[l] = corr_levels[l]; lv.width[l] = corr_widths[l]; lv.pitch[l] = corr_pitches[l];
+    if ((geo && !geo_levels[l]) || !corr_levels[l] || corr_pitches[l] < corr_widths[l]) return AS_ERR_BAD_ARG;
+    lv.geo[l] = geo ? geo_levels[l] : nullptr;
+    lv.corr[l] = corr_levels[l]; lv.width[l] = corr_widths[l]; lv.pitch[l] = corr_pitches[l];
   }
+  const int kpad = geo ? kKPad : 64;
   CUtensorMap tW_hi, tW_lo;
-  const uint64_t dims[2] = {(uint64_t)kKPad, (uint64_t)kNOut};
-  const uint64_t str[1] = {(uint64_t)kKPad * 2};
+  const uint64_t dims[2] = {(uint64_t)kpad, (uint64_t)kNOut};
+  const uint64_t str[1] = {(uint64_t)kpad * 2};
   const uint32_t box[2] = {64u, (uint32_t)kNOut};
   int rc;
   if ((rc = umma::make_tmap_bf16(&tW_hi, w_hi, 2, dims, str, box)) != AS_OK) return rc;
@@ -414,20 +421,45 @@ extern "C" int as_geo_lookup_convc1(const float* const* geo_levels, int G, int D
   cudaStream_t st = as_cu(stream);
   cudaError_t e;
   const bool f16 = as_operand_f16_internal() != 0;
-#define AS_C1_LAUNCH(LV, F)                                                                                              \
-  do {                                                                                                                   \
-    e = cudaFuncSetAttribute(geo_lookup_convc1_kernel<LV, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);       \
-    if (e != cudaSuccess) return (int)e;                                                                                 \
-    geo_lookup_convc1_kernel<LV, F><<<grid, kThreads, kSmem, st>>>(tW_hi, tW_lo, lv, Dg, disp, coords, bias,             \
-                                                                   (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, HW, W, \
-                                                                   tiles_per_img, (int)nt, nsplit);                      \
+#define AS_C1_LAUNCH(LV, F, GEO)                                                                                          \
+  do {                                                                                                                    \
+    e = cudaFuncSetAttribute(geo_lookup_convc1_kernel<LV, F, GEO>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
+                             smem_bytes(GEO));                                                                            \
+    if (e != cudaSuccess) return (int)e;                                                                                  \
+    geo_lookup_convc1_kernel<LV, F, GEO><<<grid, kThreads, smem_bytes(GEO), st>>>(                                        \
+        tW_hi, tW_lo, lv, Dg, disp, coords, bias, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, HW, W, tiles_per_img,   \
+        (int)nt, nsplit);                                                                                                 \
   } while (0)
-  if (num_levels == 2) {
-    if (f16) AS_C1_LAUNCH(2, true); else AS_C1_LAUNCH(2, false);
+  if (geo) {
+    if (num_levels == 2) { if (f16) AS_C1_LAUNCH(2, true, true); else AS_C1_LAUNCH(2, false, true); }
+    else { if (f16) AS_C1_LAUNCH(1, true, true); else AS_C1_LAUNCH(1, false, true); }
   } else {
-    if (f16) AS_C1_LAUNCH(1, true); else AS_C1_LAUNCH(1, false);
+    if (num_levels == 4) { if (f16) AS_C1_LAUNCH(4, true, false); else AS_C1_LAUNCH(4, false, false); }
+    else { if (f16) AS_C1_LAUNCH(2, true, false); else AS_C1_LAUNCH(2, false, false); }
   }
 #undef AS_C1_LAUNCH
   AS_RETURN_IF_LAUNCH_FAILED();
   return AS_OK;
+}
+
+extern "C" int as_geo_lookup_convc1(const float* const* geo_levels, int G, int Dg, const float* const* corr_levels,
+                                    const int* corr_widths, const int* corr_pitches, int num_levels, const float* disp,
+                                    const float* coords, const void* w_hi, const void* w_lo, const float* bias, int nsplit,
+                                    void* out_hi, void* out_lo, int B, int H, int W, int radius, as_stream_t stream) {
+  if (!geo_levels || !corr_levels || !corr_widths || !corr_pitches || !disp || !w_hi || !bias || !out_hi) return AS_ERR_BAD_ARG;
+  if (B <= 0 || H <= 0 || W <= 0 || Dg <= 0) return AS_ERR_BAD_ARG;
+  if (G != kG || radius != kR || num_levels < 1 || num_levels > 2) return AS_ERR_UNSUPPORTED;   // 162 (or 81) channels
+  return launch_lookup_convc1(true, geo_levels, Dg, corr_levels, corr_widths, corr_pitches, num_levels, disp, coords, w_hi, w_lo,
+                              bias, nsplit, out_hi, out_lo, B, H, W, stream);
+}
+
+extern "C" int as_corr_lookup_convc1(const float* const* corr_levels, const int* corr_widths, const int* corr_pitches,
+                                     int num_levels, const float* disp, const float* coords, const void* w_hi, const void* w_lo,
+                                     const float* bias, int nsplit, void* out_hi, void* out_lo, int B, int H, int W, int radius,
+                                     as_stream_t stream) {
+  if (!corr_levels || !corr_widths || !corr_pitches || !disp || !w_hi || !bias || !out_hi) return AS_ERR_BAD_ARG;
+  if (B <= 0 || H <= 0 || W <= 0) return AS_ERR_BAD_ARG;
+  if (radius != kR || (num_levels != 2 && num_levels != 4)) return AS_ERR_UNSUPPORTED;          // 18 or 36 channels
+  return launch_lookup_convc1(false, nullptr, 1, corr_levels, corr_widths, corr_pitches, num_levels, disp, coords, w_hi, w_lo,
+                              bias, nsplit, out_hi, out_lo, B, H, W, stream);
 }

@@ -175,6 +175,12 @@ class CorrBlock1D:
             return _CorrLookupFn.apply(disp, coords, (self._widths, self._pitches, self.radius), *self._bufs)
         return _corr_lookup(self._bufs, self._widths, self._pitches, self.radius, disp, coords)
 
+    def deferred(self, disp, coords):
+        """The same lookup, not yet run (see Combined_Geo_Encoding_Volume.deferred): the tensor-core engines fuse it
+        with BasicMotionEncoder.convc1."""
+        disp, coords = _check_disp_coords(disp, coords)
+        return DeferredCorrLookup(self, disp, coords)
+
     @staticmethod
     def corr(fmap1, fmap2, mask_invalid=False):
         """[B,D,H,W1] x [B,D,H,W2] -> [B,H,W1,1,W2] (geometry.py:46-56); no 1/sqrt(D) scaling."""
@@ -366,3 +372,47 @@ class DeferredGeoLookup:
             if self.events is not None:
                 e1.record()
                 self.events.append((e0, e1))
+
+
+class DeferredCorrLookup:
+    """(pyramid, disp, coords) of one CorrBlock1D.__call__ (corePrune_RAFT/geometry.py:24-43), evaluated by its consumer."""
+
+    def __init__(self, blk, disp, coords):
+        self.blk, self.disp, self.coords = blk, disp, coords
+        B, _, H, W = disp.shape
+        self.shape = (B, blk.num_levels * (2 * blk.radius + 1), H, W)
+        self.device = disp.device
+        self.events = None
+
+    @property
+    def fusable(self):
+        b = self.blk
+        needs_grad = torch.is_grad_enabled() and any(t.requires_grad for t in b._bufs)
+        return b.radius == 4 and b.num_levels in (2, 4) and min(b._widths) > 0 and not needs_grad
+
+    def materialize(self):
+        return self.blk(self.disp, self.coords)
+
+    @staticmethod
+    def pack_convc1_weight(weight, split=True):
+        """convc1.weight [64, L*9, 1, 1] -> bf16 hi/lo [64][64], channel (level l, tap k) at K = l*10 + k."""
+        w = weight.detach().float().reshape(weight.shape[0], -1)
+        Cout, Cin = w.shape
+        if Cout != 64 or Cin not in (18, 36):
+            raise RuntimeError("fused lookup+convc1 needs convc1: 18|36 -> 64 channels")
+        c = torch.arange(Cin, device=w.device)
+        wp = torch.zeros((Cout, 64), device=w.device, dtype=torch.float32)
+        wp[:, (c // 9) * 10 + (c % 9)] = w
+        hi = torch.empty((Cout, 64), device=w.device, dtype=torch.bfloat16)
+        lo = torch.empty_like(hi) if split else None
+        with torch.cuda.device(w.device):
+            L.call("as_pack_conv_weight_bf16", wp.data_ptr(), hi.data_ptr(), L.ptr(lo), Cout, 64, 1, 1, Cout, 64, L.stream_ptr())
+        return hi, lo
+
+    def convc1_planes(self, w_hi, w_lo, bias, out_hi, out_lo):
+        b = self.blk
+        B, _, H, W = self.disp.shape
+        with torch.cuda.device(self.device):
+            L.call("as_corr_lookup_convc1", L.ptr_array(b._bufs), L.int_array(b._widths), L.int_array(b._pitches),
+                   b.num_levels, self.disp.data_ptr(), L.ptr(self.coords), w_hi.data_ptr(), L.ptr(w_lo), bias.data_ptr(),
+                   3 if w_lo is not None else 1, out_hi.data_ptr(), L.ptr(out_lo), B, H, W, b.radius, L.stream_ptr())

@@ -94,7 +94,9 @@ def raft_iterations(update_block: BasicMultiUpdateBlock, match_left, match_right
     B, _, H, W = match_left.shape
     coords = pixel_coords(B, H, W, match_left.device)
     disp = match_left.new_zeros((B, 1, H, W))       # prune_raft_stereo.py:274
-    return _iterate(corr_fn, update_block, net_list, inp_list, disp, coords, iters, slow_fast_gru, keep_all)
+    fused = corr_fn.deferred if _FUSION["on"] and get_update_engine() != "fp32" else None
+    return _iterate(corr_fn, update_block, net_list, inp_list, disp, coords, iters, slow_fast_gru, keep_all,
+                    fused_lookup=fused)
 
 
 class HotLoopGraph:

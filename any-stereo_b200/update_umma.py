@@ -19,7 +19,9 @@ import weakref
 import torch
 
 from . import _lib as L
-from .geometry import DeferredGeoLookup
+from .geometry import DeferredGeoLookup, DeferredCorrLookup
+
+_DEFERRED = (DeferredGeoLookup, DeferredCorrLookup)
 
 
 _OVERLAP = {"on": False}
@@ -86,16 +88,16 @@ def _weights(ub, name, convs, n_pad=None, cin_pad=None, split=True):
     return hit
 
 
-def _fused_c1_weights(ub, split):
-    """convc1 weights in the K order of the fused lookup kernel (geometry.DeferredGeoLookup.pack_convc1_weight)."""
+def _fused_c1_weights(ub, split, kind=DeferredGeoLookup):
+    """convc1 weights in the K order of the fused lookup kernel (geometry.Deferred*Lookup.pack_convc1_weight)."""
     st = _state(ub)["w"]
     c = ub.encoder.convc1
-    key = (split, L.operand_format(), c.weight.data_ptr(), c.weight._version, c.bias.data_ptr(), c.bias._version)
+    key = (split, L.operand_format(), kind.__name__, c.weight.data_ptr(), c.weight._version, c.bias.data_ptr(), c.bias._version)
     hit = st.get("convc1.fused")
     if hit is not None and hit["key"] == key:
         return hit
     with torch.no_grad():
-        hi, lo = DeferredGeoLookup.pack_convc1_weight(c.weight, split)
+        hi, lo = kind.pack_convc1_weight(c.weight, split)
         bias = c.bias.detach().float().contiguous()
     hit = dict(key=key, hi=hi, lo=lo, bias=bias)
     st["convc1.fused"] = hit
@@ -262,8 +264,8 @@ def forward(ub, net, inp, corr=None, disp=None, iter04=True, iter08=True, iter16
         sw = _small_weights(ub)
         cpad = (Cc + 63) // 64 * 64
         c1 = _Planes((B, H, W, 64), dev, split)
-        if isinstance(corr, DeferredGeoLookup):      # lookup + convc1 + ReLU in one kernel, features stay on chip
-            wf = _fused_c1_weights(ub, split)
+        if isinstance(corr, _DEFERRED):              # lookup + convc1 + ReLU in one kernel, features stay on chip
+            wf = _fused_c1_weights(ub, split, type(corr))
             corr.convc1_planes(wf["hi"], wf["lo"], wf["bias"], c1.hi, c1.lo)
         else:
             wc1 = _weights(ub, "convc1", [e.convc1], cin_pad=cpad, split=split)
@@ -291,10 +293,10 @@ def forward(ub, net, inp, corr=None, disp=None, iter04=True, iter08=True, iter16
         hs = [None if t is None else _nhwc_view(t.detach().float())[0] for t in net]
         enc_job = None
         if iter04:
-            if isinstance(corr, DeferredGeoLookup):
+            if isinstance(corr, _DEFERRED):
                 if not corr.fusable or ub.encoder.convc1.out_channels != 64:
                     corr = corr.materialize()
-            if not isinstance(corr, DeferredGeoLookup):
+            if not isinstance(corr, _DEFERRED):
                 L.require_cuda(corr, "corr", contiguous=False)
                 corr = corr.detach().float().contiguous()
             L.require_cuda(disp, "disp", contiguous=False)

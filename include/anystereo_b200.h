@@ -145,6 +145,12 @@ int as_geo_lookup_convc1(const float* const* geo_levels, int G, int Dg,
                          int num_levels, const float* disp, const float* coords,
                          const void* w_hi, const void* w_lo, const float* bias, int nsplit,
                          void* out_hi, void* out_lo, int B, int H, int W, int radius, as_stream_t stream);
+/* The RAFT-family twin: CorrBlock1D.__call__ (corePrune_RAFT/geometry.py:24-43) fused with convc1 (L*9 -> 64) + ReLU.
+ * num_levels 2 or 4, radius 4.  w_hi/w_lo: bf16 [64][64] with channel (level l, tap k) at K = l*10 + k, zeros elsewhere. */
+int as_corr_lookup_convc1(const float* const* corr_levels, const int* corr_widths, const int* corr_pitches,
+                          int num_levels, const float* disp, const float* coords,
+                          const void* w_hi, const void* w_lo, const float* bias, int nsplit,
+                          void* out_hi, void* out_lo, int B, int H, int W, int radius, as_stream_t stream);
 /* index-parity probe: integer base tap (floor(x)-r) and fractional weight per pixel for one level.
  * kind 0 = geo position disp/2^l, kind 1 = corr position (coords-disp)/2^l. */
 int as_lookup_taps(const float* disp, const float* coords, int B, int H, int W, int radius,

@@ -471,3 +471,53 @@ def test_fp16_operand_format_saturates(A):
     ref = x.cpu().clamp(-65504.0, 65504.0).half().float()
     assert torch.equal(got, ref)
     assert L.lib().as_set_operand_format(7) == -1
+
+
+@pytest.mark.parametrize("engine,tol", [("bf16x3", 1e-4), ("fp16", 3e-3)])
+@pytest.mark.parametrize("shape", [(2, 5, 23, 4), (1, 9, 150, 4), (1, 16, 24, 2), (3, 7, 40, 4)])
+def test_fused_raft_lookup_convc1_vs_oracle(A, engine, tol, shape):
+    """RAFT twin of the fused kernel: CorrBlock1D lookup (L = 4 or 2 levels) + convc1 + ReLU against
+    relu(conv1x1(oracle lookup)); ragged tiles, out-of-range disparities, coarse levels narrower than the window."""
+    B, H, W, Lv = shape
+    c = cases.raft_corr_case(seed=41 + H, B=B, D=16, H=H, W=W, L=Lv)
+    rng = np.random.RandomState(W + Lv)
+    disp = torch.from_numpy(rng.uniform(-8, W + 8, (B, 1, H, W)).astype("float32"))
+    disp[0, 0, 0, :3] = torch.tensor([0.0, 1.0, 3.0])
+    coords = torch.arange(W).float().reshape(1, 1, W, 1).repeat(B, H, 1, 1)
+    w = torch.from_numpy(rng.standard_normal((64, Lv * 9, 1, 1)).astype("float32")) * 0.3
+    b = torch.from_numpy(rng.standard_normal(64).astype("float32")) * 0.1
+    feat = O.corrblock1d_lookup(O.corr_pyramid(O.all_pairs_corr(c["f1"], c["f2"]), Lv), disp, coords, 4, exact=True)
+    ref = torch.relu(torch.nn.functional.conv2d(feat.double(), w.double(), b.double())).float()
+    A.set_corr_mode("fp32")
+    A.set_update_engine(engine)
+    blk = A.CorrBlock1D(c["f1"].cuda(), c["f2"].cuda(), num_levels=Lv, radius=4)
+    split = engine == "bf16x3"
+    d = blk.deferred(disp.cuda(), coords.cuda())
+    assert d.fusable and d.shape == (B, Lv * 9, H, W)
+    w_hi, w_lo = type(d).pack_convc1_weight(w.cuda(), split)
+    out_hi = torch.full((B, H, W, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+    out_lo = torch.full_like(out_hi, float("nan")) if split else None
+    d.convc1_planes(w_hi, w_lo, b.cuda(), out_hi, out_lo)
+    torch.cuda.synchronize()
+    A.set_update_engine("fp32")
+    widen = (lambda t: t.view(torch.float16).float()) if engine == "fp16" else (lambda t: t.float())
+    got = widen(out_hi) + (widen(out_lo) if split else 0)
+    assert rel(got.permute(0, 3, 1, 2), ref) < tol
+
+
+def test_fused_raft_lookup_matches_unfused_loop(A):
+    c = cases.loop_case("raft", seed=79, B=2, H=13, W=37)
+    m = make_block(A, "raft", 9)
+    A.set_update_engine("bf16x3")
+    A.set_corr_mode("bf16x3")
+    args = [c["f1"].cuda(), c["f2"].cuda(), [t.cuda() for t in c["net"]], [[t.cuda() for t in l] for l in c["inp"]]]
+    prev = A.set_lookup_fusion(True)
+    d_f, net_f = A.raft_iterations(m, *args, 6)
+    A.set_lookup_fusion(False)
+    d_u, net_u = A.raft_iterations(m, *args, 6)
+    A.set_lookup_fusion(prev)
+    A.set_update_engine("fp32")
+    A.set_corr_mode("fp32")
+    assert rel(d_f, d_u) < 1e-5
+    for a, b in zip(net_f, net_u):
+        assert rel(a, b) < 1e-5
