@@ -210,8 +210,7 @@ def run_ours(args):
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
     A.set_update_engine(args.engine)
-    if args.overlap:
-        A.update_umma.set_encoder_overlap(True)
+    A.update_umma.set_encoder_overlap(not args.no_overlap)
     A.set_lookup_fusion(not args.no_fusion)
     A.set_corr_mode(args.corr_mode or {"fp32": "fp32", "bf16x3": "bf16x3", "bf16": "bf16", "fp16": "bf16x3"}[args.engine])
     B = args.pairs_per_gpu
@@ -476,7 +475,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true")
     ap.add_argument("--no-fusion", action="store_true", help="materialise the 162-channel lookup tensor (A/B knob)")
-    ap.add_argument("--overlap", action="store_true", help="motion encoder on a side stream (A/B knob, default off)")
+    ap.add_argument("--no-overlap", action="store_true", help="keep the motion encoder on the main stream (A/B knob)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -521,3 +521,30 @@ def test_fused_raft_lookup_matches_unfused_loop(A):
     assert rel(d_f, d_u) < 1e-5
     for a, b in zip(net_f, net_u):
         assert rel(a, b) < 1e-5
+
+
+@pytest.mark.parametrize("family", ["igev", "raft"])
+def test_encoder_side_stream_overlap_is_exact(A, family):
+    """The motion encoder forked onto a side stream (default) produces bit-identical results to the single-stream
+    schedule, eagerly and across repeated calls (stream/event ordering, record_stream lifetime)."""
+    c = cases.loop_case(family, seed=91, B=2, H=24, W=40)
+    m = make_block(A, family, 3)
+    A.set_update_engine("bf16x3")
+    A.set_corr_mode("bf16x3")
+    net = [t.cuda() for t in c["net"]]
+    inp = [[t.cuda() for t in l] for l in c["inp"]]
+
+    def run():
+        if family == "igev":
+            return A.igev_iterations(m, c["f1"].cuda(), c["f2"].cuda(), c["geo"].cuda(), net, inp, c["init_disp"].cuda(), 5)[0]
+        return A.raft_iterations(m, c["f1"].cuda(), c["f2"].cuda(), net, inp, 5)[0]
+
+    A.update_umma.set_encoder_overlap(False)
+    ref = run()
+    A.update_umma.set_encoder_overlap(True)
+    outs = [run() for _ in range(3)]
+    torch.cuda.synchronize()
+    A.set_update_engine("fp32")
+    A.set_corr_mode("fp32")
+    for o in outs:
+        assert torch.equal(o, ref)
