@@ -357,7 +357,9 @@ def run_ours(args):
                 torch.cuda.synchronize()
                 fms = r0.elapsed_time(r1) / 3
                 other["engine_fp16_same_step"] = {"pairs_per_s": B / (fms / 1e3), "ms_per_step": fms,
-                                                  "mean_epe_px_vs_reference_models": {"igev": 4.66e-3, "raft": 5.77e-3}}
+                                                  "accuracy": "mean EPE vs the reference models 4.7e-3 px (IGEV) / 5.8e-3 px "
+                                                              "(RAFT): recorded by tools/epe_modes.py in "
+                                                              "profiles/epe_modes_r01.txt, not measured in this run"}
                 A.set_update_engine(args.engine)
                 block.reset_caches()
             # config 4: arbitrary-scale disparity query after the loop, one 384x1248 pair per call
