@@ -72,8 +72,6 @@ __device__ __forceinline__ void store_split32(const float* v, __nv_bfloat16* hi,
 // accumulator lanes.  Per SM the B reads and the B ring footprint halve (4 weight stages instead of 2).
 //   full barriers live in the leader (both producers arm them remotely, TMA credits them with cta_group::2),
 //   "slot free" / "accumulator ready" are multicast commits to both CTAs, "accumulator drained" arrives remotely.
-constexpr bool kKeepA = true;   // hi*hi / hi*lo go through the A-collector helpers (plain MMAs unless AS_UMMA_KEEP_A)
-
 template <bool TWO>
 __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_constant__ ConvMaps maps,
                                                                 const ConvUmmaParams p) {
@@ -208,23 +206,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
             for (int k = 0; k < 4; ++k) {
               const uint32_t ko = (uint32_t)k * 32u;
               const uint64_t dah = umma::smem_desc_k_sw128(a_hi + ko), dbh = umma::smem_desc_k_sw128(b_hi + ko);
+              if (TWO) umma::mma_bf16_ss_2sm(tmem_d, dah, dbh, idesc, accumulate);
+              else umma::mma_bf16_ss(tmem_d, dah, dbh, idesc, accumulate);
+              accumulate = 1u;
               if (p.nsplit == 3) {
-                // hi*hi and hi*lo share the A tile: the first MMA parks it in the collector, the second reuses it
                 const uint64_t dal = umma::smem_desc_k_sw128(a_lo + ko), dbl = umma::smem_desc_k_sw128(b_lo + ko);
                 if (TWO) {
-                  if (kKeepA) { umma::mma_bf16_ss_2sm_keep_a(tmem_d, dah, dbh, idesc, accumulate); umma::mma_bf16_ss_2sm_reuse_a(tmem_d, dah, dbl, idesc, 1u); }
-                  else { umma::mma_bf16_ss_2sm(tmem_d, dah, dbh, idesc, accumulate); umma::mma_bf16_ss_2sm(tmem_d, dah, dbl, idesc, 1u); }
+                  umma::mma_bf16_ss_2sm(tmem_d, dah, dbl, idesc, 1u);
                   umma::mma_bf16_ss_2sm(tmem_d, dal, dbh, idesc, 1u);
                 } else {
-                  if (kKeepA) { umma::mma_bf16_ss_keep_a(tmem_d, dah, dbh, idesc, accumulate); umma::mma_bf16_ss_reuse_a(tmem_d, dah, dbl, idesc, 1u); }
-                  else { umma::mma_bf16_ss(tmem_d, dah, dbh, idesc, accumulate); umma::mma_bf16_ss(tmem_d, dah, dbl, idesc, 1u); }
+                  umma::mma_bf16_ss(tmem_d, dah, dbl, idesc, 1u);
                   umma::mma_bf16_ss(tmem_d, dal, dbh, idesc, 1u);
                 }
-              } else {
-                if (TWO) umma::mma_bf16_ss_2sm(tmem_d, dah, dbh, idesc, accumulate);
-                else umma::mma_bf16_ss(tmem_d, dah, dbh, idesc, accumulate);
               }
-              accumulate = 1u;
             }
             if (TWO) umma::mma_commit_2sm(&emptyB[sb], 3); else umma::mma_commit(&emptyB[sb]);
             if (++sb == p.nstB) { sb = 0; phb ^= 1; }

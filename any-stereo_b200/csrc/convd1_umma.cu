@@ -105,12 +105,10 @@ convd1_umma_kernel(const __grid_constant__ CUtensorMap tWh, const __grid_constan
       for (int k = 0; k < 4; ++k) {
         const uint32_t ko = (uint32_t)k * 32u;
         const uint64_t dah = umma::smem_desc_k_sw128(act_s + ko), dbh = umma::smem_desc_k_sw128(bh + ko);
-        if (split) {                                   // hi*hi parks the A tile in the collector, hi*lo reuses it
-          umma::mma_bf16_ss_keep_a(tmem_d, dah, dbh, idesc, k ? 1u : 0u);
-          umma::mma_bf16_ss_reuse_a(tmem_d, dah, umma::smem_desc_k_sw128(bl + ko), idesc, 1u);
+        umma::mma_bf16_ss(tmem_d, dah, dbh, idesc, k ? 1u : 0u);
+        if (split) {
+          umma::mma_bf16_ss(tmem_d, dah, umma::smem_desc_k_sw128(bl + ko), idesc, 1u);
           umma::mma_bf16_ss(tmem_d, umma::smem_desc_k_sw128(act_s + kBlk + ko), dbh, idesc, 1u);
-        } else {
-          umma::mma_bf16_ss(tmem_d, dah, dbh, idesc, k ? 1u : 0u);
         }
       }
       umma::mma_commit(mma_done);

@@ -211,13 +211,11 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
           for (int k = 0; k < nk; ++k) {
             const uint32_t ko = (uint32_t)k * 32u;   // 16 bf16 = 32 bytes inside the 128-byte swizzle row
             const uint64_t dah = umma::smem_desc_k_sw128(a_hi + ko), dbh = umma::smem_desc_k_sw128(b_hi + ko);
-            if (p.nsplit == 3) {                     // hi*hi parks the A tile in the collector, hi*lo reuses it
+            umma::mma_bf16_ss(tmem_d, dah, dbh, idesc, (kb | k) != 0);
+            if (p.nsplit == 3) {
               const uint64_t dal = umma::smem_desc_k_sw128(a_lo + ko), dbl = umma::smem_desc_k_sw128(b_lo + ko);
-              umma::mma_bf16_ss_keep_a(tmem_d, dah, dbh, idesc, (kb | k) != 0);
-              umma::mma_bf16_ss_reuse_a(tmem_d, dah, dbl, idesc, 1u);
+              umma::mma_bf16_ss(tmem_d, dah, dbl, idesc, 1u);
               umma::mma_bf16_ss(tmem_d, dal, dbh, idesc, 1u);
-            } else {
-              umma::mma_bf16_ss(tmem_d, dah, dbh, idesc, (kb | k) != 0);
             }
           }
           umma::mma_commit(&empty[stage]);          // smem slot reusable once these MMAs retire

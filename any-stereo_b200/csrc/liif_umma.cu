@@ -193,14 +193,12 @@ __device__ __forceinline__ void issue_layer(uint32_t acc, uint32_t a_hi, uint32_
       const uint32_t ko = (uint32_t)k * 32u;
       const uint64_t dah = umma::smem_desc_k_sw128(a_hi + kb * kBlk + ko);
       const uint64_t dbh = umma::smem_desc_k_sw128(b_hi + kb * b_blk_bytes + ko);
-      if (split) {                                     // hi*hi parks the A tile in the collector, hi*lo reuses it
-        umma::mma_bf16_ss_keep_a(acc, dah, dbh, idesc, accumulate);
-        umma::mma_bf16_ss_reuse_a(acc, dah, umma::smem_desc_k_sw128(b_lo + kb * b_blk_bytes + ko), idesc, 1u);
-        umma::mma_bf16_ss(acc, umma::smem_desc_k_sw128(a_lo + kb * kBlk + ko), dbh, idesc, 1u);
-      } else {
-        umma::mma_bf16_ss(acc, dah, dbh, idesc, accumulate);
-      }
+      umma::mma_bf16_ss(acc, dah, dbh, idesc, accumulate);
       accumulate = 1u;
+      if (split) {
+        umma::mma_bf16_ss(acc, dah, umma::smem_desc_k_sw128(b_lo + kb * b_blk_bytes + ko), idesc, 1u);
+        umma::mma_bf16_ss(acc, umma::smem_desc_k_sw128(a_lo + kb * kBlk + ko), dbh, idesc, 1u);
+      }
     }
   }
 }

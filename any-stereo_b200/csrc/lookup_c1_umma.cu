@@ -310,14 +310,12 @@ geo_lookup_convc1_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __gri
             const uint32_t ko = (uint32_t)k * 32u;
             const uint64_t dah = umma::smem_desc_k_sw128(ah + kb * kABlock + ko);
             const uint64_t dbh = umma::smem_desc_k_sw128(bh + kb * kBBlock + ko);
-            if (split) {                               // hi*hi parks the A tile in the collector, hi*lo reuses it
-              umma::mma_bf16_ss_keep_a(acc, dah, dbh, idesc, accumulate);
-              umma::mma_bf16_ss_reuse_a(acc, dah, umma::smem_desc_k_sw128(bl + kb * kBBlock + ko), idesc, 1u);
-              umma::mma_bf16_ss(acc, umma::smem_desc_k_sw128(al + kb * kABlock + ko), dbh, idesc, 1u);
-            } else {
-              umma::mma_bf16_ss(acc, dah, dbh, idesc, accumulate);
-            }
+            umma::mma_bf16_ss(acc, dah, dbh, idesc, accumulate);
             accumulate = 1u;
+            if (split) {
+              umma::mma_bf16_ss(acc, dah, umma::smem_desc_k_sw128(bl + kb * kBBlock + ko), idesc, 1u);
+              umma::mma_bf16_ss(acc, umma::smem_desc_k_sw128(al + kb * kABlock + ko), dbh, idesc, 1u);
+            }
           }
         }
         umma::mma_commit(a_empty + grp);

@@ -147,3 +147,20 @@ def test_no_product_import_of_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("# oracle", ""), f
+
+
+def test_no_predicated_tensor_core_mma_in_sass():
+    """Lint against a ptxas code-generation hazard hit in this repo: with an `if (split) {3 MMAs} else {1 MMA}` shape
+    around inline-asm tcgen05.mma, the non-split path of one kernel was emitted as `@UPn UTCHMMA` under a stale uniform
+    predicate and silently skipped a K-step.  Every tcgen05 MMA in the library must be unpredicated."""
+    import re
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    so = os.path.join(ROOT, "any-stereo_b200", "csrc", "libanystereo_b200.so")
+    sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True, check=True).stdout
+    mma = [l for l in sass.splitlines() if "UTCHMMA" in l]
+    assert len(mma) > 50
+    bad = [l.strip() for l in mma if re.search(r"@!?UP\d+\s+UTCHMMA", l)]
+    assert not bad, bad[:3]
