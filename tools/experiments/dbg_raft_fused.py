@@ -1,3 +1,8 @@
+"""Debug aid kept from the RAFT fused lookup+convc1 investigation ("things tried"): runs the kernel in the
+bf16x3 / bf16 / fp16 engines against relu(conv1x1(oracle lookup)) and, for the single-MMA path, fits which K-steps and
+which pyramid levels the result contains (a dropped K-step shows up as a level coefficient near 0).
+    python tools/experiments/dbg_raft_fused.py      (GPU)
+"""
 import sys, numpy as np, torch
 sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests/golden')
 import anystereo_b200 as A, cases
