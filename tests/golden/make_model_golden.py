@@ -187,7 +187,8 @@ def main_igev():
     print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024), "up_disp", tuple(up_cap["out"].shape))
     cis.Combined_Geo_Encoding_Volume = orig_geo
     cis.build_gwc_volume = orig_gwc
-    out = {"f1": captured["f1"], "f2": captured["f2"], "geo": captured["geo"], "gwc": captured["gwc"],
+    out = {"classifier_weight": model.classifier.weight.detach().clone(),      # init-disparity head, SURVEY 8(f)-3
+           "f1": captured["f1"], "f2": captured["f2"], "geo": captured["geo"], "gwc": captured["gwc"],
            "init_disp": captured["init_disp"], "disp_lowres": final, "iters": ITERS}
     for i in range(3):
         out["net%d" % i] = captured["net"][i]

@@ -401,3 +401,13 @@ def test_init_disparity_fullsize_config2(A):
     ref = O.disparity_regression(torch.softmax(torch.nn.functional.conv3d(geo, w, padding=1).squeeze(1), dim=1), 48)
     torch.cuda.synchronize()
     assert float((disp - ref).abs().max()) < 2e-3           # disparities up to 47; 1e-4 relative
+
+
+def test_model_level_init_disparity(A, golden):
+    """Initial disparity of the real reference model graph (tests/golden/model_igev_boundary.npz) from its own
+    geometry-encoding volume and classifier weight, through the fused kernel."""
+    g = golden("model_igev_boundary")
+    disp = A.init_disparity(torch.from_numpy(g["geo"]).cuda(), torch.from_numpy(g["classifier_weight"]).cuda())
+    torch.cuda.synchronize()
+    ref = torch.from_numpy(g["init_disp"])
+    assert float((disp.cpu() - ref).abs().max()) < 1e-4 * float(ref.abs().max())

@@ -245,3 +245,12 @@ def test_init_disparity_oracle_vs_reference(golden):
     assert rel(prob, g["prob"]) < 1e-5
     assert rel(disp, g["init_disp"]) < 1e-5
     assert np.array_equal(O.disparity_regression(torch.from_numpy(g["prob"]), 12).numpy(), g["init_disp"])
+
+
+def test_init_disparity_oracle_vs_model_graph(golden):
+    """The init-disparity restatement against the tensor the real continuous_IGEVStereo.forward computes
+    (classifier -> softmax -> disparity_regression, continuous_IGEVstereo.py:267-268) from its own geometry volume."""
+    g = golden("model_igev_boundary")
+    disp, _ = O.init_disparity(torch.from_numpy(g["geo"]), torch.from_numpy(g["classifier_weight"]))
+    assert disp.shape == g["init_disp"].shape
+    assert rel(disp, g["init_disp"]) < 1e-5
