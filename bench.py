@@ -448,7 +448,11 @@ def run_ours(args):
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": look_bpp * n_pix, "algorithmic_bytes_per_pixel": look_bpp,
-                     "avg_launch_us": look_avg_us, "launches_timed": len(look_us)},
+                     "avg_launch_us": look_avg_us, "launches_timed": len(look_us),
+                     "note": ("fused kernel: the three kernels it replaces (lookup, bf16 split, convc1) moved 3812 B/pixel; "
+                              "ncu shows it bound by the SM's L1/shared-memory data pipe (64 % busy), not by HBM -- "
+                              "DESIGN.md section 5; --no-fusion reports the plain lookup kernel (1372 B/pixel, frac 0.47-0.49)")
+                     if fused else "plain lookup kernel (--no-fusion)"},
         "roofline_update_block": None if args.engine == "fp32" else {
             "kernels": "conv_umma_kernel (tcgen05) + small kernels per iteration" + (" + the fused lookup/convc1 kernel" if fused else ""), "bound": "tensor",
             "achieved": issued / (upd_avg_us * 1e-6) / 1e12, "peak": tpeak, "unit": "TFLOP/s", "frac": issued / (upd_avg_us * 1e-6) / 1e12 / tpeak,
