@@ -440,7 +440,7 @@ def run_ours(args):
                    "pairs_per_gpu": B, "iters": ITERS, "engine": args.engine, "corr_mode": A.get_corr_mode(),
                    "lookup_fused_with_convc1": fused,
                    "parallelism": "pairs sharded across ranks, no data-path collective",
-                   "l2": "working set per step (~1 GB of pyramids + 155 MB lookup output per iteration) exceeds the 126 MB L2; no explicit flush"},
+                   "l2": "inputs larger than L2: per step ~1 GB of pyramids + ~1.8 GB of activations per iteration stream through the 126 MB L2; no explicit flush"},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": host_bytes(hh),
                 "d2h_bytes_per_step": 4 * B * H4 * W4, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
