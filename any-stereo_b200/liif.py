@@ -93,8 +93,8 @@ class liif_out_multi_scale_Training(nn.Module):
             raise NotImplementedError("the fused MLP kernel is built for hidden sizes [128, 64, 64]")
         if unfold not in ("with_ISU", "with_v2ISU"):
             raise NotImplementedError("unfold_similarity %r is outside the built hot path" % (unfold,))
-        if number_input not in (2, 3) or len(chanels) != number_input:
-            raise NotImplementedError("2 or 3 input feature maps")
+        if number_input not in (1, 2, 3) or len(chanels) != number_input:
+            raise NotImplementedError("1 to 3 input feature maps")
         self.unfold = unfold
         self.pos_dim = 2
         self.outputdim = 9
@@ -223,10 +223,15 @@ def context_upsample_multiscale_train(disp_low, up_weights, hr_coord):
 
 
 def upsample_disp(liif_up, disp, hidden_layer, stem_4x, stem_2x, stem_1x=None, hr_coord=None, scale=None):
-    """continuous_IGEVStereo.upsample_disp, multi_training branch without disparity_norm
-    (continuous_IGEVstereo.py:192-237) -> [B, 1, Q]."""
-    x = torch.cat((stem_4x, hidden_layer), 1)
-    feats = [x, stem_2x] if stem_1x is None else [stem_1x, stem_2x, x]
+    """continuous_IGEVStereo.upsample_disp / continuous_RaftStereo.upsample_disp, multi_training branch without
+    disparity_norm (continuous_IGEVstereo.py:192-237, prune_raft_stereo.py:200-242) -> [B, 1, Q]."""
+    x = torch.cat((stem_4x, hidden_layer), 1) if stem_4x is not None else hidden_layer    # prune_raft_stereo.py:203-206
+    if stem_1x is not None:
+        feats = [stem_1x, stem_2x, x]
+    elif stem_2x is not None:
+        feats = [x, stem_2x]
+    else:
+        feats = [x]                                                                        # prune_raft_stereo.py:221-222
     B = disp.shape[0]
     sc = torch.as_tensor(scale, device=disp.device, dtype=torch.float32).reshape(-1)
     if sc.numel() == 1:

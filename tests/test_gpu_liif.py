@@ -155,3 +155,21 @@ def test_liif_fullsize_config4_vs_torch_same_gpu(A):
     torch.cuda.synchronize()
     assert rel(got, ref) < 1e-4
     assert float((got - ref).abs().mean()) < 1e-3          # pixels of full-resolution disparity
+
+
+def test_liif_single_input_raft_style(A):
+    """continuous_RaftStereo.upsample_disp with neither stem (prune_raft_stereo.py:221-222): one feature map."""
+    rng = np.random.RandomState(8)
+    B, h, w, Q = 2, 7, 11, 500
+    hid = torch.from_numpy(np.tanh(rng.standard_normal((B, 128, h, w))).astype("float32"))
+    coords = torch.from_numpy(rng.uniform(-1, 1, (B, Q, 2)).astype("float32"))
+    disp = torch.from_numpy(rng.uniform(0, 30, (B, 1, h, w)).astype("float32"))
+    scale = torch.tensor([1.5, 2.0])
+    c = dict(feats=[hid], n_in=1, in_dim=128 + 8 + 2)
+    m = make_module(A, c, 5)
+    A.set_update_engine("bf16x3")
+    got = A.upsample_disp(m, disp.cuda(), hid.cuda(), None, None, None, hr_coord=coords.cuda(), scale=scale.cuda())
+    torch.cuda.synchronize()
+    A.set_update_engine("fp32")
+    ref = LO.upsample_disp_multiscale(LO.make_liif_params(138, seed=5), disp, [hid], coords, scale)
+    assert rel(got, ref) < 1e-4
