@@ -222,7 +222,8 @@ def context_upsample_multiscale_train(disp_low, up_weights, hr_coord):
     return out
 
 
-def upsample_disp(liif_up, disp, hidden_layer, stem_4x, stem_2x, stem_1x=None, hr_coord=None, scale=None):
+def upsample_disp(liif_up, disp, hidden_layer, stem_4x, stem_2x, stem_1x=None, hr_coord=None, scale=None,
+                  disparity_norm=False, disparity_norm2=False):
     """continuous_IGEVStereo.upsample_disp / continuous_RaftStereo.upsample_disp, multi_training branch without
     disparity_norm (continuous_IGEVstereo.py:192-237, prune_raft_stereo.py:200-242) -> [B, 1, Q]."""
     x = torch.cat((stem_4x, hidden_layer), 1) if stem_4x is not None else hidden_layer    # prune_raft_stereo.py:203-206
@@ -232,8 +233,14 @@ def upsample_disp(liif_up, disp, hidden_layer, stem_4x, stem_2x, stem_1x=None, h
         feats = [x, stem_2x]
     else:
         feats = [x]                                                                        # prune_raft_stereo.py:221-222
-    B = disp.shape[0]
+    B, w = disp.shape[0], disp.shape[-1]
     sc = torch.as_tensor(scale, device=disp.device, dtype=torch.float32).reshape(-1)
     if sc.numel() == 1:
         sc = sc.expand(B)
+    if disparity_norm or disparity_norm2:
+        # args.disparity_norm / disparity_norm2 (continuous_IGEVstereo.py:198-201, :226-235): the disparity is normalised
+        # by the low-resolution width before the upsampling and de-normalised by round(w*4*scale) after it
+        pre = torch.full_like(sc, (1.0 if disparity_norm else 1024.0) / w)
+        post = torch.round(w * 4.0 * sc) / (1.0 if disparity_norm else 1024.0)
+        return (liif_up.upsample(feats, hr_coord, disp, pre) * post.view(-1, 1)).unsqueeze(1)
     return liif_up.upsample(feats, hr_coord, disp, 4.0 * sc).unsqueeze(1)

@@ -173,3 +173,29 @@ def test_liif_single_input_raft_style(A):
     A.set_update_engine("fp32")
     ref = LO.upsample_disp_multiscale(LO.make_liif_params(138, seed=5), disp, [hid], coords, scale)
     assert rel(got, ref) < 1e-4
+
+
+@pytest.mark.parametrize("mode", ["disparity_norm", "disparity_norm2"])
+def test_upsample_disp_normalised_variants(A, mode):
+    """args.disparity_norm / disparity_norm2 branches of upsample_disp (continuous_IGEVstereo.py:198-201, :226-235)."""
+    rng = np.random.RandomState(12)
+    B, h, w, Q = 2, 6, 9, 300
+    stem4 = torch.from_numpy(rng.standard_normal((B, 48, h, w)).astype("float32"))
+    hid = torch.from_numpy(np.tanh(rng.standard_normal((B, 128, h, w))).astype("float32"))
+    stem2 = torch.from_numpy(rng.standard_normal((B, 32, 2 * h, 2 * w)).astype("float32"))
+    coords = torch.from_numpy(rng.uniform(-1, 1, (B, Q, 2)).astype("float32"))
+    disp = torch.from_numpy(rng.uniform(0, 30, (B, 1, h, w)).astype("float32"))
+    scale = torch.tensor([2.5, 3.7])
+    feats = [torch.cat([stem4, hid], 1), stem2]
+    m = make_module(A, dict(feats=feats, n_in=2, in_dim=228), 6)
+    A.set_update_engine("bf16x3")
+    got = A.upsample_disp(m, disp.cuda(), hid.cuda(), stem4.cuda(), stem2.cuda(), None, hr_coord=coords.cuda(),
+                          scale=scale.cuda(), **{mode: True})
+    torch.cuda.synchronize()
+    A.set_update_engine("fp32")
+    params = LO.make_liif_params(228, seed=6)
+    mask = torch.softmax(LO.liif_logits(params, feats, coords), dim=1)
+    k = 1.0 if mode == "disparity_norm" else 1024.0
+    up = LO.context_upsample_multiscale(disp / w * k, mask, coords).unsqueeze(1)
+    ref = up / k * torch.round(w * 4.0 * scale.view(-1, 1, 1))
+    assert rel(got, ref) < 1e-4
