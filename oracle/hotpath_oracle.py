@@ -307,7 +307,7 @@ def pixel_coords(B, H, W, device=None):
 
 
 def igev_iterations(p, fmap1, fmap2, geo_volume, net, inp, init_disp, iters,
-                    radius=4, num_levels=2, exact=False, keep_all=False):
+                    radius=4, num_levels=2, exact=False, keep_all=False, slow_fast_gru=False):
     """continuous_IGEVstereo.py:275-295: build the combined volume, then ``iters`` x
     {lookup -> update block -> disp += delta}.  Returns (disp, net[, all disps])."""
     B, _, H, W = fmap1.shape
@@ -318,6 +318,9 @@ def igev_iterations(p, fmap1, fmap2, geo_volume, net, inp, init_disp, iters,
     hist = []
     for _ in range(iters):
         feat = geo_lookup(gp, cp, disp, coords, radius, exact=exact)
+        if slow_fast_gru:   # continuous_IGEVstereo.py:288-291 (n_gru_layers == 3): extra low-resolution GRU passes
+            net = update_block(p, net, inp, iter16=True, iter08=False, iter04=False, update=False)
+            net = update_block(p, net, inp, iter16=True, iter08=True, iter04=False, update=False)
         net, delta = update_block(p, net, inp, feat, disp)
         disp = disp + delta
         if keep_all:

@@ -161,5 +161,34 @@ def main():
     save("adjoints", **arrs)
 
 
+def slowfast():
+    """args.slow_fast_gru loop (continuous_IGEVstereo.py:284-295 with :288-291 active), reference classes, 6 iterations."""
+    torch.manual_seed(0)
+    torch.set_grad_enabled(False)
+    R = ref_loader.load()
+    c = cases.loop_case("igev", seed=61, B=1, H=16, W=24)
+    args = ref_loader.update_block_args("igev")
+    mod = R.IGEVUpdateBlock(args, hidden_dims=[128, 128, 128]).eval()
+    load_params_into(mod, O.make_update_block_params(162, seed=8))
+    B, _, H, W = c["f1"].shape
+    geo_fn = R.Combined_Geo_Encoding_Volume(c["f1"].float(), c["f2"].float(), c["geo"].float(), radius=4, num_levels=2)
+    coords = coords_of(B, H, W)
+    disp = c["init_disp"]
+    net = [t.clone() for t in c["net"]]
+    hist = []
+    for _ in range(6):
+        feat = geo_fn(disp, coords)
+        net = mod(net, c["inp"], iter16=True, iter08=False, iter04=False, update=False)
+        net = mod(net, c["inp"], iter16=True, iter08=True, iter04=False, update=False)
+        net, delta = mod(net, c["inp"], feat, disp, iter16=True, iter08=True)
+        disp = disp + delta
+        hist.append(disp)
+    save("loop_igev_slowfast", disps=torch.stack(hist), iters=6)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "slowfast":
+        slowfast()
+        sys.exit(0)
     main()
+    slowfast()

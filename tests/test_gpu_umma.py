@@ -548,3 +548,21 @@ def test_encoder_side_stream_overlap_is_exact(A, family):
     A.set_corr_mode("fp32")
     for o in outs:
         assert torch.equal(o, ref)
+
+
+@pytest.mark.parametrize("engine,tol", [("fp32", 1e-4), ("bf16x3", 1e-3)])
+def test_slow_fast_gru_loop_vs_reference(A, golden, engine, tol):
+    """args.slow_fast_gru (continuous_IGEVstereo.py:288-291): two extra low-resolution GRU passes per iteration."""
+    c = cases.loop_case("igev", seed=61, B=1, H=16, W=24)
+    g = golden("loop_igev_slowfast")                         # the reference's own classes, tests/golden/make_golden.py
+    iters = int(g["iters"])
+    ref = torch.from_numpy(g["disps"][-1])
+    m = make_block(A, "igev", 8)
+    A.set_update_engine(engine)
+    A.set_corr_mode("fp32" if engine == "fp32" else "bf16x3")
+    disp, _ = A.igev_iterations(m, c["f1"].cuda(), c["f2"].cuda(), c["geo"].cuda(), [t.cuda() for t in c["net"]],
+                                [[t.cuda() for t in l] for l in c["inp"]], c["init_disp"].cuda(), iters, slow_fast_gru=True)
+    torch.cuda.synchronize()
+    A.set_update_engine("fp32")
+    A.set_corr_mode("fp32")
+    assert rel(disp, ref) < tol

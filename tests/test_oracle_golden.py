@@ -254,3 +254,12 @@ def test_init_disparity_oracle_vs_model_graph(golden):
     disp, _ = O.init_disparity(torch.from_numpy(g["geo"]), torch.from_numpy(g["classifier_weight"]))
     assert disp.shape == g["init_disp"].shape
     assert rel(disp, g["init_disp"]) < 1e-5
+
+
+def test_slow_fast_gru_loop_oracle_vs_reference(golden):
+    g = golden("loop_igev_slowfast")
+    c = cases.loop_case("igev", seed=61, B=1, H=16, W=24)
+    params = O.make_update_block_params(162, seed=8)
+    disp, _, hist = O.igev_iterations(params, c["f1"], c["f2"], c["geo"], c["net"], c["inp"], c["init_disp"], int(g["iters"]),
+                                      slow_fast_gru=True, keep_all=True)
+    assert rel(torch.stack(hist), g["disps"]) < 2e-5
