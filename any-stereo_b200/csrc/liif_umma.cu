@@ -283,9 +283,12 @@ liif_query_kernel(const __grid_constant__ CUtensorMap tW2h, const __grid_constan
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {                // one 16-byte chunk (8 channels) per store: conflict-free across rows
           const int c = half * 32 + j;
+          const float4 ba = __ldg(reinterpret_cast<const float4*>(bias + c)), bb = __ldg(reinterpret_cast<const float4*>(bias + c + 4));
           float y[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) y[i] = fmaxf(v[j + i] + __ldg(bias + c + i), 0.f);
+          y[0] = fmaxf(v[j] + ba.x, 0.f); y[1] = fmaxf(v[j + 1] + ba.y, 0.f);
+          y[2] = fmaxf(v[j + 2] + ba.z, 0.f); y[3] = fmaxf(v[j + 3] + ba.w, 0.f);
+          y[4] = fmaxf(v[j + 4] + bb.x, 0.f); y[5] = fmaxf(v[j + 5] + bb.y, 0.f);
+          y[6] = fmaxf(v[j + 6] + bb.z, 0.f); y[7] = fmaxf(v[j + 7] + bb.w, 0.f);
           put_oct(act_s, lo_off, row, c, y, split);
         }
       }

@@ -41,28 +41,61 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    """SM clock + throttle reasons sampled DURING the timed region.  Read in-process through NVML (the library
+    nvidia-smi itself uses; `nvidia_ml_py`) so that no process is forked next to the kernel-launching thread; falls back
+    to spawning `nvidia-smi --query-gpu=clocks.sm,...` when the module is unavailable."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, uuid=None):
         super().__init__(daemon=True)
         self.index = index
         self.samples = []
         self._halt = threading.Event()
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if uuid:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)) if not str(uuid).startswith("GPU-") else str(uuid))
+                except Exception:
+                    h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self._nvml = (pynvml, h)
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        nv, h = self._nvml
+        sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+        try:
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        act = lambda bit: "Active" if (r & bit) else "Not Active"      # noqa: E731
+        # bit values of nvmlClocksEventReasons: SwPowerCap 0x4, HwSlowdown 0x8, SwThermalSlowdown 0x20, HwThermalSlowdown 0x40
+        return [str(sm), str(mx), "%.1f" % pw, act(0x8), act(0x40), act(0x20), act(0x4)]
 
     def run(self):
         while not self._halt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                if len(f) >= 7:
-                    self.samples.append(f)
+                if self._nvml is not None:
+                    self.samples.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                    f = [x.strip() for x in out.strip().split(",")]
+                    if len(f) >= 7:
+                        self.samples.append(f)
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(0.1 if self._nvml is not None else 0.2)
 
     def stop(self):
         self._halt.set()
@@ -75,7 +108,8 @@ class ClockSampler(threading.Thread):
                     reasons.add(name)
         mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.samples)}
+                "reasons": sorted(reasons), "samples": len(self.samples),
+                "source": "nvml (in-process)" if self._nvml is not None else "nvidia-smi"}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -287,9 +321,16 @@ def run_ours(args):
         return ms
 
     with torch.no_grad():
-        for _ in range(max(args.warmup, 3)):
+        # untimed warm-up: at least W (>= 3) steps AND at least ~1.5 s, so that clocks / power management have settled
+        # before the timed region (two outliers at 55-60 pairs/s were seen when the bench started right after another
+        # process had left the GPU idle)
+        t_w = time.perf_counter()
+        n_w = 0
+        while n_w < max(args.warmup, 3) or (time.perf_counter() - t_w < 1.5 and n_w < 40):
             step(dd)
-        sampler = ClockSampler(local) if rank == 0 else None
+            torch.cuda.synchronize()
+            n_w += 1
+        sampler = ClockSampler(local, getattr(torch.cuda.get_device_properties(local), "uuid", None)) if rank == 0 else None
         if sampler:
             sampler.start()
         events, uevents = [], []
@@ -300,8 +341,9 @@ def run_ours(args):
         torch.cuda.synchronize()
         look_us = [a.elapsed_time(b) * 1e3 for a, b in events]
         upd_us = [a.elapsed_time(b) * 1e3 for a, b in uevents]
-        for _ in range(2):
+        for _ in range(4):
             e2e_step()
+        torch.cuda.synchronize()
         ms_e2e = timed(e2e_step, args.steps)
 
     # the other BASELINE.json configs that run the same path (parity-test cases; reported for context, rank 0, N=1)
@@ -430,7 +472,7 @@ def run_ours(args):
     cpu = cpu_reference_sample(sample_iters=args.ref_sample_iters) if not args.no_cpu_baseline else None
     line = {
         "metric": "pairs/s @384x1248, 32 iters", "value": value, "unit": "pairs/s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "warmup_steps_run": n_w, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"fp32": "f32", "bf16x3": "f32 (3x split-bf16 on tcgen05, fp32 accumulate)", "bf16": "bf16",
                   "fp16": "f16 (IEEE half operands, fp32 accumulate; mixed-precision analogue)"}[args.engine],
