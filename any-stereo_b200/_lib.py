@@ -122,6 +122,7 @@ SIGNATURES = {
     "as_relu_bwd": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _ll, _i, _vp]),
     "as_gru_bwd_gates1": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _vp]),
     "as_gru_bwd_gates2": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _ll, _i, _vp]),
+    "as_conv_epilogue_fp32": (_i, [_vp, _i, _ll, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "as_add_slice": (_i, [_vp, _i, _i, _vp, _i, _i, _ll, _i, _vp]),
     "as_pool2x_nhwc_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "as_interp_bilinear_nhwc_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),

@@ -309,7 +309,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
             }
           }
         } else if (p.epilogue == AS_UEPI_LINEAR_F32) {       // plain (1x1) linear map, fp32 NHWC out (LIIF first layer)
-          float* op = p.out_f32 + n * p.N + c0;
+          // out_pitch / out_coff (0 = dense [n][N]) place the N columns inside a wider row: chunked data gradients
+          float* op = p.out_f32 + n * (p.out_pitch ? p.out_pitch : p.N) + p.out_coff + c0;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -445,7 +446,8 @@ extern "C" int as_conv2d_umma(const as_conv_umma_desc* d, as_stream_t stream) {
       if (!d->bias || !d->w2 || !d->u || d->Cout != 256) return AS_ERR_BAD_ARG;
       break;
     case AS_UEPI_LINEAR_F32:
-      if (!d->out_f32) return AS_ERR_BAD_ARG;
+      if (!d->out_f32 || (d->out_pitch && d->out_pitch < d->out_coff + d->Cout) || (d->out_pitch & 3) || (d->out_coff & 3))
+        return AS_ERR_BAD_ARG;
       break;
     default: return AS_ERR_UNSUPPORTED;
   }

@@ -209,6 +209,41 @@ __global__ void interp_bwd_kernel(const float* __restrict__ dy, float* __restric
   atomicAdd(base + ((long long)y1 * Wi + x1) * C, g * ly * lx);
 }
 
+// the epilogues of conv_simt_kernel on a raw (acc + bias) convolution output produced by the tensor-core kernel
+__device__ __forceinline__ float sigmoid_(float x) { return 1.0f / (1.0f + expf(-x)); }
+__global__ void conv_epilogue_kernel(const float* __restrict__ raw, int raw_pitch, int Cout, int epilogue,
+                                     const float* __restrict__ ctx, int ctx_pitch, const float* __restrict__ h,
+                                     float* __restrict__ z, float* __restrict__ save, float* __restrict__ out, int out_pitch,
+                                     int out_coff, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const long long n = idx / Cout;
+  const int co = (int)(idx - n * Cout);
+  float v = raw[n * raw_pitch + co];
+  if (epilogue == AS_EPI_GRU_ZR) {
+    const int Hd = Cout >> 1;
+    v = sigmoid_(v + __ldg(ctx + n * ctx_pitch + co));
+    if (co < Hd) {
+      z[n * Hd + co] = v;                                                  // update.py:37
+    } else {
+      const int ch = co - Hd;
+      out[n * out_pitch + out_coff + ch] = v * __ldg(h + n * Hd + ch);      // r*h, update.py:38-39
+      if (save) save[n * Hd + ch] = v;
+    }
+    return;
+  }
+  if (epilogue == AS_EPI_GRU_Q) {
+    const float q = tanhf(v + __ldg(ctx + n * ctx_pitch + co));            // update.py:39
+    if (save) save[n * Cout + co] = q;
+    const float zz = z[n * Cout + co];
+    const float hh = __ldg(h + n * Cout + co);
+    v = (1.0f - zz) * hh + zz * q;                                          // update.py:40
+  } else if (epilogue == AS_EPI_BIAS_RELU) {
+    v = fmaxf(v, 0.f);
+  }
+  out[n * out_pitch + out_coff + co] = v;
+}
+
 inline unsigned blocks_for(long long total) { return (unsigned)as_ceil_div_ll(total, 256); }
 
 }  // namespace
@@ -272,6 +307,25 @@ extern "C" int as_gru_bwd_gates2(const float* drh, int drh_pitch, const float* h
                                  float* dh_acc, long long N, int Hd, as_stream_t stream) {
   if (!drh || !h || !r || !dzr_pre || !dh_acc || N <= 0 || Hd <= 0 || drh_pitch < Hd) return AS_ERR_BAD_ARG;
   gru_gates2_kernel<<<blocks_for(N * Hd), 256, 0, as_cu(stream)>>>(drh, drh_pitch, h, r, dzr_pre, dh_acc, Hd, N * Hd);
+  AS_RETURN_IF_LAUNCH_FAILED();
+  return AS_OK;
+}
+
+extern "C" int as_conv_epilogue_fp32(const float* raw, int raw_pitch, long long N, int Cout, int epilogue, const float* ctx,
+                                     int ctx_pitch, const float* h, float* z, float* save, float* out, int out_pitch,
+                                     int out_coff, as_stream_t stream) {
+  if (!raw || !out || N <= 0 || Cout <= 0 || raw_pitch < Cout) return AS_ERR_BAD_ARG;
+  if (epilogue == AS_EPI_GRU_ZR) {
+    if (!ctx || !h || !z || (Cout & 1) || ctx_pitch < Cout || out_pitch < out_coff + Cout / 2) return AS_ERR_BAD_ARG;
+  } else if (epilogue == AS_EPI_GRU_Q) {
+    if (!ctx || !h || !z || ctx_pitch < Cout || out_pitch < out_coff + Cout) return AS_ERR_BAD_ARG;
+  } else if (epilogue == AS_EPI_BIAS || epilogue == AS_EPI_BIAS_RELU) {
+    if (out_pitch < out_coff + Cout) return AS_ERR_BAD_ARG;
+  } else {
+    return AS_ERR_UNSUPPORTED;
+  }
+  conv_epilogue_kernel<<<blocks_for(N * Cout), 256, 0, as_cu(stream)>>>(raw, raw_pitch, Cout, epilogue, ctx, ctx_pitch, h, z,
+                                                                       save, out, out_pitch, out_coff, N * Cout);
   AS_RETURN_IF_LAUNCH_FAILED();
   return AS_OK;
 }

@@ -1,12 +1,17 @@
 """Differentiable execution of BasicMultiUpdateBlock.forward (training, BASELINE.json config 5).
 
-Forward and backward both run on the library's exact-fp32 CUDA-core kernels (include/anystereo_b200.h,
-section a13-vi).  The reference obtains these gradients from autograd over models/*/update.py:16-136; here the
-adjoint is written out explicitly as one ``torch.autograd.Function`` per update-block call:
+The reference obtains these gradients from autograd over models/*/update.py:16-136; here the adjoint is written
+out explicitly as one ``torch.autograd.Function`` per update-block call:
 
   conv data gradient   = the forward implicit-GEMM kernel on dY with flipped/transposed weights
   conv weight gradient = as_conv2d_wgrad_fp32 (K = pixels, fp32 atomics)
   GRU gates            = as_gru_bwd_gates1/2 (update.py:37-40), ReLU masks, pool2x / bilinear adjoints
+
+Engines (``set_update_engine``): "fp32" runs every convolution on the exact-fp32 CUDA-core kernel
+(include/anystereo_b200.h, section a13-vi).  "bf16x3" / "bf16" / "fp16" run the forward convolutions and the data
+gradients on the tcgen05 kernel (as_conv2d_umma with AS_UEPI_LINEAR_F32: raw fp32 output, then
+as_conv_epilogue_fp32 applies the gate / ReLU epilogue and keeps r and q for the backward pass); convd1 (7x7, one
+input channel), DispHead.conv2 (one output channel) and every weight gradient stay on the CUDA cores.
 
 Gradients flow to: every parameter, the hidden states ``net``, the context terms ``inp``, and the lookup
 features ``corr``.  ``disp`` receives none: both model forwards detach it every iteration
@@ -46,10 +51,49 @@ def _to_nchw(x, C=None, pitch=None, coff=0):
     return out
 
 
+def _engine():
+    """(tensor cores?, MMAs per K-step) of the current update engine."""
+    from .update import get_update_engine
+    e = get_update_engine()
+    return e != "fp32", (3 if e == "bf16x3" else 1)
+
+
+def _split(x, split):
+    """hi (+lo) operand planes of a contiguous pixel-major fp32 tensor whose channel count is a multiple of 64."""
+    from .update_umma import _Planes
+    assert x.is_contiguous() and x.shape[3] % 64 == 0, tuple(x.shape)
+    pl = _Planes(x.shape, x.device, split)
+    L.call("as_split_f32", x.data_ptr(), pl.hi.data_ptr(), L.ptr(pl.lo), x.numel(), _s())
+    return pl
+
+
+def _dgrad_weights(ub, name, convs, split):
+    """Data-gradient GEMM weights of a convolution: the [Cin][Cout][KH][KW] transpose with flipped taps, packed like
+    forward weights (rows padded to 32, K channels padded to 64), cached per parameter version."""
+    from .update_umma import _state
+    st = _state(ub)["w"]
+    key = (split, L.operand_format()) + tuple((c.weight.data_ptr(), c.weight._version) for c in convs)
+    hit = st.get("train.dgrad." + name)
+    if hit is not None and hit["key"] == key:
+        return hit
+    with torch.no_grad():
+        w = torch.cat([c.weight.detach().float() for c in convs], dim=0)
+        wt = w.transpose(0, 1).flip(2, 3).contiguous()                    # [Cin][Cout][KH][KW]
+        Cin, Cout, KH, KW = wt.shape
+        n_pad, cin_pad = (Cin + 31) // 32 * 32, (Cout + 63) // 64 * 64
+        hi = torch.empty((n_pad, KH * KW * cin_pad), device=w.device, dtype=torch.bfloat16)
+        lo = torch.empty_like(hi) if split else None
+        L.call("as_pack_conv_weight_bf16", wt.data_ptr(), hi.data_ptr(), L.ptr(lo), Cin, Cout, KH, KW, n_pad, cin_pad, _s())
+    hit = dict(key=key, hi=hi, lo=lo, n=n_pad, cin=cin_pad, k=KH)
+    st["train.dgrad." + name] = hit
+    return hit
+
+
 class _Conv:
     """One convolution (or z|r pair) with its packed forward / data-gradient weights."""
 
-    def __init__(self, convs):
+    def __init__(self, convs, ub=None, name=None):
+        self.ub, self.name = ub, name
         with torch.no_grad():
             self.w = torch.cat([c.weight.detach().float() for c in convs], 0).contiguous()
             self.b = torch.cat([c.bias.detach().float() for c in convs], 0).contiguous()
@@ -85,8 +129,46 @@ class _Conv:
         d.ctx, d.ctx_pitch, d.h, d.z, d.save = L.ptr(ctx), ctx_pitch, L.ptr(h), L.ptr(z), L.ptr(save)
         L.call("as_conv2d_fp32", d, _s())
 
+    # ---- tensor-core variants (engines other than "fp32")
+    def tc_ok(self):
+        """The tcgen05 kernel covers 1x1 / 3x3 with at least 32 input and output channels."""
+        return self.KH in (1, 3) and self.KH == self.KW and self.Cin >= 32 and self.Cout >= 32 and self.Cout <= 256
+
+    def fwd_tc(self, B, H, W, planes, nsplit, epi, out, out_pitch, out_coff=0, ctx=None, ctx_pitch=0, h=None, z=None,
+               save=None):
+        """Same contract as fwd() with NHWC output; `planes` are the hi/lo operand planes of the sources."""
+        from . import update_umma as U
+        cin_pad = sum(pl.shape[3] for pl in planes)
+        wt = U._weights(self.ub, "train." + self.name, self.convs, cin_pad=cin_pad, split=nsplit == 3)
+        raw = torch.empty((B, H, W, wt["n"]), device=out.device, dtype=torch.float32)
+        U._conv(B, H, W, planes, wt, nsplit, L.UEPI_LINEAR_F32, out_f32=raw)
+        L.call("as_conv_epilogue_fp32", raw.data_ptr(), wt["n"], B * H * W, self.Cout, epi, L.ptr(ctx), ctx_pitch, L.ptr(h),
+               L.ptr(z), L.ptr(save), out.data_ptr(), out_pitch, out_coff, _s())
+
+    def dgrad_tc(self, B, H, W, dy, nsplit):
+        """dX [B,H,W,roundup32(Cin)] from a contiguous dY [B,H,W,roundup64(Cout)] (padding channels zero)."""
+        from . import update_umma as U
+        wt = _dgrad_weights(self.ub, self.name, self.convs, nsplit == 3)
+        assert dy.shape[3] == wt["cin"], (tuple(dy.shape), wt["cin"])
+        dyS = _split(dy, nsplit == 3)
+        n_pad = wt["n"]
+        dx = torch.empty((B, H, W, n_pad), device=dy.device, dtype=torch.float32)
+        r0 = 0
+        while r0 < n_pad:                                   # GEMM N <= 256 per launch: chunk the Cin rows
+            rows = min(256, n_pad - r0)
+            chunk = dict(hi=wt["hi"][r0:r0 + rows], lo=None if wt["lo"] is None else wt["lo"][r0:r0 + rows], n=rows,
+                         cin=wt["cin"], k=wt["k"])
+            U._conv(B, H, W, [dyS], chunk, nsplit, L.UEPI_LINEAR_F32, bias=False, out_f32=dx, out_coff=r0,
+                    f32_pitch=n_pad if rows != n_pad else 0)
+            r0 += rows
+        return dx
+
     def dgrad(self, B, H, W, dy, dy_pitch):
         """dX [B,H,W,Cin] from dY [.., Cout] (pixel-major, pitch dy_pitch)."""
+        tc, nsplit = _engine()
+        if tc and self.ub is not None and self.tc_ok() and dy.shape[3] == dy_pitch \
+                and dy_pitch == (self.Cout + 63) // 64 * 64:              # note: Cin comes back padded to 32
+            return self.dgrad_tc(B, H, W, dy, nsplit)
         dx = torch.empty((B, H, W, self.Cin), device=dy.device, dtype=torch.float32)
         d = self._desc(B, H, W, [(dy, self.Cout, dy_pitch, NHWC)])
         d.Cout = self.Cin
@@ -128,14 +210,28 @@ class UpdateBlockFn(torch.autograd.Function):
             k += 2
         dev = net[0].device
         e, dh = ub.encoder, ub.disp_head
-        C = {
-            "convc1": _Conv([e.convc1]), "convc2": _Conv([e.convc2]), "convd1": _Conv([e.convd1]),
-            "convd2": _Conv([e.convd2]), "conv": _Conv([e.conv]), "dh1": _Conv([dh.conv1]), "dh2": _Conv([dh.conv2]),
-        }
+        C = {k: _Conv([m], ub, k) for k, m in (("convc1", e.convc1), ("convc2", e.convc2), ("convd1", e.convd1),
+                                               ("convd2", e.convd2), ("conv", e.conv), ("dh1", dh.conv1), ("dh2", dh.conv2))}
         for name in ("gru04", "gru08", "gru16"):
             g = getattr(ub, name)
-            C[name + ".zr"] = _Conv([g.convz, g.convr])
-            C[name + ".q"] = _Conv([g.convq])
+            C[name + ".zr"] = _Conv([g.convz, g.convr], ub, name + ".zr")
+            C[name + ".q"] = _Conv([g.convq], ub, name + ".q")
+        tc, nsplit = _engine()
+        planes = {}                                          # id(fp32 tensor) -> (tensor, hi/lo planes), this call only
+
+        def pl(x):
+            hit = planes.get(id(x))
+            if hit is None:
+                hit = planes[id(x)] = (x, _split(x, nsplit == 3))
+            return hit[1]
+
+        def conv(name, B, H, W, xs, epi, out, out_pitch, out_coff=0, **kw):
+            """One forward convolution over the pixel-major fp32 sources xs, on the engine's kernel."""
+            c = C[name]
+            if tc and c.tc_ok() and all(x.shape[3] % 64 == 0 for x in xs):
+                c.fwd_tc(B, H, W, [pl(x) for x in xs], nsplit, epi, out, out_pitch, out_coff, **kw)
+            else:
+                c.fwd(B, H, W, [_src(x) for x in xs], epi, out, out_pitch, out_coff, **kw)
         tape = {"C": C, "flags": flags, "n_net": n_net, "has_corr": has_corr, "gru": {}}
         hs = [_to_nhwc(t.detach().float()) for t in net]
 
@@ -165,9 +261,8 @@ class UpdateBlockFn(torch.autograd.Function):
             B, H, W, Hd = h.shape
             czr, cq = context(i)
             z, rh, r, q, hn = (torch.empty_like(h) for _ in range(5))
-            srcs_x = [_src(x) for x in xs]
-            C[name + ".zr"].fwd(B, H, W, [_src(h)] + srcs_x, L.EPI_GRU_ZR, rh, Hd, ctx=czr, ctx_pitch=2 * Hd, h=h, z=z, save=r)
-            C[name + ".q"].fwd(B, H, W, [_src(rh)] + srcs_x, L.EPI_GRU_Q, hn, Hd, ctx=cq, ctx_pitch=Hd, h=h, z=z, save=q)
+            conv(name + ".zr", B, H, W, [h] + xs, L.EPI_GRU_ZR, rh, Hd, ctx=czr, ctx_pitch=2 * Hd, h=h, z=z, save=r)
+            conv(name + ".q", B, H, W, [rh] + xs, L.EPI_GRU_Q, hn, Hd, ctx=cq, ctx_pitch=Hd, h=h, z=z, save=q)
             tape["gru"][name] = dict(h=h, xs=xs, z=z, r=r, q=q, rh=rh)
             return hn
 
@@ -186,15 +281,23 @@ class UpdateBlockFn(torch.autograd.Function):
             B, Cc, H, W = corr_c.shape
             corr_n = _to_nhwc(corr_c)                                   # wgrad reads pixel-major
             c1 = torch.empty((B, H, W, 64), device=dev, dtype=torch.float32)
-            C["convc1"].fwd(B, H, W, [_src(corr_n)], L.EPI_BIAS_RELU, c1, 64)
+            if tc and C["convc1"].tc_ok() and C["convc1"].Cout == 64:
+                from .update_umma import _Planes
+                cpad = (Cc + 63) // 64 * 64                             # lookup channels zero-padded to the K granule
+                corrS = _Planes((B, H, W, cpad), dev, nsplit == 3)
+                L.call("as_nchw_to_nhwc_split", corr_c.data_ptr(), corrS.hi.data_ptr(), L.ptr(corrS.lo), B, Cc, H, W, cpad,
+                       _s())
+                C["convc1"].fwd_tc(B, H, W, [corrS], nsplit, L.EPI_BIAS_RELU, c1, 64)
+            else:
+                C["convc1"].fwd(B, H, W, [_src(corr_n)], L.EPI_BIAS_RELU, c1, 64)
             cd = torch.empty((B, H, W, 128), device=dev, dtype=torch.float32)
-            C["convc2"].fwd(B, H, W, [_src(c1)], L.EPI_BIAS_RELU, cd, 128, 0)
+            conv("convc2", B, H, W, [c1], L.EPI_BIAS_RELU, cd, 128, 0)
             d1 = torch.empty((B, H, W, 64), device=dev, dtype=torch.float32)
             disp_n = disp_c.view(B, H, W, 1)
             C["convd1"].fwd(B, H, W, [_src(disp_n)], L.EPI_BIAS_RELU, d1, 64)
-            C["convd2"].fwd(B, H, W, [_src(d1)], L.EPI_BIAS_RELU, cd, 128, 64)
+            conv("convd2", B, H, W, [d1], L.EPI_BIAS_RELU, cd, 128, 64)
             mo = torch.empty((B, H, W, 128), device=dev, dtype=torch.float32)
-            C["conv"].fwd(B, H, W, [_src(cd)], L.EPI_BIAS_RELU, mo, 128, 0)
+            conv("conv", B, H, W, [cd], L.EPI_BIAS_RELU, mo, 128, 0)
             L.call("as_nchw_to_nhwc", disp_c.data_ptr(), mo.data_ptr(), B, 1, H, W, 128, 127, _s())
             tape["enc"] = dict(corr=corr_n, c1=c1, cd=cd, d1=d1, disp=disp_n, mo=mo)
             xs = [mo]
@@ -206,7 +309,7 @@ class UpdateBlockFn(torch.autograd.Function):
         if update:
             B, H, W, Hd = hs[0].shape
             t = torch.empty((B, H, W, 256), device=dev, dtype=torch.float32)
-            C["dh1"].fwd(B, H, W, [_src(hs[0])], L.EPI_BIAS_RELU, t, 256)
+            conv("dh1", B, H, W, [hs[0]], L.EPI_BIAS_RELU, t, 256)
             delta = torch.empty((B, 1, H, W), device=dev, dtype=torch.float32)
             C["dh2"].fwd(B, H, W, [_src(t)], L.EPI_BIAS, delta, 1, 0, out_layout=NCHW)
             tape["head"] = dict(h=hs[0], t=t)
@@ -245,9 +348,12 @@ class UpdateBlockFn(torch.autograd.Function):
         d_corr = None
 
         def relu_bwd(dy, dy_coff, y, y_coff, Cc):
+            """dy * (y > 0) over Cc channels; the row is zero-padded to a multiple of 64 channels when the tensor-core
+            data gradient consumes it (only `conv`, 127 channels, is affected)."""
             B, H, W, _ = y.shape
-            dx = torch.empty((B, H, W, Cc), device=dev, dtype=torch.float32)
-            L.call("as_relu_bwd", dy.data_ptr(), dy.shape[3], dy_coff, y.data_ptr(), y.shape[3], y_coff, dx.data_ptr(), Cc, 0,
+            Cp = (Cc + 63) // 64 * 64 if _engine()[0] else Cc
+            dx = (torch.empty if Cp == Cc else torch.zeros)((B, H, W, Cp), device=dev, dtype=torch.float32)
+            L.call("as_relu_bwd", dy.data_ptr(), dy.shape[3], dy_coff, y.data_ptr(), y.shape[3], y_coff, dx.data_ptr(), Cp, 0,
                    B * H * W, Cc, _s())
             return dx
 
@@ -320,8 +426,8 @@ class UpdateBlockFn(torch.autograd.Function):
             if n_layers > 1:
                 interp_bwd(dxs[1], dh[1])                       # into the NEW h08 gradient
             dpre = relu_bwd(dmo, 0, en["mo"], 0, 127)
-            acc_param(C["conv"], *C["conv"].wgrad(B, H, W, [_src(en["cd"])], dpre, 127))
-            dcd = C["conv"].dgrad(B, H, W, dpre, 127)           # [..,128]
+            acc_param(C["conv"], *C["conv"].wgrad(B, H, W, [_src(en["cd"])], dpre, dpre.shape[3]))
+            dcd = C["conv"].dgrad(B, H, W, dpre, dpre.shape[3])           # [..,128]
             dp_c2 = relu_bwd(dcd, 0, en["cd"], 0, 64)
             acc_param(C["convc2"], *C["convc2"].wgrad(B, H, W, [_src(en["c1"])], dp_c2, 64))
             dc1 = C["convc2"].dgrad(B, H, W, dp_c2, 64)
@@ -332,7 +438,8 @@ class UpdateBlockFn(torch.autograd.Function):
             acc_param(C["convd1"], *C["convd1"].wgrad(B, H, W, [_src(en["disp"])], dp_d1, 64))
             dp_c1 = relu_bwd(dc1, 0, en["c1"], 0, 64)
             acc_param(C["convc1"], *C["convc1"].wgrad(B, H, W, [_src(en["corr"])], dp_c1, 64))
-            d_corr = _to_nchw(C["convc1"].dgrad(B, H, W, dp_c1, 64))
+            dcn = C["convc1"].dgrad(B, H, W, dp_c1, 64)          # Cin channels (padded to 32 on the tensor cores)
+            d_corr = _to_nchw(dcn, C["convc1"].Cin, dcn.shape[3])
         # ---- gru08
         g1 = dh[1]
         if iter08:

@@ -166,7 +166,7 @@ def _context(ub, idx, inp_i, wzr, wq):
 
 
 def _conv(B, H, W, srcs, wt, nsplit, epilogue, out=None, out_coff=0, bias=True, ctx=None, h=None, z=None, out_f32=None,
-          disp=None, w2=None, u=None):
+          disp=None, w2=None, u=None, f32_pitch=0):
     d = L.ConvUmmaDesc()
     d.B, d.H, d.W, d.KH, d.KW, d.Cout = B, H, W, wt["k"], wt["k"], wt["n"]
     d.num_src = len(srcs)
@@ -192,6 +192,8 @@ def _conv(B, H, W, srcs, wt, nsplit, epilogue, out=None, out_coff=0, bias=True, 
         d.out_hi = out.hi.data_ptr()
         d.out_lo = L.ptr(out.lo)
         d.out_pitch = out.shape[3]
+    elif f32_pitch:                                  # LINEAR_F32 into a wider fp32 row (chunked data gradients)
+        d.out_pitch = f32_pitch
     d.out_coff = out_coff
     d.cout_valid = wt["n"]
     d.disp = L.ptr(disp)

@@ -247,7 +247,8 @@ int as_add_f32(const float* a, const float* b, float* y, long long n, as_stream_
 #define AS_UEPI_GRU_Q 3      /* h'=(1-z)h + z tanh(acc+ctx) -> out_f32 and hi/lo        (update.py:39-40) */
 #define AS_UEPI_DISPHEAD 4   /* u[n][t] = sum_c w2[t][c]*relu(acc+bias)[c]: DispHead.conv2 folded into
                                 conv1's epilogue (update.py:23-24); finish with as_disp_delta           */
-#define AS_UEPI_LINEAR_F32 5 /* out_f32[n][c] = acc (+ bias if given): plain linear map, fp32 NHWC out      */
+#define AS_UEPI_LINEAR_F32 5 /* out_f32[n][c] = acc (+ bias if given): plain linear map, fp32 NHWC out;
+                                out_pitch/out_coff != 0 place the Cout columns inside a wider fp32 row      */
 
 typedef struct as_umma_src {
   const void* hi; /* bf16 [B*H*W][channels] */
@@ -329,6 +330,14 @@ int as_gru_bwd_gates1(const float* dhn, const float* z, const float* q, const fl
                       float* dzr_pre, float* dh_acc, long long N, int Hd, as_stream_t stream);
 int as_gru_bwd_gates2(const float* drh, int drh_pitch, const float* h, const float* r, float* dzr_pre,
                       float* dh_acc, long long N, int Hd, as_stream_t stream);
+/* Tensor-core training path: the fused epilogues of as_conv2d_fp32 (AS_EPI_*) applied to a raw convolution output
+ * raw[n][raw_pitch] = acc + bias, as written by as_conv2d_umma with AS_UEPI_LINEAR_F32 (update.py:33-41,85-91,23).
+ * Same argument meaning as as_conv_desc: GRU_ZR (Cout = 2*Hd): z <- sigmoid(raw+ctx)[:Hd], save <- r, out <- r*h;
+ * GRU_Q: save <- q = tanh(raw+ctx), out <- (1-z)h + zq; BIAS_RELU: out <- max(raw,0); BIAS: out <- raw.
+ * out is pixel-major [n][out_pitch] written at channel offset out_coff; save may be NULL. */
+int as_conv_epilogue_fp32(const float* raw, int raw_pitch, long long N, int Cout, int epilogue, const float* ctx,
+                          int ctx_pitch, const float* h, float* z, float* save, float* out, int out_pitch,
+                          int out_coff, as_stream_t stream);
 /* dst[n][dcoff + c] += src[n][scoff + c] */
 int as_add_slice(const float* src, int spitch, int scoff, float* dst, int dpitch, int dcoff, long long N, int C,
                  as_stream_t stream);

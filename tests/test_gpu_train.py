@@ -28,10 +28,21 @@ def _block(A, family, seed):
     return m.cuda().train(), p
 
 
-@pytest.mark.parametrize("family", ["igev", "raft"])
-def test_update_block_backward_vs_autograd(family):
+@pytest.fixture(autouse=True)
+def _restore_engine():
     import anystereo_b200 as A
     A.set_update_engine("fp32")
+    yield
+    A.set_update_engine("fp32")
+
+
+# "bf16x3": forward convolutions and data gradients on the tcgen05 kernel (3-term split, fp32 accumulate), weight
+# gradients on CUDA cores; same tolerances as the exact-fp32 engine
+@pytest.mark.parametrize("engine", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("family", ["igev", "raft"])
+def test_update_block_backward_vs_autograd(family, engine):
+    import anystereo_b200 as A
+    A.set_update_engine(engine)
     c = cases.update_block_case(family, B=2, H=9, W=13)
     m, p = _block(A, family, 31)
     rng = np.random.RandomState(5)
@@ -66,9 +77,11 @@ def test_update_block_backward_vs_autograd(family):
         assert rel(prm.grad, pr[name].grad) < tol, name
 
 
-def test_lowres_only_backward():
+@pytest.mark.parametrize("engine", ["fp32", "bf16x3"])
+def test_lowres_only_backward(engine):
     """slow_fast_gru pre-pass (iter16/iter08 only, update=False): gradients still flow (update.py:116-133)."""
     import anystereo_b200 as A
+    A.set_update_engine(engine)
     c = cases.update_block_case("igev", B=1, H=8, W=12)
     m, p = _block(A, "igev", 32)
     pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
@@ -84,11 +97,13 @@ def test_lowres_only_backward():
     assert m.gru04.convz.weight.grad is None or float(m.gru04.convz.weight.grad.abs().max()) == 0.0
 
 
-def test_training_step_hot_path():
+@pytest.mark.parametrize("engine", ["fp32", "bf16x3"])
+def test_training_step_hot_path(engine):
     """Three unrolled iterations of the IGEV hot path with a sequence loss: gradients reach the matching features,
     the geometry volume, the context and every update-block parameter, and agree with autograd over the oracle."""
     import anystereo_b200 as A
     A.set_corr_mode("fp32")
+    A.set_update_engine(engine)
     c = cases.loop_case("igev", seed=41, B=1, H=8, W=16)
     m, p = _block(A, "igev", 33)
     iters, gamma = 3, 0.9

@@ -24,6 +24,8 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--iters", type=int, default=16)       # train_iters, train_continuous_IGEV.py:297
     ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--engine", default="fp32", choices=["fp32", "bf16x3", "bf16", "fp16"],
+                    help="update-block engine: fp32 = CUDA cores; others = forward + data gradients on tcgen05")
     ap.add_argument("--h", type=int, default=80)
     ap.add_argument("--w", type=int, default=184)
     a = ap.parse_args()
@@ -34,7 +36,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    A.set_update_engine("fp32")
+    A.set_update_engine(a.engine)
     A.set_corr_mode("fp32")
     torch.manual_seed(0)                                    # identical replicas
     args = types.SimpleNamespace(corr_levels=2, corr_radius=4, n_gru_layers=3)
@@ -83,8 +85,8 @@ def main():
         losses.append(float(loss.detach()))
         gnorms.append(float(gn))
     if rank == 0:
-        print(json.dumps({"config": "IGEV hot-path training step, %dx%d (1/4: %dx%d), batch %d/GPU, %d iters, fp32 CUDA-core kernels"
-                                    % (4 * H, 4 * W, H, W, B, a.iters),
+        print(json.dumps({"config": "IGEV hot-path training step, %dx%d (1/4: %dx%d), batch %d/GPU, %d iters, update engine %s"
+                                    % (4 * H, 4 * W, H, W, B, a.iters, a.engine),
                           "n_gpus": world, "ms_per_step": times, "pairs_per_s": world * B / (times[-1] / 1e3),
                           "loss": losses, "grad_norm_after_allreduce": gnorms,
                           "peak_mem_GB": torch.cuda.max_memory_allocated() / 2 ** 30}))
