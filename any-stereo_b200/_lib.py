@@ -59,6 +59,13 @@ class LiifQueryDesc(C.Structure):
     ]
 
 
+class WgradUmmaDesc(C.Structure):
+    _fields_ = [
+        ("B", _i), ("H", _i), ("W", _i), ("KH", _i), ("KW", _i), ("Cout", _i), ("num_src", _i),
+        ("src", UmmaSrc * 3), ("dy_hi", _vp), ("dy_lo", _vp), ("Wp", _i), ("nsplit", _i), ("ws", _vp), ("dw_acc", _vp),
+    ]
+
+
 class ConvDesc(C.Structure):
     _fields_ = [
         ("B", _i), ("H", _i), ("W", _i), ("KH", _i), ("KW", _i), ("Cout", _i), ("num_src", _i),
@@ -123,6 +130,9 @@ SIGNATURES = {
     "as_gru_bwd_gates1": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _vp]),
     "as_gru_bwd_gates2": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _ll, _i, _vp]),
     "as_conv_epilogue_fp32": (_i, [_vp, _i, _ll, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "as_bias_grad_fp32": (_i, [_vp, _i, _i, _ll, _vp, _vp]),
+    "as_transpose_split": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp]),
+    "as_conv2d_wgrad_umma": (_i, [C.POINTER(WgradUmmaDesc), _vp]),
     "as_add_slice": (_i, [_vp, _i, _i, _vp, _i, _i, _ll, _i, _vp]),
     "as_pool2x_nhwc_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "as_interp_bilinear_nhwc_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),

@@ -286,6 +286,14 @@ extern "C" int as_conv2d_wgrad_fp32(const as_conv_desc* d, const float* dy, int 
   return AS_OK;
 }
 
+extern "C" int as_bias_grad_fp32(const float* dy, int dy_pitch, int Cout, long long N, float* db_acc, as_stream_t stream) {
+  if (!dy || !db_acc || Cout <= 0 || N <= 0 || dy_pitch < Cout) return AS_ERR_BAD_ARG;
+  dim3 g2((unsigned)as_ceil_div_ll(N, 4096), as_ceil_div(Cout, 32));
+  bias_grad_kernel<<<g2, 256, 0, as_cu(stream)>>>(dy, dy_pitch, Cout, N, db_acc);
+  AS_RETURN_IF_LAUNCH_FAILED();
+  return AS_OK;
+}
+
 extern "C" int as_relu_bwd(const float* dy, int dy_pitch, int dy_coff, const float* y, int y_pitch, int y_coff, float* dx,
                            int dx_pitch, int dx_coff, long long N, int C, as_stream_t stream) {
   if (!dy || !y || !dx || N <= 0 || C <= 0) return AS_ERR_BAD_ARG;

@@ -19,6 +19,8 @@ features ``corr``.  ``disp`` receives none: both model forwards detach it every 
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib as L
@@ -49,6 +51,15 @@ def _to_nchw(x, C=None, pitch=None, coff=0):
     out = torch.empty((B, C, H, W), device=x.device, dtype=torch.float32)
     L.call("as_nhwc_to_nchw", x.data_ptr(), out.data_ptr(), B, C, H, W, pitch or P, coff, _s())
     return out
+
+
+_WGRAD_TC = {"on": os.environ.get("AS_WGRAD_TC", "1") != "0"}
+
+
+def set_wgrad_tensor_cores(on: bool):
+    """Weight gradients of the 1x1 / 3x3 convolutions on the tcgen05 kernel (as_conv2d_wgrad_umma) when the update engine
+    is a tensor-core engine; off = CUDA-core as_conv2d_wgrad_fp32 (A/B knob, also AS_WGRAD_TC=0)."""
+    _WGRAD_TC["on"] = bool(on)
 
 
 def _engine():
@@ -94,6 +105,7 @@ class _Conv:
 
     def __init__(self, convs, ub=None, name=None):
         self.ub, self.name = ub, name
+        self.tcache = None                     # per-backward cache of channel-major operand planes
         with torch.no_grad():
             self.w = torch.cat([c.weight.detach().float() for c in convs], 0).contiguous()
             self.b = torch.cat([c.bias.detach().float() for c in convs], 0).contiguous()
@@ -180,10 +192,43 @@ class _Conv:
         L.call("as_conv2d_fp32", d, _s())
         return dx
 
+    def _tplanes(self, t, ch, pitch, B, H, W, Wp, split, nshift=1):
+        """Channel-major hi/lo planes [nshift][ch][B][H][Wp] of a pixel-major fp32 tensor, copy j shifted by j - nshift/2
+        pixels along x (shared by the z|r and q weight gradients of a GRU through the per-backward cache)."""
+        cache = self.tcache if self.tcache is not None else {}
+        hit = cache.get((id(t), ch, nshift))
+        if hit is None:
+            hi = torch.empty((nshift, ch, B, H, Wp), device=t.device, dtype=torch.bfloat16)
+            lo = torch.empty_like(hi) if split else None
+            L.call("as_transpose_split", t.data_ptr(), pitch, 0, ch, B, H, W, hi.data_ptr(), L.ptr(lo), Wp, nshift, _s())
+            hit = cache[(id(t), ch, nshift)] = (t, hi, lo)
+        return hit[1], hit[2]
+
     def wgrad(self, B, H, W, srcs, dy, dy_pitch):
         """(dW [Cout,Cin,KH,KW], db [Cout]) for this call."""
         dw = torch.zeros_like(self.w)
         db = torch.zeros_like(self.b)
+        tc, nsplit = _engine()
+        if (tc and _WGRAD_TC["on"] and self.KH in (1, 3) and self.KH == self.KW and self.Cin >= 32 and self.Cout >= 32
+                and len(srcs) <= 3 and all(s[3] == NHWC for s in srcs) and all(s[1] % 128 == 0 for s in srcs[:-1])
+                and B * H <= 65535):
+            # tensor cores: K = pixels GEMM over channel-major operand planes (as_conv2d_wgrad_umma)
+            split = nsplit == 3
+            Wp = (W + 7) // 8 * 8
+            d = L.WgradUmmaDesc()
+            d.B, d.H, d.W, d.KH, d.KW, d.Cout, d.num_src = B, H, W, self.KH, self.KW, self.Cout, len(srcs)
+            keep = []
+            for i, (t, ch, pitch, _) in enumerate(srcs):
+                hi, lo = self._tplanes(t, ch, pitch, B, H, W, Wp, split, self.KW)
+                d.src[i].hi, d.src[i].lo, d.src[i].channels = hi.data_ptr(), L.ptr(lo), ch
+                keep += [hi, lo]
+            dyh, dyl = self._tplanes(dy, self.Cout, dy_pitch, B, H, W, Wp, split)
+            d.dy_hi, d.dy_lo, d.Wp, d.nsplit = dyh.data_ptr(), L.ptr(dyl), Wp, nsplit
+            ws = torch.empty((self.KH * self.KW, self.Cout, self.Cin), device=dy.device, dtype=torch.float32)
+            d.ws, d.dw_acc = ws.data_ptr(), dw.data_ptr()
+            L.call("as_conv2d_wgrad_umma", d, _s())
+            L.call("as_bias_grad_fp32", dy.data_ptr(), dy_pitch, self.Cout, B * H * W, db.data_ptr(), _s())
+            return dw, db
         d = self._desc(B, H, W, srcs)
         L.call("as_conv2d_wgrad_fp32", d, dy.data_ptr(), dy_pitch, self.Cout, dw.data_ptr(), db.data_ptr(), _s())
         L.launch_count += 1
@@ -329,6 +374,9 @@ class UpdateBlockFn(torch.autograd.Function):
         n_layers = ub.args.n_gru_layers
         dev = gouts[0].device if gouts[0] is not None else next(g.device for g in gouts if g is not None)
         pgrads = {}                                          # id(parameter) -> grad
+        tcache = {}
+        for c in C.values():
+            c.tcache = tcache
 
         def acc_param(conv, dw, db):
             off = 0
@@ -463,6 +511,7 @@ class UpdateBlockFn(torch.autograd.Function):
             grads += [d_corr, None]
         for p in ub.parameters():
             grads.append(pgrads.get(id(p)))
+        tcache.clear()
         return tuple(grads)
 
 

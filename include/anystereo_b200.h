@@ -338,6 +338,28 @@ int as_gru_bwd_gates2(const float* drh, int drh_pitch, const float* h, const flo
 int as_conv_epilogue_fp32(const float* raw, int raw_pitch, long long N, int Cout, int epilogue, const float* ctx,
                           int ctx_pitch, const float* h, float* z, float* save, float* out, int out_pitch,
                           int out_coff, as_stream_t stream);
+/* db[c] += sum_n dy[n][c] (the bias half of as_conv2d_wgrad_fp32) */
+int as_bias_grad_fp32(const float* dy, int dy_pitch, int Cout, long long N, float* db_acc, as_stream_t stream);
+/* Weight gradient on the tensor cores (tcgen05 + TMA), K = pixels.  Operands are CHANNEL-major 16-bit hi/lo planes
+ * [nshift][C][B][H][Wp] (Wp = W rounded up to 8) written by as_transpose_split from pixel-major fp32; copy j is the
+ * image shifted horizontally by j - nshift/2 pixels with zeros shifted in (nshift = KW for the inputs, 1 for dY: a TMA
+ * box cannot start at a 2-byte offset of the innermost dimension).  A K-block is 64 consecutive pixels of one image
+ * row; the vertical tap shift is a TMA coordinate offset with out-of-bounds zero fill.  1x1 / 3x3; every source but
+ * the last must have a multiple of 128 channels.
+ * dw_acc[co][ci][ky][kx] += sum_n dY[n][co] * X[n + shift(ky,kx)][ci];  ws: [KH*KW][Cout][Cin] fp32 scratch. */
+int as_transpose_split(const float* in, int pitch, int coff, int C, int B, int H, int W, void* hi, void* lo, int Wp,
+                       int nshift, as_stream_t stream);
+typedef struct as_wgrad_umma_desc {
+  int B, H, W, KH, KW, Cout;
+  int num_src;
+  as_umma_src src[3];  /* transposed planes of the concatenated inputs, KW shifted copies each */
+  const void* dy_hi;   /* transposed planes of dY [Cout][B][H][Wp] */
+  const void* dy_lo;   /* NULL when nsplit == 1 */
+  int Wp, nsplit;
+  float* ws;
+  float* dw_acc;
+} as_wgrad_umma_desc;
+int as_conv2d_wgrad_umma(const as_wgrad_umma_desc* desc, as_stream_t stream);
 /* dst[n][dcoff + c] += src[n][scoff + c] */
 int as_add_slice(const float* src, int spitch, int scoff, float* dst, int dpitch, int dcoff, long long N, int C,
                  as_stream_t stream);

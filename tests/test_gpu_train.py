@@ -148,3 +148,47 @@ def test_training_step_hot_path(engine):
     assert rel(geog.grad, geor.grad) < 2e-3
     for name, prm in m.named_parameters():
         assert rel(prm.grad, pr[name].grad) < 2e-3, name
+
+
+@pytest.mark.parametrize("shape", [
+    # (B, H, W, source channels, Cout, kernel)
+    (2, 9, 13, [128, 128, 128], 256, 3),      # gru04/gru08 z|r: three sources, two Cout tiles
+    (1, 20, 46, [128, 128], 128, 3),          # gru16 q at config 5's 1/16 scale
+    (2, 7, 70, [128], 127, 3),                # encoder.conv: 127 outputs (dY pitch 128), two 64-pixel chunks per row
+    (2, 6, 10, [162], 64, 1),                 # convc1: 1x1 over the 162 lookup channels (second N tile is partial)
+    (1, 5, 8, [64], 64, 3),                   # convc2 / convd2
+])
+def test_wgrad_tensor_cores_vs_cuda_cores(shape):
+    """as_conv2d_wgrad_umma (tcgen05, K = pixels over channel-major planes) against as_conv2d_wgrad_fp32 and torch."""
+    import anystereo_b200 as A
+    from anystereo_b200 import update_train as T
+    B, H, W, chans, Cout, k = shape
+    g = torch.Generator(device="cpu").manual_seed(sum(shape[:3]) + Cout)
+    conv = torch.nn.Conv2d(sum(chans), Cout, k, padding=k // 2).cuda()
+    xs = [torch.randn(B, H, W, c, generator=g).cuda() for c in chans]
+    pitch = (Cout + 63) // 64 * 64
+    dy = torch.zeros(B, H, W, pitch).cuda()
+    dy[..., :Cout] = torch.randn(B, H, W, Cout, generator=g).cuda()
+    c = T._Conv([conv])
+    srcs = [T._src(x) for x in xs]
+    A.set_update_engine("fp32")
+    dw0, db0 = c.wgrad(B, H, W, srcs, dy, pitch)
+    A.set_update_engine("bf16x3")
+    assert T._WGRAD_TC["on"]
+    before = T.L.launch_count
+    dw1, db1 = c.wgrad(B, H, W, srcs, dy, pitch)
+    assert T.L.launch_count - before >= 3 + len(xs)          # transposes + tensor-core GEMM + bias reduction
+    torch.cuda.synchronize()
+    # torch autograd on the same GPU, strict fp32
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        x = torch.cat(xs, 3).permute(0, 3, 1, 2).contiguous()
+        y = conv(x)
+        gw, gb = torch.autograd.grad(y, [conv.weight, conv.bias], dy[..., :Cout].permute(0, 3, 1, 2).contiguous())
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    assert rel(dw0, gw) < 1e-4
+    assert rel(dw1, gw) < 1e-4, "tensor-core weight gradient"
+    assert rel(dw1, dw0) < 1e-4
+    assert rel(db1, gb) < 1e-4
