@@ -13,7 +13,6 @@
 // TMA producer thread -> 3-stage ring -> tcgen05.mma M=128,N=128 (hi*hi + hi*lo + lo*hi in the fp32-parity mode),
 // fp32 accumulator in TMEM -> registers -> smem transpose -> coalesced fp32 atomics into ws[tap][co][ci];
 // wgrad_finish_kernel adds ws into the nn.Conv2d layout [co][ci][ky][kx].
-#include <cstdlib>
 #include "umma.cuh"
 
 namespace {
@@ -34,7 +33,7 @@ struct WgParams {
   int num_src;
   int src_c0[4];                                 // first concatenated input channel of each source; [num_src] = Cin
   int ntiles, ksplit, kblocks;
-  int nsplit, f16, debug;
+  int nsplit, f16;
   float* ws;                                     // [KH*KW][Cout][Cin]
 };
 
@@ -86,9 +85,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_umma_kernel(const __grid_co
   const int kb0 = (int)((long long)ks * p.kblocks / p.ksplit);
   const int kb1 = (int)((long long)(ks + 1) * p.kblocks / p.ksplit);
 
-  if (p.debug == 1) {                            // diagnostic: no TMA, no MMA
-    if (tid == 0) umma::mbar_arrive(done);
-  } else if (warp == 0 && lane == 0) {           // ---- TMA producer
+  if (warp == 0 && lane == 0) {                  // ---- TMA producer
     const CUtensorMap* bh = si == 0 ? &maps.b_hi[0] : si == 1 ? &maps.b_hi[1] : &maps.b_hi[2];
     const CUtensorMap* bl = si == 0 ? &maps.b_lo[0] : si == 1 ? &maps.b_lo[1] : &maps.b_lo[2];
     for (int kb = kb0; kb < kb1; ++kb) {
@@ -109,7 +106,6 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_umma_kernel(const __grid_co
       const int it = kb - kb0, s = it % kStages, r = it / kStages;
       umma::mbar_wait(&full[s], (uint32_t)(r & 1));
       umma::tc_fence_after();
-      if (p.debug == 2) { umma::mbar_arrive(&empty[s]); continue; }   // diagnostic: TMA only
       const uint32_t base = umma::smem_u32(smem + s * kStageBytes);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -123,7 +119,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_umma_kernel(const __grid_co
       }
       umma::mma_commit(&empty[s]);               // stage reusable once these MMAs have read it
     }
-    if (p.debug == 2) umma::mbar_arrive(done); else umma::mma_commit(done);
+    umma::mma_commit(done);
   }
   __syncwarp();
 
@@ -248,12 +244,10 @@ extern "C" int as_conv2d_wgrad_umma(const as_wgrad_umma_desc* d, as_stream_t str
   p.nsplit = d->nsplit;
   p.f16 = as_operand_f16_internal();
   p.ws = d->ws;
-  { const char* dbg = getenv("AS_WGRAD_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
 
   WgMaps maps;
   const uint64_t rowb = (uint64_t)d->Wp * 2;
-  const char* dimx = getenv("AS_WGRAD_DIMX");
-  const uint64_t gx = (dimx && dimx[0] == '1') ? (uint64_t)d->Wp : (uint64_t)d->W;   // diagnostic
+  const uint64_t gx = (uint64_t)d->W;                 // columns W..Wp-1 of a row are out of bounds = zero fill
   const uint32_t box[4] = {64u, 1u, 1u, 128u};
   int rc;
   {

@@ -436,6 +436,23 @@ def run_ours(args):
                     "Mqueries_per_s": hr.shape[1] / ums / 1e3,
                     "loop_plus_upsampler_pairs_per_s": 1e3 / (loop_ms_per_pair + ums)}
                 del hr
+        # config 5 structure: one training step of the hot path (forward + explicit adjoints + AdamW), 8 pairs of
+        # 320x736, 16 iterations; tensor-core engine = forward / data / weight gradients on tcgen05 (tools/train_step.py)
+        if args.engine != "fp32":
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import train_step
+                with torch.enable_grad():
+                    tr = train_step.run(args.engine, 8, 16, 2, 80, 184, dev)
+                other["config5_igev_train_step_320x736_b8"] = {
+                    "ms_per_step": tr["ms_per_step"][-1], "pairs_per_s": tr["pairs_per_s"], "iters": 16,
+                    "engine": args.engine, "loss": tr["loss"][-1], "peak_mem_GB": tr["peak_mem_GB"],
+                    "note": "update block only is trained (backbones are synthetic leaf tensors); fp32 CUDA-core engine: "
+                            "profiles/train_step_r01_engines_1gpu.json"}
+            except Exception as e:                        # context only: never fail the bench line
+                other["config5_igev_train_step_320x736_b8"] = {"error": repr(e)[:200]}
+            finally:
+                block.reset_caches()
     pairs = world * B * args.steps
     value = pairs / (ms / 1e3)
     e2e_value = pairs / (ms_e2e / 1e3)

@@ -19,30 +19,24 @@ sys.path.insert(0, ROOT)
 import anystereo_b200 as A  # noqa: E402
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--batch", type=int, default=8)
-    ap.add_argument("--iters", type=int, default=16)       # train_iters, train_continuous_IGEV.py:297
-    ap.add_argument("--steps", type=int, default=2)
-    ap.add_argument("--engine", default="fp32", choices=["fp32", "bf16x3", "bf16", "fp16"],
-                    help="update-block engine: fp32 = CUDA cores; others = forward + data gradients on tcgen05")
-    ap.add_argument("--h", type=int, default=80)
-    ap.add_argument("--w", type=int, default=184)
-    a = ap.parse_args()
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    A.set_update_engine(a.engine)
-    A.set_corr_mode("fp32")
+def run(engine="fp32", batch=8, iters=16, steps=2, H=80, W=184, dev=None, world=1, rank=0):
+    """`steps` training steps of the IGEV hot path (structure of train_continuous_IGEV.py:186-240); returns the
+    per-step device times (ms), losses and gradient norms.  The update engine / correlation mode are restored."""
+    prev_engine, prev_corr = A.get_update_engine(), A.get_corr_mode()
+    try:
+        A.set_update_engine(engine)
+        A.set_corr_mode("fp32")
+        return _run(engine, batch, iters, steps, H, W, dev, world, rank)
+    finally:
+        A.set_update_engine(prev_engine)
+        A.set_corr_mode(prev_corr)
+
+
+def _run(engine, B, iters, steps, H, W, dev, world, rank):
     torch.manual_seed(0)                                    # identical replicas
     args = types.SimpleNamespace(corr_levels=2, corr_radius=4, n_gru_layers=3)
     block = A.BasicMultiUpdateBlock(args, hidden_dims=[128, 128, 128]).to(dev).train()
     opt = torch.optim.AdamW(block.parameters(), lr=2e-4, weight_decay=1e-5, eps=1e-8)   # train_continuous_IGEV.py:127
-    B, H, W = a.batch, a.h, a.w
     g = torch.Generator(device="cpu").manual_seed(100 + rank)   # each rank its own pairs
     sizes = [(H, W), (H // 2, W // 2), (H // 4, W // 4)]
 
@@ -57,7 +51,7 @@ def main():
     gt = (torch.rand(B, 1, H, W, generator=g) * 48).to(dev)
     coords = torch.arange(W, device=dev, dtype=torch.float32).reshape(1, 1, W, 1).repeat(B, H, 1, 1)
     times, losses, gnorms = [], [], []
-    for step in range(a.steps):
+    for step in range(steps):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -66,12 +60,12 @@ def main():
         opt.zero_grad(set_to_none=True)
         fn = A.Combined_Geo_Encoding_Volume(f1, f2, geo, num_levels=2, radius=4)
         net, disp, loss = list(net0), init_disp, 0.0
-        for it in range(a.iters):
+        for it in range(iters):
             disp = disp.detach()
             feat = fn(disp, coords)
             net, delta = block(net, inp, feat, disp)
             disp = disp + delta
-            loss = loss + 0.9 ** (a.iters - 1 - it) * (disp - gt).abs().mean()
+            loss = loss + 0.9 ** (iters - 1 - it) * (disp - gt).abs().mean()
         loss.backward()
         A.allreduce_gradients(list(block.parameters()))
         gn = torch.nn.utils.clip_grad_norm_(block.parameters(), 1.0)       # train_continuous_IGEV.py:234
@@ -84,12 +78,33 @@ def main():
         times.append(float(ms))
         losses.append(float(loss.detach()))
         gnorms.append(float(gn))
+    return {"config": "IGEV hot-path training step, %dx%d (1/4: %dx%d), batch %d/GPU, %d iters, update engine %s"
+                      % (4 * H, 4 * W, H, W, B, iters, engine),
+            "n_gpus": world, "ms_per_step": times, "pairs_per_s": world * B / (times[-1] / 1e3),
+            "loss": losses, "grad_norm_after_allreduce": gnorms,
+            "peak_mem_GB": torch.cuda.max_memory_allocated() / 2 ** 30}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--iters", type=int, default=16)       # train_iters, train_continuous_IGEV.py:297
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--engine", default="fp32", choices=["fp32", "bf16x3", "bf16", "fp16"],
+                    help="update-block engine: fp32 = CUDA cores; others = forward, data and weight gradients on tcgen05")
+    ap.add_argument("--h", type=int, default=80)
+    ap.add_argument("--w", type=int, default=184)
+    a = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    res = run(a.engine, a.batch, a.iters, a.steps, a.h, a.w, dev, world, rank)
     if rank == 0:
-        print(json.dumps({"config": "IGEV hot-path training step, %dx%d (1/4: %dx%d), batch %d/GPU, %d iters, update engine %s"
-                                    % (4 * H, 4 * W, H, W, B, a.iters, a.engine),
-                          "n_gpus": world, "ms_per_step": times, "pairs_per_s": world * B / (times[-1] / 1e3),
-                          "loss": losses, "grad_norm_after_allreduce": gnorms,
-                          "peak_mem_GB": torch.cuda.max_memory_allocated() / 2 ** 30}))
+        print(json.dumps(res))
     if world > 1:
         dist.destroy_process_group()
 
