@@ -130,6 +130,8 @@ SIGNATURES = {
     "as_gru_bwd_gates1": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _vp]),
     "as_gru_bwd_gates2": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _ll, _i, _vp]),
     "as_conv_epilogue_fp32": (_i, [_vp, _i, _ll, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "as_convd1_fp32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "as_convd1_wgrad_fp32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "as_bias_grad_fp32": (_i, [_vp, _i, _i, _ll, _vp, _vp]),
     "as_transpose_split": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp]),
     "as_conv2d_wgrad_umma": (_i, [C.POINTER(WgradUmmaDesc), _vp]),

@@ -114,9 +114,12 @@ __global__ void pack_weight_bf16_kernel(const float* __restrict__ w, __nv_bfloat
 // 64x49 weights live in shared memory.  One thread = 4 adjacent pixels x 16 output channels: per kernel row it reads
 // 10 patch values and 7x16 weights (warp-uniform 128-bit broadcasts) for 448 FMAs -- ~12 FMAs per smem load.
 constexpr int kD1TX = 32, kD1TY = 8;
+// F32OUT: the same arithmetic with an fp32 pixel-major output (training keeps relu(convd1) for the backward pass)
+template <bool F32OUT>
 __global__ void __launch_bounds__(256) convd1_split_kernel(const float* __restrict__ disp, const float* __restrict__ w,
                                                            const float* __restrict__ bias, __nv_bfloat16* __restrict__ hi,
-                                                           __nv_bfloat16* __restrict__ lo, int H, int W, int pitch, int coff, bool f16) {
+                                                           __nv_bfloat16* __restrict__ lo, float* __restrict__ out_f32, int H,
+                                                           int W, int pitch, int coff, bool f16) {
   __shared__ __align__(16) float ws[49 * 64];     // [tap][channel]
   __shared__ float bs[64];
   __shared__ float patch[kD1TY + 6][kD1TX + 6 + 2];
@@ -166,10 +169,12 @@ __global__ void __launch_bounds__(256) convd1_split_kernel(const float* __restri
     if (x >= W) continue;
     const long long n = (long long)b * HW + (long long)y * W + x;
 #pragma unroll
-    for (int j = 0; j < 16; j += 4)
-      store_split4(make_float4(fmaxf(acc[px][j], 0.f), fmaxf(acc[px][j + 1], 0.f), fmaxf(acc[px][j + 2], 0.f),
-                               fmaxf(acc[px][j + 3], 0.f)),
-                   hi, lo, n * pitch + coff + cg + j, f16);
+    for (int j = 0; j < 16; j += 4) {
+      const float4 y4 = make_float4(fmaxf(acc[px][j], 0.f), fmaxf(acc[px][j + 1], 0.f), fmaxf(acc[px][j + 2], 0.f),
+                                    fmaxf(acc[px][j + 3], 0.f));
+      if (F32OUT) *reinterpret_cast<float4*>(out_f32 + n * pitch + coff + cg + j) = y4;
+      else store_split4(y4, hi, lo, n * pitch + coff + cg + j, f16);
+    }
   }
 }
 
@@ -253,8 +258,20 @@ extern "C" int as_convd1_split(const float* disp, const float* w, const float* b
   if ((out_pitch & 3) || (out_coff & 3)) return AS_ERR_ALIGNMENT;
   if (B > 65535 || as_ceil_div(H, kD1TY) > 65535) return AS_ERR_UNSUPPORTED;
   dim3 grid(as_ceil_div(W, kD1TX), as_ceil_div(H, kD1TY), B);
-  convd1_split_kernel<<<grid, 256, 0, as_cu(stream)>>>(disp, w, bias, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, H, W,
-                                                       out_pitch, out_coff, as_operand_f16_internal() != 0);
+  convd1_split_kernel<false><<<grid, 256, 0, as_cu(stream)>>>(disp, w, bias, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, nullptr,
+                                                              H, W, out_pitch, out_coff, as_operand_f16_internal() != 0);
+  AS_RETURN_IF_LAUNCH_FAILED();
+  return AS_OK;
+}
+
+extern "C" int as_convd1_fp32(const float* disp, const float* w, const float* bias, float* out, int B, int H, int W,
+                              int out_pitch, int out_coff, as_stream_t stream) {
+  if (!disp || !w || !bias || !out || B <= 0 || H <= 0 || W <= 0 || out_pitch < out_coff + 64) return AS_ERR_BAD_ARG;
+  if ((out_pitch & 3) || (out_coff & 3) || !as_aligned16(out)) return AS_ERR_ALIGNMENT;
+  if (B > 65535 || as_ceil_div(H, kD1TY) > 65535) return AS_ERR_UNSUPPORTED;
+  dim3 grid(as_ceil_div(W, kD1TX), as_ceil_div(H, kD1TY), B);
+  convd1_split_kernel<true><<<grid, 256, 0, as_cu(stream)>>>(disp, w, bias, nullptr, nullptr, out, H, W, out_pitch, out_coff,
+                                                             false);
   AS_RETURN_IF_LAUNCH_FAILED();
   return AS_OK;
 }

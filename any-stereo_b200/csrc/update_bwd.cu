@@ -244,6 +244,51 @@ __global__ void conv_epilogue_kernel(const float* __restrict__ raw, int raw_pitc
   out[n * out_pitch + out_coff + co] = v;
 }
 
+// weight gradient of BasicMotionEncoder.convd1 (7x7, 1 -> 64, update.py:80): dW[co][t] += sum_px dY[px][co] * disp[px + t].
+// The generic wgrad kernel wastes 63/64 of its 64x64 tile on the single input channel; here a block owns a
+// 32x8 pixel tile, thread = (output channel, group of 13 taps), the disparity patch and one dY row live in smem.
+__global__ void __launch_bounds__(256) convd1_wgrad_kernel(const float* __restrict__ disp, const float* __restrict__ dy,
+                                                           int dy_pitch, int H, int W, float* __restrict__ dw) {
+  __shared__ float patch[8 + 6][32 + 6];
+  __shared__ float sdy[32][64];
+  const int tid = threadIdx.x;
+  const int b = blockIdx.z, x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
+  const long long HW = (long long)H * W;
+  for (int i = tid; i < 14 * 38; i += 256) {
+    const int r = i / 38, c = i - r * 38;
+    const int yy = y0 + r - 3, xx = x0 + c - 3;
+    patch[r][c] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(disp + (long long)b * HW + (long long)yy * W + xx) : 0.f;
+  }
+  const int co = tid & 63, t0 = (tid >> 6) * 13;          // taps t0 .. min(49, t0 + 13)
+  int ky[13], kx[13];
+#pragma unroll
+  for (int j = 0; j < 13; ++j) {
+    const int t = min(t0 + j, 48);
+    ky[j] = t / 7;
+    kx[j] = t - ky[j] * 7;
+  }
+  float acc[13];
+#pragma unroll
+  for (int j = 0; j < 13; ++j) acc[j] = 0.f;
+  for (int ty = 0; ty < 8; ++ty) {
+    __syncthreads();                                       // patch ready (first pass) / previous row consumed
+    const int y = y0 + ty;
+    for (int i = tid; i < 32 * 64; i += 256) {
+      const int px = i >> 6, c = i & 63, x = x0 + px;
+      sdy[px][c] = (y < H && x < W) ? __ldg(dy + ((long long)b * HW + (long long)y * W + x) * dy_pitch + c) : 0.f;
+    }
+    __syncthreads();
+    for (int px = 0; px < 32; ++px) {
+      const float g = sdy[px][co];
+#pragma unroll
+      for (int j = 0; j < 13; ++j) acc[j] = fmaf(g, patch[ty + ky[j]][px + kx[j]], acc[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 13; ++j)
+    if (t0 + j < 49) atomicAdd(dw + co * 49 + t0 + j, acc[j]);
+}
+
 inline unsigned blocks_for(long long total) { return (unsigned)as_ceil_div_ll(total, 256); }
 
 }  // namespace
@@ -283,6 +328,16 @@ extern "C" int as_conv2d_wgrad_fp32(const as_conv_desc* d, const float* dy, int 
     bias_grad_kernel<<<g2, 256, 0, as_cu(stream)>>>(dy, dy_pitch, Cout, N, db_acc);
     AS_RETURN_IF_LAUNCH_FAILED();
   }
+  return AS_OK;
+}
+
+extern "C" int as_convd1_wgrad_fp32(const float* disp, const float* dy, int dy_pitch, int B, int H, int W, float* dw_acc,
+                                    as_stream_t stream) {
+  if (!disp || !dy || !dw_acc || B <= 0 || H <= 0 || W <= 0 || dy_pitch < 64) return AS_ERR_BAD_ARG;
+  if (B > 65535 || as_ceil_div(H, 8) > 65535) return AS_ERR_UNSUPPORTED;
+  dim3 grid(as_ceil_div(W, 32), as_ceil_div(H, 8), B);
+  convd1_wgrad_kernel<<<grid, 256, 0, as_cu(stream)>>>(disp, dy, dy_pitch, H, W, dw_acc);
+  AS_RETURN_IF_LAUNCH_FAILED();
   return AS_OK;
 }
 

@@ -62,6 +62,15 @@ def set_wgrad_tensor_cores(on: bool):
     _WGRAD_TC["on"] = bool(on)
 
 
+# A/B knobs of the tensor-core training path (OFF by default until validated on a B200; AS_TRAIN_SMALL_TC=1 /
+# AS_TRAIN_CONVD1=1 turn them on):
+#  small_tc: DispHead.conv2 (one output channel) forward / data gradient / weight gradient on the tcgen05 kernels
+#            (rows / channels zero-padded to the kernels' granules) instead of the 64x64-tile CUDA-core kernels
+#  convd1:   dedicated CUDA-core kernels for the 7x7 single-input-channel convd1 (forward and weight gradient)
+_KNOBS = {"small_tc": os.environ.get("AS_TRAIN_SMALL_TC", "0") != "0",
+          "convd1": os.environ.get("AS_TRAIN_CONVD1", "0") != "0"}
+
+
 def _engine():
     """(tensor cores?, MMAs per K-step) of the current update engine."""
     from .update import get_update_engine
@@ -143,15 +152,19 @@ class _Conv:
 
     # ---- tensor-core variants (engines other than "fp32")
     def tc_ok(self):
-        """The tcgen05 kernel covers 1x1 / 3x3 with at least 32 input and output channels."""
-        return self.KH in (1, 3) and self.KH == self.KW and self.Cin >= 32 and self.Cout >= 32 and self.Cout <= 256
+        """The tcgen05 kernel covers 1x1 / 3x3 with at least 32 input channels; fewer than 32 output channels are
+        zero-padded rows of the packed weights (DispHead.conv2)."""
+        return (self.KH in (1, 3) and self.KH == self.KW and self.Cin >= 32 and self.Cout <= 256
+                and (self.Cout >= 32 or _KNOBS["small_tc"]))
 
     def fwd_tc(self, B, H, W, planes, nsplit, epi, out, out_pitch, out_coff=0, ctx=None, ctx_pitch=0, h=None, z=None,
                save=None):
         """Same contract as fwd() with NHWC output; `planes` are the hi/lo operand planes of the sources."""
         from . import update_umma as U
         cin_pad = sum(pl.shape[3] for pl in planes)
-        wt = U._weights(self.ub, "train." + self.name, self.convs, cin_pad=cin_pad, split=nsplit == 3)
+        # fewer than 32 outputs (DispHead.conv2): zero rows up to N = 64, the narrowest GEMM the encoder convs exercise
+        wt = U._weights(self.ub, "train." + self.name, self.convs, n_pad=None if self.Cout >= 32 else 64, cin_pad=cin_pad,
+                        split=nsplit == 3)
         raw = torch.empty((B, H, W, wt["n"]), device=out.device, dtype=torch.float32)
         U._conv(B, H, W, planes, wt, nsplit, L.UEPI_LINEAR_F32, out_f32=raw)
         L.call("as_conv_epilogue_fp32", raw.data_ptr(), wt["n"], B * H * W, self.Cout, epi, L.ptr(ctx), ctx_pitch, L.ptr(h),
@@ -178,9 +191,14 @@ class _Conv:
     def dgrad(self, B, H, W, dy, dy_pitch):
         """dX [B,H,W,Cin] from dY [.., Cout] (pixel-major, pitch dy_pitch)."""
         tc, nsplit = _engine()
-        if tc and self.ub is not None and self.tc_ok() and dy.shape[3] == dy_pitch \
-                and dy_pitch == (self.Cout + 63) // 64 * 64:              # note: Cin comes back padded to 32
-            return self.dgrad_tc(B, H, W, dy, nsplit)
+        if tc and self.ub is not None and self.tc_ok() and dy.shape[3] == dy_pitch:
+            cpad = (self.Cout + 63) // 64 * 64
+            if dy_pitch == cpad:                                          # note: Cin comes back padded to 32
+                return self.dgrad_tc(B, H, W, dy, nsplit)
+            if dy_pitch == self.Cout and _KNOBS["small_tc"]:              # DispHead.conv2: pad dY to the K granule
+                dyp = torch.zeros((B, H, W, cpad), device=dy.device, dtype=torch.float32)
+                L.call("as_add_slice", dy.data_ptr(), dy_pitch, 0, dyp.data_ptr(), cpad, 0, B * H * W, self.Cout, _s())
+                return self.dgrad_tc(B, H, W, dyp, nsplit)
         dx = torch.empty((B, H, W, self.Cin), device=dy.device, dtype=torch.float32)
         d = self._desc(B, H, W, [(dy, self.Cout, dy_pitch, NHWC)])
         d.Cout = self.Cin
@@ -209,8 +227,13 @@ class _Conv:
         dw = torch.zeros_like(self.w)
         db = torch.zeros_like(self.b)
         tc, nsplit = _engine()
-        if (tc and _WGRAD_TC["on"] and self.KH in (1, 3) and self.KH == self.KW and self.Cin >= 32 and self.Cout >= 32
-                and len(srcs) <= 3 and all(s[3] == NHWC for s in srcs) and all(s[1] % 128 == 0 for s in srcs[:-1])
+        if tc and _KNOBS["convd1"] and self.KH == 7 and self.KW == 7 and self.Cin == 1 and self.Cout == 64 \
+                and len(srcs) == 1 and srcs[0][2] == 1:
+            L.call("as_convd1_wgrad_fp32", srcs[0][0].data_ptr(), dy.data_ptr(), dy_pitch, B, H, W, dw.data_ptr(), _s())
+            L.call("as_bias_grad_fp32", dy.data_ptr(), dy_pitch, self.Cout, B * H * W, db.data_ptr(), _s())
+            return dw, db
+        if (tc and _WGRAD_TC["on"] and self.KH in (1, 3) and self.KH == self.KW and self.Cin >= 32
+                and (self.Cout >= 32 or _KNOBS["small_tc"]) and len(srcs) <= 3 and all(s[3] == NHWC for s in srcs) and all(s[1] % 128 == 0 for s in srcs[:-1])
                 and B * H <= 65535):
             # tensor cores: K = pixels GEMM over channel-major operand planes (as_conv2d_wgrad_umma)
             split = nsplit == 3
@@ -339,7 +362,11 @@ class UpdateBlockFn(torch.autograd.Function):
             conv("convc2", B, H, W, [c1], L.EPI_BIAS_RELU, cd, 128, 0)
             d1 = torch.empty((B, H, W, 64), device=dev, dtype=torch.float32)
             disp_n = disp_c.view(B, H, W, 1)
-            C["convd1"].fwd(B, H, W, [_src(disp_n)], L.EPI_BIAS_RELU, d1, 64)
+            if tc and _KNOBS["convd1"] and tuple(C["convd1"].w.shape) == (64, 1, 7, 7):
+                L.call("as_convd1_fp32", disp_c.data_ptr(), C["convd1"].w.data_ptr(), C["convd1"].b.data_ptr(), d1.data_ptr(),
+                       B, H, W, 64, 0, _s())
+            else:
+                C["convd1"].fwd(B, H, W, [_src(disp_n)], L.EPI_BIAS_RELU, d1, 64)
             conv("convd2", B, H, W, [d1], L.EPI_BIAS_RELU, cd, 128, 64)
             mo = torch.empty((B, H, W, 128), device=dev, dtype=torch.float32)
             conv("conv", B, H, W, [cd], L.EPI_BIAS_RELU, mo, 128, 0)
@@ -356,7 +383,10 @@ class UpdateBlockFn(torch.autograd.Function):
             t = torch.empty((B, H, W, 256), device=dev, dtype=torch.float32)
             conv("dh1", B, H, W, [hs[0]], L.EPI_BIAS_RELU, t, 256)
             delta = torch.empty((B, 1, H, W), device=dev, dtype=torch.float32)
-            C["dh2"].fwd(B, H, W, [_src(t)], L.EPI_BIAS, delta, 1, 0, out_layout=NCHW)
+            if tc and C["dh2"].tc_ok() and C["dh2"].Cout == 1:          # [B,1,H,W] is [B,H,W,1]
+                C["dh2"].fwd_tc(B, H, W, [pl(t)], nsplit, L.EPI_BIAS, delta, 1, 0)
+            else:
+                C["dh2"].fwd(B, H, W, [_src(t)], L.EPI_BIAS, delta, 1, 0, out_layout=NCHW)
             tape["head"] = dict(h=hs[0], t=t)
             outs.append(delta)
         tape["shapes"] = [tuple(h.shape) for h in hs]

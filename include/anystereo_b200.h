@@ -338,6 +338,13 @@ int as_gru_bwd_gates2(const float* drh, int drh_pitch, const float* h, const flo
 int as_conv_epilogue_fp32(const float* raw, int raw_pitch, long long N, int Cout, int epilogue, const float* ctx,
                           int ctx_pitch, const float* h, float* z, float* save, float* out, int out_pitch,
                           int out_coff, as_stream_t stream);
+/* BasicMotionEncoder.convd1 (7x7, 1 -> 64, update.py:80,87) for training: relu(conv + bias) as fp32 pixel-major
+ * [N][out_pitch] at out_coff (the arithmetic of as_convd1_split), and its weight gradient
+ * dw_acc[co][ky*7+kx] += sum_n dY[n][co] * disp[n + shift(ky,kx)] (exact fp32, CUDA cores). */
+int as_convd1_fp32(const float* disp, const float* w /*[64][49]*/, const float* bias, float* out, int B, int H, int W,
+                   int out_pitch, int out_coff, as_stream_t stream);
+int as_convd1_wgrad_fp32(const float* disp, const float* dy, int dy_pitch, int B, int H, int W, float* dw_acc,
+                         as_stream_t stream);
 /* db[c] += sum_n dy[n][c] (the bias half of as_conv2d_wgrad_fp32) */
 int as_bias_grad_fp32(const float* dy, int dy_pitch, int Cout, long long N, float* db_acc, as_stream_t stream);
 /* Weight gradient on the tensor cores (tcgen05 + TMA), K = pixels.  Operands are CHANNEL-major 16-bit hi/lo planes
