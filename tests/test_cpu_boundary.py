@@ -1,5 +1,6 @@
 """CPU tests (no GPU): the C-ABI library loads and exports every symbol the header declares, host-side
 logic, the C restatement of the sampler against the golden vectors, and error behaviour at the boundary."""
+import ctypes
 import os
 import re
 import types
@@ -56,6 +57,8 @@ int main(void) {
          offsetof(as_conv_umma_desc, w_hi), offsetof(as_conv_umma_desc, out_hi), offsetof(as_conv_umma_desc, u));
   printf("%zu %zu %zu %zu %zu %zu\n", sizeof(as_liif_query_desc), offsetof(as_liif_query_desc, P), offsetof(as_liif_query_desc, coords),
          offsetof(as_liif_query_desc, w2_hi), offsetof(as_liif_query_desc, disp), offsetof(as_liif_query_desc, out));
+  printf("%zu %zu %zu %zu %zu %zu\n", sizeof(as_wgrad_umma_desc), offsetof(as_wgrad_umma_desc, src), offsetof(as_wgrad_umma_desc, dy_hi),
+         offsetof(as_wgrad_umma_desc, Wp), offsetof(as_wgrad_umma_desc, ws), offsetof(as_wgrad_umma_desc, dw_acc));
   return 0;
 }
 """)
@@ -68,7 +71,9 @@ int main(void) {
     assert c[:6] == [ctypes.sizeof(L.ConvSrc), ctypes.sizeof(d), d.src.offset, d.weight.offset, d.out.offset, d.save.offset]
     assert c[6:12] == [ctypes.sizeof(L.UmmaSrc), ctypes.sizeof(u), u.src.offset, u.w_hi.offset, u.out_hi.offset, u.u.offset]
     q = L.LiifQueryDesc
-    assert c[12:] == [ctypes.sizeof(q), q.P.offset, q.coords.offset, q.w2_hi.offset, q.disp.offset, q.out.offset]
+    assert c[12:18] == [ctypes.sizeof(q), q.P.offset, q.coords.offset, q.w2_hi.offset, q.disp.offset, q.out.offset]
+    g = L.WgradUmmaDesc
+    assert c[18:] == [ctypes.sizeof(g), g.src.offset, g.dy_hi.offset, g.Wp.offset, g.ws.offset, g.dw_acc.offset]
 
 
 def test_argument_errors_without_gpu(A):
@@ -81,6 +86,16 @@ def test_argument_errors_without_gpu(A):
     assert lib.as_liif_query(None, None) == -1
     assert lib.as_context_upsample_multiscale(None, None, None, None, 1, 2, 2, 4, None) == -1
     assert lib.as_corr1d_workspace_bytes(1, 8, 2, 4, 4, 0) == 0
+    # training entry points (a13-vi): epilogue on a raw conv output, channel-major planes, tensor-core weight gradient
+    assert lib.as_conv_epilogue_fp32(None, 64, 16, 64, 1, None, 0, None, None, None, None, 64, 0, None) == -1
+    assert lib.as_transpose_split(None, 64, 0, 64, 1, 4, 4, None, None, 8, 1, None) == -1
+    assert lib.as_conv2d_wgrad_umma(None, None) == -1
+    wd = A._lib.WgradUmmaDesc()                      # a descriptor without planes is rejected before any CUDA call
+    wd.B, wd.H, wd.W, wd.KH, wd.KW, wd.Cout, wd.num_src, wd.Wp, wd.nsplit = 1, 4, 4, 3, 3, 64, 1, 8, 3
+    assert lib.as_conv2d_wgrad_umma(ctypes.byref(wd), None) == -1
+    assert lib.as_bias_grad_fp32(None, 64, 64, 16, None, None) == -1
+    assert lib.as_convd1_fp32(None, None, None, None, 1, 4, 4, 64, 0, None) == -1
+    assert lib.as_convd1_wgrad_fp32(None, None, 64, 1, 4, 4, None, None) == -1
     with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
         A.corr_sampler.forward(torch.zeros(1, 2, 3, 4), torch.zeros(1, 1, 2, 3), 4)
     with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
