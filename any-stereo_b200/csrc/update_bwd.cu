@@ -88,13 +88,14 @@ __global__ void __launch_bounds__(WT::kThreads) wgrad_kernel(WgradParams p) {
   }
 }
 
-// db[c] += sum_n dy[n][c]
+// db[c] += sum_n dy[n][c]; one block = kBiasRows pixels x 32 channels (1024 rows: ~900 blocks at config 5, all resident)
+constexpr int kBiasRows = 1024;
 __global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict__ dy, int pitch, int C, long long N,
                                                         float* __restrict__ db) {
   const int c = blockIdx.y * 32 + (threadIdx.x & 31);
   const int rl = threadIdx.x >> 5;                      // 8 row lanes
-  const long long n_begin = (long long)blockIdx.x * 4096;
-  const long long n_end = n_begin + 4096 < N ? n_begin + 4096 : N;
+  const long long n_begin = (long long)blockIdx.x * kBiasRows;
+  const long long n_end = n_begin + kBiasRows < N ? n_begin + kBiasRows : N;
   float acc = 0.f;
   if (c < C)
     for (long long n = n_begin + rl; n < n_end; n += 8) acc += __ldg(dy + n * pitch + c);
@@ -324,7 +325,7 @@ extern "C" int as_conv2d_wgrad_fp32(const as_conv_desc* d, const float* dy, int 
   wgrad_kernel<<<grid, WT::kThreads, 0, as_cu(stream)>>>(p);
   AS_RETURN_IF_LAUNCH_FAILED();
   if (db_acc) {
-    dim3 g2((unsigned)as_ceil_div_ll(N, 4096), as_ceil_div(Cout, 32));
+    dim3 g2((unsigned)as_ceil_div_ll(N, kBiasRows), as_ceil_div(Cout, 32));
     bias_grad_kernel<<<g2, 256, 0, as_cu(stream)>>>(dy, dy_pitch, Cout, N, db_acc);
     AS_RETURN_IF_LAUNCH_FAILED();
   }
@@ -343,7 +344,7 @@ extern "C" int as_convd1_wgrad_fp32(const float* disp, const float* dy, int dy_p
 
 extern "C" int as_bias_grad_fp32(const float* dy, int dy_pitch, int Cout, long long N, float* db_acc, as_stream_t stream) {
   if (!dy || !db_acc || Cout <= 0 || N <= 0 || dy_pitch < Cout) return AS_ERR_BAD_ARG;
-  dim3 g2((unsigned)as_ceil_div_ll(N, 4096), as_ceil_div(Cout, 32));
+  dim3 g2((unsigned)as_ceil_div_ll(N, kBiasRows), as_ceil_div(Cout, 32));
   bias_grad_kernel<<<g2, 256, 0, as_cu(stream)>>>(dy, dy_pitch, Cout, N, db_acc);
   AS_RETURN_IF_LAUNCH_FAILED();
   return AS_OK;

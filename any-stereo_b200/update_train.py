@@ -115,17 +115,40 @@ class _Conv:
     def __init__(self, convs, ub=None, name=None):
         self.ub, self.name = ub, name
         self.tcache = None                     # per-backward cache of channel-major operand planes
-        with torch.no_grad():
-            self.w = torch.cat([c.weight.detach().float() for c in convs], 0).contiguous()
-            self.b = torch.cat([c.bias.detach().float() for c in convs], 0).contiguous()
-        self.Cout, self.Cin, self.KH, self.KW = self.w.shape
         self.convs = convs
-        dev = self.w.device
-        self.wf = torch.empty((self.KH * self.KW * self.Cin, self.Cout), device=dev, dtype=torch.float32)
-        L.call("as_pack_conv_weight", self.w.data_ptr(), self.wf.data_ptr(), self.Cout, self.Cin, self.KH, self.KW, _s())
-        self.wd = torch.empty((self.KH * self.KW * self.Cout, self.Cin), device=dev, dtype=torch.float32)
-        L.call("as_pack_conv_weight_dgrad", self.w.data_ptr(), self.wd.data_ptr(), self.Cout, self.Cin, self.KH, self.KW,
-               _s())
+        self.Cout = sum(c.weight.shape[0] for c in convs)
+        _, self.Cin, self.KH, self.KW = convs[0].weight.shape
+        self.dev = convs[0].weight.device
+        self._w = self._b = self._wf = self._wd = None     # fp32 copies / CUDA-core packings, made on first use only
+
+    @property
+    def w(self):
+        if self._w is None:
+            with torch.no_grad():
+                self._w = torch.cat([c.weight.detach().float() for c in self.convs], 0).contiguous()
+        return self._w
+
+    @property
+    def b(self):
+        if self._b is None:
+            with torch.no_grad():
+                self._b = torch.cat([c.bias.detach().float() for c in self.convs], 0).contiguous()
+        return self._b
+
+    @property
+    def wf(self):
+        if self._wf is None:
+            self._wf = torch.empty((self.KH * self.KW * self.Cin, self.Cout), device=self.dev, dtype=torch.float32)
+            L.call("as_pack_conv_weight", self.w.data_ptr(), self._wf.data_ptr(), self.Cout, self.Cin, self.KH, self.KW, _s())
+        return self._wf
+
+    @property
+    def wd(self):
+        if self._wd is None:
+            self._wd = torch.empty((self.KH * self.KW * self.Cout, self.Cin), device=self.dev, dtype=torch.float32)
+            L.call("as_pack_conv_weight_dgrad", self.w.data_ptr(), self._wd.data_ptr(), self.Cout, self.Cin, self.KH, self.KW,
+                   _s())
+        return self._wd
 
     def _desc(self, B, H, W, srcs):
         d = L.ConvDesc()
@@ -224,8 +247,8 @@ class _Conv:
 
     def wgrad(self, B, H, W, srcs, dy, dy_pitch):
         """(dW [Cout,Cin,KH,KW], db [Cout]) for this call."""
-        dw = torch.zeros_like(self.w)
-        db = torch.zeros_like(self.b)
+        dw = torch.zeros((self.Cout, self.Cin, self.KH, self.KW), device=self.dev, dtype=torch.float32)
+        db = torch.zeros((self.Cout,), device=self.dev, dtype=torch.float32)
         tc, nsplit = _engine()
         if tc and _KNOBS["convd1"] and self.KH == 7 and self.KW == 7 and self.Cin == 1 and self.Cout == 64 \
                 and len(srcs) == 1 and srcs[0][2] == 1:
@@ -362,7 +385,8 @@ class UpdateBlockFn(torch.autograd.Function):
             conv("convc2", B, H, W, [c1], L.EPI_BIAS_RELU, cd, 128, 0)
             d1 = torch.empty((B, H, W, 64), device=dev, dtype=torch.float32)
             disp_n = disp_c.view(B, H, W, 1)
-            if tc and _KNOBS["convd1"] and tuple(C["convd1"].w.shape) == (64, 1, 7, 7):
+            cd1 = C["convd1"]
+            if tc and _KNOBS["convd1"] and (cd1.Cout, cd1.Cin, cd1.KH, cd1.KW) == (64, 1, 7, 7):
                 L.call("as_convd1_fp32", disp_c.data_ptr(), C["convd1"].w.data_ptr(), C["convd1"].b.data_ptr(), d1.data_ptr(),
                        B, H, W, 64, 0, _s())
             else:
