@@ -1,6 +1,8 @@
 """Per-kernel micro-benchmarks at BASELINE.json config-2 shapes (IGEV 384x1248 -> 96x312, B=8) and config-3
 for the RAFT lookup: CUDA-event timing, >=20 reps after warm-up, L2 flushed between reps.  Algorithmic bytes
-per SURVEY.md 8(d).  Usage: python tools/microbench.py [--B 8] [--json out.json]"""
+per SURVEY.md 8(d).  Usage: python tools/microbench.py [--B 8] [--json out.json]
+`--only train` times the weight-gradient kernels of the training path at config-5 sizes, tensor cores vs CUDA cores
+(added at the end of round 1 after the GPU budget was spent: first numbers are due in round 2)."""
 import argparse
 import json
 import os
@@ -102,6 +104,36 @@ def main():
             res["corr_build_c3_" + mode]["TFLOPs_issued"] = round(flops * (3 if mode == "bf16x3" else 1) / med / 1e6, 1)
             print("   ", res["corr_build_c3_" + mode])
         A.set_corr_mode("fp32")
+        if a.json:
+            json.dump(res, open(a.json, "w"), indent=1)
+        return
+    if a.only == "train":
+        # a13-vi kernels of the tensor-core training path at BASELINE config 5 (8 pairs of 320x736 -> 80x184)
+        from anystereo_b200 import update_train as T
+        Bt, Ht, Wt = a.B, 80, 184
+        Nt = Bt * Ht * Wt
+        A.set_update_engine("bf16x3")
+        shapes = {"gru04.zr": ([128, 128, 128], 256, 3), "gru04.q": ([128, 128, 128], 128, 3), "dh1": ([128], 256, 3),
+                  "conv": ([128], 127, 3), "convc2": ([64], 64, 3), "convc1": ([162], 64, 1), "dh2": ([256], 1, 3)}
+        for name, (chans, Cout, k) in shapes.items():
+            conv = torch.nn.Conv2d(sum(chans), Cout, k, padding=k // 2).to(dev)
+            xs = [torch.randn(Bt, Ht, Wt, c, device=dev) for c in chans]
+            pitch = (Cout + 63) // 64 * 64 if Cout >= 32 else Cout
+            dy = torch.zeros(Bt, Ht, Wt, pitch, device=dev)
+            dy[..., :Cout] = torch.randn(Bt, Ht, Wt, Cout, device=dev)
+            c = T._Conv([conv])
+            srcs = [T._src(x) for x in xs]
+            flops = 2.0 * k * k * Cout * sum(chans) * Nt
+            byts = 4 * Nt * (sum(chans) + Cout) + 4 * k * k * Cout * sum(chans)      # fp32 operands read once + dW
+            for label, on in (("wgrad_tcgen05_incl_transposes", True), ("wgrad_cuda_cores", False)):
+                T.set_wgrad_tensor_cores(on)
+                T._KNOBS["small_tc"] = on
+                med, best = timeit(lambda: c.wgrad(Bt, Ht, Wt, srcs, dy, pitch), reps=5 if not on else 10)
+                rec("%s_%s" % (name, label), med, best, byts)
+                res["%s_%s" % (name, label)]["TFLOPs_logical"] = round(flops / med / 1e6, 1)
+            T.set_wgrad_tensor_cores(True)
+            T._KNOBS["small_tc"] = True
+        A.set_update_engine("fp32")
         if a.json:
             json.dump(res, open(a.json, "w"), indent=1)
         return
