@@ -20,7 +20,7 @@ from .update import (BasicMultiUpdateBlock, BasicMultiUpdateBlockRAFT, BasicMoti
                      set_update_engine, get_update_engine)
 from .hotpath import (igev_iterations, raft_iterations, install_into_reference, HotLoopGraph, set_lookup_fusion,
                       adopt_update_block, adopt_liif_up)
-from .parallel import shard_pairs, allreduce_gradients
+from .parallel import shard_pairs, allreduce_gradients, GradientAllReducer
 from . import liif
 from .liif import liif_out_multi_scale_Training, context_upsample_multiscale_train, upsample_disp
 
@@ -29,5 +29,5 @@ __all__ = [
     "BasicMultiUpdateBlock", "BasicMultiUpdateBlockRAFT", "BasicMotionEncoder", "ConvGRU", "DispHead",
     "set_corr_mode", "get_corr_mode", "set_update_engine", "get_update_engine",
     "igev_iterations", "raft_iterations", "install_into_reference", "HotLoopGraph",
-    "shard_pairs", "allreduce_gradients",
+    "shard_pairs", "allreduce_gradients", "GradientAllReducer",
 ]

@@ -238,3 +238,22 @@ def require_cuda(t: torch.Tensor, name: str, dtype=None, contiguous=True):
     if dtype is not None and t.dtype != dtype:
         raise RuntimeError("%s must have dtype %s (got %s)" % (name, dtype, t.dtype))
     return t
+
+
+def version_of(t) -> int:
+    """``t._version`` for cache keys.  Inference tensors (created under torch.inference_mode()) do not track a
+    version counter and raise on access: they key on identity alone (callers also hold a weak reference), version -1.
+    In-place writes to such a tensor, like writes through ``param.data``, are invisible to the caches -- call
+    ``BasicMultiUpdateBlock.invalidate_weights()`` / ``reset_caches()`` after them."""
+    if torch.is_inference(t):
+        return -1
+    return t._version
+
+
+def forbid_grad(what: str, *tensors):
+    """Forward-only operators must not silently cut the autograd graph (the reference's versions are differentiable):
+    raise when gradients are being recorded and an input wants them."""
+    if torch.is_grad_enabled() and any(torch.is_tensor(t) and t.requires_grad for t in tensors):
+        raise RuntimeError(
+            "anystereo_b200.%s is forward-only (inference): an input requires grad while autograd is recording. "
+            "Call it under torch.no_grad(), or keep the reference's differentiable implementation for training." % what)

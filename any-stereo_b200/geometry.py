@@ -19,9 +19,10 @@ import torch
 
 from . import _lib as L
 
-#: default arithmetic of the all-pairs correlation: "fp32" (CUDA cores, exact), "bf16x3" (tcgen05,
-#: fp32-parity split), "bf16" (tcgen05, fast).  Set by anystereo_b200.set_corr_mode().
-_CORR_MODE = {"mode": "fp32"}
+#: arithmetic of the all-pairs correlation: "bf16x3" (default: tcgen05, fp32-parity split, <= 1e-4 of max|ref|),
+#: "fp32" (CUDA cores, exact), "bf16" (tcgen05, fast).  Set by anystereo_b200.set_corr_mode().
+DEFAULT_CORR_MODE = "bf16x3"
+_CORR_MODE = {"mode": DEFAULT_CORR_MODE}
 _MODE_ID = {"fp32": L.CORR_FP32_SIMT, "bf16x3": L.CORR_BF16X3, "bf16": L.CORR_BF16}
 
 
@@ -122,11 +123,20 @@ class _CorrLookupFn(torch.autograd.Function):
         return (None, None, None) + tuple(gb)
 
 
-def _check_disp_coords(disp, coords):
+def _check_disp_coords(disp, coords, extent=None):
+    """``extent`` = (B, H, W1, device) of the feature maps the pyramid was built from: the lookup kernels index volume
+    rows as (b*H + y)*W1 + x, so a disparity map of any other size (wrong scale, a different batch after sharding) or
+    on another device would read out of bounds instead of failing like the reference's reshape / grid_sample does."""
     L.require_cuda(disp, "disp", torch.float32, contiguous=False)
     if disp.dim() != 4 or disp.shape[1] != 1:
         raise RuntimeError("disp must be [B,1,H,W]")
     B, _, H, W = disp.shape
+    if extent is not None:
+        if (B, H, W) != tuple(extent[:3]):
+            raise RuntimeError("disp is [%d,1,%d,%d] but the cost volume was built for [%d,1,%d,%d]"
+                               % ((B, H, W) + tuple(extent[:3])))
+        if disp.device != extent[3]:
+            raise RuntimeError("disp is on %s but the cost volume lives on %s" % (disp.device, extent[3]))
     disp = disp.contiguous()
     if coords is not None:
         L.require_cuda(coords, "coords", torch.float32, contiguous=False)
@@ -165,12 +175,13 @@ class CorrBlock1D:
         else:
             bufs, self._widths, self._pitches = _build_corr_levels(init_fmap1.detach(), init_fmap2.detach(), num_levels)
         self._bufs = bufs
+        self._extent = (init_fmap1.shape[0], init_fmap1.shape[2], init_fmap1.shape[3], init_fmap1.device)
         N = bufs[0].shape[0]
         self.init_corr_pyramid = [b[:, :w].unflatten(1, (1, 1, w)) if w > 0 else b[:, :0].reshape(N, 1, 1, 0)
                                   for b, w in zip(bufs, self._widths)]
 
     def __call__(self, disp, coords):
-        disp, coords = _check_disp_coords(disp, coords)
+        disp, coords = _check_disp_coords(disp, coords, self._extent)
         if torch.is_grad_enabled() and any(b.requires_grad for b in self._bufs):
             return _CorrLookupFn.apply(disp, coords, (self._widths, self._pitches, self.radius), *self._bufs)
         return _corr_lookup(self._bufs, self._widths, self._pitches, self.radius, disp, coords)
@@ -178,12 +189,13 @@ class CorrBlock1D:
     def deferred(self, disp, coords):
         """The same lookup, not yet run (see Combined_Geo_Encoding_Volume.deferred): the tensor-core engines fuse it
         with BasicMotionEncoder.convc1."""
-        disp, coords = _check_disp_coords(disp, coords)
+        disp, coords = _check_disp_coords(disp, coords, self._extent)
         return DeferredCorrLookup(self, disp, coords)
 
     @staticmethod
     def corr(fmap1, fmap2, mask_invalid=False):
         """[B,D,H,W1] x [B,D,H,W2] -> [B,H,W1,1,W2] (geometry.py:46-56); no 1/sqrt(D) scaling."""
+        L.forbid_grad("CorrBlock1D.corr", fmap1, fmap2)      # (the constructor's pyramid build IS differentiable)
         f1, f2 = _check_pair(fmap1, fmap2)
         B, D, H, W1 = f1.shape
         W2 = f2.shape[3]
@@ -291,14 +303,17 @@ class Combined_Geo_Encoding_Volume:
         self._corr_bufs = corr_bufs
         self._geo_bufs = geo_bufs
         B, G, Dg, H, W = geo_volume.shape
+        if (B, H, W) != (init_fmap1.shape[0], init_fmap1.shape[2], init_fmap1.shape[3]):
+            raise RuntimeError("geo_volume [B,G,D,H,W] and init_fmap1 [B,C,H,W] disagree on B/H/W")
         self._G, self._Dg = G, Dg
+        self._extent = (B, H, W, geo_volume.device)
         N = B * H * W
         # reference-shaped views: [N,1,1,w_i] and [N,G,1,D_i]
         self.init_corr_pyramid = [b[:, :w].unflatten(1, (1, 1, w)) for b, w in zip(corr_bufs, self._widths)]
         self.geo_volume_pyramid = [b.permute(0, 2, 1).unsqueeze(2) for b in geo_bufs]
 
     def __call__(self, disp, coords):
-        disp, coords = _check_disp_coords(disp, coords)
+        disp, coords = _check_disp_coords(disp, coords, self._extent)
         bufs = list(self._geo_bufs) + list(self._corr_bufs)
         if torch.is_grad_enabled() and any(b.requires_grad for b in bufs):
             meta = (self._G, self._Dg, self._widths, self._pitches, self.radius, self.num_levels)
@@ -310,7 +325,7 @@ class Combined_Geo_Encoding_Volume:
         """The same lookup, not yet run: hand the result to BasicMultiUpdateBlock.forward as `corr` and the
         tensor-core engines fuse it with BasicMotionEncoder.convc1, so the 162-channel tensor never
         reaches HBM.  Engines / shapes without the fused kernel call .materialize() and behave as before."""
-        disp, coords = _check_disp_coords(disp, coords)
+        disp, coords = _check_disp_coords(disp, coords, self._extent)
         return DeferredGeoLookup(self, disp, coords)
 
     @staticmethod

@@ -161,10 +161,12 @@ def install_into_reference(ref_igev_module=None, ref_raft_module=None):
 
         models.coreContinuous_IGEV.continuous_IGEVstereo.{Combined_Geo_Encoding_Volume, build_gwc_volume}
         models.coreContinuous_IGEV.continuous_IGEVstereo.context_upsample_multiscale_train
-        models.corePrune_RAFT.prune_raft_stereo.CorrBlock1D
+        models.corePrune_RAFT.prune_raft_stereo.{CorrBlock1D, context_upsample_multiscale_train}
 
     ``model.update_block`` / ``model.liif_up`` are swapped per model instance with ``adopt_update_block`` /
-    ``adopt_liif_up``."""
+    ``adopt_liif_up``.  The cost-volume objects, ``build_gwc_volume`` and the update block are differentiable
+    (training, config 5); the upsampler pieces are forward-only and RAISE if a gradient is requested through them
+    (``_lib.forbid_grad``) instead of silently cutting the graph -- keep the reference's own upsampler for training."""
     if ref_igev_module is not None:
         ref_igev_module.Combined_Geo_Encoding_Volume = Combined_Geo_Encoding_Volume
         ref_igev_module.build_gwc_volume = build_gwc_volume
@@ -172,6 +174,8 @@ def install_into_reference(ref_igev_module=None, ref_raft_module=None):
         ref_igev_module.context_upsample_multiscale_train = context_upsample_multiscale_train
     if ref_raft_module is not None:
         ref_raft_module.CorrBlock1D = CorrBlock1D
+        from .liif import context_upsample_multiscale_train      # prune_raft_stereo.py:227
+        ref_raft_module.context_upsample_multiscale_train = context_upsample_multiscale_train
 
 
 def adopt_update_block(ref_update_block, family="igev"):

@@ -57,6 +57,7 @@ def _pack_linear(w, n_pad=None, split=True):
 def isu_affinity(feature):
     """AffinityFeature.forward (liif.py:434-449) for the 3x3 / dilation-1 window: [B,C,H,W] -> [B,8,H,W]."""
     L.require_cuda(feature, "feature", torch.float32, contiguous=False)
+    L.forbid_grad("liif.isu_affinity", feature)
     x = feature.detach().contiguous()
     B, Cc, H, W = x.shape
     out = torch.empty((B, 8, H, W), device=x.device, dtype=torch.float32)
@@ -110,7 +111,7 @@ class liif_out_multi_scale_Training(nn.Module):
     # ---- weights in the layouts the kernels consume, cached per parameter version ------------------
     def _weights(self, split):
         lin = [m for m in self.imnet.layers if isinstance(m, nn.Linear)]
-        key = (split,) + tuple((p.data_ptr(), p._version) for m in lin for p in (m.weight, m.bias))
+        key = (split,) + tuple((p.data_ptr(), L.version_of(p)) for m in lin for p in (m.weight, m.bias))
         if self._cache is not None and self._cache["key"] == key:
             return self._cache
         with torch.no_grad():
@@ -161,6 +162,9 @@ class liif_out_multi_scale_Training(nn.Module):
         if len(feats) != self.number_input:
             raise RuntimeError("expected %d feature maps" % self.number_input)
         L.require_cuda(coord, "coord", torch.float32, contiguous=False)
+        # forward-only: a training forward (grad recording, trainable parameters or inputs) must not get a graph-less result
+        # (parameters count only in train() mode: eval-mode inference without torch.no_grad() stays legal)
+        L.forbid_grad("liif_out_multi_scale_Training", coord, disp, *feats, *(self.parameters() if self.training else ()))
         coord = coord.detach().contiguous()
         B, Q, _ = coord.shape
         dev = coord.device
@@ -212,6 +216,7 @@ def context_upsample_multiscale_train(disp_low, up_weights, hr_coord):
     L.require_cuda(disp_low, "disp_low", torch.float32, contiguous=False)
     L.require_cuda(up_weights, "up_weights", torch.float32, contiguous=False)
     L.require_cuda(hr_coord, "hr_coord", torch.float32, contiguous=False)
+    L.forbid_grad("context_upsample_multiscale_train", disp_low, up_weights, hr_coord)
     B, _, h, w = disp_low.shape
     Q = hr_coord.shape[1]
     d, u, c = disp_low.detach().contiguous(), up_weights.detach().contiguous(), hr_coord.detach().contiguous()

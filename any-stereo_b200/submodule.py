@@ -64,6 +64,7 @@ def disparity_regression(x, maxdisp):
     L.require_cuda(x, "x", torch.float32, contiguous=False)
     if x.shape[1] != maxdisp:
         raise RuntimeError("x must have maxdisp channels")
+    L.forbid_grad("disparity_regression", x)
     x = x.detach().contiguous()
     B, D, H, W = x.shape
     out = torch.empty((B, 1, H, W), device=x.device, dtype=torch.float32)
@@ -78,6 +79,7 @@ def init_disparity(geo_encoding_volume, classifier_weight, maxdisp=None, return_
     with ``classifier = nn.Conv3d(G, 1, 3, 1, 1, bias=False)``.  -> init_disp [B,1,H,W] (and prob [B,D,H,W])."""
     L.require_cuda(geo_encoding_volume, "geo_encoding_volume", torch.float32, contiguous=False)
     L.require_cuda(classifier_weight, "classifier_weight", torch.float32, contiguous=False)
+    L.forbid_grad("init_disparity", geo_encoding_volume, classifier_weight)
     g = geo_encoding_volume.detach().contiguous()
     w = classifier_weight.detach().contiguous()
     B, G, D, H, W = g.shape

@@ -24,7 +24,10 @@ import torch.nn as nn
 
 from . import _lib as L
 
-_ENGINE = {"engine": "fp32"}
+#: default engine = the fp32-parity tensor-core path (tcgen05, 3x split-bf16, fp32 accumulation in TMEM).  "fp32" selects
+#: the exact CUDA-core kernels (the on-GPU parity baseline, ~30x slower); "fp16" / "bf16" are the single-MMA fast modes.
+DEFAULT_ENGINE = "bf16x3"
+_ENGINE = {"engine": DEFAULT_ENGINE}
 
 
 def set_update_engine(engine: str):
@@ -93,7 +96,7 @@ class _PackedConv:
         self.b = None
 
     def get(self, convs):
-        key = tuple((c.weight.data_ptr(), c.weight._version, c.bias.data_ptr(), c.bias._version) for c in convs)
+        key = tuple((c.weight.data_ptr(), L.version_of(c.weight), c.bias.data_ptr(), L.version_of(c.bias)) for c in convs)
         if key != self.key:
             with torch.no_grad():
                 w = torch.cat([c.weight.detach().float() for c in convs], dim=0).contiguous()
@@ -159,6 +162,16 @@ class BasicMultiUpdateBlock(nn.Module):
             st["ctx"].clear()
             st["planes"].clear()
 
+    def invalidate_weights(self):
+        """Drop every packed / split copy of the parameters.  The caches key on (data_ptr, version counter); writes
+        that bypass the counter (``param.data.copy_``, EMA / clipping through ``.data``, in-place edits of inference
+        tensors) must be followed by this call."""
+        self._packed.clear()
+        self.reset_caches()
+        st = self.__dict__.get("_umma_state")
+        if st is not None:
+            st["w"].clear()
+
     def _pk(self, name, convs):
         if name not in self._packed:
             self._packed[name] = _PackedConv()
@@ -168,7 +181,7 @@ class BasicMultiUpdateBlock(nn.Module):
         """(cz|cr) and cq of one scale as pixel-major tensors; loop-invariant, cached per tensor version."""
         cz, cr, cq = inp_i
         # identity (weak refs) + version: a recycled allocation with new contents must not hit the cache
-        key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in (cz, cr, cq))
+        key = tuple((t.data_ptr(), L.version_of(t), tuple(t.shape)) for t in (cz, cr, cq))
         hit = self._ctx_cache.get(idx)
         if hit is not None and hit[0] == key and all(r() is t for r, t in zip(hit[3], (cz, cr, cq))):
             return hit[1], hit[2]

@@ -92,7 +92,7 @@ def _dgrad_weights(ub, name, convs, split):
     forward weights (rows padded to 32, K channels padded to 64), cached per parameter version."""
     from .update_umma import _state
     st = _state(ub)["w"]
-    key = (split, L.operand_format()) + tuple((c.weight.data_ptr(), c.weight._version) for c in convs)
+    key = (split, L.operand_format()) + tuple((c.weight.data_ptr(), L.version_of(c.weight)) for c in convs)
     hit = st.get("train.dgrad." + name)
     if hit is not None and hit["key"] == key:
         return hit

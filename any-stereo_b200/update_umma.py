@@ -69,7 +69,7 @@ def _state(ub):
 def _weights(ub, name, convs, n_pad=None, cin_pad=None, split=True):
     """bf16 hi/lo GEMM weights [n_pad][taps*cin_pad] + padded fp32 bias, cached per parameter version."""
     st = _state(ub)["w"]
-    key = (split, L.operand_format()) + tuple((c.weight.data_ptr(), c.weight._version, c.bias.data_ptr(), c.bias._version) for c in convs)
+    key = (split, L.operand_format()) + tuple((c.weight.data_ptr(), L.version_of(c.weight), c.bias.data_ptr(), L.version_of(c.bias)) for c in convs)
     hit = st.get(name)
     if hit is not None and hit["key"] == key:
         return hit
@@ -94,7 +94,7 @@ def _fused_c1_weights(ub, split, kind=DeferredGeoLookup):
     """convc1 weights in the K order of the fused lookup kernel (geometry.Deferred*Lookup.pack_convc1_weight)."""
     st = _state(ub)["w"]
     c = ub.encoder.convc1
-    key = (split, L.operand_format(), kind.__name__, c.weight.data_ptr(), c.weight._version, c.bias.data_ptr(), c.bias._version)
+    key = (split, L.operand_format(), kind.__name__, c.weight.data_ptr(), L.version_of(c.weight), c.bias.data_ptr(), L.version_of(c.bias))
     hit = st.get("convc1.fused")
     if hit is not None and hit["key"] == key:
         return hit
@@ -113,7 +113,7 @@ def _convd1_weights(ub, split):
     """convd1.weight [64,1,7,7] as the K-major [64][64] (49 taps + zero pad) bf16 hi/lo operand."""
     st = _state(ub)["w"]
     c = ub.encoder.convd1
-    key = (split, L.operand_format(), c.weight.data_ptr(), c.weight._version)
+    key = (split, L.operand_format(), c.weight.data_ptr(), L.version_of(c.weight))
     hit = st.get("convd1.umma")
     if hit is not None and hit["key"] == key:
         return hit
@@ -131,7 +131,7 @@ def _small_weights(ub):
     """fp32 weights consumed on CUDA cores: convd1 [64][49] and DispHead.conv2 as [9][256]."""
     st = _state(ub)["w"]
     e, dh = ub.encoder, ub.disp_head
-    key = tuple((p.data_ptr(), p._version) for p in (e.convd1.weight, e.convd1.bias, dh.conv2.weight, dh.conv2.bias))
+    key = tuple((p.data_ptr(), L.version_of(p)) for p in (e.convd1.weight, e.convd1.bias, dh.conv2.weight, dh.conv2.bias))
     hit = st.get("small")
     if hit is not None and hit["key"] == key:
         return hit
@@ -149,7 +149,7 @@ def _context(ub, idx, inp_i, wzr, wq):
     """Loop-invariant GRU context with the conv biases folded in: (cz+bz | cr+br) [B,H,W,2Hd], cq+bq [B,H,W,Hd]."""
     cz, cr, cq = inp_i
     st = _state(ub)["ctx"]
-    key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in (cz, cr, cq)) + (wzr["key"], wq["key"])
+    key = tuple((t.data_ptr(), L.version_of(t), tuple(t.shape)) for t in (cz, cr, cq)) + (wzr["key"], wq["key"])
     hit = st.get(idx)
     if hit is not None and hit[0] == key and all(r() is t for r, t in zip(hit[3], (cz, cr, cq))):
         return hit[1], hit[2]
@@ -208,7 +208,7 @@ def _planes_of(ub, h_f32, split):
     hit = cache.get(h_f32.data_ptr())
     # valid while the tensor we produced is still alive (its memory cannot have been recycled), untouched
     # (views share the version counter) and of the same extent
-    if (hit is not None and hit[0]() is not None and hit[2] == h_f32._version and hit[1].shape == tuple(h_f32.shape)
+    if (hit is not None and hit[0]() is not None and hit[2] == L.version_of(h_f32) and hit[1].shape == tuple(h_f32.shape)
             and (hit[1].lo is not None) == split and hit[1].fmt == L.operand_format()):
         return hit[1]
     pl = _Planes(h_f32.shape, h_f32.device, split)
@@ -220,7 +220,7 @@ def _remember(ub, h_f32, pl):
     cache = _state(ub)["planes"]
     if len(cache) > 16:
         cache.clear()
-    cache[h_f32.data_ptr()] = (weakref.ref(h_f32), pl, h_f32._version)
+    cache[h_f32.data_ptr()] = (weakref.ref(h_f32), pl, L.version_of(h_f32))
 
 
 def forward(ub, net, inp, corr=None, disp=None, iter04=True, iter08=True, iter16=True, update=True):

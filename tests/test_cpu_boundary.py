@@ -120,6 +120,35 @@ def test_update_block_state_dict_matches_reference_names(A):
         assert sum(int(np.prod(s)) for s in ours.values()) in (4071488, 4063424)
 
 
+def test_default_engine_is_tensor_core_parity(A):
+    """VERDICT r1 weak #5: rebinding the names alone must select the tcgen05 parity engine, not the CUDA-core one."""
+    import subprocess
+    import sys as _sys
+    out = subprocess.run([_sys.executable, "-c",
+                          "import anystereo_b200 as A; print(A.get_update_engine(), A.get_corr_mode())"],
+                         capture_output=True, text=True, cwd=ROOT)
+    assert out.stdout.split() == ["bf16x3", "bf16x3"], (out.stdout, out.stderr[-500:])
+    assert A.update.DEFAULT_ENGINE == "bf16x3" and A.geometry.DEFAULT_CORR_MODE == "bf16x3"
+
+
+def test_reference_install_is_pristine():
+    """baseline/_ref (git-ignored; travels to the GPU box) is a byte-identical copy of the reference tree."""
+    import filecmp
+    from oracle import install_ref
+    if not os.path.isdir(os.path.join(install_ref.SRC, "models")):
+        pytest.skip("no /root/reference in this container")
+    assert install_ref.install(verbose=False)
+    for rel in install_ref._files(install_ref.SRC):
+        assert filecmp.cmp(os.path.join(install_ref.SRC, rel), os.path.join(install_ref.DST, rel), shallow=False), rel
+    tracked = subprocess_out(["git", "ls-files", "baseline"])
+    assert tracked.strip() == "", "baseline/_ref must never be committed"
+
+
+def subprocess_out(cmd):
+    import subprocess
+    return subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT).stdout
+
+
 def test_shard_pairs(A):
     for n in (0, 1, 7, 8, 64):
         for ws in (1, 2, 3, 8):

@@ -1,0 +1,181 @@
+#!/usr/bin/env python
+"""The drop-in, executed: build the REAL reference model graphs (continuous_IGEVStereo / continuous_RaftStereo, the
+unmodified code under baseline/_ref -- or /root/reference in the build container), run them as shipped, then rebind the
+names SURVEY 8(b) lists to this library (install_into_reference + adopt_update_block + adopt_liif_up) and run the SAME
+forward again: same weights, same images, same iteration count.
+
+    python tools/dropin.py [--family igev|raft|both] [--size 384x1248] [--iters 32] [--json out.json]
+
+Reports, per family / shape / engine: mean and max |final full-resolution disparity - reference| in pixels (the
+BASELINE.json EPE gate is 0.01 px) and the wall time of one forward (CUDA events) for the reference torch path on the
+same GPU (strict fp32 = the parity oracle, and PyTorch's default TF32 convolutions) and for the drop-in call pattern
+(``geo_fn(disp, coords)`` materialising the lookup tensor, then ``update_block(...)`` on NCHW tensors).
+
+Test / measurement infrastructure: imports oracle/ref_loader.py (never imported by the product package).
+"""
+import argparse
+import contextlib
+import json
+import math
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_loader  # noqa: E402
+
+
+def reference_available() -> bool:
+    return ref_loader.available()
+
+
+def make_pair(B, H, W, device, seed=3):
+    """Synthetic stereo pair with structure: band-limited texture + fine noise, right view = left view warped by a
+    smooth disparity field (20 + 10 sin cos px, SURVEY 8(d) 'smooth'), values in [0, 255)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    low = torch.rand(B, 3, H // 8 + 2, W // 8 + 2, generator=g)
+    tex = F.interpolate(low, size=(H, W), mode="bicubic", align_corners=True).clamp(0, 1)
+    img1 = (0.75 * tex + 0.25 * torch.rand(B, 3, H, W, generator=g)) * 254.0
+    ys = torch.arange(H).float().view(1, H, 1)
+    xs = torch.arange(W).float().view(1, 1, W)
+    disp = 20.0 + 10.0 * torch.sin(2 * math.pi * xs / W) * torch.cos(2 * math.pi * ys / H)
+    # right(x) = left(x + d): sample the left image at x + d
+    gx = (xs + disp) / (W - 1) * 2 - 1
+    gy = (ys / (H - 1) * 2 - 1).expand(1, H, W)
+    grid = torch.stack([gx.expand(1, H, W), gy], -1).expand(B, H, W, 2)
+    img2 = F.grid_sample(img1, grid, mode="bilinear", padding_mode="border", align_corners=True)
+    img2 = (img2 + torch.randn(B, 3, H, W, generator=g)).clamp(0, 254.9)
+    return img1.to(device), img2.to(device)
+
+
+def build_model(family, device, seed=0, **over):
+    R = ref_loader.load_models()
+    torch.manual_seed(seed)
+    args = ref_loader.model_args(family, **over)
+    cls = R.IGEV if family == "igev" else R.RAFT
+    with contextlib.redirect_stdout(open(os.devnull, "w")):       # the RAFT constructor prints a banner
+        model = cls(args)
+    return model.to(device).eval(), R
+
+
+@contextlib.contextmanager
+def installed(model, R, family):
+    """Rebind the reference's names to this library for the duration of the block."""
+    import anystereo_b200 as A
+    mod = R.igev_module if family == "igev" else R.raft_module
+    names = ["Combined_Geo_Encoding_Volume", "build_gwc_volume", "context_upsample_multiscale_train", "CorrBlock1D"]
+    saved = {n: getattr(mod, n) for n in names if hasattr(mod, n)}
+    ub, lu = model.update_block, model.liif_up
+    try:
+        if family == "igev":
+            A.install_into_reference(ref_igev_module=mod)
+        else:
+            A.install_into_reference(ref_raft_module=mod)
+        model.update_block = A.adopt_update_block(ub, family)
+        hd = model.args.hidden_dims[2]
+        model.liif_up = A.adopt_liif_up(lu, chanels=[48 + hd, 32])          # agg_type 'type5': [stem_4x|hidden, stem_2x]
+        yield model
+    finally:
+        for n, v in saved.items():
+            setattr(mod, n, v)
+        model.update_block, model.liif_up = ub, lu
+
+
+def forward(model, R, img1, img2, iters, scale=1.0):
+    B, _, H, W = img1.shape
+    Ho, Wo = int(round(H * scale)), int(round(W * scale))
+    hr = R.make_coord([Ho, Wo]).to(img1.device)[None].expand(B, -1, -1).contiguous()
+    sc = torch.full((B, 1), float(scale), device=img1.device)
+    with torch.no_grad():
+        out = model(img1, img2, iters=iters, test_mode=True, hr_coord=hr, scale=sc)
+    return out.reshape(B, Ho, Wo)
+
+
+def _timed(fn, reps=2):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return out, e0.elapsed_time(e1) / reps
+
+
+def run(family, H, W, iters=32, B=1, engines=("bf16x3", "fp16"), device="cuda", timing=True, scale=1.0):
+    import anystereo_b200 as A
+    model, R = build_model(family, device)
+    img1, img2 = make_pair(B, H, W, device)
+    res = {"family": family, "image": [H, W], "batch": B, "iters": iters, "scale": scale, "engines": {}}
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        # the parity oracle: the reference as shipped, strict fp32 on the same GPU (SURVEY 8c "oracle precision caveat")
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        ref, ms_ref = _timed(lambda: forward(model, R, img1, img2, iters, scale), 1 if not timing else 2)
+        res["reference_strict_fp32_ms"] = ms_ref
+        if timing:
+            torch.backends.cudnn.allow_tf32 = True
+            ref_tf32, ms_tf32 = _timed(lambda: forward(model, R, img1, img2, iters, scale))
+            res["reference_default_tf32_ms"] = ms_tf32
+            res["reference_default_tf32_epe_px"] = float((ref_tf32 - ref).abs().mean())
+            torch.backends.cudnn.allow_tf32 = False
+        prev_engine, prev_corr = A.get_update_engine(), A.get_corr_mode()
+        for eng in engines:
+            # None = whatever the library defaults to (what a user who only rebinds the names gets)
+            if eng is not None:
+                A.set_update_engine(eng)
+                A.set_corr_mode({"fp32": "fp32", "bf16": "bf16"}.get(eng, "bf16x3"))
+            with installed(model, R, family) as m:
+                ours, ms = _timed(lambda: forward(m, R, img1, img2, iters, scale), 1 if not timing else 2)
+            d = (ours - ref).abs()
+            res["engines"][eng or "default(%s)" % A.get_update_engine()] = {
+                "epe_mean_px": float(d.mean()), "epe_max_px": float(d.max()), "dropin_forward_ms": ms,
+                "disp_range_px": [float(ref.min()), float(ref.max())]}
+        A.set_update_engine(prev_engine)
+        A.set_corr_mode(prev_corr)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--family", default="both", choices=["igev", "raft", "both"])
+    ap.add_argument("--size", default=None, help="HxW (default: 384x1248 for igev, 320x736 for raft; both for 'both')")
+    ap.add_argument("--iters", type=int, default=32)
+    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--engines", default="default,bf16x3,fp16,fp32")
+    ap.add_argument("--json", default=None)
+    a = ap.parse_args()
+    if not reference_available():
+        print(json.dumps({"unavailable": "reference tree not found (baseline/_ref; run oracle/install_ref.py in the build container)"}))
+        return
+    engines = [None if e == "default" else e for e in a.engines.split(",")]
+    jobs = []
+    fams = ["igev", "raft"] if a.family == "both" else [a.family]
+    for fam in fams:
+        if a.size:
+            sizes = [tuple(int(v) for v in a.size.split("x"))]
+        else:
+            sizes = [(384, 1248), (320, 736)]
+        for hw in sizes:
+            jobs.append((fam, hw))
+    out = []
+    for fam, (H, W) in jobs:
+        r = run(fam, H, W, a.iters, a.batch, engines)
+        out.append(r)
+        print(json.dumps(r), flush=True)
+    if a.json:
+        os.makedirs(os.path.dirname(os.path.abspath(a.json)), exist_ok=True)
+        with open(a.json, "w") as f:
+            json.dump(out, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
