@@ -161,7 +161,7 @@ def lib():
     return _lib
 
 
-FMT_BF16, FMT_F16 = 0, 1
+FMT_BF16, FMT_F16, FMT_F16F8 = 0, 1, 2
 _operand_format = FMT_BF16
 
 

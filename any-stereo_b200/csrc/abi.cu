@@ -25,12 +25,13 @@ extern "C" const char* as_error_string(int code) {
   return "anystereo_b200: unknown error";
 }
 
-static int g_operand_f16 = 0;
-int as_operand_f16_internal() { return g_operand_f16; }
+static int g_operand_fmt = AS_FMT_BF16;
+int as_operand_f16_internal() { return g_operand_fmt != AS_FMT_BF16; }
+int as_operand_fmt_internal() { return g_operand_fmt; }
 
 extern "C" int as_set_operand_format(int fmt) {
-  if (fmt != AS_FMT_BF16 && fmt != AS_FMT_F16) return AS_ERR_BAD_ARG;
-  g_operand_f16 = fmt == AS_FMT_F16;
+  if (fmt != AS_FMT_BF16 && fmt != AS_FMT_F16 && fmt != AS_FMT_F16F8) return AS_ERR_BAD_ARG;
+  g_operand_fmt = fmt;
   return AS_OK;
 }
-extern "C" int as_get_operand_format(void) { return g_operand_f16 ? AS_FMT_F16 : AS_FMT_BF16; }
+extern "C" int as_get_operand_format(void) { return g_operand_fmt; }

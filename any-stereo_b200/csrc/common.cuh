@@ -41,7 +41,8 @@ __device__ __forceinline__ void as_stg_stream4(float4* p, float4 v) {
 // (as_set_operand_format(AS_FMT_F16): single-MMA fast mode with 11-bit mantissas, the analogue of the reference's
 // autocast mixed precision).  Process-wide, read by every launcher at call time.
 // ----------------------------------------------------------------------------------------------
-int as_operand_f16_internal();
+int as_operand_f16_internal();      // hi planes are IEEE half (AS_FMT_F16 or AS_FMT_F16F8)
+int as_operand_fmt_internal();      // AS_FMT_BF16 / AS_FMT_F16 / AS_FMT_F16F8
 
 // two floats -> packed 16-bit pair (lo in bits [0,16)), round to nearest even
 __device__ __forceinline__ uint32_t as_cvt16x2(float lo, float hi, bool f16) {
@@ -60,4 +61,66 @@ __device__ __forceinline__ float as_widen_hi16(uint32_t pk, bool f16) {
 __device__ __forceinline__ void as_split2(float v0, float v1, uint32_t& hi, uint32_t& lo, bool f16) {
   hi = as_cvt16x2(v0, v1, f16);
   lo = as_cvt16x2(v0 - as_widen_lo16(hi, f16), v1 - as_widen_hi16(hi, f16), f16);
+}
+
+// ----------------------------------------------------------------------------------------------
+// AS_FMT_F16F8 -- the 2-pass fp32-parity format: x = hi + lo with hi in IEEE half; the "lo" plane (same bytes as a 16-bit
+// plane) carries, per 64-channel chunk, 128 bytes [ e5m2(lo * 2^6) x 64 | e5m2(hi * 2^-8) x 64 ] for activations and
+// [ e5m2(hi * 2^-6) x 64 | e5m2(lo * 2^8) x 64 ] for weights.  One kind::f16 MMA computes a_hi * w_hi and ONE kind::f8f6f4
+// MMA over the 128-byte rows computes a_lo * w_hi + a_hi * w_lo (the scales cancel; fp8 runs at twice the f16 rate, so the
+// doubled K costs one f16 pass): 2 pass-equivalents instead of the 3 of hi/lo split products.  The cross terms are
+// 2^-12 of the result, so the 2-bit mantissas of e5m2 leave a 2^-15 relative error -- measured on the reference models:
+// final-disparity drift 1.0e-4 px (IGEV) / 3.4e-4 px (RAFT) against 0.96e-4 / 1.9e-4 for the 3-pass bf16 split
+// (tools/experiments/precision_sim.py).
+// ----------------------------------------------------------------------------------------------
+constexpr float kX8ActLoScale = 64.0f, kX8ActHiScale = 1.0f / 256.0f;     // activations: lo * 2^6, hi * 2^-8
+constexpr float kX8WgtHiScale = 1.0f / 64.0f, kX8WgtLoScale = 256.0f;     // weights:     hi * 2^-6, lo * 2^8
+
+// 4 floats -> 4 e5m2 bytes, `a` in the lowest byte
+__device__ __forceinline__ uint32_t as_e5m2x4(float a, float b, float c, float d) {
+  uint16_t lo, hi;
+  asm("cvt.rn.satfinite.e5m2x2.f32 %0, %1, %2;" : "=h"(lo) : "f"(b), "f"(a));   // first source -> upper byte
+  asm("cvt.rn.satfinite.e5m2x2.f32 %0, %1, %2;" : "=h"(hi) : "f"(d), "f"(c));
+  return (uint32_t)lo | ((uint32_t)hi << 16);
+}
+// byte offset inside an x8 plane of the element at flat index `off` (channel pitch a multiple of 64)
+__device__ __forceinline__ long long as_x8_byte(long long off) { return ((off >> 6) << 7) + (off & 63); }
+
+// "lo" information of 4 consecutive channels (off % 4 == 0): v = exact values, h = their packed 16-bit hi halves
+__device__ __forceinline__ void as_store_lo4(void* lo, long long off, float4 v, uint2 h, int fmt) {
+  const bool f16 = fmt != 0;
+  const float h0 = as_widen_lo16(h.x, f16), h1 = as_widen_hi16(h.x, f16), h2 = as_widen_lo16(h.y, f16), h3 = as_widen_hi16(h.y, f16);
+  if (fmt != 2) {
+    uint2 l;
+    l.x = as_cvt16x2(v.x - h0, v.y - h1, f16);
+    l.y = as_cvt16x2(v.z - h2, v.w - h3, f16);
+    *reinterpret_cast<uint2*>(reinterpret_cast<unsigned short*>(lo) + off) = l;
+  } else {
+    uint8_t* b = reinterpret_cast<uint8_t*>(lo) + as_x8_byte(off);
+    *reinterpret_cast<uint32_t*>(b) = as_e5m2x4((v.x - h0) * kX8ActLoScale, (v.y - h1) * kX8ActLoScale, (v.z - h2) * kX8ActLoScale,
+                                                (v.w - h3) * kX8ActLoScale);
+    *reinterpret_cast<uint32_t*>(b + 64) = as_e5m2x4(h0 * kX8ActHiScale, h1 * kX8ActHiScale, h2 * kX8ActHiScale, h3 * kX8ActHiScale);
+  }
+}
+// 8 consecutive channels (off % 8 == 0): v[8] exact values, h[4] packed hi halves
+__device__ __forceinline__ void as_store_lo8(void* lo, long long off, const float* v, const uint32_t* h, int fmt) {
+  const bool f16 = fmt != 0;
+  float hv[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { hv[2 * i] = as_widen_lo16(h[i], f16); hv[2 * i + 1] = as_widen_hi16(h[i], f16); }
+  if (fmt != 2) {
+    uint4 l;
+    l.x = as_cvt16x2(v[0] - hv[0], v[1] - hv[1], f16); l.y = as_cvt16x2(v[2] - hv[2], v[3] - hv[3], f16);
+    l.z = as_cvt16x2(v[4] - hv[4], v[5] - hv[5], f16); l.w = as_cvt16x2(v[6] - hv[6], v[7] - hv[7], f16);
+    *reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(lo) + off) = l;
+  } else {
+    uint8_t* b = reinterpret_cast<uint8_t*>(lo) + as_x8_byte(off);
+    uint2 a, c;
+    a.x = as_e5m2x4((v[0] - hv[0]) * kX8ActLoScale, (v[1] - hv[1]) * kX8ActLoScale, (v[2] - hv[2]) * kX8ActLoScale, (v[3] - hv[3]) * kX8ActLoScale);
+    a.y = as_e5m2x4((v[4] - hv[4]) * kX8ActLoScale, (v[5] - hv[5]) * kX8ActLoScale, (v[6] - hv[6]) * kX8ActLoScale, (v[7] - hv[7]) * kX8ActLoScale);
+    c.x = as_e5m2x4(hv[0] * kX8ActHiScale, hv[1] * kX8ActHiScale, hv[2] * kX8ActHiScale, hv[3] * kX8ActHiScale);
+    c.y = as_e5m2x4(hv[4] * kX8ActHiScale, hv[5] * kX8ActHiScale, hv[6] * kX8ActHiScale, hv[7] * kX8ActHiScale);
+    *reinterpret_cast<uint2*>(b) = a;
+    *reinterpret_cast<uint2*>(b + 64) = c;
+  }
 }

@@ -40,28 +40,22 @@ struct ConvUmmaParams {
   const float* bias; const float* ctx; int ctx_pitch; const float* h; float* z;
   float* out_f32; __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; int out_pitch, out_coff, cout_valid;
   const float* disp; const float* w2; float* u;
-  bool f16;                                   // operand planes / weights are IEEE half instead of bf16
+  bool f16;                                   // hi planes / weights are IEEE half instead of bf16
+  int fmt;                                    // AS_FMT_* of the planes this launch reads and writes
 };
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
-// 8 floats -> 8 16-bit hi (+ 8 lo = x - hi)
-__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo, bool f16) {
-  uint32_t h[4], l[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) as_split2(v[2 * i], v[2 * i + 1], h[i], l[i], f16);
-  hi = make_uint4(h[0], h[1], h[2], h[3]);
-  lo = make_uint4(l[0], l[1], l[2], l[3]);
-}
-
-// store 32 consecutive channels of one pixel as bf16 hi (/lo) planes
-__device__ __forceinline__ void store_split32(const float* v, __nv_bfloat16* hi, __nv_bfloat16* lo, long long off, bool f16) {
+// store 32 consecutive channels of one pixel as 16-bit hi planes (+ the lo plane of the format: x - hi in 16 bits, or the
+// e5m2 pair encoding of AS_FMT_F16F8, common.cuh)
+__device__ __forceinline__ void store_split32(const float* v, __nv_bfloat16* hi, __nv_bfloat16* lo, long long off, int fmt) {
 #pragma unroll
   for (int j = 0; j < 32; j += 8) {
-    uint4 h, l;
-    split8(v + j, h, l, f16);
-    *reinterpret_cast<uint4*>(hi + off + j) = h;
-    if (lo) *reinterpret_cast<uint4*>(lo + off + j) = l;
+    uint32_t h[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = as_cvt16x2(v[j + 2 * i], v[j + 2 * i + 1], fmt != 0);
+    *reinterpret_cast<uint4*>(hi + off + j) = make_uint4(h[0], h[1], h[2], h[3]);
+    if (lo) as_store_lo8(lo, off + j, v + j, h, fmt);
   }
 }
 
@@ -72,7 +66,10 @@ __device__ __forceinline__ void store_split32(const float* v, __nv_bfloat16* hi,
 // accumulator lanes.  Per SM the B reads and the B ring footprint halve (4 weight stages instead of 2).
 //   full barriers live in the leader (both producers arm them remotely, TMA credits them with cta_group::2),
 //   "slot free" / "accumulator ready" are multicast commits to both CTAs, "accumulator drained" arrives remotely.
-template <bool TWO>
+// NS = tensor-core passes per K-step: 1 = hi*hi; 3 = hi*hi + hi*lo + lo*hi (16-bit hi/lo planes); 2 = hi*hi in kind::f16 plus
+// ONE kind::f8f6f4 MMA over the e5m2 pair planes of AS_FMT_F16F8 (both cross terms, common.cuh).  Compile-time so that no
+// MMA sits under a run-time branch (see the predicated-MMA lint in tests/test_cpu_boundary.py).
+template <bool TWO, int NS>
 __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_constant__ ConvMaps maps,
                                                                 const ConvUmmaParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -99,10 +96,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.num_src; ++s) {
       umma::prefetch_tmap(&maps.a_hi[s]);
-      if (p.nsplit == 3) umma::prefetch_tmap(&maps.a_lo[s]);
+      if (NS > 1) umma::prefetch_tmap(&maps.a_lo[s]);
     }
     umma::prefetch_tmap(&maps.b_hi);
-    if (p.nsplit == 3) umma::prefetch_tmap(&maps.b_lo);
+    if (NS > 1) umma::prefetch_tmap(&maps.b_lo);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kMaxStages; ++s) {
@@ -132,8 +129,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   if (warp == 0) {
     if (lane == 0) {
       int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
-      const uint32_t txA = (uint32_t)p.a_plane * (p.nsplit == 3 ? 2u : 1u);
-      const uint32_t txB = (uint32_t)b_bytes * (p.nsplit == 3 ? 2u : 1u);
+      const uint32_t txA = (uint32_t)p.a_plane * (NS > 1 ? 2u : 1u);
+      const uint32_t txB = (uint32_t)b_bytes * (NS > 1 ? 2u : 1u);
       const int ph = p.KH >> 1, pw = p.KW >> 1;
       const int brow0 = (int)crank * nb_rows;    // first weight row of my half
       for (int itn = 0; itn < niter; ++itn) {
@@ -152,12 +149,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
               if (!TWO) {
                 umma::mbar_expect_tx(&fullA[sa], txA);
                 umma::tma_load_4d(sta, &maps.a_hi[s], &fullA[sa], c0, x0 + kx - pw, y0 - ph, b);
-                if (p.nsplit == 3) umma::tma_load_4d(sta + p.a_plane, &maps.a_lo[s], &fullA[sa], c0, x0 + kx - pw, y0 - ph, b);
+                if (NS > 1) umma::tma_load_4d(sta + p.a_plane, &maps.a_lo[s], &fullA[sa], c0, x0 + kx - pw, y0 - ph, b);
               } else {
                 const uint32_t bar = umma::mapa(umma::smem_u32(&fullA[sa]), 0);
                 umma::mbar_expect_tx_cluster(bar, txA);
                 umma::tma_load_4d_2sm(sta, &maps.a_hi[s], bar, c0, x0 + kx - pw, y0 - ph, b);
-                if (p.nsplit == 3) umma::tma_load_4d_2sm(sta + p.a_plane, &maps.a_lo[s], bar, c0, x0 + kx - pw, y0 - ph, b);
+                if (NS > 1) umma::tma_load_4d_2sm(sta + p.a_plane, &maps.a_lo[s], bar, c0, x0 + kx - pw, y0 - ph, b);
               }
               if (++sa == p.nstA) { sa = 0; pha ^= 1; }
               for (int ky = 0; ky < p.KH; ++ky) {
@@ -167,12 +164,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                 if (!TWO) {
                   umma::mbar_expect_tx(&fullB[sb], txB);
                   umma::tma_load_2d(stb, &maps.b_hi, &fullB[sb], kcoord, 0);
-                  if (p.nsplit == 3) umma::tma_load_2d(stb + b_bytes, &maps.b_lo, &fullB[sb], kcoord, 0);
+                  if (NS > 1) umma::tma_load_2d(stb + b_bytes, &maps.b_lo, &fullB[sb], kcoord, 0);
                 } else {
                   const uint32_t bar = umma::mapa(umma::smem_u32(&fullB[sb]), 0);
                   umma::mbar_expect_tx_cluster(bar, txB);
                   umma::tma_load_2d_2sm(stb, &maps.b_hi, bar, kcoord, brow0);
-                  if (p.nsplit == 3) umma::tma_load_2d_2sm(stb + b_bytes, &maps.b_lo, bar, kcoord, brow0);
+                  if (NS > 1) umma::tma_load_2d_2sm(stb + b_bytes, &maps.b_lo, bar, kcoord, brow0);
                 }
                 if (++sb == p.nstB) { sb = 0; phb ^= 1; }
               }
@@ -187,6 +184,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     if (lane == 0 && leader) {
       int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
       const uint32_t idesc = umma::idesc_16_f32(TWO ? 256 : 128, p.N, p.f16);
+      const uint32_t idesc8 = umma::idesc_e5m2_f32(TWO ? 256 : 128, p.N);
       for (int it = 0; it < niter; ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
@@ -209,7 +207,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
               if (TWO) umma::mma_bf16_ss_2sm(tmem_d, dah, dbh, idesc, accumulate);
               else umma::mma_bf16_ss(tmem_d, dah, dbh, idesc, accumulate);
               accumulate = 1u;
-              if (p.nsplit == 3) {
+              if (NS == 3) {
                 const uint64_t dal = umma::smem_desc_k_sw128(a_lo + ko), dbl = umma::smem_desc_k_sw128(b_lo + ko);
                 if (TWO) {
                   umma::mma_bf16_ss_2sm(tmem_d, dah, dbl, idesc, 1u);
@@ -218,6 +216,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                   umma::mma_bf16_ss(tmem_d, dah, dbl, idesc, 1u);
                   umma::mma_bf16_ss(tmem_d, dal, dbh, idesc, 1u);
                 }
+              } else if (NS == 2) {      // [a_lo*2^6 | a_hi*2^-8] . [w_hi*2^-6 | w_lo*2^8] in e5m2: 32 of the 128 K-bytes per step
+                const uint64_t dal = umma::smem_desc_k_sw128(a_lo + ko), dbl = umma::smem_desc_k_sw128(b_lo + ko);
+                if (TWO) umma::mma_f8_ss_2sm(tmem_d, dal, dbl, idesc8, 1u);
+                else umma::mma_f8_ss(tmem_d, dal, dbl, idesc8, 1u);
               }
             }
             if (TWO) umma::mma_commit_2sm(&emptyB[sb], 3); else umma::mma_commit(&emptyB[sb]);
@@ -276,7 +278,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
               const float4 h4 = __ldg(reinterpret_cast<const float4*>(hp + j));
               v[j] *= h4.x; v[j + 1] *= h4.y; v[j + 2] *= h4.z; v[j + 3] *= h4.w;
             }
-            store_split32(v, p.out_hi, p.out_lo, n * p.out_pitch + p.out_coff + (c0 - Hd), p.f16);
+            store_split32(v, p.out_hi, p.out_lo, n * p.out_pitch + p.out_coff + (c0 - Hd), p.fmt);
           }
         } else if (p.epilogue == AS_UEPI_GRU_Q) {            // h' = (1-z) h + z tanh(convq + cq)   update.py:39-40
           const float* cx = p.ctx + n * p.ctx_pitch + c0;
@@ -295,7 +297,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
           float* op = p.out_f32 + n * p.N + c0;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          store_split32(v, p.out_hi, p.out_lo, n * p.out_pitch + p.out_coff + c0, p.f16);
+          store_split32(v, p.out_hi, p.out_lo, n * p.out_pitch + p.out_coff + c0, p.fmt);
         } else if (p.epilogue == AS_UEPI_DISPHEAD) {         // relu(conv1) dotted with conv2's 9 taps  update.py:23-24
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -325,7 +327,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
             v[j + 2] = fmaxf(v[j + 2] + b4.z, 0.f); v[j + 3] = fmaxf(v[j + 3] + b4.w, 0.f);
           }
           if (p.epilogue == AS_UEPI_MOTION && c0 + 32 == p.N) v[31] = __ldg(p.disp + n);   // cat(out, disp) update.py:92
-          store_split32(v, p.out_hi, p.out_lo, n * p.out_pitch + p.out_coff + c0, p.f16);
+          store_split32(v, p.out_hi, p.out_lo, n * p.out_pitch + p.out_coff + c0, p.fmt);
         }
         }
         __syncwarp();     // reconverge before the next warp-aligned tcgen05.ld
@@ -350,9 +352,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   }
 }
 
-template <bool TWO>
+template <bool TWO, int NS>
 int launch_conv(const ConvMaps& maps, const ConvUmmaParams& p, int sms, int smem, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<TWO, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return (int)e;
   constexpr int CS = TWO ? 2 : 1;
   int grid = p.num_tiles < sms ? p.num_tiles : sms;
@@ -368,7 +370,7 @@ int launch_conv(const ConvMaps& maps, const ConvUmmaParams& p, int sms, int smem
   attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<TWO>, maps, p);
+  e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<TWO, NS>, maps, p);
   if (e != cudaSuccess) return (int)e;
   AS_RETURN_IF_LAUNCH_FAILED();
   return AS_OK;
@@ -387,8 +389,10 @@ extern "C" int as_conv2d_umma(const as_conv_umma_desc* d, as_stream_t stream) {
   if (d->B <= 0 || d->H <= 0 || d->W <= 0 || d->num_src < 1 || d->num_src > 3) return AS_ERR_BAD_ARG;
   if (!((d->KH == 1 && d->KW == 1) || (d->KH == 3 && d->KW == 3))) return AS_ERR_UNSUPPORTED;
   if (d->Cout < 32 || d->Cout > 256 || (d->Cout & 31)) return AS_ERR_UNSUPPORTED;
-  if (d->nsplit != 1 && d->nsplit != 3) return AS_ERR_BAD_ARG;
-  if (d->nsplit == 3 && !d->w_lo) return AS_ERR_BAD_ARG;
+  if (d->nsplit < 1 || d->nsplit > 3) return AS_ERR_BAD_ARG;
+  if (d->nsplit > 1 && !d->w_lo) return AS_ERR_BAD_ARG;
+  // 2 passes = the e5m2 pair planes of AS_FMT_F16F8; 3 passes = 16-bit hi/lo planes: the plane format must match
+  if ((d->nsplit == 2) != (as_operand_fmt_internal() == AS_FMT_F16F8) && d->nsplit != 1) return AS_ERR_BAD_ARG;
   ConvUmmaParams p{};
   p.B = d->B; p.H = d->H; p.W = d->W; p.KH = d->KH; p.KW = d->KW;
   // 128-pixel patch 16 (x) x 8 (y).  Measured on B200 at 312x96: the 8x16 orientation tiles the image exactly (2.5 %
@@ -405,7 +409,7 @@ extern "C" int as_conv2d_umma(const as_conv_umma_desc* d, as_stream_t stream) {
   p.num_src = d->num_src;
   int cin = 0;
   for (int s = 0; s < d->num_src; ++s) {
-    if (!d->src[s].hi || (d->nsplit == 3 && !d->src[s].lo)) return AS_ERR_BAD_ARG;
+    if (!d->src[s].hi || (d->nsplit > 1 && !d->src[s].lo)) return AS_ERR_BAD_ARG;
     if (d->src[s].channels <= 0 || (d->src[s].channels & 63)) return AS_ERR_UNSUPPORTED;
     if (!as_aligned16(d->src[s].hi) || (d->src[s].lo && !as_aligned16(d->src[s].lo))) return AS_ERR_ALIGNMENT;
     p.src_ch[s] = d->src[s].channels;
@@ -414,6 +418,7 @@ extern "C" int as_conv2d_umma(const as_conv_umma_desc* d, as_stream_t stream) {
   p.cin_total = cin;
   p.N = d->Cout; p.nsplit = d->nsplit; p.epilogue = d->epilogue;
   p.f16 = as_operand_f16_internal() != 0;
+  p.fmt = as_operand_fmt_internal();
   const bool two = two_cta_enabled() && p.num_tiles >= 4 && (p.N % 32) == 0;
   p.a_plane = (p.TH + d->KH - 1) * p.TW * 128;          // (TH+2)-row patch for 3x3, the tile itself for 1x1
   p.a_stage = 2 * p.a_plane;
@@ -461,7 +466,7 @@ extern "C" int as_conv2d_umma(const as_conv_umma_desc* d, as_stream_t stream) {
     const uint64_t str[3] = {C * 2, (uint64_t)d->W * C * 2, (uint64_t)d->H * d->W * C * 2};
     const uint32_t box[4] = {64u, (uint32_t)p.TW, (uint32_t)(p.TH + d->KH - 1), 1u};
     if ((rc = umma::make_tmap_bf16(&maps.a_hi[s], d->src[s].hi, 4, dims, str, box)) != AS_OK) return rc;
-    if (d->nsplit == 3) {
+    if (d->nsplit > 1) {       // (the e5m2 pair plane has the same 128 bytes per 64-channel chunk: same map, TMA moves bytes)
       if ((rc = umma::make_tmap_bf16(&maps.a_lo[s], d->src[s].lo, 4, dims, str, box)) != AS_OK) return rc;
     } else {
       maps.a_lo[s] = maps.a_hi[s];
@@ -474,7 +479,7 @@ extern "C" int as_conv2d_umma(const as_conv_umma_desc* d, as_stream_t stream) {
     const uint64_t str[1] = {Kt * 2};
     const uint32_t box[2] = {64u, (uint32_t)p.N};
     if ((rc = umma::make_tmap_bf16(&maps.b_hi, d->w_hi, 2, dims, str, box)) != AS_OK) return rc;
-    if (d->nsplit == 3) {
+    if (d->nsplit > 1) {
       if ((rc = umma::make_tmap_bf16(&maps.b_lo, d->w_lo, 2, dims, str, box)) != AS_OK) return rc;
     } else {
       maps.b_lo = maps.b_hi;
@@ -490,12 +495,16 @@ extern "C" int as_conv2d_umma(const as_conv_umma_desc* d, as_stream_t stream) {
     const uint64_t str[1] = {Kt * 2};
     const uint32_t box[2] = {64u, (uint32_t)(p.N / 2)};
     if ((rc = umma::make_tmap_bf16(&maps.b_hi, d->w_hi, 2, dims, str, box)) != AS_OK) return rc;
-    if (d->nsplit == 3) {
+    if (d->nsplit > 1) {
       if ((rc = umma::make_tmap_bf16(&maps.b_lo, d->w_lo, 2, dims, str, box)) != AS_OK) return rc;
     } else {
       maps.b_lo = maps.b_hi;
     }
-    return launch_conv<true>(maps, p, sms, smem, as_cu(stream));
+    if (d->nsplit == 3) return launch_conv<true, 3>(maps, p, sms, smem, as_cu(stream));
+    if (d->nsplit == 2) return launch_conv<true, 2>(maps, p, sms, smem, as_cu(stream));
+    return launch_conv<true, 1>(maps, p, sms, smem, as_cu(stream));
   }
-  return launch_conv<false>(maps, p, sms, smem, as_cu(stream));
+  if (d->nsplit == 3) return launch_conv<false, 3>(maps, p, sms, smem, as_cu(stream));
+  if (d->nsplit == 2) return launch_conv<false, 2>(maps, p, sms, smem, as_cu(stream));
+  return launch_conv<false, 1>(maps, p, sms, smem, as_cu(stream));
 }

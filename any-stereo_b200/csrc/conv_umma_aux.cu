@@ -7,24 +7,25 @@
 
 namespace {
 
-__device__ __forceinline__ void store_split4(float4 v, __nv_bfloat16* hi, __nv_bfloat16* lo, long long off, bool f16) {
-  uint2 h, l;
-  as_split2(v.x, v.y, h.x, l.x, f16);
-  as_split2(v.z, v.w, h.y, l.y, f16);
+// fmt: AS_FMT_BF16 / AS_FMT_F16 (16-bit hi + lo = x - hi) / AS_FMT_F16F8 (half hi + e5m2 pair plane, common.cuh)
+__device__ __forceinline__ void store_split4(float4 v, __nv_bfloat16* hi, __nv_bfloat16* lo, long long off, int fmt) {
+  uint2 h;
+  h.x = as_cvt16x2(v.x, v.y, fmt != 0);
+  h.y = as_cvt16x2(v.z, v.w, fmt != 0);
   *reinterpret_cast<uint2*>(hi + off) = h;
-  if (lo) *reinterpret_cast<uint2*>(lo + off) = l;
+  if (lo) as_store_lo4(lo, off, v, h, fmt);
 }
 
 __global__ void split_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                             long long n4, bool f16) {
+                             long long n4, int fmt) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
-  store_split4(__ldg(reinterpret_cast<const float4*>(in) + i), hi, lo, i * 4, f16);
+  store_split4(__ldg(reinterpret_cast<const float4*>(in) + i), hi, lo, i * 4, fmt);
 }
 
 // [B,C,HW] fp32 -> [B*HW][Cp] bf16 hi/lo, channels >= C zero-filled
 __global__ void __launch_bounds__(256) nchw_to_nhwc_split_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi,
-                                                                 __nv_bfloat16* __restrict__ lo, int C, long long HW, int Cp, bool f16) {
+                                                                 __nv_bfloat16* __restrict__ lo, int C, long long HW, int Cp, int fmt) {
   __shared__ float t[32][33];
   const int b = blockIdx.z;
   const long long p0 = (long long)blockIdx.x * 32;
@@ -42,12 +43,12 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_split_kernel(const float* __
   const long long pp = p0 + pr;
   if (pp < HW && c0 + cq < Cp)
     store_split4(make_float4(t[cq][pr], t[cq + 1][pr], t[cq + 2][pr], t[cq + 3][pr]), hi, lo,
-                 ((long long)b * HW + pp) * Cp + c0 + cq, f16);
+                 ((long long)b * HW + pp) * Cp + c0 + cq, fmt);
 }
 
 // grid = (ceil(Wo*C4 / 256), Ho, B): the row / image indices come from the block, one 32-bit division per thread
 __global__ void pool2x_split_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                                    int H, int W, int Ho, int Wo, int C4, bool f16) {
+                                    int H, int W, int Ho, int Wo, int C4, int fmt) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= Wo * C4) return;
   const int xo = r / C4, c4 = r - xo * C4;
@@ -67,11 +68,11 @@ __global__ void pool2x_split_kernel(const float* __restrict__ in, __nv_bfloat16*
   }
   const float inv = 1.0f / 9.0f;
   const long long idx = (((long long)b * Ho + yo) * Wo + xo) * C4 + c4;
-  store_split4(make_float4(s.x * inv, s.y * inv, s.z * inv, s.w * inv), hi, lo, idx * 4, f16);
+  store_split4(make_float4(s.x * inv, s.y * inv, s.z * inv, s.w * inv), hi, lo, idx * 4, fmt);
 }
 
 __global__ void interp_split_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                                    int Hi, int Wi, int Ho, int Wo, int C4, float sy, float sx, bool f16) {
+                                    int Hi, int Wi, int Ho, int Wo, int C4, float sy, float sx, int fmt) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= Wo * C4) return;
   const int xo = r / C4, c4 = r - xo * C4;
@@ -89,12 +90,12 @@ __global__ void interp_split_kernel(const float* __restrict__ in, __nv_bfloat16*
   o.z = hy * (hx * v00.z + lx * v01.z) + ly * (hx * v10.z + lx * v11.z);
   o.w = hy * (hx * v00.w + lx * v01.w) + ly * (hx * v10.w + lx * v11.w);
   const long long idx = (((long long)b * Ho + yo) * Wo + xo) * C4 + c4;
-  store_split4(o, hi, lo, idx * 4, f16);
+  store_split4(o, hi, lo, idx * 4, fmt);
 }
 
 __global__ void pack_weight_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi,
                                         __nv_bfloat16* __restrict__ lo, int Cout, int Cin, int T, int n_pad, int cin_pad,
-                                        long long total, bool f16) {
+                                        long long total, int fmt) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   // idx = (n * T + tap) * cin_pad + c
@@ -104,10 +105,19 @@ __global__ void pack_weight_bf16_kernel(const float* __restrict__ w, __nv_bfloat
   const int n = (int)(r / T);
   float v = 0.f;
   if (n < Cout && c < Cin) v = w[((long long)n * Cin + c) * T + tap];
-  uint32_t h, l;
-  as_split2(v, 0.f, h, l, f16);
+  const bool f16 = fmt != 0;
+  const uint32_t h = as_cvt16x2(v, 0.f, f16);
   reinterpret_cast<unsigned short*>(hi)[idx] = (unsigned short)(h & 0xFFFFu);
-  if (lo) reinterpret_cast<unsigned short*>(lo)[idx] = (unsigned short)(l & 0xFFFFu);
+  if (lo) {
+    const float hv = as_widen_lo16(h, f16);
+    if (fmt != 2) {
+      reinterpret_cast<unsigned short*>(lo)[idx] = (unsigned short)(as_cvt16x2(v - hv, 0.f, f16) & 0xFFFFu);
+    } else {            // AS_FMT_F16F8 weights: [ e5m2(hi * 2^-6) | e5m2(lo * 2^8) ] per 64-wide K chunk (row length % 64 == 0)
+      uint8_t* b = reinterpret_cast<uint8_t*>(lo) + as_x8_byte(idx);
+      b[0] = (uint8_t)(as_e5m2x4(hv * kX8WgtHiScale, 0.f, 0.f, 0.f) & 0xFFu);
+      b[64] = (uint8_t)(as_e5m2x4((v - hv) * kX8WgtLoScale, 0.f, 0.f, 0.f) & 0xFFu);
+    }
+  }
 }
 
 // 7x7 conv, 1 input channel -> 64, + bias, relu.  CTA = 32x8 pixel tile: the (8+6)x(32+6) disparity patch and the
@@ -119,7 +129,7 @@ template <bool F32OUT>
 __global__ void __launch_bounds__(256) convd1_split_kernel(const float* __restrict__ disp, const float* __restrict__ w,
                                                            const float* __restrict__ bias, __nv_bfloat16* __restrict__ hi,
                                                            __nv_bfloat16* __restrict__ lo, float* __restrict__ out_f32, int H,
-                                                           int W, int pitch, int coff, bool f16) {
+                                                           int W, int pitch, int coff, int fmt) {
   __shared__ __align__(16) float ws[49 * 64];     // [tap][channel]
   __shared__ float bs[64];
   __shared__ float patch[kD1TY + 6][kD1TX + 6 + 2];
@@ -173,7 +183,7 @@ __global__ void __launch_bounds__(256) convd1_split_kernel(const float* __restri
       const float4 y4 = make_float4(fmaxf(acc[px][j], 0.f), fmaxf(acc[px][j + 1], 0.f), fmaxf(acc[px][j + 2], 0.f),
                                     fmaxf(acc[px][j + 3], 0.f));
       if (F32OUT) *reinterpret_cast<float4*>(out_f32 + n * pitch + coff + cg + j) = y4;
-      else store_split4(y4, hi, lo, n * pitch + coff + cg + j, f16);
+      else store_split4(y4, hi, lo, n * pitch + coff + cg + j, fmt);
     }
   }
 }
@@ -200,7 +210,8 @@ __global__ void disp_delta_kernel(const float* __restrict__ u, const float* __re
 extern "C" int as_split_f32(const float* in, void* hi, void* lo, long long n, as_stream_t stream) {
   if (!in || !hi || n <= 0) return AS_ERR_BAD_ARG;
   if ((n & 3) || !as_aligned16(in)) return AS_ERR_ALIGNMENT;
-  split_kernel<<<(unsigned)as_ceil_div_ll(n / 4, 256), 256, 0, as_cu(stream)>>>(in, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n / 4, as_operand_f16_internal() != 0);
+  if (lo && as_operand_fmt_internal() == AS_FMT_F16F8 && (n & 63)) return AS_ERR_UNSUPPORTED;   // whole 64-channel chunks
+  split_kernel<<<(unsigned)as_ceil_div_ll(n / 4, 256), 256, 0, as_cu(stream)>>>(in, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n / 4, as_operand_fmt_internal());
   AS_RETURN_IF_LAUNCH_FAILED();
   return AS_OK;
 }
@@ -209,9 +220,10 @@ extern "C" int as_nchw_to_nhwc_split(const float* in, void* hi, void* lo, int B,
                                      as_stream_t stream) {
   if (!in || !hi || B <= 0 || C <= 0 || H <= 0 || W <= 0 || c_pad < C) return AS_ERR_BAD_ARG;
   if ((c_pad & 31) || B > 65535) return AS_ERR_UNSUPPORTED;
+  if (lo && as_operand_fmt_internal() == AS_FMT_F16F8 && (c_pad & 63)) return AS_ERR_UNSUPPORTED;
   const long long HW = (long long)H * W;
   dim3 grid((unsigned)as_ceil_div_ll(HW, 32), c_pad / 32, B);
-  nchw_to_nhwc_split_kernel<<<grid, 256, 0, as_cu(stream)>>>(in, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, C, HW, c_pad, as_operand_f16_internal() != 0);
+  nchw_to_nhwc_split_kernel<<<grid, 256, 0, as_cu(stream)>>>(in, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, C, HW, c_pad, as_operand_fmt_internal());
   AS_RETURN_IF_LAUNCH_FAILED();
   return AS_OK;
 }
@@ -223,7 +235,7 @@ extern "C" int as_pool2x_nhwc_split(const float* in, void* hi, void* lo, int B, 
   if (B > 65535 || Ho > 65535 || (long long)Wo * (C / 4) >= (1LL << 31)) return AS_ERR_INDEX_RANGE;
   dim3 grid(as_ceil_div(Wo * (C / 4), 256), Ho, B);
   pool2x_split_kernel<<<grid, 256, 0, as_cu(stream)>>>(in, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, H, W, Ho, Wo, C / 4,
-                                                       as_operand_f16_internal() != 0);
+                                                       as_operand_fmt_internal());
   AS_RETURN_IF_LAUNCH_FAILED();
   return AS_OK;
 }
@@ -237,7 +249,7 @@ extern "C" int as_interp_bilinear_nhwc_split(const float* in, void* hi, void* lo
   if (B > 65535 || Hout > 65535 || (long long)Wout * (C / 4) >= (1LL << 31)) return AS_ERR_INDEX_RANGE;
   dim3 grid(as_ceil_div(Wout * (C / 4), 256), Hout, B);
   interp_split_kernel<<<grid, 256, 0, as_cu(stream)>>>(in, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, Hin, Win, Hout, Wout, C / 4,
-                                                       sy, sx, as_operand_f16_internal() != 0);
+                                                       sy, sx, as_operand_fmt_internal());
   AS_RETURN_IF_LAUNCH_FAILED();
   return AS_OK;
 }
@@ -246,8 +258,9 @@ extern "C" int as_pack_conv_weight_bf16(const float* w_oihw, void* w_hi, void* w
                                         int n_pad, int cin_pad, as_stream_t stream) {
   if (!w_oihw || !w_hi || Cout <= 0 || Cin <= 0 || KH <= 0 || KW <= 0 || n_pad < Cout || cin_pad < Cin) return AS_ERR_BAD_ARG;
   const long long total = (long long)n_pad * KH * KW * cin_pad;
+  if (w_lo && as_operand_fmt_internal() == AS_FMT_F16F8 && (((long long)KH * KW * cin_pad) & 63)) return AS_ERR_UNSUPPORTED;
   pack_weight_bf16_kernel<<<(unsigned)as_ceil_div_ll(total, 256), 256, 0, as_cu(stream)>>>(
-      w_oihw, (__nv_bfloat16*)w_hi, (__nv_bfloat16*)w_lo, Cout, Cin, KH * KW, n_pad, cin_pad, total, as_operand_f16_internal() != 0);
+      w_oihw, (__nv_bfloat16*)w_hi, (__nv_bfloat16*)w_lo, Cout, Cin, KH * KW, n_pad, cin_pad, total, as_operand_fmt_internal());
   AS_RETURN_IF_LAUNCH_FAILED();
   return AS_OK;
 }
@@ -259,7 +272,7 @@ extern "C" int as_convd1_split(const float* disp, const float* w, const float* b
   if (B > 65535 || as_ceil_div(H, kD1TY) > 65535) return AS_ERR_UNSUPPORTED;
   dim3 grid(as_ceil_div(W, kD1TX), as_ceil_div(H, kD1TY), B);
   convd1_split_kernel<false><<<grid, 256, 0, as_cu(stream)>>>(disp, w, bias, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, nullptr,
-                                                              H, W, out_pitch, out_coff, as_operand_f16_internal() != 0);
+                                                              H, W, out_pitch, out_coff, as_operand_fmt_internal());
   AS_RETURN_IF_LAUNCH_FAILED();
   return AS_OK;
 }
@@ -271,7 +284,7 @@ extern "C" int as_convd1_fp32(const float* disp, const float* w, const float* bi
   if (B > 65535 || as_ceil_div(H, kD1TY) > 65535) return AS_ERR_UNSUPPORTED;
   dim3 grid(as_ceil_div(W, kD1TX), as_ceil_div(H, kD1TY), B);
   convd1_split_kernel<true><<<grid, 256, 0, as_cu(stream)>>>(disp, w, bias, nullptr, nullptr, out, H, W, out_pitch, out_coff,
-                                                             false);
+                                                             0);
   AS_RETURN_IF_LAUNCH_FAILED();
   return AS_OK;
 }

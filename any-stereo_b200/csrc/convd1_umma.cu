@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(kThreads, 3)
 convd1_umma_kernel(const __grid_constant__ CUtensorMap tWh, const __grid_constant__ CUtensorMap tWl,
                    const float* __restrict__ disp, const float* __restrict__ bias, __nv_bfloat16* __restrict__ out_hi,
                    __nv_bfloat16* __restrict__ out_lo, int H, int W, int tiles_x, int tiles_y, int num_tiles, int pitch,
-                   int coff, int nsplit, bool f16) {
+                   int coff, int nsplit, bool f16, int out_fmt) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* act = smem;                                   // hi | lo
@@ -128,15 +128,14 @@ convd1_umma_kernel(const __grid_constant__ CUtensorMap tWh, const __grid_constan
         const long long o = ((long long)b * HW + (long long)y * W + x) * pitch + coff + half * 32;
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
-          uint32_t h[4], l[4];
+          uint32_t h[4];
+          float yv[8];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float y0f = fmaxf(v[j + 2 * i] + __ldg(bias + half * 32 + j + 2 * i), 0.f);
-            const float y1f = fmaxf(v[j + 2 * i + 1] + __ldg(bias + half * 32 + j + 2 * i + 1), 0.f);
-            as_split2(y0f, y1f, h[i], l[i], f16);
-          }
+          for (int i = 0; i < 8; ++i) yv[i] = fmaxf(v[j + i] + __ldg(bias + half * 32 + j + i), 0.f);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) h[i] = as_cvt16x2(yv[2 * i], yv[2 * i + 1], f16);
           *reinterpret_cast<uint4*>(out_hi + o + j) = make_uint4(h[0], h[1], h[2], h[3]);
-          if (out_lo) *reinterpret_cast<uint4*>(out_lo + o + j) = make_uint4(l[0], l[1], l[2], l[3]);
+          if (out_lo) as_store_lo8(out_lo, o + j, yv, h, out_fmt);                 // 16-bit lo or the e5m2 pair plane
         }
       }
     }
@@ -179,7 +178,7 @@ extern "C" int as_convd1_umma(const float* disp, const void* w_hi, const void* w
   const int grid = nt < 3LL * sms ? (int)nt : 3 * sms;
   convd1_umma_kernel<<<grid, kThreads, kSmem, as_cu(stream)>>>(tWh, tWl, disp, bias, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo,
                                                                H, W, tiles_x, tiles_y, (int)nt, out_pitch, out_coff, nsplit,
-                                                               as_operand_f16_internal() != 0);
+                                                               as_operand_f16_internal() != 0, as_operand_fmt_internal());
   AS_RETURN_IF_LAUNCH_FAILED();
   return AS_OK;
 }

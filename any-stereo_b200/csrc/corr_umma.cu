@@ -13,6 +13,7 @@
 //                                concurrently (tcgen05.ld -> registers -> pairwise pooling for every level ->
 //                                shared-memory transpose -> 128-bit row-contiguous global stores)
 // The volume is written exactly once; pooled levels never re-read level 0 from HBM.
+#include <cstdlib>
 #include "umma.cuh"
 
 namespace {
@@ -23,14 +24,21 @@ constexpr int kStages = 2;
 constexpr int kThreads = 384;
 constexpr int kMaxBN = 160;
 constexpr int kStageBytes = 2 * (kBM * 128) + 2 * (kMaxBN * 128);   // A hi/lo + B hi/lo
-constexpr int kStgStride = 68;                                      // floats per epilogue staging row
-constexpr int kStgBytes = 8 * 32 * kStgStride * 4;
+constexpr int kStgStride = 68;                                      // floats per epilogue staging row (manual-store path)
+// per-warp epilogue staging, 1024-byte aligned.  TMA-store path: one swizzled box per level (level 0: 32 rows x 128 B at +0,
+// level 1: 32 x 64 B at +4096, level 2: 32 x 32 B at +6144, level 3: 32 x 16 B at +7168 = 7680 B).  Manual path (L > 4,
+// narrow or unaligned levels): [32][kStgStride] floats = 8704 B.
+constexpr int kStgWarpBytes = 32 * kStgStride * 4;
+constexpr int kStgWarpPitch = (kStgWarpBytes + 1023) / 1024 * 1024;
+constexpr int kStgBytes = 8 * kStgWarpPitch;
 constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kStgBytes + 256;
+static_assert(kSmemBytes <= 227 * 1024, "corr_umma shared memory");
 constexpr int kMaxPoolLevels = 6;                                   // 32 columns pool down to 1
 
 struct CorrUmmaParams {
   int BH, W1, W2, D;
   int BN, MT, NT, num_tiles, nsplit, L;
+  int tma_store;                        // epilogue leaves through cp.async.bulk.tensor stores (L <= 4, 16-byte pitches)
   float* lvl[AS_MAX_LEVELS];
   int pitch[AS_MAX_LEVELS];
 };
@@ -130,14 +138,18 @@ __device__ __forceinline__ void flush_level(const float* stg, int off, int w, fl
   }
 }
 
+struct StoreMaps {
+  CUtensorMap lvl[4];
+};
+
 __global__ void __launch_bounds__(kThreads, 1)
 corr_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                  const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-                 const CorrUmmaParams p) {
+                 const __grid_constant__ StoreMaps tmS, const CorrUmmaParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* stages = smem;
-  float* stg_all = reinterpret_cast<float*>(smem + kStages * kStageBytes);
+  uint8_t* stg_all = smem + kStages * kStageBytes;                   // 1024-byte aligned (kStageBytes is a multiple of 1024)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + kStgBytes);
   uint64_t* full = bars;                 // [kStages]
   uint64_t* empty = bars + kStages;      // [kStages]
@@ -152,6 +164,7 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     umma::prefetch_tmap(&tmA_hi);
     umma::prefetch_tmap(&tmB_hi);
     if (p.nsplit == 3) { umma::prefetch_tmap(&tmA_lo); umma::prefetch_tmap(&tmB_lo); }
+    if (p.tma_store) for (int l = 0; l < p.L; ++l) umma::prefetch_tmap(&tmS.lvl[l]);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { umma::mbar_init(&full[s], 1); umma::mbar_init(&empty[s], 1); }
@@ -228,7 +241,8 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   } else if (warp >= 4) {
     const int q = warp & 3;                          // TMEM lane quarter == warp % 4
     const int group = (warp - 4) >> 2;               // which accumulator buffer this warp drains
-    float* stg = stg_all + (warp - 4) * 32 * kStgStride;
+    uint8_t* stg_b = stg_all + (warp - 4) * kStgWarpPitch;
+    float* stg = reinterpret_cast<float*>(stg_b);
     float* mine = stg + lane * kStgStride;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
@@ -247,7 +261,46 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         umma::tmem_ld_32x32(tmem_base + (uint32_t)acc * 256u + (uint32_t)c * 32u + ((uint32_t)(q * 32) << 16), r0);
         umma::tmem_ld_wait();
         const int ncol0 = nt * p.BN + c * 32;
-        if (rows_valid > 0 && ncol0 < p.pitch[0]) {
+        if (p.tma_store) {
+          // TMEM -> registers -> (pool) -> one swizzled box per level in shared memory -> ONE TMA store per level.
+          // The store engine streams full 128/64/32/16-byte rows and clips rows >= W1 / columns >= pitch itself; the warp
+          // goes straight back to the next tcgen05.ld (the manual path below kept 8 warps per SM busy with
+          // LDS -> STG chains and reached 13.5 B/clk/SM of stores: the kernel was bound by its own epilogue).
+          if (rows_valid > 0 && ncol0 < p.pitch[0]) {
+            float r1[16], r2[8], r3[4];
+            if (p.L > 1) pool_regs<16>(r0, r1);
+            if (p.L > 2) pool_regs<8>(r1, r2);
+            if (p.L > 3) pool_regs<4>(r2, r3);
+            if (lane == 0) umma::bulk_wait_group_read<0>();       // the previous chunk's stores have read the staging
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(stg_b + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                  make_float4(r0[4 * j], r0[4 * j + 1], r0[4 * j + 2], r0[4 * j + 3]);
+            if (p.L > 1) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<float4*>(stg_b + 4096 + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
+                    make_float4(r1[4 * j], r1[4 * j + 1], r1[4 * j + 2], r1[4 * j + 3]);
+            }
+            if (p.L > 2) {
+#pragma unroll
+              for (int j = 0; j < 2; ++j)
+                *reinterpret_cast<float4*>(stg_b + 6144 + lane * 32 + ((j ^ ((lane >> 2) & 1)) << 4)) =
+                    make_float4(r2[4 * j], r2[4 * j + 1], r2[4 * j + 2], r2[4 * j + 3]);
+            }
+            if (p.L > 3) *reinterpret_cast<float4*>(stg_b + 7168 + lane * 16) = make_float4(r3[0], r3[1], r3[2], r3[3]);
+            umma::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              umma::tma_store_3d(&tmS.lvl[0], stg_b, ncol0, row_in_img, by);
+              if (p.L > 1) umma::tma_store_3d(&tmS.lvl[1], stg_b + 4096, ncol0 >> 1, row_in_img, by);
+              if (p.L > 2) umma::tma_store_3d(&tmS.lvl[2], stg_b + 6144, ncol0 >> 2, row_in_img, by);
+              if (p.L > 3) umma::tma_store_3d(&tmS.lvl[3], stg_b + 7168, ncol0 >> 3, row_in_img, by);
+              umma::bulk_commit_group();
+            }
+          }
+        } else if (rows_valid > 0 && ncol0 < p.pitch[0]) {
           stage_regs<32>(mine, r0);
           if (p.L > 1) {
             float r1[16]; pool_regs<16>(r0, r1); stage_regs<16>(mine + 32, r1);
@@ -277,6 +330,7 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       if (lane == 0) umma::mbar_arrive(&tempty[acc]);
     }
   }
+  if (p.tma_store && warp >= 4 && lane == 0) umma::bulk_wait_group<0>();   // every store of this thread has completed
   umma::tc_fence_before();
   __syncthreads();
   if (warp == 2) umma::tmem_dealloc(tmem_base, 512);
@@ -344,8 +398,23 @@ int as_corr_umma_launch(const float* f1, const float* f2, int B, int D, int H, i
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaError_t e = cudaFuncSetAttribute(corr_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
   if (e != cudaSuccess) return (int)e;
+  // TMA-store epilogue: one fp32 map per level, dims {pitch_l, W1, B*H}, box {32 >> l, 32, 1}; needs L <= 4 (a 16-byte
+  // inner box at level 3) and 16-byte aligned level buffers (pitches are multiples of 4 floats by construction)
+  StoreMaps tS;
+  static const bool allow_tma_store = !(getenv("AS_CORR_TMA_STORE") && getenv("AS_CORR_TMA_STORE")[0] == '0');   // A/B knob
+  p.tma_store = allow_tma_store && num_levels <= 4;
+  for (int l = 0; l < num_levels && p.tma_store; ++l)
+    if ((pitches[l] & 3) || !as_aligned16(levels[l]) || pitches[l] < (32 >> l)) p.tma_store = 0;
+  for (int l = 0; l < 4; ++l) {
+    const int ll = (p.tma_store && l < num_levels) ? l : 0;
+    if (!p.tma_store) { tS.lvl[l] = tA_hi; continue; }
+    const uint64_t dS[3] = {(uint64_t)pitches[ll], (uint64_t)W1, (uint64_t)BH};
+    const uint64_t sS[2] = {(uint64_t)pitches[ll] * 4, (uint64_t)W1 * pitches[ll] * 4};
+    const uint32_t bS[3] = {(uint32_t)(32 >> ll), 32u, 1u};
+    if ((rc = umma::make_tmap_f32_store(&tS.lvl[l], levels[ll], 3, dS, sS, bS)) != AS_OK) return rc;
+  }
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
-  corr_umma_kernel<<<grid, kThreads, kSmemBytes, st>>>(tA_hi, tA_lo, tB_hi, tB_lo, p);
+  corr_umma_kernel<<<grid, kThreads, kSmemBytes, st>>>(tA_hi, tA_lo, tB_hi, tB_lo, tS, p);
   AS_RETURN_IF_LAUNCH_FAILED();
   return AS_OK;
 }

@@ -16,6 +16,7 @@
 //    each output channel as full 128-byte lines.
 //  * The geometry pyramid is stored [pixel][disparity][group] (see pyramid.cu) so the (2r+2) taps x 8
 //    groups of one pixel are ONE contiguous, 32-byte aligned 320-byte run: zero sector waste.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace {
@@ -244,8 +245,8 @@ __global__ void corr_lookup_bwd_kernel(LevelSetRW lv, int L, const float* __rest
 // IGEV: geometry volume (8 groups) + correlation, fast path G == 8, r == 4
 // ------------------------------------------------------------------------------------------------
 constexpr int kGP = 64;    // pixels per tile: each output channel is written as 256 contiguous bytes
-constexpr int kGT = 192;   // 6 warps
-constexpr int kGSP = 66;   // smem row stride (floats): 4*66 % 32 == 8 -> conflict-free transposing stores
+constexpr int kGT = 192;   // 6 warps (4-byte emit)
+constexpr int kGT4 = 288;  // 9 warps (128-bit emit): L*(G+1)*16 = 288 (row, pixel-quad) tasks per tile at L = 2
 #ifndef AS_GEO_MINB
 #define AS_GEO_MINB 2
 #endif
@@ -258,17 +259,24 @@ struct GeoTile {
 // Persistent, software-pipelined: while tile i is interpolated and written (phase C), the 128-bit window loads
 // of tile i+1 are already in flight in registers and the disparities of tile i+2 are being fetched, so every CTA
 // keeps HBM reads and writes overlapped instead of alternating between a load phase and a store phase.
-template <int L>
-__global__ void __launch_bounds__(kGT, AS_GEO_MINB) geo_lookup_fwd_kernel(LevelSet geo, int Dg, LevelSet corr,
+// V4 = 128-bit output stores: one thread interpolates 4 consecutive pixels of one (level, group) row and writes every
+// channel as float4 (a warp instruction = 2 x 256 contiguous bytes).  B200 needs 16 bytes per lane to approach the copy
+// rate on plane-strided writes: 162 planes written with 4-byte stores top out at 3.6 TB/s, with 16-byte stores at
+// 5.8 TB/s (tools/experiments/gather_bw.cu).  Needs H*W % 4 == 0; smem rows are 16-byte aligned (stride 68: the
+// transposing 4-byte stores of `stash` become 2-way conflicted, 1.5 % of the kernel's wavefronts).
+template <int L, int NT, bool V4>
+__global__ void __launch_bounds__(NT, AS_GEO_MINB) geo_lookup_fwd_kernel(LevelSet geo, int Dg, LevelSet corr,
                                                                 const float* __restrict__ disp,
                                                                 const float* __restrict__ coords,
                                                                 float* __restrict__ out, int HW, int W,
                                                                 int tiles_per_img, int num_tiles) {
+  constexpr int kGT = NT;
+  constexpr int kGSP = V4 ? 68 : 66;                     // smem row stride (floats)
   extern __shared__ __align__(16) float smem[];
   float* s_geo = smem;                                   // [L][kTaps*kG = 80][kGSP]
   float* s_cor = smem + L * kTaps * kG * kGSP;           // [L][16][kGSP]
-  __shared__ int s_tg[2][L][kGP], s_tc[2][L][kGP];
-  __shared__ float s_fg[2][L][kGP], s_fc[2][L][kGP];
+  __shared__ __align__(16) int s_tg[2][L][kGP], s_tc[2][L][kGP];
+  __shared__ __align__(16) float s_fg[2][L][kGP], s_fc[2][L][kGP];
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -403,6 +411,66 @@ __global__ void __launch_bounds__(kGT, AS_GEO_MINB) geo_lookup_fwd_kernel(LevelS
     }
   };
 
+  // (C') 128-bit emit: thread = (row, 4 consecutive pixels)
+  auto emit4 = [&](int t, int buf) {
+    GeoTile g; tile_of(t, g);
+    for (int task = tid; task < L * (kG + 1) * (kGP / 4); task += kGT) {
+      const int row = task / (kGP / 4);
+      const int pq = (task - row * (kGP / 4)) * 4;
+      const int p = g.p0 + pq;
+      if (p >= HW) continue;                               // HW % 4 == 0: a quad is inside or outside as a whole
+      const int l = row / (kG + 1);
+      const int gi = row - l * (kG + 1);
+      float* o = out + (long long)g.b * C * HW + p;
+      if (gi < kG) {
+        const int4 t0 = *reinterpret_cast<const int4*>(&s_tg[buf][l][pq]);
+        const float4 f = *reinterpret_cast<const float4*>(&s_fg[buf][l][pq]);
+        const unsigned Dl = (unsigned)(Dg >> l);
+        const float* w = s_geo + (l * kTaps * kG + gi) * kGSP + pq;
+        float* oc = o + (long long)(l * (kG + 1) * kK + gi * kK) * HW;
+        float4 prev = *reinterpret_cast<const float4*>(w);
+        prev.x = (unsigned)t0.x < Dl ? prev.x : 0.f; prev.y = (unsigned)t0.y < Dl ? prev.y : 0.f;
+        prev.z = (unsigned)t0.z < Dl ? prev.z : 0.f; prev.w = (unsigned)t0.w < Dl ? prev.w : 0.f;
+#pragma unroll
+        for (int k = 0; k < kK; ++k) {
+          float4 cur = *reinterpret_cast<const float4*>(w + (k + 1) * kG * kGSP);
+          cur.x = (unsigned)(t0.x + k + 1) < Dl ? cur.x : 0.f; cur.y = (unsigned)(t0.y + k + 1) < Dl ? cur.y : 0.f;
+          cur.z = (unsigned)(t0.z + k + 1) < Dl ? cur.z : 0.f; cur.w = (unsigned)(t0.w + k + 1) < Dl ? cur.w : 0.f;
+          as_stg_stream4(reinterpret_cast<float4*>(oc + (long long)k * HW),
+                         make_float4(prev.x * (1.0f - f.x) + cur.x * f.x, prev.y * (1.0f - f.y) + cur.y * f.y,
+                                     prev.z * (1.0f - f.z) + cur.z * f.z, prev.w * (1.0f - f.w) + cur.w * f.w));
+          prev = cur;
+        }
+      } else {
+        const int4 t0v = *reinterpret_cast<const int4*>(&s_tc[buf][l][pq]);
+        const float4 fv = *reinterpret_cast<const float4*>(&s_fc[buf][l][pq]);
+        const int t0a[4] = {t0v.x, t0v.y, t0v.z, t0v.w};
+        const float fa[4] = {fv.x, fv.y, fv.z, fv.w};
+        const unsigned Wl = (unsigned)corr.width[l];
+        float* oc = o + (long long)(l * (kG + 1) * kK + kG * kK) * HW;
+        const float* wq[4];
+        float prev[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {                       // every pixel has its own row offset inside the 16-float window
+          const int off = t0a[i] - as_floor4(t0a[i]) * 4;
+          wq[i] = s_cor + (l * 16 + off) * kGSP + pq + i;
+          prev[i] = (unsigned)t0a[i] < Wl ? wq[i][0] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < kK; ++k) {
+          float r[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float cur = (unsigned)(t0a[i] + k + 1) < Wl ? wq[i][(k + 1) * kGSP] : 0.f;
+            r[i] = prev[i] * (1.0f - fa[i]) + cur * fa[i];
+            prev[i] = cur;
+          }
+          as_stg_stream4(reinterpret_cast<float4*>(oc + (long long)k * HW), make_float4(r[0], r[1], r[2], r[3]));
+        }
+      }
+    }
+  };
+
   // ---- prologue: parameters + loads of the first tile, disparities of the second
   int t = blockIdx.x;
   if (t >= num_tiles) return;
@@ -420,7 +488,7 @@ __global__ void __launch_bounds__(kGT, AS_GEO_MINB) geo_lookup_fwd_kernel(LevelS
     __syncthreads();
     if (tn < num_tiles) issue_loads(tn, buf ^ 1);          // in flight during emit(t)
     fetch_dc(tn + gridDim.x, d_nxt, c_nxt);
-    emit(t, buf);
+    if (V4) emit4(t, buf); else emit(t, buf);
     __syncthreads();
   }
 }
@@ -610,19 +678,24 @@ extern "C" int as_geo_lookup_fwd(const float* const* geo_levels, int G, int Dg, 
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const size_t smem = sizeof(float) * num_levels * (kTaps * kG + 16) * kGSP;
-#define AS_LAUNCH_GEO(LV)                                                                                      \
-  case LV: {                                                                                                   \
-    cudaError_t e = cudaFuncSetAttribute(geo_lookup_fwd_kernel<LV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                         (int)smem);                                                           \
+    static const bool allow_v4 = !(getenv("AS_GEO_LOOKUP_V4") && getenv("AS_GEO_LOOKUP_V4")[0] == '0');   // A/B knob
+    const bool v4 = allow_v4 && (HW % 4 == 0) && as_aligned16(out);
+    const size_t smem = sizeof(float) * num_levels * (kTaps * kG + 16) * (v4 ? 68 : 66);
+#define AS_LAUNCH_GEO_K(KERNEL, NT)                                                                            \
+  {                                                                                                            \
+    cudaError_t e = cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
     if (e != cudaSuccess) return (int)e;                                                                       \
     int occ = 1;                                                                                               \
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, geo_lookup_fwd_kernel<LV>, kGT, smem);                 \
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, KERNEL, NT, smem);                                     \
     if (occ < 1) occ = 1;                                                                                      \
     const int grid = num_tiles < occ * sms ? num_tiles : occ * sms; /* persistent: all CTAs resident */        \
-    geo_lookup_fwd_kernel<LV><<<grid, kGT, smem, st>>>(gs, Dg, cs, disp, coords, out, HW, W, tiles_per_img,    \
-                                                       num_tiles);                                              \
-  } break;
+    KERNEL<<<grid, NT, smem, st>>>(gs, Dg, cs, disp, coords, out, HW, W, tiles_per_img, num_tiles);            \
+  }
+#define AS_LAUNCH_GEO(LV)                                                                                      \
+  case LV:                                                                                                     \
+    if (v4) AS_LAUNCH_GEO_K((geo_lookup_fwd_kernel<LV, kGT4, true>), kGT4)                                     \
+    else AS_LAUNCH_GEO_K((geo_lookup_fwd_kernel<LV, kGT, false>), kGT)                                         \
+    break;
     switch (num_levels) {
       AS_LAUNCH_GEO(1)
       AS_LAUNCH_GEO(2)
@@ -630,6 +703,7 @@ extern "C" int as_geo_lookup_fwd(const float* const* geo_levels, int G, int Dg, 
       AS_LAUNCH_GEO(4)
     }
 #undef AS_LAUNCH_GEO
+#undef AS_LAUNCH_GEO_K
   } else {
     const long long total = (long long)B * HW * num_levels * (G + 1);
     geo_lookup_fwd_generic_kernel<<<(unsigned)as_ceil_div_ll(total, 256), 256, 0, st>>>(

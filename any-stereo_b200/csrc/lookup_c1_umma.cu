@@ -182,7 +182,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 geo_lookup_convc1_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
                          const C1Levels lv, int Dg, const float* __restrict__ disp, const float* __restrict__ coords,
                          const float* __restrict__ bias, __nv_bfloat16* __restrict__ out_hi,
-                         __nv_bfloat16* __restrict__ out_lo, int HW, int W, int tiles_per_img, int num_tiles, int nsplit) {
+                         __nv_bfloat16* __restrict__ out_lo, int HW, int W, int tiles_per_img, int num_tiles, int nsplit,
+                         int out_fmt) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int kKB = k_blocks(GEO), kAStage = a_stage_bytes(GEO);
@@ -363,16 +364,14 @@ geo_lookup_convc1_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __gri
         for (int hf = 0; hf < 2; ++hf) {
 #pragma unroll
           for (int jj = 0; jj < 32; jj += 8) {
-            uint32_t h[4], l[4];
+            uint32_t h[4];
+            float y[8];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int ch = hf * 32 + jj + 2 * i;
-              const float y0 = fmaxf(v[hf][jj + 2 * i] + __ldg(bias + ch), 0.f);
-              const float y1 = fmaxf(v[hf][jj + 2 * i + 1] + __ldg(bias + ch + 1), 0.f);
-              as_split2(y0, y1, h[i], l[i], kF16);
-            }
+            for (int i = 0; i < 8; ++i) y[i] = fmaxf(v[hf][jj + i] + __ldg(bias + hf * 32 + jj + i), 0.f);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) h[i] = as_cvt16x2(y[2 * i], y[2 * i + 1], kF16);
             *reinterpret_cast<uint4*>(out_hi + o + hf * 32 + jj) = make_uint4(h[0], h[1], h[2], h[3]);
-            if (out_lo) *reinterpret_cast<uint4*>(out_lo + o + hf * 32 + jj) = make_uint4(l[0], l[1], l[2], l[3]);
+            if (out_lo) as_store_lo8(out_lo, o + hf * 32 + jj, y, h, out_fmt);     // 16-bit lo or the e5m2 pair plane
           }
         }
       }
@@ -420,7 +419,10 @@ static int launch_lookup_convc1(bool geo, const float* const* geo_levels, int Dg
   const int grid = nt < sms ? (int)nt : sms;
   cudaStream_t st = as_cu(stream);
   cudaError_t e;
+  // the kernel's own GEMM always runs on 16-bit hi(/lo) operands (it is bound by the L1 / shared-memory pipe, not by the
+  // tensor pipe); under AS_FMT_F16F8 only its OUTPUT planes switch to the e5m2 pair encoding convc2 consumes
   const bool f16 = as_operand_f16_internal() != 0;
+  const int out_fmt = as_operand_fmt_internal();
 #define AS_C1_LAUNCH(LV, F, GEO)                                                                                          \
   do {                                                                                                                    \
     e = cudaFuncSetAttribute(geo_lookup_convc1_kernel<LV, F, GEO>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
@@ -428,7 +430,7 @@ static int launch_lookup_convc1(bool geo, const float* const* geo_levels, int Dg
     if (e != cudaSuccess) return (int)e;                                                                                  \
     geo_lookup_convc1_kernel<LV, F, GEO><<<grid, kThreads, smem_bytes(GEO), st>>>(                                        \
         tW_hi, tW_lo, lv, Dg, disp, coords, bias, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, HW, W, tiles_per_img,   \
-        (int)nt, nsplit);                                                                                                 \
+        (int)nt, nsplit, out_fmt);                                                                                        \
   } while (0)
   if (geo) {
     if (num_levels == 2) { if (f16) AS_C1_LAUNCH(2, true, true); else AS_C1_LAUNCH(2, false, true); }

@@ -6,6 +6,7 @@
 //    (coreContinuous_IGEV/geometry.py:18) fused with every pooling level (:24) in ONE pass:
 //    [B,G,D,H,W] is read once with 128-byte coalesced rows, transposed through shared memory and
 //    written as [pixel][d][g] (+ pooled levels) in fully contiguous runs.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace {
@@ -113,6 +114,86 @@ __global__ void __launch_bounds__(256) geo_pyramid_kernel(const float* __restric
   }
 }
 
+
+// 128-bit variant for the IGEV shape (G = 8 groups, 16-disparity chunks, W % 4 == 0, L <= 2).
+// The r1 kernel above moves 4 bytes per lane, runs four passes over shared memory (tile in, level 0 out, pooling, level 1
+// out) and executes 5,100 warp instructions per CTA: ncu showed it bound by shared-memory wavefronts (14.6 M) and issue
+// slots, DRAM 49 % busy.  Here the tile crosses shared memory ONCE:
+//   load : a warp instruction reads 4 rows ((d, g) planes) x 128 B as float4 and stores them as 128-bit rows
+//          [e = d*8+g][32 px] whose 16-byte chunks are XOR-swizzled with (e >> 2) & 7;
+//   store: thread = (d, half of the groups) x 4 pixels: four 128-bit smem reads give it a 4(g) x 4(px) block, i.e. for each
+//          of its 4 pixels 16 contiguous bytes of the [pixel][d][g] record; lane = (d, half) makes every store
+//          instruction one contiguous 512-byte run of one pixel record.  The pooled level comes from registers: the
+//          partner disparity d+1 sits two lanes up (warp shuffle), (a+b)*0.5 is bit-identical to F.avg_pool2d, and the
+//          even-d lanes write the level-1 record (256 contiguous bytes per instruction).
+template <int L>
+__global__ void __launch_bounds__(256) geo_pyramid_v4_kernel(const float* __restrict__ geo, float* __restrict__ out0,
+                                                             float* __restrict__ out1, int Dg, int H, int W, int nchunks) {
+  constexpr int G = 8, DC = 16, E0 = DC * G;
+  __shared__ __align__(16) float tile[E0 * kTX];   // 16 KB
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int x0 = blockIdx.x * kTX, y = blockIdx.y;
+  const int b = blockIdx.z / nchunks, ch = blockIdx.z - b * nchunks;
+  const int d0 = ch * DC;
+  const int nx = min(kTX, W - x0);                 // multiple of 4
+  const long long HW = (long long)H * W;
+  {
+    const int lr = lane >> 3, c4 = lane & 7;       // row within the 4-row group, 16-byte chunk (4 pixels) of the row
+    const float* src = geo + (long long)b * G * Dg * HW + (long long)y * W + x0 + c4 * 4;
+    float4 v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = i * 8 + warp;                  // (disparity, half of the groups)
+      const int dd = c >> 1, g = (c & 1) * 4 + lr;
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c4 * 4 < nx && d0 + dd < Dg) v[i] = as_ldg_stream(reinterpret_cast<const float4*>(src + ((long long)g * Dg + d0 + dd) * HW));
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = i * 8 + warp;
+      const int e = (c >> 1) * G + (c & 1) * 4 + lr;
+      *reinterpret_cast<float4*>(tile + e * kTX + ((c4 ^ ((e >> 2) & 7)) << 2)) = v[i];
+    }
+  }
+  __syncthreads();
+  // reader: warp w owns the pixel quad w (pixels 4w..4w+3); lane = (d = lane >> 1, half = lane & 1)
+  const int pq = warp;
+  if (pq * 4 >= nx) return;
+  const int dd = lane >> 1, half = lane & 1;
+  const int e0 = dd * G + half * 4;                // (e0 >> 2) & 7 == lane & 7: the 8 lanes of a quarter warp hit 8 distinct chunks
+  float4 r[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) r[j] = *reinterpret_cast<const float4*>(tile + (e0 + j) * kTX + ((pq ^ (lane & 7)) << 2));
+  // r[j] = group (half*4 + j) at pixels 4pq..4pq+3 -> per pixel i the 4 groups are contiguous in the record
+  const long long n0 = ((long long)b * H + y) * W + x0 + pq * 4;
+  const bool dvalid = d0 + dd < Dg;
+  float4 px[4];
+  px[0] = make_float4(r[0].x, r[1].x, r[2].x, r[3].x);
+  px[1] = make_float4(r[0].y, r[1].y, r[2].y, r[3].y);
+  px[2] = make_float4(r[0].z, r[1].z, r[2].z, r[3].z);
+  px[3] = make_float4(r[0].w, r[1].w, r[2].w, r[3].w);
+  if (dvalid) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      as_stg_stream4(reinterpret_cast<float4*>(out0 + ((n0 + i) * Dg + d0 + dd) * G + half * 4), px[i]);
+  }
+  if (L > 1) {
+    const int D1 = Dg >> 1;
+    const int d1 = (d0 + dd) >> 1;
+    const bool writer = ((dd & 1) == 0) && d1 < D1;   // odd tail of Dg is dropped (avg_pool2d floor semantics)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float4 o;
+      o.x = (px[i].x + __shfl_down_sync(0xffffffffu, px[i].x, 2)) * 0.5f;
+      o.y = (px[i].y + __shfl_down_sync(0xffffffffu, px[i].y, 2)) * 0.5f;
+      o.z = (px[i].z + __shfl_down_sync(0xffffffffu, px[i].z, 2)) * 0.5f;
+      o.w = (px[i].w + __shfl_down_sync(0xffffffffu, px[i].w, 2)) * 0.5f;
+      if (writer) as_stg_stream4(reinterpret_cast<float4*>(out1 + ((n0 + i) * D1 + d1) * G + half * 4), o);
+    }
+  }
+}
+
 // adjoint: g_geo[b,g,d,y,x] = sum over levels of the pooled-gradient chain, inverse permute fused
 __global__ void __launch_bounds__(256) geo_pyramid_bwd_kernel(GeoIn gl, float* __restrict__ ggeo, int G, int Dg,
                                                               int H, int W, int L) {
@@ -193,7 +274,13 @@ extern "C" int as_geo_pyramid_build(const float* geo, int B, int G, int Dg, int 
   if (smem > 220 * 1024) return AS_ERR_UNSUPPORTED;
   dim3 grid(as_ceil_div(W, kTX), H, B * nchunks);
   cudaError_t e;
-  if (G == 8 && DC == 16) {                         // the IGEV shape: constant-folded index arithmetic
+  bool aligned = as_aligned16(geo) && (W % 4 == 0);
+  for (int l = 0; l < num_levels; ++l) aligned = aligned && as_aligned16(levels[l]);
+  static const bool use_v4 = !(getenv("AS_GEOPYR_V4") && getenv("AS_GEOPYR_V4")[0] == '0');      // A/B knob
+  if (G == 8 && DC == 16 && aligned && use_v4 && num_levels <= 2) {    // the IGEV shape, 128-bit accesses on both sides
+    if (num_levels == 1) geo_pyramid_v4_kernel<1><<<grid, 256, 0, as_cu(stream)>>>(geo, o.ptr[0], nullptr, Dg, H, W, nchunks);
+    else geo_pyramid_v4_kernel<2><<<grid, 256, 0, as_cu(stream)>>>(geo, o.ptr[0], o.ptr[1], Dg, H, W, nchunks);
+  } else if (G == 8 && DC == 16) {                  // the IGEV shape: constant-folded index arithmetic
     e = cudaFuncSetAttribute(geo_pyramid_kernel<8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     geo_pyramid_kernel<8, 16><<<grid, 256, smem, as_cu(stream)>>>(geo, o, G, Dg, H, W, num_levels, DC, nchunks);

@@ -30,12 +30,20 @@ DEFAULT_ENGINE = "bf16x3"
 _ENGINE = {"engine": DEFAULT_ENGINE}
 
 
+ENGINES = ("fp32", "bf16x3", "f16f8", "bf16", "fp16")
+
+
 def set_update_engine(engine: str):
-    if engine not in ("fp32", "bf16x3", "bf16", "fp16"):
-        raise ValueError("engine must be fp32, bf16x3, bf16 or fp16")
+    """fp32   exact CUDA-core kernels (parity baseline on the GPU)
+    bf16x3 tcgen05, 3 passes: x = hi + lo in bf16, hi*hi + hi*lo + lo*hi -- fp32 parity (default)
+    f16f8  tcgen05, 2 pass-equivalents: hi*hi in IEEE half + BOTH cross terms in one e5m2 pass (csrc/common.cuh) -- fp32
+           parity class (final-disparity drift 1e-4 px like bf16x3), 1.5x fewer tensor-core cycles
+    fp16 / bf16  single pass -- fast modes, outside the 1e-4 operator tolerance (fp16 inside the 0.01 px EPE gate)"""
+    if engine not in ENGINES:
+        raise ValueError("engine must be one of %s" % (ENGINES,))
     # "fp16": single-MMA fast mode with IEEE-half operands (11-bit mantissas) -- the analogue of the reference's
-    # autocast mixed precision (continuous_IGEVstereo.py:287); every other engine uses bf16 bit patterns
-    L.set_operand_format(L.FMT_F16 if engine == "fp16" else L.FMT_BF16)
+    # autocast mixed precision (continuous_IGEVstereo.py:287)
+    L.set_operand_format({"fp16": L.FMT_F16, "f16f8": L.FMT_F16F8}.get(engine, L.FMT_BF16))
     _ENGINE["engine"] = engine
 
 

@@ -285,11 +285,37 @@ def _src(t):
     return (t, t.shape[3], t.shape[3], NHWC)
 
 
+class _train_engine:
+    """The training path has no 2-pass kernels: under the "f16f8" inference engine its tensor-core kernels run in the
+    3-pass split-bf16 mode (same fp32-parity class), for the forward and -- whenever autograd calls it -- the backward."""
+
+    def __enter__(self):
+        from .update import get_update_engine, set_update_engine
+        self.prev = get_update_engine()
+        if self.prev == "f16f8":
+            set_update_engine("bf16x3")
+
+    def __exit__(self, *exc):
+        if self.prev == "f16f8":
+            from .update import set_update_engine
+            set_update_engine("f16f8")
+
+
 class UpdateBlockFn(torch.autograd.Function):
     """forward(ub, flags, *tensors) with tensors = net[0..n) + flat(inp) + [corr, disp] + parameters."""
 
     @staticmethod
     def forward(ctx, ub, flags, n_net, has_corr, *tensors):
+        with _train_engine():
+            return UpdateBlockFn._forward(ctx, ub, flags, n_net, has_corr, *tensors)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        with _train_engine():
+            return UpdateBlockFn._backward(ctx, *gouts)
+
+    @staticmethod
+    def _forward(ctx, ub, flags, n_net, has_corr, *tensors):
         iter04, iter08, iter16, update = flags
         n_layers = ub.args.n_gru_layers
         net = list(tensors[:n_net])
@@ -420,7 +446,7 @@ class UpdateBlockFn(torch.autograd.Function):
         return tuple(outs)
 
     @staticmethod
-    def backward(ctx, *gouts):
+    def _backward(ctx, *gouts):
         tape, ub = ctx.tape, ctx.ub
         C = tape["C"]
         iter04, iter08, iter16, update = tape["flags"]

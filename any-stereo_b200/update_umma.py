@@ -98,12 +98,19 @@ def _fused_c1_weights(ub, split, kind=DeferredGeoLookup):
     hit = st.get("convc1.fused")
     if hit is not None and hit["key"] == key:
         return hit
-    with torch.no_grad():
+    # the fused kernel's own GEMM runs on 16-bit hi/lo operands in every engine: under "f16f8" its weights are IEEE-half
+    # hi/lo pairs (3 internal passes; the kernel is not tensor-bound), only its OUTPUT planes use the e5m2 pair encoding
+    with torch.no_grad(), L.operand_format_scope(_sixteen_bit_format()):
         hi, lo = kind.pack_convc1_weight(c.weight, split)
         bias = c.bias.detach().float().contiguous()
     hit = dict(key=key, hi=hi, lo=lo, bias=bias)
     st["convc1.fused"] = hit
     return hit
+
+
+def _sixteen_bit_format():
+    """Operand format of the kernels that keep 16-bit hi/lo operands internally (fused lookup, convd1)."""
+    return L.FMT_F16 if L.operand_format() == L.FMT_F16F8 else L.operand_format()
 
 
 _CONVD1_SIMT = os.environ.get("AS_CONVD1_SIMT", "0") == "1"     # A/B knob: CUDA-core convd1 kernel
@@ -117,7 +124,7 @@ def _convd1_weights(ub, split):
     hit = st.get("convd1.umma")
     if hit is not None and hit["key"] == key:
         return hit
-    with torch.no_grad():
+    with torch.no_grad(), L.operand_format_scope(_sixteen_bit_format()):
         w = c.weight.detach().float().reshape(64, 49).contiguous()
         hi = torch.empty((64, 64), device=w.device, dtype=torch.bfloat16)
         lo = torch.empty_like(hi) if split else None
@@ -225,8 +232,9 @@ def _remember(ub, h_f32, pl):
 
 def forward(ub, net, inp, corr=None, disp=None, iter04=True, iter08=True, iter16=True, update=True):
     from .update import _nhwc_view, get_update_engine
-    split = get_update_engine() == "bf16x3"
-    nsplit = 3 if split else 1
+    engine = get_update_engine()
+    split = engine in ("bf16x3", "f16f8")            # conv inputs carry a second ("lo") plane
+    nsplit = {"bf16x3": 3, "f16f8": 2}.get(engine, 1)  # tensor-core passes per K-step
     n_layers = ub.args.n_gru_layers
     dev = net[0].device
     s = L.stream_ptr
@@ -285,7 +293,7 @@ def forward(ub, net, inp, corr=None, disp=None, iter04=True, iter08=True, iter16
         else:                                            # 49 taps as one K = 64 row per pixel on the tensor cores
             wd = _convd1_weights(ub, split)
             L.call("as_convd1_umma", disp.data_ptr(), wd["hi"].data_ptr(), L.ptr(wd["lo"]), sw["bd1"].data_ptr(),
-                   d1.hi.data_ptr(), L.ptr(d1.lo), B, H, W, 64, 0, nsplit, s())
+                   d1.hi.data_ptr(), L.ptr(d1.lo), B, H, W, 64, 0, 3 if split else 1, s())
         _conv(B, H, W, [d1], _weights(ub, "convd2", [e.convd2], split=split), nsplit, L.UEPI_RELU_SPLIT, out=enc,
               out_coff=64)
         mo = _Planes((B, H, W, 128), dev, split)

@@ -28,7 +28,8 @@ sys.path.insert(0, ROOT)
 H4, W4, FEAT_D, GEO_D, GROUPS, ITERS = 96, 312, 96, 48, 8, 32     # 384x1248 at 1/4 resolution
 LOOKUP_BYTES_PER_PIXEL = 1372                                      # IGEV L=2, r=4, G=8
 # fused lookup+convc1: the same 724 B of windows + 4 B disp read, 64 bf16 hi(+lo) channels written
-FUSED_BYTES_PER_PIXEL = {"bf16x3": 728 + 256, "bf16": 728 + 128, "fp16": 728 + 128}
+FUSED_BYTES_PER_PIXEL = {"bf16x3": 728 + 256, "f16f8": 728 + 256, "bf16": 728 + 128, "fp16": 728 + 128}
+PASSES = {"bf16x3": 3, "f16f8": 2}          # tensor-core pass-equivalents per MAC of the fp32-parity engines
 
 
 def load_peaks():
@@ -288,7 +289,7 @@ def run_ours(args):
     A.set_update_engine(args.engine)
     A.update_umma.set_encoder_overlap(not args.no_overlap)
     A.set_lookup_fusion(not args.no_fusion)
-    A.set_corr_mode(args.corr_mode or {"fp32": "fp32", "bf16x3": "bf16x3", "bf16": "bf16", "fp16": "bf16x3"}[args.engine])
+    A.set_corr_mode(args.corr_mode or {"fp32": "fp32", "bf16": "bf16"}.get(args.engine, "bf16x3"))
     B = args.pairs_per_gpu
     torch.manual_seed(0)
     uargs = types.SimpleNamespace(corr_levels=2, corr_radius=4, n_gru_layers=3)
@@ -435,7 +436,7 @@ def run_ours(args):
             # the mixed-precision analogue (IEEE-half operands, single MMA): same step, reported for context only --
             # inside the 0.01 px EPE gate at the BASELINE shapes (tests/test_gpu_dropin.py, profiles/dropin_epe_r02.json)
             # but not inside the 1e-4 operator tolerance, so never the headline
-            if args.engine == "bf16x3":
+            if args.engine in ("bf16x3", "f16f8"):
                 A.set_update_engine("fp16")
                 block.reset_caches()
                 for _ in range(2):
@@ -537,7 +538,7 @@ def run_ours(args):
     # issued 3 times, so "issued" is what the tensor pipe executes; peak = measured sustained cuBLAS bf16.
     upd_avg_us = sum(upd_us) / max(len(upd_us), 1)
     upd_flops = 2.0 * (n_pix * (1847488 + 64 * 162) + n_pix / 4 * 1327104 + n_pix / 16 * 884736)
-    issued = upd_flops * (3 if args.engine == "bf16x3" else 1)
+    issued = upd_flops * PASSES.get(args.engine, 1)
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             tpeak = float(json.load(f)["bf16_tflops_sustained"])
@@ -549,7 +550,9 @@ def run_ours(args):
         "metric": "pairs/s @384x1248, 32 iters", "value": value, "unit": "pairs/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "warmup_steps_run": n_w, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"fp32": "f32", "bf16x3": "f32 (3x split-bf16 on tcgen05, fp32 accumulate)", "bf16": "bf16",
+        "dtype": {"fp32": "f32", "bf16x3": "f32 (3x split-bf16 on tcgen05, fp32 accumulate)",
+                  "f16f8": "f32 (2-pass split on tcgen05: IEEE-half hi*hi + one e5m2 pass for both cross terms, fp32 accumulate)",
+                  "bf16": "bf16",
                   "fp16": "f16 (IEEE half operands, fp32 accumulate; mixed-precision analogue)"}[args.engine],
         "data": "synthetic",
         "config": {"workload": WORKLOAD % B, "pairs_per_gpu": B, "iters": ITERS, "engine": args.engine, "corr_mode": A.get_corr_mode(),
@@ -571,7 +574,7 @@ def run_ours(args):
         "roofline_update_block": None if args.engine == "fp32" else {
             "kernels": "conv_umma_kernel (tcgen05) + small kernels per iteration" + (" + the fused lookup/convc1 kernel" if fused else ""), "bound": "tensor",
             "achieved": issued / (upd_avg_us * 1e-6) / 1e12, "peak": tpeak, "unit": "TFLOP/s", "frac": issued / (upd_avg_us * 1e-6) / 1e12 / tpeak,
-            "logical_tflops": upd_flops / (upd_avg_us * 1e-6) / 1e12, "mma_issue_factor": 3 if args.engine == "bf16x3" else 1,
+            "logical_tflops": upd_flops / (upd_avg_us * 1e-6) / 1e12, "mma_issue_factor": PASSES.get(args.engine, 1),
             "avg_us_per_iteration": upd_avg_us, "peak_source": tpeak_src},
         "cpu_baseline": None if cpu is None else {"value": cpu["pairs_per_s"], "unit": "pairs/s", "cores": cpu["cores"],
                                                   "kind": cpu["kind"], "sample": cpu["sample"]},
@@ -589,7 +592,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--engine", default=os.environ.get("ANYSTEREO_ENGINE", "bf16x3"), choices=["fp32", "bf16x3", "bf16", "fp16"])
+    ap.add_argument("--engine", default=os.environ.get("ANYSTEREO_ENGINE", "bf16x3"), choices=["fp32", "bf16x3", "f16f8", "bf16", "fp16"])
     ap.add_argument("--corr-mode", default=None, choices=[None, "fp32", "bf16x3", "bf16"])
     ap.add_argument("--pairs-per-gpu", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")

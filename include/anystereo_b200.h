@@ -285,6 +285,7 @@ int as_conv2d_umma(const as_conv_umma_desc* desc, as_stream_t stream);
  * precision, continuous_IGEVstereo.py:287).  Process-wide; planes and weights must be (re)produced after a switch. */
 #define AS_FMT_BF16 0
 #define AS_FMT_F16 1
+#define AS_FMT_F16F8 2   /* hi = IEEE half, "lo" plane = e5m2 pairs: 2-pass fp32-parity mode (nsplit 2), see csrc/common.cuh */
 int as_set_operand_format(int fmt);
 int as_get_operand_format(void);
 /* nn.Conv2d weight [Cout][Cin][KH][KW] fp32 -> bf16 hi/lo [n_pad][KH*KW*cin_pad] (zero padded rows/channels) */

@@ -108,7 +108,7 @@ def make_block(A, family, seed):
     return m.cuda().eval()
 
 
-@pytest.mark.parametrize("engine,tol", [("bf16x3", 2e-4), ("bf16", 5e-2), ("fp16", 6e-3)])
+@pytest.mark.parametrize("engine,tol", [("bf16x3", 2e-4), ("f16f8", 2e-4), ("bf16", 5e-2), ("fp16", 6e-3)])
 @pytest.mark.parametrize("family", ["igev", "raft"])
 def test_update_block_umma_golden(A, golden, family, engine, tol):
     g = golden("update_block_" + family)
@@ -128,7 +128,7 @@ def test_update_block_umma_golden(A, golden, family, engine, tol):
     A.set_update_engine("fp32")
 
 
-@pytest.mark.parametrize("engine", ["bf16x3", "fp16"])
+@pytest.mark.parametrize("engine", ["bf16x3", "f16f8", "fp16"])
 @pytest.mark.parametrize("family", ["igev", "raft"])
 def test_iteration_loop_epe_umma(A, golden, family, engine):
     """fp32-parity tensor-core mode (and the IEEE-half fast mode): final disparity within 0.01 px of the reference
@@ -264,7 +264,7 @@ def test_config3_middlebury_full_res_smoke(A):
     assert float((hist[0] - hist32[0]).abs().max()) < 2e-4 * max(1.0, float(hist32[0].abs().max()))
 
 
-@pytest.mark.parametrize("engine", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("engine", ["fp32", "bf16x3", "f16f8"])
 def test_model_level_raft_epe(A, golden, engine):
     """Drop-in at the model level: the tensors the real reference RAFT model feeds into its hot path (captured on
     CPU, tests/golden/make_model_golden.py) replayed through our operators for the same 32 iterations give the
@@ -277,7 +277,7 @@ def test_model_level_raft_epe(A, golden, engine):
     m.load_state_dict(O.make_update_block_params(36, seed=77), strict=True)
     m = m.cuda().eval()
     A.set_update_engine(engine)
-    A.set_corr_mode(engine)
+    A.set_corr_mode("bf16x3" if engine == "f16f8" else engine)
     disp, _ = A.raft_iterations(m, torch.from_numpy(g["f1"]).cuda(), torch.from_numpy(g["f2"]).cuda(), net, inp,
                                 int(g["iters"]))
     A.set_update_engine("fp32")
@@ -286,7 +286,7 @@ def test_model_level_raft_epe(A, golden, engine):
     assert epe < 0.01, epe
 
 
-@pytest.mark.parametrize("engine", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("engine", ["fp32", "bf16x3", "f16f8"])
 def test_model_level_igev_epe(A, golden, engine):
     """IGEV family at the model level: build_gwc_volume on the real model's matching features, then the combined
     volume + 32 iterations from the real model's boundary tensors -> within 0.01 px of the reference model."""
@@ -301,7 +301,7 @@ def test_model_level_igev_epe(A, golden, engine):
     m.load_state_dict(O.make_update_block_params(162, seed=78), strict=True)
     m = m.cuda().eval()
     A.set_update_engine(engine)
-    A.set_corr_mode(engine)
+    A.set_corr_mode("bf16x3" if engine == "f16f8" else engine)
     disp, _ = A.igev_iterations(m, f1, f2, torch.from_numpy(g["geo"]).cuda(), net, inp,
                                 torch.from_numpy(g["init_disp"]).cuda(), int(g["iters"]))
     A.set_update_engine("fp32")
@@ -310,7 +310,7 @@ def test_model_level_igev_epe(A, golden, engine):
     assert epe < 0.01, epe
 
 
-@pytest.mark.parametrize("engine,tol", [("fp32", 1e-4), ("bf16x3", 3e-4)])
+@pytest.mark.parametrize("engine,tol", [("fp32", 1e-4), ("bf16x3", 3e-4), ("f16f8", 3e-4)])
 @pytest.mark.parametrize("n_layers", [1, 2])
 def test_update_block_fewer_gru_layers(A, engine, tol, n_layers):
     """n_gru_layers = 1 / 2 variants of BasicMultiUpdateBlock (update.py:111-112,121-130) and half-precision inputs."""
@@ -379,7 +379,7 @@ def test_fused_lookup_convc1_vs_oracle(A, engine, tol, shape):
     assert torch.equal(out2.view(torch.int16), out_hi.view(torch.int16))
 
 
-@pytest.mark.parametrize("engine", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("engine", ["bf16x3", "f16f8", "bf16"])
 def test_fused_lookup_matches_unfused_loop(A, engine):
     """igev_iterations with the lookup fused into the update block == the same loop with the 162-channel tensor
     materialised (identical arithmetic: fp32 interpolation, same bf16 split, same K order on the MMA)."""
@@ -403,7 +403,7 @@ def test_fused_lookup_matches_unfused_loop(A, engine):
     A.set_update_engine("fp32")
     A.set_corr_mode("fp32")
     assert (n2 - n1) - (n1 - n0) >= 6, (n0, n1, n2)         # at least one launch fewer per iteration
-    tol = 1e-5 if engine == "bf16x3" else 2e-3       # K order differs: fp32 accumulation order, amplified by 6 GRU steps
+    tol = {"bf16x3": 1e-5, "f16f8": 1e-4}.get(engine, 2e-3)       # K order differs: fp32 accumulation order, amplified by 6 GRU steps
     assert rel(d_f, d_u) < tol
     for a, b in zip(net_f, net_u):
         assert rel(a, b) < tol
@@ -550,7 +550,7 @@ def test_encoder_side_stream_overlap_is_exact(A, family):
         assert torch.equal(o, ref)
 
 
-@pytest.mark.parametrize("engine,tol", [("fp32", 1e-4), ("bf16x3", 1e-3)])
+@pytest.mark.parametrize("engine,tol", [("fp32", 1e-4), ("bf16x3", 1e-3), ("f16f8", 1e-3)])
 def test_slow_fast_gru_loop_vs_reference(A, golden, engine, tol):
     """args.slow_fast_gru (continuous_IGEVstereo.py:288-291): two extra low-resolution GRU passes per iteration."""
     c = cases.loop_case("igev", seed=61, B=1, H=16, W=24)
@@ -566,3 +566,76 @@ def test_slow_fast_gru_loop_vs_reference(A, golden, engine, tol):
     A.set_update_engine("fp32")
     A.set_corr_mode("fp32")
     assert rel(disp, ref) < tol
+
+
+def _decode_x8(lo_plane, C, weights=False):
+    """AS_FMT_F16F8 "lo" plane (csrc/common.cuh): per 64-channel chunk 128 bytes [first | second] of e5m2 values.
+    Activations: first = lo * 2^6, second = hi * 2^-8; weights: first = hi * 2^-6, second = lo * 2^8."""
+    raw = lo_plane.contiguous().view(torch.uint8).reshape(-1, C // 64, 2, 64)
+    f8 = raw.view(torch.float8_e5m2).float()
+    first, second = f8[:, :, 0, :].reshape(-1, C), f8[:, :, 1, :].reshape(-1, C)
+    if weights:
+        return first * 64.0, second / 256.0           # hi, lo
+    return second * 256.0, first / 64.0               # hi, lo
+
+
+def test_f16f8_plane_and_weight_encoding(A):
+    """The 2-pass parity format: hi = IEEE half, lo plane = e5m2 pairs with power-of-two scales (bit-exact encoding)."""
+    L = A._lib
+    torch.manual_seed(3)
+    x = (torch.randn(2, 5, 7, 128, device="cuda") * torch.logspace(-3, 1, 128, device="cuda")).contiguous()
+    A.set_update_engine("f16f8")
+    try:
+        hi = torch.empty(x.shape, device="cuda", dtype=torch.bfloat16)
+        lo = torch.empty_like(hi)
+        L.call("as_split_f32", x.data_ptr(), hi.data_ptr(), lo.data_ptr(), x.numel(), L.stream_ptr())
+        w = torch.randn(96, 64, 3, 3, device="cuda") * 0.05
+        whi = torch.empty((96, 9 * 64), device="cuda", dtype=torch.bfloat16)
+        wlo = torch.empty_like(whi)
+        L.call("as_pack_conv_weight_bf16", w.data_ptr(), whi.data_ptr(), wlo.data_ptr(), 96, 64, 3, 3, 96, 64, L.stream_ptr())
+        torch.cuda.synchronize()
+    finally:
+        A.set_update_engine("fp32")
+    xh = x.half().float()
+    assert torch.equal(hi.view(torch.float16).float(), xh)
+    dec_hi, dec_lo = _decode_x8(lo, 128)
+    exp_lo = ((x - xh) * 64.0).to(torch.float8_e5m2).float() / 64.0
+    exp_hi = (xh / 256.0).to(torch.float8_e5m2).float() * 256.0
+    assert torch.equal(dec_lo, exp_lo.reshape(-1, 128))
+    assert torch.equal(dec_hi, exp_hi.reshape(-1, 128))
+    wk = w.permute(0, 2, 3, 1).reshape(96, 9 * 64)                    # [n][tap][c]
+    wh = wk.half().float()
+    assert torch.equal(whi.view(torch.float16).float(), wh)
+    dwh, dwl = _decode_x8(wlo, 9 * 64, weights=True)
+    assert torch.equal(dwh, ((wh / 64.0).to(torch.float8_e5m2).float() * 64.0))
+    assert torch.equal(dwl, (((wk - wh) * 256.0).to(torch.float8_e5m2).float() / 256.0))
+
+
+@pytest.mark.parametrize("shape", [(1, 16, 24), (2, 40, 72)])
+def test_f16f8_conv_matches_fp32(A, shape):
+    """One 3x3 convolution (N = 256, z|r shape) on the 2-pass engine against torch fp64: error at the level of the 3-pass
+    split (<= 1e-4 of max|ref|), far below a single half pass."""
+    import types
+    B, H, W = shape
+    torch.manual_seed(5)
+    args = types.SimpleNamespace(corr_levels=2, corr_radius=4, n_gru_layers=3)
+    ub = A.BasicMultiUpdateBlock(args, hidden_dims=[128, 128, 128]).cuda().eval()
+    from anystereo_b200 import update_umma as U
+    x = torch.randn(B, H, W, 128, device="cuda")
+    errs = {}
+    for engine in ("f16f8", "bf16x3", "fp16"):
+        A.set_update_engine(engine)
+        split = engine != "fp16"
+        ns = {"f16f8": 2, "bf16x3": 3, "fp16": 1}[engine]
+        pl = U._Planes(x.shape, "cuda", split)
+        A._lib.call("as_split_f32", x.data_ptr(), pl.hi.data_ptr(), A._lib.ptr(pl.lo), x.numel(), A._lib.stream_ptr())
+        wt = U._weights(ub, "t." + engine, [ub.disp_head.conv1], split=split)
+        out = torch.empty(B, H, W, 256, device="cuda")
+        U._conv(B, H, W, [pl], wt, ns, A._lib.UEPI_LINEAR_F32, out_f32=out)
+        torch.cuda.synchronize()
+        ref = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), ub.disp_head.conv1.weight.double(),
+                                         ub.disp_head.conv1.bias.double(), padding=1).permute(0, 2, 3, 1)
+        errs[engine] = float((out.double() - ref).abs().max() / ref.abs().max())
+    A.set_update_engine("fp32")
+    assert errs["f16f8"] < 1e-4 and errs["bf16x3"] < 1e-4, errs
+    assert errs["fp16"] > 3 * errs["f16f8"], errs

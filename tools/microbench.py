@@ -158,6 +158,17 @@ def main():
             json.dump(res, open(a.json, "w"), indent=1)
         return
     gwc = A.build_gwc_volume(f1, f2, Dg, 8)
+    if a.only == "mem":
+        # the memory-bound volume kernels only, few repetitions (the command ncu wraps)
+        blk = A.Combined_Geo_Encoding_Volume(f1, f2, gwc, num_levels=2, radius=4)
+        coords = torch.arange(W, device=dev, dtype=torch.float32).reshape(1, 1, W, 1).repeat(B, H, 1, 1)
+        d = (torch.rand(B, 1, H, W, device=dev) * Dg).contiguous()
+        for _ in range(3):
+            A.build_gwc_volume(f1, f2, Dg, 8)
+            A.geometry._build_geo_levels(gwc, 2)
+            blk(d, coords)
+        torch.cuda.synchronize()
+        return
     if a.only == "initdisp":
         # classifier Conv3d + softmax + disparity_regression fused; bytes = geo read once + disp written
         geo = torch.randn(B, 8, Dg, H, W, device=dev)
@@ -210,6 +221,7 @@ def main():
         d = d.float().contiguous()
         med, best = timeit(lambda: blk(d, coords))
         rec("geo_lookup_" + name, med, best, 1372 * N)
+    fused_lookup_bench(blk, disps["uniform"].float().contiguous(), coords, rec, N)
     # a6 sampler on the level-0 volume
     vol = blk.init_corr_pyramid[0].reshape(B, H, W, W)
     x0 = (coords.reshape(B, 1, H, W) - disps["uniform"]).contiguous()
@@ -229,6 +241,30 @@ def main():
             rec("REFERENCE_sampler_bwd", med, best, (36 + 4) * N + 4 * N * W)
     except Exception as e:
         print("reference sampler unavailable:", e)
+    # a6 at the size SURVEY 8(d) names: config-3 level-0 volume [1,496,720,720] (1.03 GB), 357,120 pixels x 80 B = 28.6 MB
+    del vol
+    Bs, Hs, Ws = 1, 496, 720
+    vol3 = torch.randn(Bs, Hs, Ws, Ws, device=dev)
+    c3 = torch.arange(Ws, device=dev, dtype=torch.float32).reshape(1, 1, 1, Ws).repeat(Bs, 1, Hs, 1)
+    x3 = (c3 - torch.rand(Bs, 1, Hs, Ws, device=dev) * 64).contiguous()
+    N3 = Bs * Hs * Ws
+    med, best = timeit(lambda: A.corr_sampler.forward(vol3, x3, 4))
+    rec("sampler_fwd_c3_level0", med, best, 80 * N3)
+    g3 = torch.randn(Bs, 9, Hs, Ws, device=dev)
+    med, best = timeit(lambda: A.corr_sampler.backward(vol3, x3, g3, 4))
+    rec("sampler_bwd_c3_level0", med, best, (36 + 4) * N3 + 4 * N3 * Ws)
+    try:
+        from oracle import ref_sampler
+        rs = ref_sampler.load()
+        if rs is not None:
+            x32 = torch.cat([x3, torch.zeros_like(x3)], 1).contiguous()
+            med, best = timeit(lambda: rs.forward(vol3, x32, 4))
+            rec("REFERENCE_sampler_fwd_c3_level0", med, best, 80 * N3)
+            med, best = timeit(lambda: rs.backward(vol3, x32, g3, 4))
+            rec("REFERENCE_sampler_bwd_c3_level0", med, best, (36 + 4) * N3 + 4 * N3 * Ws)
+    except Exception as e:
+        print("reference sampler unavailable:", e)
+    del vol3, g3
     # a3 RAFT lookup at config 3 (496x720, L=4), D reduced to keep the build short: only the lookup is timed
     Br, Hr, Wr = 1, 496, 720
     r1 = torch.randn(Br, 64, Hr, Wr, device=dev)
