@@ -20,8 +20,17 @@
 
 namespace {
 
-constexpr int kThreads = 256;
 constexpr int kMaxStages = 4;
+// warps: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 3 idle, 4-11 epilogue.  EIGHT epilogue warps: two per TMEM lane
+// quarter.  With one sub-tile per CTA (SUB = 1) the two warps of a quarter split the accumulator columns (chunks of 32,
+// alternating); with SUB = 2 each drains one sub-tile.  r1 had four epilogue warps (one per scheduler, every instruction
+// of a 300-instruction chunk waiting for the previous one): ~4 us per 32-column chunk and tile, which is LONGER than the
+// MMAs of a tile in the N <= 128 layers and, in the 2- and 1-pass engines, at N = 256 too (ncu: tensor pipe 23-49 % on
+// convc2 / convd2 / motion / q, L2 33 %, DRAM 17 %: neither memory nor tensor bound).
+constexpr int kEpiWarps = 8;
+constexpr int kConvThreads = 128 + 32 * kEpiWarps;
+constexpr int kUFloats = 128 * 9;                 // DISPHEAD: partial sums of the second column half (SUB = 1)
+__host__ __device__ constexpr int conv_threads(int) { return kConvThreads; }
 constexpr int kW2Floats = 9 * 256;
 constexpr int kSmemBudget = 227 * 1024;
 
@@ -69,15 +78,22 @@ __device__ __forceinline__ void store_split32(const float* v, __nv_bfloat16* hi,
 // NS = tensor-core passes per K-step: 1 = hi*hi; 3 = hi*hi + hi*lo + lo*hi (16-bit hi/lo planes); 2 = hi*hi in kind::f16 plus
 // ONE kind::f8f6f4 MMA over the e5m2 pair planes of AS_FMT_F16F8 (both cross terms, common.cuh).  Compile-time so that no
 // MMA sits under a run-time branch (see the predicated-MMA lint in tests/test_cpu_boundary.py).
-template <bool TWO, int NS>
-__global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_constant__ ConvMaps maps,
+// SUB = 128-pixel sub-tiles per CTA and weight pass.  SUB = 2 ("tall" tile, 16 x 16 pixels): ONE (16+2)-row activation patch
+// per (dx, channel chunk) and ONE weight stage feed two accumulators, so the L2 -> shared-memory weight traffic per
+// output pixel halves and the patch halo shrinks from 10/8 to 18/16 rows.  The 2-pass and 1-pass engines are bound by that
+// traffic (45.6 KB per K-block and CTA against 1024 / 512 tensor-core cycles: the 42 B/clk/SM that the L2 delivers), the
+// 3-pass engine is tensor-bound and keeps SUB = 1 (no tile-count quantisation loss).  With N > 128 the two accumulators
+// fill TMEM (2 x 256 columns): no double buffering, the epilogue (~5 % of a tile) is exposed.
+template <bool TWO, int NS, int SUB>
+__global__ void __launch_bounds__(conv_threads(SUB), 1) conv_umma_kernel(const __grid_constant__ ConvMaps maps,
                                                                 const ConvUmmaParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* a_ring = smem;
   uint8_t* b_ring = smem + p.nstA * p.a_stage;
   float* w2s = reinterpret_cast<float*>(b_ring + p.nstB * p.b_stage);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(w2s + kW2Floats);
+  float* ubuf = w2s + kW2Floats;                 // [128][9]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ubuf + kUFloats);
   uint64_t* fullA = bars;
   uint64_t* emptyA = bars + kMaxStages;
   uint64_t* fullB = bars + 2 * kMaxStages;
@@ -106,7 +122,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
       umma::mbar_init(&fullA[s], TWO ? 2 : 1); umma::mbar_init(&emptyA[s], 1);
       umma::mbar_init(&fullB[s], TWO ? 2 : 1); umma::mbar_init(&emptyB[s], 1);
     }
-    for (int a = 0; a < 2; ++a) { umma::mbar_init(&tfull[a], 1); umma::mbar_init(&tempty[a], TWO ? 8 : 4); }
+    for (int a = 0; a < 2; ++a) { umma::mbar_init(&tfull[a], 1); umma::mbar_init(&tempty[a], (TWO ? 2 : 1) * kEpiWarps); }
     umma::fence_barrier_init();
   }
   if (warp == 2) {
@@ -114,17 +130,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     else { umma::tmem_alloc(tmem_slot, 512); umma::tmem_relinquish(); }
   }
   if (p.epilogue == AS_UEPI_DISPHEAD) {
-    for (int i = threadIdx.x; i < kW2Floats; i += kThreads) w2s[i] = p.w2[i];
+    for (int i = threadIdx.x; i < kW2Floats; i += conv_threads(SUB)) w2s[i] = p.w2[i];
   }
   umma::tc_fence_before();
   __syncthreads();
   if (TWO) umma::cluster_sync_all();             // both CTAs' barriers exist before anyone signals them
   umma::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  // The kernel allocates all 512 TMEM columns of its SM (1 CTA/SM), so the allocation starts at column 0, lane 0.  Using
+  // the constant keeps the accumulator address of every MMA in a uniform register (a value read back from shared memory
+  // is not provably uniform: ptxas wrapped each tcgen05.mma in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop).
+  const uint32_t tmem_base = 0u;
+  if (*tmem_slot != 0u) __trap();
   const int chunks = p.cin_total >> 6;           // 64-channel chunks per tap
   const int ngroups = p.KW * chunks;             // A patches per tile; each feeds KH taps
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   const int dy_bytes = p.TW * 128;               // row offset of one dy step inside a patch (multiple of 1024)
+  // accumulators: (buffer, sub-tile) -> TMEM column.  SUB = 1: two buffers of <= 256 columns; SUB = 2: two buffers x two
+  // sub-tiles of <= 128 columns, or ONE buffer x two sub-tiles of 256 columns
+  const int nbuf = (SUB * p.N <= 256) ? 2 : 1;
+  const uint32_t sub_cols = SUB == 1 ? 0u : (nbuf == 2 ? 128u : 256u);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -186,11 +210,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
       const uint32_t idesc = umma::idesc_16_f32(TWO ? 256 : 128, p.N, p.f16);
       const uint32_t idesc8 = umma::idesc_e5m2_f32(TWO ? 256 : 128, p.N);
       for (int it = 0; it < niter; ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+        const int acc = it % nbuf;
+        const uint32_t acc_phase = (uint32_t)(it / nbuf) & 1u;
         umma::mbar_wait(&tempty[acc], acc_phase ^ 1);
         umma::tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)acc * 256u;
+        const uint32_t tmem_d0 = tmem_base + (uint32_t)acc * 256u;
         uint32_t accumulate = 0;
         for (int g = 0; g < ngroups; ++g) {
           umma::mbar_wait(&fullA[sa], pha);
@@ -200,28 +224,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
             umma::tc_fence_after();
             const uint32_t a_hi = sta + (uint32_t)(ky * dy_bytes), a_lo = a_hi + (uint32_t)p.a_plane;
             const uint32_t b_hi = umma::smem_u32(b_ring + sb * p.b_stage), b_lo = b_hi + (uint32_t)b_bytes;
+            // descriptor low words at K offset 0; a K-step of 32 bytes adds 2 (addresses are in 16-byte units)
+            const uint32_t dbh0 = umma::desc_lo_sw128(b_hi), dbl0 = umma::desc_lo_sw128(b_lo);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint32_t ko = (uint32_t)k * 32u;
-              const uint64_t dah = umma::smem_desc_k_sw128(a_hi + ko), dbh = umma::smem_desc_k_sw128(b_hi + ko);
-              if (TWO) umma::mma_bf16_ss_2sm(tmem_d, dah, dbh, idesc, accumulate);
-              else umma::mma_bf16_ss(tmem_d, dah, dbh, idesc, accumulate);
-              accumulate = 1u;
-              if (NS == 3) {
-                const uint64_t dal = umma::smem_desc_k_sw128(a_lo + ko), dbl = umma::smem_desc_k_sw128(b_lo + ko);
-                if (TWO) {
-                  umma::mma_bf16_ss_2sm(tmem_d, dah, dbl, idesc, 1u);
-                  umma::mma_bf16_ss_2sm(tmem_d, dal, dbh, idesc, 1u);
-                } else {
-                  umma::mma_bf16_ss(tmem_d, dah, dbl, idesc, 1u);
-                  umma::mma_bf16_ss(tmem_d, dal, dbh, idesc, 1u);
+            for (int t = 0; t < SUB; ++t) {          // sub-tile t = patch rows 8t .. 8t+7 (+ dy): the same weight stage
+              const uint32_t tmem_d = tmem_d0 + (uint32_t)t * sub_cols;
+              const uint32_t dah0 = umma::desc_lo_sw128(a_hi + (uint32_t)(t * 8 * dy_bytes));
+              const uint32_t dal0 = umma::desc_lo_sw128(a_lo + (uint32_t)(t * 8 * dy_bytes));
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t k2 = 2u * (uint32_t)k;
+                umma::mma_ss_lohi<TWO, false>(tmem_d, dah0 + k2, dbh0 + k2, idesc, k == 0 ? accumulate : 1u);
+                if (NS == 3) {
+                  umma::mma_ss_lohi<TWO, false>(tmem_d, dah0 + k2, dbl0 + k2, idesc, 1u);
+                  umma::mma_ss_lohi<TWO, false>(tmem_d, dal0 + k2, dbh0 + k2, idesc, 1u);
+                } else if (NS == 2) {  // [a_lo*2^6 | a_hi*2^-8] . [w_hi*2^-6 | w_lo*2^8] in e5m2: 32 of the 128 K-bytes per step
+                  umma::mma_ss_lohi<TWO, true>(tmem_d, dal0 + k2, dbl0 + k2, idesc8, 1u);
                 }
-              } else if (NS == 2) {      // [a_lo*2^6 | a_hi*2^-8] . [w_hi*2^-6 | w_lo*2^8] in e5m2: 32 of the 128 K-bytes per step
-                const uint64_t dal = umma::smem_desc_k_sw128(a_lo + ko), dbl = umma::smem_desc_k_sw128(b_lo + ko);
-                if (TWO) umma::mma_f8_ss_2sm(tmem_d, dal, dbl, idesc8, 1u);
-                else umma::mma_f8_ss(tmem_d, dal, dbl, idesc8, 1u);
               }
             }
+            accumulate = 1u;
             if (TWO) umma::mma_commit_2sm(&emptyB[sb], 3); else umma::mma_commit(&emptyB[sb]);
             if (++sb == p.nstB) { sb = 0; phb ^= 1; }
           }
@@ -233,9 +255,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     }
     __syncwarp();
   } else if (warp >= 4) {
-    const int q = warp - 4;
-    const int m = q * 32 + lane;                 // accumulator row == TMEM lane == pixel within the patch
-    const int py = m / p.TW, px = m - py * p.TW;
+    const int q = (warp - 4) & 3;                // TMEM lane quarter
+    const int st = SUB > 1 ? (warp - 4) >> 2 : 0;        // sub-tile drained by this warp
+    const int chalf = SUB > 1 ? 0 : (warp - 4) >> 2;     // SUB = 1: which half of the 32-column chunks
+    constexpr int kCStep = SUB > 1 ? 32 : 64;
+    const int m = q * 32 + lane;                 // accumulator row == TMEM lane == pixel within the sub-tile
+    const int py = m / p.TW + (SUB > 1 ? st * 8 : 0), px = m % p.TW;
     for (int it = 0; it < niter; ++it) {
       const int tile = blockIdx.x + it * gridDim.x;
       const bool real_tile = tile < p.num_tiles;
@@ -245,25 +270,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
       const int x = txi * p.TW + px, y = ty * p.TH + py;
       const bool valid = real_tile && (x < p.W) && (y < p.H);
       const long long n = ((long long)b * p.H + y) * p.W + x;
-      const int acc = it & 1;
-      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      const int acc = it % nbuf;
+      const uint32_t acc_phase = (uint32_t)(it / nbuf) & 1u;
       umma::mbar_wait(&tfull[acc], acc_phase);
       umma::tc_fence_after();
-      const uint32_t trow = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(q * 32) << 16);
+      const uint32_t trow = tmem_base + (uint32_t)acc * 256u + (uint32_t)st * sub_cols + ((uint32_t)(q * 32) << 16);
       float u[9];
 #pragma unroll
       for (int t = 0; t < 9; ++t) u[t] = 0.f;
-      for (int c0 = 0; c0 < p.N; c0 += 32) {
+      for (int c0 = chalf * 32; c0 < p.N; c0 += kCStep) {
         float v[32];
         umma::tmem_ld_32x32(trow + (uint32_t)c0, v);
+        // the context row of the GRU epilogues is fetched while the TMEM load is in flight
+        float4 cpre[8];
+        const bool gru = p.epilogue == AS_UEPI_GRU_ZR || p.epilogue == AS_UEPI_GRU_Q;
+        if (gru && valid) {
+          const float* cx = p.ctx + n * p.ctx_pitch + c0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) cpre[j] = __ldg(reinterpret_cast<const float4*>(cx + 4 * j));
+        }
         umma::tmem_ld_wait();
         if (valid) {
         if (p.epilogue == AS_UEPI_GRU_ZR) {
           const int Hd = p.N >> 1;
-          const float* cx = p.ctx + n * p.ctx_pitch + c0;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            const float4 c4 = __ldg(reinterpret_cast<const float4*>(cx + j));
+            const float4 c4 = cpre[j >> 2];
             v[j] = sigmoidf_(v[j] + c4.x); v[j + 1] = sigmoidf_(v[j + 1] + c4.y);
             v[j + 2] = sigmoidf_(v[j + 2] + c4.z); v[j + 3] = sigmoidf_(v[j + 3] + c4.w);
           }
@@ -281,12 +313,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
             store_split32(v, p.out_hi, p.out_lo, n * p.out_pitch + p.out_coff + (c0 - Hd), p.fmt);
           }
         } else if (p.epilogue == AS_UEPI_GRU_Q) {            // h' = (1-z) h + z tanh(convq + cq)   update.py:39-40
-          const float* cx = p.ctx + n * p.ctx_pitch + c0;
           const float* zp = p.z + n * p.N + c0;
           const float* hp = p.h + n * p.N + c0;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            const float4 c4 = __ldg(reinterpret_cast<const float4*>(cx + j));
+            const float4 c4 = cpre[j >> 2];
             const float4 z4 = *reinterpret_cast<const float4*>(zp + j);
             const float4 h4 = __ldg(reinterpret_cast<const float4*>(hp + j));
             v[j] = (1.0f - z4.x) * h4.x + z4.x * tanhf(v[j] + c4.x);
@@ -332,9 +363,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
         }
         __syncwarp();     // reconverge before the next warp-aligned tcgen05.ld
       }
-      if (p.epilogue == AS_UEPI_DISPHEAD && valid) {
+      if (p.epilogue == AS_UEPI_DISPHEAD) {
+        if (SUB == 1) {       // the two warps of a lane quarter each hold the dot products over half of the 256 channels
+          if (chalf == 1) {
 #pragma unroll
-        for (int t = 0; t < 9; ++t) p.u[n * 9 + t] = u[t];
+            for (int t = 0; t < 9; ++t) ubuf[m * 9 + t] = u[t];
+          }
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+          if (chalf == 0) {
+#pragma unroll
+            for (int t = 0; t < 9; ++t) u[t] += ubuf[m * 9 + t];
+          }
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");   // ubuf may be overwritten by the next tile
+        }
+        if (valid && chalf == 0) {
+#pragma unroll
+          for (int t = 0; t < 9; ++t) p.u[n * 9 + t] = u[t];
+        }
       }
       umma::tc_fence_before();
       __syncwarp();
@@ -352,9 +397,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   }
 }
 
-template <bool TWO, int NS>
+template <bool TWO, int NS, int SUB>
 int launch_conv(const ConvMaps& maps, const ConvUmmaParams& p, int sms, int smem, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<TWO, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<TWO, NS, SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return (int)e;
   constexpr int CS = TWO ? 2 : 1;
   int grid = p.num_tiles < sms ? p.num_tiles : sms;
@@ -362,7 +407,7 @@ int launch_conv(const ConvMaps& maps, const ConvUmmaParams& p, int sms, int smem
   if (grid < CS) grid = CS;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(conv_threads(SUB));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -370,7 +415,7 @@ int launch_conv(const ConvMaps& maps, const ConvUmmaParams& p, int sms, int smem
   attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<TWO, NS>, maps, p);
+  e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<TWO, NS, SUB>, maps, p);
   if (e != cudaSuccess) return (int)e;
   AS_RETURN_IF_LAUNCH_FAILED();
   return AS_OK;
@@ -404,6 +449,22 @@ extern "C" int as_conv2d_umma(const as_conv_umma_desc* d, as_stream_t stream) {
     if (force && force[0] == '1' && d->W > 8) { p.TW = 16; p.TH = 8; }
     if (force && force[0] == '8') { p.TW = 8; p.TH = 16; }
   }
+  // tall tiles (two 16x8 sub-tiles per weight pass, AS_CONV_TALL=1): halves the weight traffic per pixel, but at N = 256
+  // the two accumulators fill TMEM (no epilogue overlap) and the tile count quantises worse -- measured slower
+  // (gru04 z|r 692 -> 886 us, q 443 -> 451 us in the 2-pass engine), so it is an experiment knob, not the default.
+  // Taken only when two weight stages still fit next to the two 72 KB activation stages.
+  int sub = 1;
+  {
+    const char* tall = getenv("AS_CONV_TALL");
+    const bool want = tall && tall[0] == '1';      // off by default: measured slower than SUB = 1 with a deeper patch ring
+    if (want && d->KH == 3 && p.TW == 16 && d->H > 8) {
+      const int tiles2 = as_ceil_div(d->W, 16) * as_ceil_div(d->H, 16) * d->B;
+      const bool two2 = two_cta_enabled() && tiles2 >= 4;
+      const int a_stage2 = 2 * (16 + 2) * 16 * 128;
+      const int b_stage2 = 2 * (two2 ? d->Cout / 2 : d->Cout) * 128;
+      if ((kSmemBudget - (1024 + (kW2Floats + kUFloats) * 4 + 256) - 2 * a_stage2) / b_stage2 >= 2) { sub = 2; p.TH = 16; }
+    }
+  }
   p.tiles_x = as_ceil_div(d->W, p.TW); p.tiles_y = as_ceil_div(d->H, p.TH);
   p.num_tiles = p.tiles_x * p.tiles_y * d->B;
   p.num_src = d->num_src;
@@ -423,12 +484,30 @@ extern "C" int as_conv2d_umma(const as_conv_umma_desc* d, as_stream_t stream) {
   p.a_plane = (p.TH + d->KH - 1) * p.TW * 128;          // (TH+2)-row patch for 3x3, the tile itself for 1x1
   p.a_stage = 2 * p.a_plane;
   p.b_stage = 2 * (two ? p.N / 2 : p.N) * 128;           // CTA-pair mode: each CTA holds half of the weight rows
-  const int fixed = 1024 + kW2Floats * 4 + 256;
-  // ring depths: B is consumed KH times faster than A; give B at least 2 (3 if it fits) stages, A 2
-  p.nstA = 2;
-  p.nstB = (kSmemBudget - fixed - p.nstA * p.a_stage) / p.b_stage;
-  if (p.nstB > kMaxStages) p.nstB = kMaxStages;
-  if (p.nstB >= 4 && p.nstA * p.a_stage + 4 * p.b_stage + p.a_stage + fixed <= kSmemBudget) p.nstA = 3;
+  const int fixed = 1024 + (kW2Floats + kUFloats) * 4 + 256;
+  // Ring depths.  The activation patches stream from HBM (each conv input is read once, 60-370 MB), the weights from L2:
+  // the ACTIVATION ring is the one that has to cover DRAM latency.  One patch stage feeds KH K-blocks, i.e. 3 x 12 MMAs
+  // (2.8 us) in the 3-pass engine but only 3 x 8 / 3 x 4 (1.8 / 0.9 us, half of that at N = 128) in the 2- and 1-pass
+  // engines: with 2 patch stages the MMA issuer starved on `fullA` (ncu: tensor pipe 65 % / 49 % on gru04 z|r / q with
+  // L2 at 33 %, DRAM at 17 %).  So: 3 weight stages (2 when a stage is 64 KB), then as many patch stages as fit.
+  // AS_CONV_RING=r1 restores the round-1 split (2 patch stages, up to 4 weight stages) for A/B runs.
+  {
+    const char* ring = getenv("AS_CONV_RING");
+    const int avail = kSmemBudget - fixed;
+    if (ring && ring[0] == 'r') {
+      p.nstA = 2;
+      p.nstB = (avail - p.nstA * p.a_stage) / p.b_stage;
+      if (p.nstB > kMaxStages) p.nstB = kMaxStages;
+      if (p.nstB >= 4 && p.nstA * p.a_stage + 4 * p.b_stage + p.a_stage <= avail) p.nstA = 3;
+    } else {
+      const int nb_min = p.b_stage <= 32 * 1024 ? 3 : 2;
+      p.nstA = (avail - nb_min * p.b_stage) / p.a_stage;
+      if (p.nstA > kMaxStages) p.nstA = kMaxStages;
+      if (p.nstA < 2) p.nstA = 2;
+      p.nstB = (avail - p.nstA * p.a_stage) / p.b_stage;
+      if (p.nstB > kMaxStages) p.nstB = kMaxStages;
+    }
+  }
   if (p.nstB < 2) return AS_ERR_UNSUPPORTED;
   p.bias = d->bias; p.ctx = d->ctx; p.ctx_pitch = d->ctx_pitch; p.h = d->h; p.z = d->z;
   p.out_f32 = d->out_f32; p.out_hi = (__nv_bfloat16*)d->out_hi; p.out_lo = (__nv_bfloat16*)d->out_lo;
@@ -500,11 +579,19 @@ extern "C" int as_conv2d_umma(const as_conv_umma_desc* d, as_stream_t stream) {
     } else {
       maps.b_lo = maps.b_hi;
     }
-    if (d->nsplit == 3) return launch_conv<true, 3>(maps, p, sms, smem, as_cu(stream));
-    if (d->nsplit == 2) return launch_conv<true, 2>(maps, p, sms, smem, as_cu(stream));
-    return launch_conv<true, 1>(maps, p, sms, smem, as_cu(stream));
+#define AS_CONV_DISPATCH(TWO_)                                                                     \
+  do {                                                                                             \
+    if (sub == 2) {                                                                                \
+      if (d->nsplit == 3) return launch_conv<TWO_, 3, 2>(maps, p, sms, smem, as_cu(stream));       \
+      if (d->nsplit == 2) return launch_conv<TWO_, 2, 2>(maps, p, sms, smem, as_cu(stream));       \
+      return launch_conv<TWO_, 1, 2>(maps, p, sms, smem, as_cu(stream));                           \
+    }                                                                                              \
+    if (d->nsplit == 3) return launch_conv<TWO_, 3, 1>(maps, p, sms, smem, as_cu(stream));         \
+    if (d->nsplit == 2) return launch_conv<TWO_, 2, 1>(maps, p, sms, smem, as_cu(stream));         \
+    return launch_conv<TWO_, 1, 1>(maps, p, sms, smem, as_cu(stream));                             \
+  } while (0)
+    AS_CONV_DISPATCH(true);
   }
-  if (d->nsplit == 3) return launch_conv<false, 3>(maps, p, sms, smem, as_cu(stream));
-  if (d->nsplit == 2) return launch_conv<false, 2>(maps, p, sms, smem, as_cu(stream));
-  return launch_conv<false, 1>(maps, p, sms, smem, as_cu(stream));
+  AS_CONV_DISPATCH(false);
+#undef AS_CONV_DISPATCH
 }

@@ -210,6 +210,30 @@ __device__ __forceinline__ void mma_f8_ss_2sm(uint32_t tmem_d, uint64_t desc_a, 
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Low-overhead issue path: the 64-bit shared-memory descriptors are passed as (low word, constant high word) so that
+// stepping along K is ONE 32-bit add per operand.  (The MMA-issuing thread is a serial resource: r1 spent ~135 cycles
+// per tcgen05.mma on descriptor arithmetic and a divergent R2UR loop for the TMEM address, which left every N <= 128
+// layer issue-bound: tensor pipe 47 % at N = 128, 22 % at N = 64, independent of the arithmetic mode.)
+constexpr uint32_t kDescHiSw128 = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B | version 1 | SWIZZLE_128B
+__device__ __forceinline__ uint32_t desc_lo_sw128(uint32_t smem_addr_bytes) {
+  return ((smem_addr_bytes >> 4) & 0x3FFFu) | (1u << 16);
+}
+// Issued by ONE thread (the caller is inside `if (lane == 0)`).  The alternative -- all lanes of a converged warp calling
+// an elect.sync-predicated MMA -- makes ptxas emit `@UPn UTCHMMA` with the descriptors travelling through R2UR, the
+// uniform-predicated form that once dropped a K-step in this repo (tests/test_cpu_boundary.py lints against it).
+template <bool TWO, bool F8>
+__device__ __forceinline__ void mma_ss_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+#define AS_MMA_LOHI(GROUP, KIND)                                                                                        \
+  asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"                                                          \
+               "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\tsetp.ne.b32 p, %4, 0;\n\t"                            \
+               "tcgen05.mma.cta_group::" GROUP ".kind::" KIND " [%0], da, db, %3, p;\n\t}" ::"r"(tmem_d),                \
+               "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHiSw128) : "memory")
+  if (TWO && F8) AS_MMA_LOHI("2", "f8f6f4");
+  else if (TWO) AS_MMA_LOHI("2", "f16");
+  else if (F8) AS_MMA_LOHI("1", "f8f6f4");
+  else AS_MMA_LOHI("1", "f16");
+#undef AS_MMA_LOHI
+}
 // arrive on an mbarrier when all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))

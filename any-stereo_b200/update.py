@@ -24,9 +24,10 @@ import torch.nn as nn
 
 from . import _lib as L
 
-#: default engine = the fp32-parity tensor-core path (tcgen05, 3x split-bf16, fp32 accumulation in TMEM).  "fp32" selects
-#: the exact CUDA-core kernels (the on-GPU parity baseline, ~30x slower); "fp16" / "bf16" are the single-MMA fast modes.
-DEFAULT_ENGINE = "bf16x3"
+#: default engine = the 2-pass fp32-parity tensor-core path ("f16f8": IEEE-half hi*hi + one e5m2 pass for both cross terms,
+#: fp32 accumulation in TMEM; training runs its kernels in the 3-pass "bf16x3" split).  "fp32" selects the exact CUDA-core
+#: kernels (the on-GPU parity baseline, ~30x slower); "fp16" / "bf16" are the single-pass fast modes.
+DEFAULT_ENGINE = "f16f8"
 _ENGINE = {"engine": DEFAULT_ENGINE}
 
 
@@ -41,10 +42,16 @@ def set_update_engine(engine: str):
     fp16 / bf16  single pass -- fast modes, outside the 1e-4 operator tolerance (fp16 inside the 0.01 px EPE gate)"""
     if engine not in ENGINES:
         raise ValueError("engine must be one of %s" % (ENGINES,))
-    # "fp16": single-MMA fast mode with IEEE-half operands (11-bit mantissas) -- the analogue of the reference's
-    # autocast mixed precision (continuous_IGEVstereo.py:287)
-    L.set_operand_format({"fp16": L.FMT_F16, "f16f8": L.FMT_F16F8}.get(engine, L.FMT_BF16))
     _ENGINE["engine"] = engine
+    sync_operand_format()
+
+
+def sync_operand_format():
+    """Make the library's process-wide operand format the one the current engine uses ("fp16": IEEE half, the analogue of
+    the reference's autocast mixed precision, continuous_IGEVstereo.py:287; "f16f8": half + e5m2 pair planes; else bf16).
+    Called by set_update_engine and at the top of every forward (the import-time default engine has not touched the
+    CUDA library yet: importing works without a GPU)."""
+    L.set_operand_format({"fp16": L.FMT_F16, "f16f8": L.FMT_F16F8}.get(_ENGINE["engine"], L.FMT_BF16))
 
 
 def get_update_engine() -> str:
@@ -273,6 +280,7 @@ class BasicMultiUpdateBlock(nn.Module):
             return update_train.forward(self, net, inp, corr, disp, iter04, iter08, iter16, update)
         if get_update_engine() != "fp32":
             from . import update_umma
+            sync_operand_format()
             return update_umma.forward(self, net, inp, corr, disp, iter04, iter08, iter16, update)
         for t in net:
             L.require_cuda(t, "net[i]", contiguous=False)

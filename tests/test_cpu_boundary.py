@@ -127,8 +127,8 @@ def test_default_engine_is_tensor_core_parity(A):
     out = subprocess.run([_sys.executable, "-c",
                           "import anystereo_b200 as A; print(A.get_update_engine(), A.get_corr_mode())"],
                          capture_output=True, text=True, cwd=ROOT)
-    assert out.stdout.split() == ["bf16x3", "bf16x3"], (out.stdout, out.stderr[-500:])
-    assert A.update.DEFAULT_ENGINE == "bf16x3" and A.geometry.DEFAULT_CORR_MODE == "bf16x3"
+    assert out.stdout.split() == ["f16f8", "bf16x3"], (out.stdout, out.stderr[-500:])
+    assert A.update.DEFAULT_ENGINE in ("f16f8", "bf16x3") and A.geometry.DEFAULT_CORR_MODE == "bf16x3"
 
 
 def test_reference_install_is_pristine():

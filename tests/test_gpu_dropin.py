@@ -45,14 +45,15 @@ def _record(res):
 @needs_ref
 @pytest.mark.parametrize("family,H,W", [("igev", 384, 1248), ("igev", 320, 736), ("raft", 320, 736), ("raft", 384, 1248)])
 def test_dropin_epe_at_baseline_shapes(family, H, W):
-    # engines: None = the library's defaults, i.e. what rebinding the names alone selects (must be the tensor-core
-    # parity engine); "fp16" is recorded live, gated at the same 0.01 px, and reported separately
-    res = dropin.run(family, H, W, iters=32, B=1, engines=(None, "fp16"), timing=False)
+    # engines: None = the library's defaults, i.e. what rebinding the names alone selects (must be a tensor-core engine of
+    # the fp32-parity class); both parity engines are gated at 1e-3 px (10x inside the BASELINE gate); "fp16" is
+    # recorded live, gated at 0.01 px, and reported separately
+    res = dropin.run(family, H, W, iters=32, B=1, engines=(None, "bf16x3", "f16f8", "fp16"), timing=False)
     _record(res)
     default = [k for k in res["engines"] if k.startswith("default")]
-    assert default == ["default(bf16x3)"], res["engines"].keys()
-    e = res["engines"][default[0]]
-    assert e["epe_mean_px"] <= 0.01, res
+    assert default in (["default(bf16x3)"], ["default(f16f8)"]), res["engines"].keys()
+    for k in (default[0], "bf16x3", "f16f8"):
+        assert res["engines"][k]["epe_mean_px"] <= 1e-3, (k, res)
     assert res["engines"]["fp16"]["epe_mean_px"] <= 0.01, res
 
 
