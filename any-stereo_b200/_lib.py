@@ -248,12 +248,3 @@ def version_of(t) -> int:
     if torch.is_inference(t):
         return -1
     return t._version
-
-
-def forbid_grad(what: str, *tensors):
-    """Forward-only operators must not silently cut the autograd graph (the reference's versions are differentiable):
-    raise when gradients are being recorded and an input wants them."""
-    if torch.is_grad_enabled() and any(torch.is_tensor(t) and t.requires_grad for t in tensors):
-        raise RuntimeError(
-            "anystereo_b200.%s is forward-only (inference): an input requires grad while autograd is recording. "
-            "Call it under torch.no_grad(), or keep the reference's differentiable implementation for training." % what)

@@ -302,10 +302,39 @@ inline EncodeTiledFn get_encode_fn() {
   return reinterpret_cast<EncodeTiledFn>(fn);
 }
 
+// Per-thread cache of encoded tensor maps.  A map is a pure function of (base, rank, dims, strides, box): the update block
+// re-launches the same ~10 convolutions on the same buffers every iteration (the caching allocator hands back the same
+// addresses), so r1's 8 cuTensorMapEncodeTiled calls per launch (~320 launches per step) were pure launch-thread overhead.
+struct TmapKey {
+  const void* base;
+  uint64_t dims[5], strides[4];
+  uint32_t box[5];
+  int rank;
+  bool operator==(const TmapKey& o) const {
+    if (base != o.base || rank != o.rank) return false;
+    for (int i = 0; i < rank; ++i) if (dims[i] != o.dims[i] || box[i] != o.box[i]) return false;
+    for (int i = 0; i + 1 < rank; ++i) if (strides[i] != o.strides[i]) return false;
+    return true;
+  }
+};
+struct TmapSlot { TmapKey key; CUtensorMap map; bool used; };
+constexpr int kTmapSlots = 512;            // direct-mapped; a collision just re-encodes
+inline TmapSlot* tmap_cache() {
+  static thread_local TmapSlot slots[kTmapSlots] = {};
+  return slots;
+}
+
 // bf16 tensor, innermost dim first.  dims/strides: strides[i] = byte stride of dim i+1.  128B swizzle, zero OOB fill.
 inline int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                           const uint32_t* box) {
-  EncodeTiledFn enc = get_encode_fn();
+  TmapKey key{};
+  key.base = base; key.rank = rank;
+  uint64_t h = reinterpret_cast<uintptr_t>(base) >> 4;
+  for (int i = 0; i < rank; ++i) { key.dims[i] = dims[i]; key.box[i] = box[i]; h = h * 1000003ull + dims[i] * 31ull + box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) { key.strides[i] = strides_bytes[i]; h = h * 1000003ull + strides_bytes[i]; }
+  TmapSlot& slot = tmap_cache()[(h ^ (h >> 17)) % kTmapSlots];
+  if (slot.used && slot.key == key) { *out = slot.map; return AS_OK; }
+  static EncodeTiledFn enc = get_encode_fn();
   if (!enc) return AS_ERR_DRIVER;
   cuuint64_t gdim[5];
   cuuint64_t gstr[4];
@@ -315,7 +344,9 @@ inline int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const ui
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? AS_OK : AS_ERR_DRIVER;
+  if (r != CUDA_SUCCESS) return AS_ERR_DRIVER;
+  slot.key = key; slot.map = *out; slot.used = true;
+  return AS_OK;
 }
 
 // fp32 tensor for TMA STORES (cp.async.bulk.tensor ... global.shared::cta), innermost dim first.  `inner_box_bytes` selects

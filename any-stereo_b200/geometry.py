@@ -195,12 +195,15 @@ class CorrBlock1D:
     @staticmethod
     def corr(fmap1, fmap2, mask_invalid=False):
         """[B,D,H,W1] x [B,D,H,W2] -> [B,H,W1,1,W2] (geometry.py:46-56); no 1/sqrt(D) scaling."""
-        L.forbid_grad("CorrBlock1D.corr", fmap1, fmap2)      # (the constructor's pyramid build IS differentiable)
         f1, f2 = _check_pair(fmap1, fmap2)
         B, D, H, W1 = f1.shape
         W2 = f2.shape[3]
-        bufs, widths, pitches = _build_corr_levels(f1.detach(), f2.detach(), 1)
-        lvl = bufs[0]
+        if torch.is_grad_enabled() and (f1.requires_grad or f2.requires_grad):
+            lvl = _CorrBuildFn.apply(f1, f2, 1, None)[0]      # differentiable like the constructor's pyramid build
+            pitches = [_pitch(W2)]
+        else:
+            bufs, widths, pitches = _build_corr_levels(f1.detach(), f2.detach(), 1)
+            lvl = bufs[0]
         if pitches[0] != W2:
             lvl = lvl[:, :W2].contiguous()
         return lvl.view(B, H, W1, 1, W2)

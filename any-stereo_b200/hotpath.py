@@ -164,9 +164,10 @@ def install_into_reference(ref_igev_module=None, ref_raft_module=None):
         models.corePrune_RAFT.prune_raft_stereo.{CorrBlock1D, context_upsample_multiscale_train}
 
     ``model.update_block`` / ``model.liif_up`` are swapped per model instance with ``adopt_update_block`` /
-    ``adopt_liif_up``.  The cost-volume objects, ``build_gwc_volume`` and the update block are differentiable
-    (training, config 5); the upsampler pieces are forward-only and RAISE if a gradient is requested through them
-    (``_lib.forbid_grad``) instead of silently cutting the graph -- keep the reference's own upsampler for training."""
+    ``adopt_liif_up``.  Everything installed is differentiable (training, config 5): the cost-volume objects,
+    ``build_gwc_volume`` and the update block through hand-written adjoint kernels; the upsampler pieces (forward-only
+    fused kernels) switch to the same arithmetic in differentiable ATen ops whenever a gradient is requested through
+    them, so no ``disp_preds`` loss term ever loses its graph."""
     if ref_igev_module is not None:
         ref_igev_module.Combined_Geo_Encoding_Volume = Combined_Geo_Encoding_Volume
         ref_igev_module.build_gwc_volume = build_gwc_volume

@@ -38,6 +38,69 @@ class MLP(nn.Module):
         self.layers = nn.Sequential(*layers)
 
 
+def _wants_grad(*tensors):
+    return torch.is_grad_enabled() and any(torch.is_tensor(t) and t.requires_grad for t in tensors)
+
+
+# ---- differentiable formulation (training) ----------------------------------------------------------------------------
+# The fused kernels below are forward-only.  When a gradient is requested through the upsampler -- the reference runs it
+# every iteration in training and every `disp_preds` loss term flows through it (continuous_IGEVstereo.py:296-301,
+# train_continuous_IGEV.py:37-122) -- the SAME arithmetic is evaluated with differentiable ATen ops (index gathers,
+# F.linear), so autograd provides the adjoint: gradients reach the low-resolution disparity, the hidden state, the stem
+# features and the MLP parameters exactly as in the reference.  Hand-written adjoint kernels (tcgen05 MLP dgrad / wgrad,
+# scatter-add into the source-resolution maps) are the open part of SURVEY 8(f)-2; nothing here is used for inference.
+
+def _nearest_index(c, n):
+    """Index F.grid_sample(mode='nearest', align_corners=False) picks after the reference's clamp (liif.py:118)."""
+    c = c.float().clamp(-1 + 1e-6, 1 - 1e-6)
+    return torch.round(((c + 1) * n - 1) / 2).long().clamp(0, n - 1)
+
+
+def _coord_axis(n, device):
+    r = 1.0 / n                                          # make_coord, liif.py:32-45
+    return -1 + r + (2 * r) * torch.arange(n, device=device).float()
+
+
+def _isu_affinity_torch(x):
+    """AffinityFeature.forward (liif.py:434-449), 3x3 window, dilation 1 -- differentiable."""
+    B, Cc, H, W = x.shape
+    n = x / x.norm(dim=1, keepdim=True).clamp_min(1e-12)
+    pad = torch.nn.functional.pad(n, (1, 1, 1, 1))
+    out = [(pad[:, :, dy:dy + H, dx:dx + W] * n).sum(1) for dy in range(3) for dx in range(3) if not (dy == 1 and dx == 1)]
+    a = torch.stack(out, dim=1)
+    return torch.where(a < 0, torch.zeros_like(a), a)    # `affinity[affinity < 0] = 0` (liif.py:446): the gradient passes at a == 0
+
+
+def _logits_torch(module, feats, coord):
+    """liif_out_multi_scale_Training.forward (liif.py:652-678) in differentiable ops -> [B, 9, Q]."""
+    latent = []
+    for f in feats:
+        f = f.float()
+        sf = torch.cat([f, _isu_affinity_torch(f)], dim=1)
+        B, Cc, h, w = sf.shape
+        iy, ix = _nearest_index(coord[:, :, 0], h), _nearest_index(coord[:, :, 1], w)
+        bidx = torch.arange(B, device=sf.device).view(B, 1).expand_as(iy)
+        q = sf[bidx, :, iy, ix]                                                          # [B,Q,C+8]
+        rel = torch.stack([(coord[:, :, 0].float() - _coord_axis(h, sf.device)[iy]) * h,
+                           (coord[:, :, 1].float() - _coord_axis(w, sf.device)[ix]) * w], dim=-1)
+        latent += [q, rel]
+    z = torch.cat(latent, dim=-1)
+    B, Q, _ = z.shape
+    return module.imnet.layers(z.reshape(B * Q, -1)).reshape(B, Q, -1).permute(0, 2, 1).contiguous()
+
+
+def _context_upsample_torch(disp_low, up_weights, hr_coord):
+    """context_upsample_multiscale_train (submodule.py:357-372) in differentiable ops -> [B, Q]."""
+    B, _, h, w = disp_low.shape
+    iy, ix = _nearest_index(hr_coord[:, :, 0], h), _nearest_index(hr_coord[:, :, 1], w)
+    pad = torch.nn.functional.pad(disp_low[:, 0].float(), (1, 1, 1, 1))
+    bidx = torch.arange(B, device=disp_low.device).view(B, 1).expand_as(iy)
+    out = 0
+    for k in range(9):
+        out = out + pad[bidx, iy + k // 3, ix + k % 3] * up_weights[:, k]
+    return out
+
+
 def _split_mode():
     eng = get_update_engine()
     return eng != "bf16"          # "fp32" and "bf16x3" both mean fp32 parity here (split bf16, fp32 accumulate)
@@ -56,8 +119,9 @@ def _pack_linear(w, n_pad=None, split=True):
 
 def isu_affinity(feature):
     """AffinityFeature.forward (liif.py:434-449) for the 3x3 / dilation-1 window: [B,C,H,W] -> [B,8,H,W]."""
+    if _wants_grad(feature):
+        return _isu_affinity_torch(feature)
     L.require_cuda(feature, "feature", torch.float32, contiguous=False)
-    L.forbid_grad("liif.isu_affinity", feature)
     x = feature.detach().contiguous()
     B, Cc, H, W = x.shape
     out = torch.empty((B, 8, H, W), device=x.device, dtype=torch.float32)
@@ -162,9 +226,6 @@ class liif_out_multi_scale_Training(nn.Module):
         if len(feats) != self.number_input:
             raise RuntimeError("expected %d feature maps" % self.number_input)
         L.require_cuda(coord, "coord", torch.float32, contiguous=False)
-        # forward-only: a training forward (grad recording, trainable parameters or inputs) must not get a graph-less result
-        # (parameters count only in train() mode: eval-mode inference without torch.no_grad() stays legal)
-        L.forbid_grad("liif_out_multi_scale_Training", coord, disp, *feats, *(self.parameters() if self.training else ()))
         coord = coord.detach().contiguous()
         B, Q, _ = coord.shape
         dev = coord.device
@@ -202,21 +263,32 @@ class liif_out_multi_scale_Training(nn.Module):
             L.call("as_liif_query", C.byref(d), L.stream_ptr())
         return logits, out
 
+    def _training_forward(self, *tensors):
+        """A gradient is wanted through this call: inputs that require grad, or trainable parameters while the module is
+        in train() mode (eval-mode inference without torch.no_grad() keeps the fused kernels)."""
+        return _wants_grad(*tensors) or (self.training and _wants_grad(*self.parameters()))
+
     def forward(self, feats, coord, scale=None):
+        if self._training_forward(coord, *feats):
+            return _logits_torch(self, feats, coord)
         return self._query(feats, coord)[0]
 
     def upsample(self, feats, coord, disp_low, disp_scale=None):
         """Fused tail of continuous_IGEVStereo.upsample_disp: softmax(logits) applied to the 3x3 neighbourhood of
         ``disp_low * disp_scale[b]`` -> [B, Q]; the logits never reach HBM."""
+        if self._training_forward(coord, disp_low, *feats):
+            d = disp_low.float() if disp_scale is None else disp_low.float() * disp_scale.view(-1, 1, 1, 1).float()
+            return _context_upsample_torch(d, torch.softmax(_logits_torch(self, feats, coord), dim=1), coord)
         return self._query(feats, coord, disp=disp_low, disp_scale=disp_scale, want_logits=False)[1]
 
 
 def context_upsample_multiscale_train(disp_low, up_weights, hr_coord):
     """submodule.py:357-372: [B,1,h,w], [B,9,Q] (already soft-maxed), [B,Q,2] -> [B,Q]."""
+    if _wants_grad(disp_low, up_weights):
+        return _context_upsample_torch(disp_low, up_weights, hr_coord)
     L.require_cuda(disp_low, "disp_low", torch.float32, contiguous=False)
     L.require_cuda(up_weights, "up_weights", torch.float32, contiguous=False)
     L.require_cuda(hr_coord, "hr_coord", torch.float32, contiguous=False)
-    L.forbid_grad("context_upsample_multiscale_train", disp_low, up_weights, hr_coord)
     B, _, h, w = disp_low.shape
     Q = hr_coord.shape[1]
     d, u, c = disp_low.detach().contiguous(), up_weights.detach().contiguous(), hr_coord.detach().contiguous()

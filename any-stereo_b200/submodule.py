@@ -61,10 +61,11 @@ def build_gwc_volume(refimg_fea, targetimg_fea, maxdisp, num_groups):
 def disparity_regression(x, maxdisp):
     """submodule.py:321-325: sum_d x[:, d] * d  -> [B,1,H,W]."""
     assert len(x.shape) == 4
-    L.require_cuda(x, "x", torch.float32, contiguous=False)
     if x.shape[1] != maxdisp:
         raise RuntimeError("x must have maxdisp channels")
-    L.forbid_grad("disparity_regression", x)
+    if torch.is_grad_enabled() and x.requires_grad:      # training (`--supervise_init`): differentiable formulation
+        return (x * torch.arange(maxdisp, device=x.device, dtype=x.dtype).view(1, maxdisp, 1, 1)).sum(1, keepdim=True)
+    L.require_cuda(x, "x", torch.float32, contiguous=False)
     x = x.detach().contiguous()
     B, D, H, W = x.shape
     out = torch.empty((B, 1, H, W), device=x.device, dtype=torch.float32)
@@ -77,9 +78,15 @@ def init_disparity(geo_encoding_volume, classifier_weight, maxdisp=None, return_
     """The initial-disparity head in one kernel (continuous_IGEVstereo.py:267-268):
         prob = F.softmax(classifier(geo_encoding_volume).squeeze(1), dim=1); init_disp = disparity_regression(prob, D)
     with ``classifier = nn.Conv3d(G, 1, 3, 1, 1, bias=False)``.  -> init_disp [B,1,H,W] (and prob [B,D,H,W])."""
+    if torch.is_grad_enabled() and (geo_encoding_volume.requires_grad or classifier_weight.requires_grad):
+        # training (`--supervise_init`, train_continuous_IGEV.py:106): the fused kernel is forward-only, so the same
+        # arithmetic runs in differentiable ATen ops and autograd provides the adjoint
+        D = geo_encoding_volume.shape[2]
+        prob = torch.softmax(torch.nn.functional.conv3d(geo_encoding_volume, classifier_weight, padding=1).squeeze(1), dim=1)
+        disp = (prob * torch.arange(D, device=prob.device, dtype=prob.dtype).view(1, D, 1, 1)).sum(1, keepdim=True)
+        return (disp, prob) if return_prob else disp
     L.require_cuda(geo_encoding_volume, "geo_encoding_volume", torch.float32, contiguous=False)
     L.require_cuda(classifier_weight, "classifier_weight", torch.float32, contiguous=False)
-    L.forbid_grad("init_disparity", geo_encoding_volume, classifier_weight)
     g = geo_encoding_volume.detach().contiguous()
     w = classifier_weight.detach().contiguous()
     B, G, D, H, W = g.shape

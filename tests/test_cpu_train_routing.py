@@ -93,3 +93,43 @@ def test_wgrad_knob_falls_back_to_cuda_cores(recorder):
         T.set_wgrad_tensor_cores(True)
     n = collections.Counter(calls)
     assert n["as_conv2d_wgrad_fp32"] == 12 and n["as_convd1_wgrad_fp32"] == 1 and "as_conv2d_wgrad_umma" not in n
+
+
+def test_upsampler_differentiable_path_matches_oracle_autograd():
+    """ADVICE r1 (high/medium): whenever a gradient is requested through the forward-only upsampler pieces they switch to a
+    differentiable formulation (device-agnostic ATen ops, so this runs on the CPU): values and gradients must equal the
+    oracle restatement of the reference (oracle/liif_oracle.py, itself pinned to the reference's outputs)."""
+    import anystereo_b200 as A
+    from oracle import liif_oracle as LO
+    torch.manual_seed(0)
+    lc = cases.liif_case(2, h=5, w=7, scale=1.7, extra_q=5)
+    chanels = [f.shape[1] for f in lc["feats"]]
+    m = A.liif_out_multi_scale_Training(encoder_dim=sum(chanels), mlphidden_list=[128, 64, 64], pos_dim=0,
+                                        unfold="with_v2ISU", affinity_settings={"win_w": 3, "win_h": 3, "dilation": [1, 2, 4, 8]},
+                                        number_input=2, chanels=chanels)
+    lp = LO.make_liif_params(lc["in_dim"], seed=2)
+    m.load_state_dict(lp, strict=True)
+    m.train()
+    feats = [f.clone().requires_grad_(True) for f in lc["feats"]]
+    disp = lc["disp"].clone().requires_grad_(True)
+    out = A.upsample_disp(m, disp, feats[0][:, 48:], feats[0][:, :48], feats[1], None, hr_coord=lc["coords"], scale=lc["scale"])
+    assert out.grad_fn is not None
+    wgt = torch.linspace(0.5, 1.5, out.numel()).view_as(out)
+    (out * wgt).sum().backward()
+    p2 = {k: v.clone().requires_grad_(True) for k, v in lp.items()}
+    f2 = [f.clone().requires_grad_(True) for f in lc["feats"]]
+    d2 = lc["disp"].clone().requires_grad_(True)
+    ref = LO.upsample_disp_multiscale(p2, d2, f2, lc["coords"], lc["scale"])
+    (ref * wgt).sum().backward()
+    assert torch.allclose(out, ref, atol=1e-5, rtol=1e-5)
+    assert torch.allclose(disp.grad, d2.grad, atol=1e-6, rtol=1e-4)
+    for a, b in zip(feats, f2):
+        assert torch.allclose(a.grad, b.grad, atol=1e-6, rtol=1e-4)
+    for k, v in m.state_dict(keep_vars=True).items():
+        assert torch.allclose(v.grad, p2[k].grad, atol=1e-6, rtol=1e-4), k
+    # the small pieces on their own
+    x = torch.rand(1, 6, 4, 5, requires_grad=True)
+    assert torch.allclose(A.liif.isu_affinity(x), LO.isu_affinity(x.detach()), atol=1e-6)
+    pr = torch.softmax(torch.rand(1, 12, 3, 4, requires_grad=True), 1)
+    dr = A.disparity_regression(pr, 12)
+    assert dr.grad_fn is not None and torch.allclose(dr, (pr * torch.arange(12.0).view(1, 12, 1, 1)).sum(1, keepdim=True))

@@ -85,26 +85,51 @@ def test_dropin_batch_and_restores_reference_names():
 
 
 @needs_ref
-def test_forward_only_upsampler_raises_in_training():
-    """the forward-only upsampler must not silently cut the graph of a training forward."""
-    import anystereo_b200 as A
+def test_dropin_training_step_matches_reference():
+    """Config-5 structure through the REAL reference graph (ADVICE r1 high / VERDICT missing #1): train() mode, frozen BN,
+    sequence loss over every iteration's upsampled disparity AND the supervised initial disparity, backward.  With this
+    library installed the loss and the gradients of the update block, the LIIF MLP, the stems, the context network and
+    the cost-aggregation classifier must equal the reference's own autograd."""
     model, R = dropin.build_model("igev", "cuda")
-    img1, img2 = dropin.make_pair(1, 64, 128, "cuda")
-    hr = R.make_coord([64, 128]).cuda()[None]
-    with dropin.installed(model, R, "igev") as m:
+    H, W, iters = 64, 128, 3
+    img1, img2 = dropin.make_pair(2, H, W, "cuda")
+    hr = R.make_coord([H, W]).cuda()[None].expand(2, -1, -1).contiguous()
+    sc = torch.ones(2, 1, device="cuda")
+    gt = torch.rand(2, 1, H * W, device="cuda") * 40.0
+    names = ["update_block.gru04.convz.weight", "update_block.encoder.convc1.weight", "update_block.disp_head.conv2.weight",
+             "liif_up.imnet.layers.0.weight", "liif_up.imnet.layers.6.bias", "stem_2.conv1.conv.weight",
+             "classifier.weight", "desc.weight", "context_zqr_convs.0.weight"]
+    params = dict(model.named_parameters())
+    names = [n for n in names if n in params]
+    assert len(names) >= 7, names
+
+    def run(m):
         m.train()
         m.freeze_bn()
-        with pytest.raises(RuntimeError, match="forward-only"):
-            m(img1, img2, iters=2, test_mode=False, hr_coord=hr, scale=torch.ones(1, 1, device="cuda"))
+        m.zero_grad(set_to_none=True)
+        init_disp, preds = m(img1, img2, iters=iters, test_mode=False, hr_coord=hr, scale=sc)
+        loss = 0.0
+        for i, p in enumerate(preds):                                   # train_continuous_IGEV.py:37-122 structure
+            loss = loss + 0.9 ** (len(preds) - 1 - i) * (p - gt).abs().mean()
+        loss = loss + init_disp.abs().mean()                           # --supervise_init path: init_disp carries a graph
+        loss.backward()
+        g = {n: dict(m.named_parameters())[n].grad.detach().clone() for n in names}
         m.eval()
-    d = torch.rand(1, 1, 8, 8, device="cuda", requires_grad=True)
-    w = torch.softmax(torch.rand(1, 9, 16, device="cuda"), 1)
-    c = torch.rand(1, 16, 2, device="cuda") * 2 - 1
-    with pytest.raises(RuntimeError, match="forward-only"):
-        A.context_upsample_multiscale_train(d, w, c)
-    x = torch.rand(1, 48, 8, 8, device="cuda", requires_grad=True)
-    with pytest.raises(RuntimeError, match="forward-only"):
-        A.disparity_regression(torch.softmax(x, 1), 48)
+        return float(loss.detach()), g
+
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        loss_ref, g_ref = run(model)
+        with dropin.installed(model, R, "igev") as m:
+            loss_our, g_our = run(m)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    assert abs(loss_our - loss_ref) <= 1e-4 * abs(loss_ref), (loss_our, loss_ref)
+    for n in names:
+        err = float((g_our[n] - g_ref[n]).abs().max() / g_ref[n].abs().max().clamp_min(1e-20))
+        assert err <= 5e-3, (n, err)
 
 
 def test_lookup_rejects_mismatched_disp():

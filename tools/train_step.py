@@ -48,18 +48,23 @@ def _run(engine, B, iters, steps, H, W, dev, world, rank, overlap):
     # bucket order = the order in which the first iteration's backward completes the gradients
     order = [p for name in ("disp_head", "gru04", "encoder", "gru08", "gru16") for p in getattr(block, name).parameters()]
     reducer = A.GradientAllReducer(order) if (world > 1 and overlap) else None
-    g = torch.Generator(device="cpu").manual_seed(100 + rank)   # each rank its own pairs
+    # every PAIR has its own generator (seeded by its global index): rank r owns pairs [r*B, (r+1)*B), so N ranks x B pairs
+    # and one rank x N*B pairs see the same global batch (the loss / gradient-norm equality check of SURVEY 4 item 5)
+    gens = [torch.Generator(device="cpu").manual_seed(100 + rank * B + i) for i in range(B)]
     sizes = [(H, W), (H // 2, W // 2), (H // 4, W // 4)]
 
-    def leaf(*shape, scale=1.0):
-        return (torch.randn(*shape, generator=g) * scale).to(dev).requires_grad_(True)
+    def per_pair(fn):
+        return torch.cat([fn(g) for g in gens], 0).to(dev)
 
-    f1, f2 = leaf(B, 96, H, W), leaf(B, 96, H, W)
-    geo = leaf(B, 8, 48, H, W)
-    net0 = [torch.tanh(torch.randn(B, 128, h, w, generator=g)).to(dev).requires_grad_(True) for h, w in sizes]
-    inp = [[leaf(B, 128, h, w, scale=0.5) for _ in range(3)] for h, w in sizes]
-    init_disp = (torch.rand(B, 1, H, W, generator=g) * 40).to(dev)
-    gt = (torch.rand(B, 1, H, W, generator=g) * 48).to(dev)
+    def leaf(*shape, scale=1.0):
+        return per_pair(lambda g: torch.randn(1, *shape, generator=g) * scale).requires_grad_(True)
+
+    f1, f2 = leaf(96, H, W), leaf(96, H, W)
+    geo = leaf(8, 48, H, W)
+    net0 = [per_pair(lambda g: torch.tanh(torch.randn(1, 128, h, w, generator=g))).requires_grad_(True) for h, w in sizes]
+    inp = [[leaf(128, h, w, scale=0.5) for _ in range(3)] for h, w in sizes]
+    init_disp = per_pair(lambda g: torch.rand(1, 1, H, W, generator=g) * 40)
+    gt = per_pair(lambda g: torch.rand(1, 1, H, W, generator=g) * 48)
     coords = torch.arange(W, device=dev, dtype=torch.float32).reshape(1, 1, W, 1).repeat(B, H, 1, 1)
     times, losses, gnorms, phases = [], [], [], []
     leaves = [f1, f2, geo] + net0 + [t for l in inp for t in l]
@@ -98,7 +103,11 @@ def _run(engine, B, iters, steps, H, W, dev, world, rank, overlap):
         ms = [float(v) for v in ms]
         times.append(ms[0])
         phases.append(ms[1:])
-        losses.append(float(loss.detach()))
+        lt = loss.detach().clone().reshape(1)
+        if world > 1:
+            dist.all_reduce(lt)                           # mean over ranks = the loss of the global batch
+            lt /= world
+        losses.append(float(lt))
         gnorms.append(float(gn))
     if reducer is not None:
         reducer.remove()
