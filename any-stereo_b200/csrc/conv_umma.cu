@@ -136,6 +136,11 @@ __global__ void __launch_bounds__(conv_threads(SUB), 1) conv_umma_kernel(const _
   __syncthreads();
   if (TWO) umma::cluster_sync_all();             // both CTAs' barriers exist before anyone signals them
   umma::tc_fence_after();
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, tensor-map prefetch, cluster sync)
+  // touched no global memory and overlaps the tail of the previous kernel in the stream; from here on the kernel reads
+  // what its predecessors wrote.  launch_dependents lets the NEXT kernel's prologue overlap this kernel's tail.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // The kernel allocates all 512 TMEM columns of its SM (1 CTA/SM), so the allocation starts at column 0, lane 0.  Using
   // the constant keeps the accumulator address of every MMA in a uniform register (a value read back from shared memory
   // is not provably uniform: ptxas wrapped each tcgen05.mma in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop).
@@ -410,11 +415,14 @@ int launch_conv(const ConvMaps& maps, const ConvUmmaParams& p, int sms, int smem
   cfg.blockDim = dim3(conv_threads(SUB));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  static const bool pdl = !(getenv("AS_CONV_PDL") && getenv("AS_CONV_PDL")[0] == '0');   // A/B knob
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl ? 2 : 1;
   e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<TWO, NS, SUB>, maps, p);
   if (e != cudaSuccess) return (int)e;
   AS_RETURN_IF_LAUNCH_FAILED();

@@ -51,16 +51,20 @@ def timeit(fn, reps=20, warm=3, flush=True):
 
 
 def fused_lookup_bench(blk, d, coords, rec, N):
-    """8(f)-1: lookup + convc1 + ReLU in one kernel; algorithmic bytes 728 read + 256 written per pixel (bf16x3)."""
+    """8(f)-1: lookup + convc1 + ReLU in one kernel; algorithmic bytes 728 read + 256 written per pixel (two output planes)
+    or + 128 (one plane).  One line per arithmetic mode of the kernel's own GEMM / output planes."""
     B, _, H, W = d.shape
-    for split in (True, False):
-        w_hi, w_lo = A.geometry.DeferredGeoLookup.pack_convc1_weight(torch.randn(64, 162, 1, 1, device="cuda") * 0.1, split)
+    for engine, split in (("bf16x3", True), ("f16f8", True), ("bf16", False)):
+        A.set_update_engine(engine)
+        with A._lib.operand_format_scope(A.update_umma._sixteen_bit_format()):      # the kernel's own GEMM: 16-bit hi/lo
+            w_hi, w_lo = A.geometry.DeferredGeoLookup.pack_convc1_weight(torch.randn(64, 162, 1, 1, device="cuda") * 0.1, split)
         bias = torch.randn(64, device="cuda")
         o_hi = torch.empty(B, H, W, 64, device="cuda", dtype=torch.bfloat16)
         o_lo = torch.empty_like(o_hi) if split else None
         dl = blk.deferred(d, coords)
         med, best = timeit(lambda: dl.convc1_planes(w_hi, w_lo, bias, o_hi, o_lo))
-        rec("geo_lookup_convc1_fused_" + ("bf16x3" if split else "bf16"), med, best, (728 + (256 if split else 128)) * N)
+        rec("geo_lookup_convc1_fused_" + engine, med, best, (728 + (256 if split else 128)) * N)
+    A.set_update_engine("fp32")
 
 
 def main():
@@ -163,11 +167,19 @@ def main():
         blk = A.Combined_Geo_Encoding_Volume(f1, f2, gwc, num_levels=2, radius=4)
         coords = torch.arange(W, device=dev, dtype=torch.float32).reshape(1, 1, W, 1).repeat(B, H, 1, 1)
         d = (torch.rand(B, 1, H, W, device=dev) * Dg).contiguous()
+        A.set_update_engine("f16f8")
+        with A._lib.operand_format_scope(A.update_umma._sixteen_bit_format()):
+            w_hi, w_lo = A.geometry.DeferredGeoLookup.pack_convc1_weight(torch.randn(64, 162, 1, 1, device="cuda") * 0.1, True)
+        bias = torch.randn(64, device="cuda")
+        o_hi = torch.empty(B, H, W, 64, device="cuda", dtype=torch.bfloat16)
+        o_lo = torch.empty_like(o_hi)
         for _ in range(3):
             A.build_gwc_volume(f1, f2, Dg, 8)
             A.geometry._build_geo_levels(gwc, 2)
             blk(d, coords)
+            blk.deferred(d, coords).convc1_planes(w_hi, w_lo, bias, o_hi, o_lo)
         torch.cuda.synchronize()
+        A.set_update_engine("fp32")
         return
     if a.only == "initdisp":
         # classifier Conv3d + softmax + disparity_regression fused; bytes = geo read once + disp written
