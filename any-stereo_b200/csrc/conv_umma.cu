@@ -49,7 +49,6 @@ struct ConvUmmaParams {
   const float* bias; const float* ctx; int ctx_pitch; const float* h; float* z;
   float* out_f32; __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; int out_pitch, out_coff, cout_valid;
   const float* disp; const float* w2; float* u;
-  int ksplit;                                 // 2: two MMA-issuing threads, alternate K-blocks, two accumulators (N <= 128)
   bool f16;                                   // hi planes / weights are IEEE half instead of bf16
   int fmt;                                    // AS_FMT_* of the planes this launch reads and writes
 };
@@ -120,10 +119,10 @@ __global__ void __launch_bounds__(conv_threads(SUB), 1) conv_umma_kernel(const _
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kMaxStages; ++s) {
-      umma::mbar_init(&fullA[s], TWO ? 2 : 1); umma::mbar_init(&emptyA[s], p.ksplit);
+      umma::mbar_init(&fullA[s], TWO ? 2 : 1); umma::mbar_init(&emptyA[s], 1);
       umma::mbar_init(&fullB[s], TWO ? 2 : 1); umma::mbar_init(&emptyB[s], 1);
     }
-    for (int a = 0; a < 2; ++a) { umma::mbar_init(&tfull[a], p.ksplit); umma::mbar_init(&tempty[a], (TWO ? 2 : 1) * kEpiWarps); }
+    for (int a = 0; a < 2; ++a) { umma::mbar_init(&tfull[a], 1); umma::mbar_init(&tempty[a], (TWO ? 2 : 1) * kEpiWarps); }
     umma::fence_barrier_init();
   }
   if (warp == 2) {
@@ -210,14 +209,8 @@ __global__ void __launch_bounds__(conv_threads(SUB), 1) conv_umma_kernel(const _
       }
     }
     __syncwarp();
-  } else if (warp == 1 || (warp == 3 && p.ksplit == 2)) {
-    // The issuing thread is a serial resource (~115 cycles per tcgen05.mma: uniform-datapath descriptor arithmetic and an
-    // ELECT loop per instruction), and an MMA of N <= 128 occupies the tensor pipe for <= 64 cycles: those layers were
-    // issue-bound (tensor pipe 55 % at N = 128, 26 % at N = 64).  ksplit = 2: warps 1 and 3 each issue every other
-    // K-block into their OWN accumulator (TMEM columns +0 / +128); the epilogue adds the two partial sums.
+  } else if (warp == 1) {
     if (lane == 0 && leader) {
-      const int me = warp == 1 ? 0 : 1;
-      int kbi = 0;                               // running K-block index within the tile
       int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
       const uint32_t idesc = umma::idesc_16_f32(TWO ? 256 : 128, p.N, p.f16);
       const uint32_t idesc8 = umma::idesc_e5m2_f32(TWO ? 256 : 128, p.N);
@@ -226,17 +219,12 @@ __global__ void __launch_bounds__(conv_threads(SUB), 1) conv_umma_kernel(const _
         const uint32_t acc_phase = (uint32_t)(it / nbuf) & 1u;
         umma::mbar_wait(&tempty[acc], acc_phase ^ 1);
         umma::tc_fence_after();
-        const uint32_t tmem_d0 = tmem_base + (uint32_t)acc * 256u + (uint32_t)me * 128u;
+        const uint32_t tmem_d0 = tmem_base + (uint32_t)acc * 256u;
         uint32_t accumulate = 0;
-        kbi = 0;
         for (int g = 0; g < ngroups; ++g) {
           umma::mbar_wait(&fullA[sa], pha);
           const uint32_t sta = umma::smem_u32(a_ring + sa * p.a_stage);
-          for (int ky = 0; ky < p.KH; ++ky, ++kbi) {
-            if (p.ksplit == 2 && (kbi & 1) != me) {            // the other issuer's K-block: only keep the ring position
-              if (++sb == p.nstB) { sb = 0; phb ^= 1; }
-              continue;
-            }
+          for (int ky = 0; ky < p.KH; ++ky) {
             umma::mbar_wait(&fullB[sb], phb);
             umma::tc_fence_after();
             const uint32_t a_hi = sta + (uint32_t)(ky * dy_bytes), a_lo = a_hi + (uint32_t)p.a_plane;
@@ -298,13 +286,6 @@ __global__ void __launch_bounds__(conv_threads(SUB), 1) conv_umma_kernel(const _
       for (int c0 = chalf * 32; c0 < p.N; c0 += kCStep) {
         float v[32];
         umma::tmem_ld_32x32(trow + (uint32_t)c0, v);
-        if (p.ksplit == 2) {                                   // second issuer's partial sums (other half of the K-blocks)
-          float v2[32];
-          umma::tmem_ld_32x32(trow + 128u + (uint32_t)c0, v2);
-          umma::tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += v2[j];
-        }
         // the context row of the GRU epilogues is fetched while the TMEM load is in flight
         float4 cpre[8];
         const bool gru = p.epilogue == AS_UEPI_GRU_ZR || p.epilogue == AS_UEPI_GRU_Q;
@@ -507,11 +488,6 @@ extern "C" int as_conv2d_umma(const as_conv_umma_desc* d, as_stream_t stream) {
   p.N = d->Cout; p.nsplit = d->nsplit; p.epilogue = d->epilogue;
   p.f16 = as_operand_f16_internal() != 0;
   p.fmt = as_operand_fmt_internal();
-  {
-    static const bool allow = !(getenv("AS_CONV_KSPLIT") && getenv("AS_CONV_KSPLIT")[0] == '0');     // A/B knob
-    const int kblocks = d->KH * d->KW * (cin >> 6);
-    p.ksplit = (allow && sub == 1 && d->Cout <= 128 && kblocks >= 2) ? 2 : 1;
-  }
   const bool two = two_cta_enabled() && p.num_tiles >= 4 && (p.N % 32) == 0;
   p.a_plane = (p.TH + d->KH - 1) * p.TW * 128;          // (TH+2)-row patch for 3x3, the tile itself for 1x1
   p.a_stage = 2 * p.a_plane;
