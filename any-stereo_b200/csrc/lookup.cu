@@ -246,7 +246,7 @@ __global__ void corr_lookup_bwd_kernel(LevelSetRW lv, int L, const float* __rest
 // ------------------------------------------------------------------------------------------------
 constexpr int kGP = 64;    // pixels per tile: each output channel is written as 256 contiguous bytes
 constexpr int kGT = 192;   // 6 warps (4-byte emit)
-constexpr int kGT4 = 288;  // 9 warps (128-bit emit): L*(G+1)*16 = 288 (row, pixel-quad) tasks per tile at L = 2
+constexpr int kGT4 = 192;  // 128-bit emit: the same 6 warps; L*(G+1)*16 = 288 (row, pixel-quad) tasks per tile at L = 2
 #ifndef AS_GEO_MINB
 #define AS_GEO_MINB 2
 #endif
@@ -262,8 +262,7 @@ struct GeoTile {
 // V4 = 128-bit output stores: one thread interpolates 4 consecutive pixels of one (level, group) row and writes every
 // channel as float4 (a warp instruction = 2 x 256 contiguous bytes).  B200 needs 16 bytes per lane to approach the copy
 // rate on plane-strided writes: 162 planes written with 4-byte stores top out at 3.6 TB/s, with 16-byte stores at
-// 5.8 TB/s (tools/experiments/gather_bw.cu).  Needs H*W % 4 == 0; smem rows are 16-byte aligned (stride 68: the
-// transposing 4-byte stores of `stash` become 2-way conflicted, 1.5 % of the kernel's wavefronts).
+// 5.8 TB/s (tools/experiments/gather_bw.cu).  Needs H*W % 4 == 0.
 template <int L, int NT, bool V4>
 __global__ void __launch_bounds__(NT, AS_GEO_MINB) geo_lookup_fwd_kernel(LevelSet geo, int Dg, LevelSet corr,
                                                                 const float* __restrict__ disp,
@@ -271,7 +270,7 @@ __global__ void __launch_bounds__(NT, AS_GEO_MINB) geo_lookup_fwd_kernel(LevelSe
                                                                 float* __restrict__ out, int HW, int W,
                                                                 int tiles_per_img, int num_tiles) {
   constexpr int kGT = NT;
-  constexpr int kGSP = V4 ? 68 : 66;                     // smem row stride (floats)
+  constexpr int kGSP = 66;                               // smem row stride (floats): conflict-free transposing stores, 8-byte aligned rows
   extern __shared__ __align__(16) float smem[];
   float* s_geo = smem;                                   // [L][kTaps*kG = 80][kGSP]
   float* s_cor = smem + L * kTaps * kG * kGSP;           // [L][16][kGSP]
@@ -428,12 +427,16 @@ __global__ void __launch_bounds__(NT, AS_GEO_MINB) geo_lookup_fwd_kernel(LevelSe
         const unsigned Dl = (unsigned)(Dg >> l);
         const float* w = s_geo + (l * kTaps * kG + gi) * kGSP + pq;
         float* oc = o + (long long)(l * (kG + 1) * kK + gi * kK) * HW;
-        float4 prev = *reinterpret_cast<const float4*>(w);
+        auto ld4 = [](const float* q) {                     // rows are 8-byte aligned (stride 66): two 64-bit reads
+          const float2 a = *reinterpret_cast<const float2*>(q), b = *reinterpret_cast<const float2*>(q + 2);
+          return make_float4(a.x, a.y, b.x, b.y);
+        };
+        float4 prev = ld4(w);
         prev.x = (unsigned)t0.x < Dl ? prev.x : 0.f; prev.y = (unsigned)t0.y < Dl ? prev.y : 0.f;
         prev.z = (unsigned)t0.z < Dl ? prev.z : 0.f; prev.w = (unsigned)t0.w < Dl ? prev.w : 0.f;
 #pragma unroll
         for (int k = 0; k < kK; ++k) {
-          float4 cur = *reinterpret_cast<const float4*>(w + (k + 1) * kG * kGSP);
+          float4 cur = ld4(w + (k + 1) * kG * kGSP);
           cur.x = (unsigned)(t0.x + k + 1) < Dl ? cur.x : 0.f; cur.y = (unsigned)(t0.y + k + 1) < Dl ? cur.y : 0.f;
           cur.z = (unsigned)(t0.z + k + 1) < Dl ? cur.z : 0.f; cur.w = (unsigned)(t0.w + k + 1) < Dl ? cur.w : 0.f;
           as_stg_stream4(reinterpret_cast<float4*>(oc + (long long)k * HW),
@@ -680,7 +683,7 @@ extern "C" int as_geo_lookup_fwd(const float* const* geo_levels, int G, int Dg, 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     static const bool allow_v4 = !(getenv("AS_GEO_LOOKUP_V4") && getenv("AS_GEO_LOOKUP_V4")[0] == '0');   // A/B knob
     const bool v4 = allow_v4 && (HW % 4 == 0) && as_aligned16(out);
-    const size_t smem = sizeof(float) * num_levels * (kTaps * kG + 16) * (v4 ? 68 : 66);
+    const size_t smem = sizeof(float) * num_levels * (kTaps * kG + 16) * 66;
 #define AS_LAUNCH_GEO_K(KERNEL, NT)                                                                            \
   {                                                                                                            \
     cudaError_t e = cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \

@@ -122,14 +122,17 @@ def test_dropin_training_step_matches_reference():
     torch.backends.cuda.matmul.allow_tf32 = False
     try:
         loss_ref, g_ref = run(model)
+        _, g_ref2 = run(model)          # the reference's own run-to-run noise (atomics in its grid_sample / index adjoints)
         with dropin.installed(model, R, "igev") as m:
             loss_our, g_our = run(m)
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
     assert abs(loss_our - loss_ref) <= 1e-4 * abs(loss_ref), (loss_our, loss_ref)
     for n in names:
-        err = float((g_our[n] - g_ref[n]).abs().max() / g_ref[n].abs().max().clamp_min(1e-20))
-        assert err <= 5e-3, (n, err)
+        scale = g_ref[n].abs().max().clamp_min(1e-20)
+        err = float((g_our[n] - g_ref[n]).abs().max() / scale)
+        noise = float((g_ref2[n] - g_ref[n]).abs().max() / scale)      # up to 3.5e-3 on `desc.weight` (measured)
+        assert err <= max(2e-3, 3.0 * noise), (n, err, noise)
 
 
 def test_lookup_rejects_mismatched_disp():
