@@ -464,7 +464,8 @@ extern "C" int as_conv2d_umma(const as_conv_umma_desc* d, as_stream_t stream) {
   int sub = 1;
   {
     const char* tall = getenv("AS_CONV_TALL");
-    const bool want = tall && tall[0] == '1';      // off by default: measured slower than SUB = 1 with a deeper patch ring
+    // off by default; '1' = every 3x3 layer, '2' = only the N <= 128 layers (they keep accumulator double buffering)
+    const bool want = tall && (tall[0] == '1' || (tall[0] == '2' && d->Cout <= 128));
     if (want && d->KH == 3 && p.TW == 16 && d->H > 8) {
       const int tiles2 = as_ceil_div(d->W, 16) * as_ceil_div(d->H, 16) * d->B;
       const bool two2 = two_cta_enabled() && tiles2 >= 4;
