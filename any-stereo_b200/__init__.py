@@ -19,7 +19,7 @@ from .submodule import build_gwc_volume, disparity_regression, init_disparity
 from .update import (BasicMultiUpdateBlock, BasicMultiUpdateBlockRAFT, BasicMotionEncoder, ConvGRU, DispHead,
                      set_update_engine, get_update_engine)
 from .hotpath import (igev_iterations, raft_iterations, install_into_reference, HotLoopGraph, set_lookup_fusion,
-                      adopt_update_block, adopt_liif_up)
+                      adopt_update_block, adopt_liif_up, set_graph_replay)
 from .parallel import shard_pairs, allreduce_gradients, GradientAllReducer
 from . import liif
 from .liif import liif_out_multi_scale_Training, context_upsample_multiscale_train, upsample_disp

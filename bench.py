@@ -376,11 +376,20 @@ def run_ours(args):
         sampler = ClockSampler(local, getattr(torch.cuda.get_device_properties(local), "uuid", None)) if rank == 0 else None
         if sampler:
             sampler.start()
-        events, uevents = [], []
+        # timed region: the public call (igev_iterations replays its captured step; bench.py --eager times launches one by one)
+        A.set_graph_replay(not args.eager)
+        step(dd)                                          # builds the graph outside the timed region
+        torch.cuda.synchronize()
         l0 = L.launch_count
-        ms = timed(lambda: step(dd, events, uevents), args.steps)
+        ms = timed(lambda: step(dd), args.steps)
         launches = L.launch_count - l0
         clocks = sampler.stop() if sampler else None
+        torch.cuda.synchronize()
+        # per-kernel event timing needs eager launches: two more steps of the same loop with CUDA events around the lookup
+        # launch and around the update block
+        events, uevents = [], []
+        for _ in range(2):
+            step(dd, events, uevents)
         torch.cuda.synchronize()
         look_us = [a.elapsed_time(b) * 1e3 for a, b in events]
         upd_us = [a.elapsed_time(b) * 1e3 for a, b in uevents]
@@ -433,18 +442,21 @@ def run_ours(args):
                 rf2 = (torch.randn(rb, 256, rh, rw, generator=g) / 4).to(dev)
                 rnet = [torch.tanh(torch.randn(rb, 128, h_, w_, generator=g)).to(dev) for h_, w_ in rs]
                 rinp = [[torch.relu(torch.randn(rb, 128, h_, w_, generator=g)).to(dev) for _ in range(3)] for h_, w_ in rs]
+                A.set_graph_replay(False)                       # every kernel launched one by one
                 for _ in range(2):
                     A.raft_iterations(rblock, rf1, rf2, rnet, rinp, ITERS)
                 rms = ev_ms(lambda: A.raft_iterations(rblock, rf1, rf2, rnet, rinp, ITERS), 3)
-                other[name] = {"ms_per_pair": rms / rb, "pairs_per_s": world * rb / (rms / 1e3), "iters": ITERS,
-                               "corr_levels": 4, "pairs_per_gpu": rb}
-                # same step replayed from a CUDA graph (launch-bound at small shapes)
-                hg = A.HotLoopGraph(rblock, rf1, rf2, net_list=rnet, inp_list=rinp, iters=ITERS)
-                hg.replay()
-                gms = ev_ms(hg.replay, 3)
-                other[name]["cuda_graph_ms_per_pair"] = gms / rb
-                other[name]["cuda_graph_pairs_per_s"] = world * rb / (gms / 1e3)
-                del hg, rf1, rf2, rnet, rinp
+                A.set_graph_replay(not args.eager)              # the public call as it is: replays its captured step
+                for _ in range(2):
+                    A.raft_iterations(rblock, rf1, rf2, rnet, rinp, ITERS)
+                gms = ev_ms(lambda: A.raft_iterations(rblock, rf1, rf2, rnet, rinp, ITERS), 3)
+                other[name] = {"ms_per_pair": gms / rb, "pairs_per_s": world * rb / (gms / 1e3), "iters": ITERS,
+                               "corr_levels": 4, "pairs_per_gpu": rb, "eager_ms_per_pair": rms / rb,
+                               "eager_pairs_per_s": world * rb / (rms / 1e3),
+                               "note": "raft_iterations() as called by a user (CUDA-graph replay incl. the copies into its "
+                                       "static buffers); eager_* = the same call with set_graph_replay(False)"}
+                A.hotpath.graph_cache_clear()
+                del rf1, rf2, rnet, rinp
             # the mixed-precision analogue (IEEE-half operands, single MMA): same step, reported for context only --
             # inside the 0.01 px EPE gate at the BASELINE shapes (tests/test_gpu_dropin.py, profiles/dropin_epe_r02.json)
             # but not inside the 1e-4 operator tolerance, so never the headline
@@ -577,7 +589,7 @@ def run_ours(args):
                   "fp16": "f16 (IEEE half operands, fp32 accumulate; mixed-precision analogue)"}[args.engine],
         "data": "synthetic",
         "config": {"workload": WORKLOAD % B, "pairs_per_gpu": B, "iters": ITERS, "engine": args.engine, "corr_mode": A.get_corr_mode(),
-                   "lookup_fused_with_convc1": fused,
+                   "lookup_fused_with_convc1": fused, "cuda_graph_replay": not args.eager,
                    "parallelism": "pairs sharded across ranks, no data-path collective",
                    "l2": "inputs larger than L2: per step ~1 GB of pyramids + ~1.8 GB of activations per iteration stream through the 126 MB L2; no explicit flush"},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": host_bytes(hh),
@@ -625,6 +637,7 @@ def main():
     ap.add_argument("--train-steps", type=int, default=8)
     ap.add_argument("--no-fusion", action="store_true", help="materialise the 162-channel lookup tensor (A/B knob)")
     ap.add_argument("--no-overlap", action="store_true", help="keep the motion encoder on the main stream (A/B knob)")
+    ap.add_argument("--eager", action="store_true", help="launch every kernel of the step instead of replaying the captured step")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -639,3 +639,48 @@ def test_f16f8_conv_matches_fp32(A, shape):
     A.set_update_engine("fp32")
     assert errs["f16f8"] < 1e-4 and errs["bf16x3"] < 1e-4, errs
     assert errs["fp16"] > 3 * errs["f16f8"], errs
+
+
+def test_iterations_replay_their_captured_step_by_default(A):
+    """igev_iterations / raft_iterations replay a CUDA graph of the step by default: same bits as the
+    eager launches, rebuilt when a parameter changes, new inputs honoured, launches accounted for."""
+    c = cases.loop_case("igev", seed=9, B=1, H=16, W=24)
+    args = types.SimpleNamespace(corr_levels=2, corr_radius=4, n_gru_layers=3)
+    m = A.BasicMultiUpdateBlock(args, hidden_dims=[128, 128, 128])
+    m.load_state_dict(O.make_update_block_params(162, seed=5), strict=True)
+    m = m.cuda().eval()
+    cu = lambda t: t.cuda()                                                      # noqa: E731
+    A.set_update_engine("f16f8")
+    A.set_corr_mode("bf16x3")
+
+    def run(scale=1.0):
+        return A.igev_iterations(m, cu(c["f1"]) * scale, cu(c["f2"]), cu(c["geo"]), [cu(t) for t in c["net"]],
+                                 [[cu(t) for t in l] for l in c["inp"]], cu(c["init_disp"]), 4)
+    try:
+        prev = A.set_graph_replay(False)
+        d_eager, n_eager = run()
+        d_eager2, _ = run(0.5)
+        A.set_graph_replay(True)
+        n0 = A._lib.launch_count
+        d1, n1 = run()
+        built = A._lib.launch_count - n0
+        d2, n2 = run()                                   # pure replay
+        replayed = A._lib.launch_count - n0 - built
+        assert len(A.hotpath._GRAPH["cache"]) == 1 and replayed > 20
+        assert torch.equal(d1, d_eager) and torch.equal(d2, d_eager)
+        for a, b in zip(n2, n_eager):
+            assert torch.equal(a, b)
+        d3, _ = run(0.5)                                 # same graph, different inputs
+        assert torch.equal(d3, d_eager2) and len(A.hotpath._GRAPH["cache"]) == 1
+        with torch.no_grad():
+            m.disp_head.conv2.bias.add_(0.25)            # parameter version changes -> the step is captured again
+        d4, _ = run()
+        assert len(A.hotpath._GRAPH["cache"]) == 2
+        A.set_graph_replay(False)
+        d4e, _ = run()
+        assert torch.equal(d4, d4e) and not torch.equal(d4, d1)
+    finally:
+        A.set_graph_replay(prev)
+        A.hotpath.graph_cache_clear()
+        A.set_update_engine("fp32")
+        A.set_corr_mode("fp32")
