@@ -96,6 +96,8 @@ SIGNATURES = {
     "as_geo_lookup_bwd": (_i, [_pp, _i, _i, _pp, _ip, _ip, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "as_geo_lookup_convc1": (_i, [_pp, _i, _i, _pp, _ip, _ip, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i,
                                   _vp]),
+    "as_geo_lookup_convc1_tap": (_i, [_pp, _i, _i, _pp, _ip, _ip, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i,
+                                      _vp]),
     "as_isu_affinity": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp]),
     "as_liif_query": (_i, [C.POINTER(LiifQueryDesc), _vp]),
     "as_context_upsample_multiscale": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),

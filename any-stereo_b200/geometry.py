@@ -15,6 +15,8 @@ Same constructor/``__call__``/``corr`` signatures, same public attributes (``num
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib as L
@@ -23,6 +25,7 @@ from . import _lib as L
 #: "fp32" (CUDA cores, exact), "bf16" (tcgen05, fast).  Set by anystereo_b200.set_corr_mode().
 DEFAULT_CORR_MODE = "bf16x3"
 _CORR_MODE = {"mode": DEFAULT_CORR_MODE}
+_TAP_MAJOR = os.environ.get("AS_LOOKUP_C1_TAP", "1") != "0"     # second-generation fused IGEV lookup + convc1 kernel
 _MODE_ID = {"fp32": L.CORR_FP32_SIMT, "bf16x3": L.CORR_BF16X3, "bf16": L.CORR_BF16}
 
 
@@ -356,18 +359,36 @@ class DeferredGeoLookup:
     def materialize(self):
         return self.vol(self.disp, self.coords)
 
+    @property
+    def tap_major(self):
+        """True when the second-generation kernel (as_geo_lookup_convc1_tap) takes this lookup: 2 levels, 16-byte aligned
+        level buffers, correlation pitches in multiples of 4 floats (AS_LOOKUP_C1_TAP=0 keeps the first kernel)."""
+        v = self.vol
+        return (_TAP_MAJOR and v.num_levels == 2 and v._Dg >= 2 and all(p % 4 == 0 for p in v._pitches)
+                and all(b.data_ptr() % 16 == 0 for b in list(v._geo_bufs) + list(v._corr_bufs)))
+
     @staticmethod
-    def pack_convc1_weight(weight, split=True):
+    def pack_convc1_weight(weight, split=True, tap_major=False, bias=None):
         """convc1.weight [64, L*81, 1, 1] -> bf16 hi/lo [64][192] in the K order of the fused kernel:
-        channel (level l, group g, tap k) at K = l*96 + g*10 + k (g == 8: correlation taps); pads are zero."""
+        channel (level l, group g, tap k) at K = l*96 + g*10 + k (g == 8: correlation taps); pads are zero.
+        tap_major: K = l*96 + k*8 + g, correlation taps at l*96 + 72 + k, and `bias` (required) in column 81
+        (as_geo_lookup_convc1_tap feeds a constant 1 there, so the bias goes through the GEMM)."""
         w = weight.detach().float().reshape(weight.shape[0], -1)
         Cout, Cin = w.shape
         if Cout != 64 or Cin not in (81, 162):
             raise RuntimeError("fused lookup+convc1 needs convc1: 81|162 -> 64 channels")
         c = torch.arange(Cin, device=w.device)
-        kidx = (c // 81) * 96 + ((c % 81) // 9) * 10 + (c % 9)
+        g, k = (c % 81) // 9, c % 9
+        if tap_major:
+            kidx = (c // 81) * 96 + torch.where(g < 8, k * 8 + g, 72 + k)
+        else:
+            kidx = (c // 81) * 96 + g * 10 + k
         wp = torch.zeros((Cout, 192), device=w.device, dtype=torch.float32)
         wp[:, kidx] = w
+        if tap_major:
+            if bias is None:
+                raise RuntimeError("the tap-major packing carries the bias in column 81")
+            wp[:, 81] = bias.detach().float().to(w.device)
         hi = torch.empty((Cout, 192), device=w.device, dtype=torch.bfloat16)
         lo = torch.empty_like(hi) if split else None
         with torch.cuda.device(w.device):
@@ -375,15 +396,17 @@ class DeferredGeoLookup:
                    L.stream_ptr())
         return hi, lo
 
-    def convc1_planes(self, w_hi, w_lo, bias, out_hi, out_lo):
-        """relu(convc1(lookup)) as bf16 planes [B,H,W,64] (update.py:78,85 applied to geometry.py:34-60)."""
+    def convc1_planes(self, w_hi, w_lo, bias, out_hi, out_lo, tap_major=False):
+        """relu(convc1(lookup)) as bf16 planes [B,H,W,64] (update.py:78,85 applied to geometry.py:34-60).
+        tap_major must say how pack_convc1_weight laid the weights out."""
         v = self.vol
         B, _, H, W = self.disp.shape
         with torch.cuda.device(self.device):
             if self.events is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-            L.call("as_geo_lookup_convc1", L.ptr_array(v._geo_bufs), v._G, v._Dg, L.ptr_array(v._corr_bufs),
+            L.call("as_geo_lookup_convc1_tap" if tap_major else "as_geo_lookup_convc1",
+                   L.ptr_array(v._geo_bufs), v._G, v._Dg, L.ptr_array(v._corr_bufs),
                    L.int_array(v._widths), L.int_array(v._pitches), v.num_levels, self.disp.data_ptr(),
                    L.ptr(self.coords), w_hi.data_ptr(), L.ptr(w_lo), bias.data_ptr(), 3 if w_lo is not None else 1,
                    out_hi.data_ptr(), L.ptr(out_lo), B, H, W, v.radius, L.stream_ptr())

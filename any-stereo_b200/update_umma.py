@@ -90,18 +90,19 @@ def _weights(ub, name, convs, n_pad=None, cin_pad=None, split=True):
     return hit
 
 
-def _fused_c1_weights(ub, split, kind=DeferredGeoLookup):
+def _fused_c1_weights(ub, split, kind=DeferredGeoLookup, tap_major=False):
     """convc1 weights in the K order of the fused lookup kernel (geometry.Deferred*Lookup.pack_convc1_weight)."""
     st = _state(ub)["w"]
     c = ub.encoder.convc1
-    key = (split, L.operand_format(), kind.__name__, c.weight.data_ptr(), L.version_of(c.weight), c.bias.data_ptr(), L.version_of(c.bias))
+    key = (split, L.operand_format(), kind.__name__, tap_major, c.weight.data_ptr(), L.version_of(c.weight), c.bias.data_ptr(),
+           L.version_of(c.bias))
     hit = st.get("convc1.fused")
     if hit is not None and hit["key"] == key:
         return hit
     # the fused kernel's own GEMM runs on 16-bit hi/lo operands in every engine: under "f16f8" its weights are IEEE-half
     # hi/lo pairs (3 internal passes; the kernel is not tensor-bound), only its OUTPUT planes use the e5m2 pair encoding
     with torch.no_grad(), L.operand_format_scope(_sixteen_bit_format()):
-        hi, lo = kind.pack_convc1_weight(c.weight, split)
+        hi, lo = kind.pack_convc1_weight(c.weight, split, True, c.bias) if tap_major else kind.pack_convc1_weight(c.weight, split)
         bias = c.bias.detach().float().contiguous()
     hit = dict(key=key, hi=hi, lo=lo, bias=bias)
     st["convc1.fused"] = hit
@@ -277,8 +278,12 @@ def forward(ub, net, inp, corr=None, disp=None, iter04=True, iter08=True, iter16
         cpad = (Cc + 63) // 64 * 64
         c1 = _Planes((B, H, W, 64), dev, split)
         if isinstance(corr, _DEFERRED):              # lookup + convc1 + ReLU in one kernel, features stay on chip
-            wf = _fused_c1_weights(ub, split, type(corr))
-            corr.convc1_planes(wf["hi"], wf["lo"], wf["bias"], c1.hi, c1.lo)
+            tap = bool(getattr(corr, "tap_major", False))
+            wf = _fused_c1_weights(ub, split, type(corr), tap)
+            if tap:
+                corr.convc1_planes(wf["hi"], wf["lo"], wf["bias"], c1.hi, c1.lo, tap_major=True)
+            else:
+                corr.convc1_planes(wf["hi"], wf["lo"], wf["bias"], c1.hi, c1.lo)
         else:
             wc1 = _weights(ub, "convc1", [e.convc1], cin_pad=cpad, split=split)
             corrS = _Planes((B, H, W, cpad), dev, split)

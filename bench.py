@@ -557,8 +557,9 @@ def run_ours(args):
     look_avg_us = sum(look_us) / max(len(look_us), 1)
     fused = (not args.no_fusion) and args.engine != "fp32"
     look_bpp = FUSED_BYTES_PER_PIXEL[args.engine] if fused else LOOKUP_BYTES_PER_PIXEL
-    look_kernel = ("geo_lookup_convc1_kernel<2> (Combined_Geo_Encoding_Volume.__call__ fused with "
-                   "BasicMotionEncoder.convc1+ReLU)" if fused else
+    tap = fused and A.geometry._TAP_MAJOR
+    look_kernel = (("geo_lookup_convc1_tap_kernel" if tap else "geo_lookup_convc1_kernel<2>") +
+                   " (Combined_Geo_Encoding_Volume.__call__ fused with BasicMotionEncoder.convc1+ReLU)" if fused else
                    "geo_lookup_fwd_kernel<2> (Combined_Geo_Encoding_Volume.__call__)")
     achieved = look_bpp * n_pix / (look_avg_us * 1e-6) / 1e9
     traffic = None
@@ -605,8 +606,10 @@ def run_ours(args):
                                "extra steps of the same loop without the side stream (in the timed region the kernel overlaps "
                                "the low-resolution GRU convolutions, so its event-to-event time there is not its own)",
                      "note": ("fused kernel: the three kernels it replaces (lookup, bf16 split, convc1) moved 3812 B/pixel; "
-                              "ncu shows it bound by the SM's L1/shared-memory data pipe (64 % busy), not by HBM -- "
-                              "DESIGN.md section 5; --no-fusion reports the plain lookup kernel (1372 B/pixel, frac 0.47-0.49)")
+                              "second generation (16-byte gathers, shuffle interpolation, 32-byte stores; AS_LOOKUP_C1_TAP=0 "
+                              "selects the first): gather and interpolation do not fully overlap (LDG issue blocks in the LSU "
+                              "queue), see DESIGN.md section 5.2; --no-fusion reports the plain lookup kernel (1372 B/pixel, "
+                              "frac 0.47-0.49)")
                      if fused else "plain lookup kernel (--no-fusion)"},
         "roofline_update_block": None if args.engine == "fp32" else {
             "kernels": "conv_umma_kernel (tcgen05) + small kernels per iteration" + (" + the fused lookup/convc1 kernel" if fused else ""), "bound": "tensor",

@@ -145,6 +145,17 @@ int as_geo_lookup_convc1(const float* const* geo_levels, int G, int Dg,
                          int num_levels, const float* disp, const float* coords,
                          const void* w_hi, const void* w_lo, const float* bias, int nsplit,
                          void* out_hi, void* out_lo, int B, int H, int W, int radius, as_stream_t stream);
+/* Same operator, second kernel generation for the IGEV shape (num_levels == 2): 16-byte gathers, shuffle interpolation,
+ * M = 128 real pixels per MMA.  Same arguments and outputs; the weights are packed in the TAP-MAJOR K order instead:
+ * channel (level l, group g, tap k) at K = l*96 + k*8 + g, correlation tap k of level l at K = l*96 + 72 + k, and the
+ * convc1 BIAS in column K = 81 (the kernel multiplies it by a constant 1; `bias` itself is not read).
+ * Returns AS_ERR_UNSUPPORTED (callers then use as_geo_lookup_convc1) unless num_levels == 2, every level buffer is
+ * 16-byte aligned and every correlation pitch is a multiple of 4 floats. */
+int as_geo_lookup_convc1_tap(const float* const* geo_levels, int G, int Dg,
+                             const float* const* corr_levels, const int* corr_widths, const int* corr_pitches,
+                             int num_levels, const float* disp, const float* coords,
+                             const void* w_hi, const void* w_lo, const float* bias, int nsplit,
+                             void* out_hi, void* out_lo, int B, int H, int W, int radius, as_stream_t stream);
 /* The RAFT-family twin: CorrBlock1D.__call__ (corePrune_RAFT/geometry.py:24-43) fused with convc1 (L*9 -> 64) + ReLU.
  * num_levels 2 or 4, radius 4.  w_hi/w_lo: bf16 [64][64] with channel (level l, tap k) at K = l*10 + k, zeros elsewhere. */
 int as_corr_lookup_convc1(const float* const* corr_levels, const int* corr_widths, const int* corr_pitches,

@@ -343,10 +343,14 @@ def test_update_block_fewer_gru_layers(A, engine, tol, n_layers):
 
 @pytest.mark.parametrize("engine,tol", [("bf16x3", 1e-4), ("bf16", 2e-2), ("fp16", 3e-3)])
 @pytest.mark.parametrize("shape", [(2, 5, 23, 16, 2), (1, 16, 24, 48, 2), (1, 7, 150, 24, 1), (3, 9, 40, 20, 2)])
-def test_fused_lookup_convc1_vs_oracle(A, engine, tol, shape):
+@pytest.mark.parametrize("tap", [False, True])
+def test_fused_lookup_convc1_vs_oracle(A, engine, tol, shape, tap):
     """lookup fused with BasicMotionEncoder.convc1 + ReLU on the tensor cores against
-    relu(conv1x1(oracle lookup)); ragged 128-pixel tiles, out-of-range disparities, 1 and 2 levels."""
+    relu(conv1x1(oracle lookup)); ragged 128-pixel tiles, out-of-range disparities, 1 and 2 levels; both kernel
+    generations (tap: as_geo_lookup_convc1_tap, tap-major K order, 2 levels only)."""
     B, H, W, Dg, Lv = shape
+    if tap and Lv != 2:
+        pytest.skip("the tap-major kernel is built for 2 levels")
     c = cases.igev_geo_case(seed=31 + H, B=B, D=16, H=H, W=W, Dg=Dg)
     rng = np.random.RandomState(W)
     disp = torch.from_numpy(rng.uniform(-6, Dg + 6, (B, 1, H, W)).astype("float32"))
@@ -361,18 +365,19 @@ def test_fused_lookup_convc1_vs_oracle(A, engine, tol, shape):
     A.set_update_engine(engine)                       # selects the 16-bit operand format (bf16 / IEEE half)
     vol = A.Combined_Geo_Encoding_Volume(c["f1"].cuda(), c["f2"].cuda(), c["geo"].cuda(), num_levels=Lv, radius=4)
     split = engine == "bf16x3"
-    w_hi, w_lo = A.geometry.DeferredGeoLookup.pack_convc1_weight(w.cuda(), split)
+    w_hi, w_lo = A.geometry.DeferredGeoLookup.pack_convc1_weight(w.cuda(), split, tap, b.cuda() if tap else None)
     out_hi = torch.full((B, H, W, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
     out_lo = torch.full_like(out_hi, float("nan")) if split else None
     d = vol.deferred(disp.cuda(), coords.cuda())
     assert d.fusable and d.shape == (B, Lv * 81, H, W)
-    d.convc1_planes(w_hi, w_lo, b.cuda(), out_hi, out_lo)
+    assert d.tap_major == (Lv == 2)
+    d.convc1_planes(w_hi, w_lo, b.cuda(), out_hi, out_lo, tap)
     torch.cuda.synchronize()
     widen = (lambda t: t.view(torch.float16).float()) if engine == "fp16" else (lambda t: t.float())
     got = widen(out_hi) + (widen(out_lo) if split else 0)
     # coords=None means the default pixel grid
     out2 = torch.empty_like(out_hi)
-    vol.deferred(disp.cuda(), None).convc1_planes(w_hi, w_lo, b.cuda(), out2, torch.empty_like(out_hi) if split else None)
+    vol.deferred(disp.cuda(), None).convc1_planes(w_hi, w_lo, b.cuda(), out2, torch.empty_like(out_hi) if split else None, tap)
     torch.cuda.synchronize()
     A.set_update_engine("fp32")
     assert rel(got.permute(0, 3, 1, 2), ref) < tol
@@ -423,13 +428,14 @@ def test_fused_lookup_falls_back(A):
         n_a, d_a = m(list(net), inp, vol.deferred(disp, None), disp)
         n_b, d_b = m(list(net), inp, vol(disp, None), disp)
     assert torch.equal(d_a, d_b)
-    rc = A._lib.lib().as_geo_lookup_convc1(None, 4, 8, None, None, None, 2, None, None, None, None, None, 3, None, None,
-                                           1, 1, 1, 4, None)
-    assert rc == -1          # AS_ERR_BAD_ARG
+    for fn in (A._lib.lib().as_geo_lookup_convc1, A._lib.lib().as_geo_lookup_convc1_tap):
+        rc = fn(None, 4, 8, None, None, None, 2, None, None, None, None, None, 3, None, None, 1, 1, 1, 4, None)
+        assert rc == -1      # AS_ERR_BAD_ARG
 
 
-def test_fused_lookup_fullsize_config2(A):
-    """Config-2 size (8 x 96x312, Dg=48): the fused lookup+convc1 kernel against the unfused kernels
+@pytest.mark.parametrize("tap", [False, True])
+def test_fused_lookup_fullsize_config2(A, tap):
+    """Config-2 size (8 x 96x312, Dg=48): the fused lookup+convc1 kernels against the unfused kernels
     (lookup -> bf16 split -> 1x1 tcgen05 conv), same arithmetic up to the K order of the fp32 accumulation."""
     torch.manual_seed(2)
     dev = "cuda"
@@ -443,10 +449,10 @@ def test_fused_lookup_fullsize_config2(A):
     disp = (torch.rand(B, 1, H, W, device=dev) * (Dg + 8) - 4).contiguous()
     m = make_block(A, "igev", 4)
     from anystereo_b200 import update_umma as U
-    wf = U._fused_c1_weights(m, True)
+    wf = U._fused_c1_weights(m, True, tap_major=tap)
     out_hi = torch.empty(B, H, W, 64, device=dev, dtype=torch.bfloat16)
     out_lo = torch.empty_like(out_hi)
-    vol.deferred(disp, None).convc1_planes(wf["hi"], wf["lo"], wf["bias"], out_hi, out_lo)
+    vol.deferred(disp, None).convc1_planes(wf["hi"], wf["lo"], wf["bias"], out_hi, out_lo, tap)
     feat = vol(disp, None)
     ref = torch.relu(torch.nn.functional.conv2d(feat.double(), m.encoder.convc1.weight.double(), m.encoder.convc1.bias.double()))
     torch.cuda.synchronize()

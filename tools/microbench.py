@@ -55,15 +55,17 @@ def fused_lookup_bench(blk, d, coords, rec, N):
     or + 128 (one plane).  One line per arithmetic mode of the kernel's own GEMM / output planes."""
     B, _, H, W = d.shape
     for engine, split in (("bf16x3", True), ("f16f8", True), ("bf16", False)):
-        A.set_update_engine(engine)
-        with A._lib.operand_format_scope(A.update_umma._sixteen_bit_format()):      # the kernel's own GEMM: 16-bit hi/lo
-            w_hi, w_lo = A.geometry.DeferredGeoLookup.pack_convc1_weight(torch.randn(64, 162, 1, 1, device="cuda") * 0.1, split)
-        bias = torch.randn(64, device="cuda")
-        o_hi = torch.empty(B, H, W, 64, device="cuda", dtype=torch.bfloat16)
-        o_lo = torch.empty_like(o_hi) if split else None
-        dl = blk.deferred(d, coords)
-        med, best = timeit(lambda: dl.convc1_planes(w_hi, w_lo, bias, o_hi, o_lo))
-        rec("geo_lookup_convc1_fused_" + engine, med, best, (728 + (256 if split else 128)) * N)
+        for tap in (False, True):                   # first kernel / tap-major kernel (as_geo_lookup_convc1_tap)
+            A.set_update_engine(engine)
+            bias = torch.randn(64, device="cuda")
+            with A._lib.operand_format_scope(A.update_umma._sixteen_bit_format()):
+                w_hi, w_lo = A.geometry.DeferredGeoLookup.pack_convc1_weight(torch.randn(64, 162, 1, 1, device="cuda") * 0.1,
+                                                                             split, tap, bias)
+            o_hi = torch.empty(B, H, W, 64, device="cuda", dtype=torch.bfloat16)
+            o_lo = torch.empty_like(o_hi) if split else None
+            dl = blk.deferred(d, coords)
+            med, best = timeit(lambda: dl.convc1_planes(w_hi, w_lo, bias, o_hi, o_lo, tap))
+            rec("geo_lookup_convc1_fused_" + engine + ("_tap" if tap else ""), med, best, (728 + (256 if split else 128)) * N)
     A.set_update_engine("fp32")
 
 
