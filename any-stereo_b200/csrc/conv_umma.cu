@@ -15,6 +15,7 @@
 // Operand reuse: for a 3x3 kernel the producer loads ONE (TH+2)-row patch per (dx, channel chunk); the three dy taps
 // are 1024-byte-aligned row offsets into that patch (TW*128 B = one or two swizzle atoms), i.e. three UMMA descriptors
 // over the same shared memory.  L2->smem traffic of the activations drops from 9 to 3.75 tile loads per chunk.
+#include <cstdio>
 #include <cstdlib>
 #include "umma.cuh"
 
@@ -55,6 +56,20 @@ struct ConvUmmaParams {
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+#ifdef AS_CONV_TRACE
+// experiment builds only (make EXTRA=-DAS_CONV_TRACE): where the MMA-issuing thread of CTA 0 spends its time.
+// [0] waiting for an activation patch, [1] for a weight stage, [2] for a drained accumulator, [3] whole loop, [4] MMAs issued
+__device__ long long g_conv_trace[8];
+#define CONV_TRACE_WAIT(slot, stmt)                          \
+  do {                                                       \
+    const long long t__ = clock64();                         \
+    stmt;                                                    \
+    if (blockIdx.x == 0) tr[slot] += clock64() - t__;        \
+  } while (0)
+#else
+#define CONV_TRACE_WAIT(slot, stmt) stmt
+#endif
+
 // store 32 consecutive channels of one pixel as 16-bit hi planes (+ the lo plane of the format: x - hi in 16 bits, or the
 // e5m2 pair encoding of AS_FMT_F16F8, common.cuh)
 __device__ __forceinline__ void store_split32(const float* v, __nv_bfloat16* hi, __nv_bfloat16* lo, long long off, int fmt) {
@@ -84,14 +99,20 @@ __device__ __forceinline__ void store_split32(const float* v, __nv_bfloat16* hi,
 // traffic (45.6 KB per K-block and CTA against 1024 / 512 tensor-core cycles: the 42 B/clk/SM that the L2 delivers), the
 // 3-pass engine is tensor-bound and keeps SUB = 1 (no tile-count quantisation loss).  With N > 128 the two accumulators
 // fill TMEM (2 x 256 columns): no double buffering, the epilogue (~5 % of a tile) is exposed.
-template <bool TWO, int NS, int SUB>
+// GRP = "group stages" (3x3 layers with N <= 128): one ring whose stage holds an activation patch AND the KH weight tiles it
+// feeds, one full / one empty barrier per stage, i.e. ONE tcgen05.commit per 3 K-blocks instead of four per 3.  Measured
+// (tools/experiments/mma_rate.cu): an SS-mode MMA occupies the tensor core for max(75, N/2) cycles whatever M and the
+// operand kind are, and every tcgen05.commit between MMAs adds ~170 cycles during which the pipe drains; with a commit
+// per K-block (8 MMAs) the N <= 128 layers ran at 110 cycles per MMA (tools/experiments/conv_trace.sh) although the issuing
+// thread waited for data only 12 % of the time.
+template <bool TWO, int NS, int SUB, bool GRP>
 __global__ void __launch_bounds__(conv_threads(SUB), 1) conv_umma_kernel(const __grid_constant__ ConvMaps maps,
                                                                 const ConvUmmaParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* a_ring = smem;
   uint8_t* b_ring = smem + p.nstA * p.a_stage;
-  float* w2s = reinterpret_cast<float*>(b_ring + p.nstB * p.b_stage);
+  float* w2s = reinterpret_cast<float*>(GRP ? smem + p.nstA * (p.a_stage + p.KH * p.b_stage) : b_ring + p.nstB * p.b_stage);
   float* ubuf = w2s + kW2Floats;                 // [128][9]
   uint64_t* bars = reinterpret_cast<uint64_t*>(ubuf + kUFloats);
   uint64_t* fullA = bars;
@@ -174,7 +195,32 @@ __global__ void __launch_bounds__(conv_threads(SUB), 1) conv_umma_kernel(const _
           for (int s = 0; s < p.num_src; ++s) {
             for (int c0 = 0; c0 < p.src_ch[s]; c0 += 64) {
               umma::mbar_wait(&emptyA[sa], pha ^ 1);
-              uint8_t* sta = a_ring + sa * p.a_stage;
+              uint8_t* sta = a_ring + sa * (GRP ? p.a_stage + p.KH * p.b_stage : p.a_stage);
+              if (GRP) {                       // the patch and its KH weight tiles land in one stage, behind one barrier
+                const uint32_t tx = txA + (uint32_t)p.KH * txB;
+                const uint32_t bar = TWO ? umma::mapa(umma::smem_u32(&fullA[sa]), 0) : 0u;
+                if (TWO) umma::mbar_expect_tx_cluster(bar, tx); else umma::mbar_expect_tx(&fullA[sa], tx);
+                if (TWO) {
+                  umma::tma_load_4d_2sm(sta, &maps.a_hi[s], bar, c0, x0 + kx - pw, y0 - ph, b);
+                  if (NS > 1) umma::tma_load_4d_2sm(sta + p.a_plane, &maps.a_lo[s], bar, c0, x0 + kx - pw, y0 - ph, b);
+                } else {
+                  umma::tma_load_4d(sta, &maps.a_hi[s], &fullA[sa], c0, x0 + kx - pw, y0 - ph, b);
+                  if (NS > 1) umma::tma_load_4d(sta + p.a_plane, &maps.a_lo[s], &fullA[sa], c0, x0 + kx - pw, y0 - ph, b);
+                }
+                for (int ky = 0; ky < p.KH; ++ky) {
+                  uint8_t* stb = sta + p.a_stage + ky * p.b_stage;
+                  const int kcoord = (ky * p.KW + kx) * p.cin_total + coff + c0;
+                  if (TWO) {
+                    umma::tma_load_2d_2sm(stb, &maps.b_hi, bar, kcoord, brow0);
+                    if (NS > 1) umma::tma_load_2d_2sm(stb + b_bytes, &maps.b_lo, bar, kcoord, brow0);
+                  } else {
+                    umma::tma_load_2d(stb, &maps.b_hi, &fullA[sa], kcoord, 0);
+                    if (NS > 1) umma::tma_load_2d(stb + b_bytes, &maps.b_lo, &fullA[sa], kcoord, 0);
+                  }
+                }
+                if (++sa == p.nstA) { sa = 0; pha ^= 1; }
+                continue;
+              }
               if (!TWO) {
                 umma::mbar_expect_tx(&fullA[sa], txA);
                 umma::tma_load_4d(sta, &maps.a_hi[s], &fullA[sa], c0, x0 + kx - pw, y0 - ph, b);
@@ -214,21 +260,29 @@ __global__ void __launch_bounds__(conv_threads(SUB), 1) conv_umma_kernel(const _
       int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
       const uint32_t idesc = umma::idesc_16_f32(TWO ? 256 : 128, p.N, p.f16);
       const uint32_t idesc8 = umma::idesc_e5m2_f32(TWO ? 256 : 128, p.N);
+#ifdef AS_CONV_TRACE
+      long long tr[5] = {0, 0, 0, 0, 0};
+      const long long t_loop = clock64();
+#endif
       for (int it = 0; it < niter; ++it) {
         const int acc = it % nbuf;
         const uint32_t acc_phase = (uint32_t)(it / nbuf) & 1u;
-        umma::mbar_wait(&tempty[acc], acc_phase ^ 1);
+        CONV_TRACE_WAIT(2, umma::mbar_wait(&tempty[acc], acc_phase ^ 1));
         umma::tc_fence_after();
         const uint32_t tmem_d0 = tmem_base + (uint32_t)acc * 256u;
         uint32_t accumulate = 0;
         for (int g = 0; g < ngroups; ++g) {
-          umma::mbar_wait(&fullA[sa], pha);
-          const uint32_t sta = umma::smem_u32(a_ring + sa * p.a_stage);
+          CONV_TRACE_WAIT(0, umma::mbar_wait(&fullA[sa], pha));
+          const uint32_t sta = umma::smem_u32(a_ring + sa * (GRP ? p.a_stage + p.KH * p.b_stage : p.a_stage));
+          if (GRP) umma::tc_fence_after();
           for (int ky = 0; ky < p.KH; ++ky) {
-            umma::mbar_wait(&fullB[sb], phb);
-            umma::tc_fence_after();
+            if (!GRP) {
+              CONV_TRACE_WAIT(1, umma::mbar_wait(&fullB[sb], phb));
+              umma::tc_fence_after();
+            }
             const uint32_t a_hi = sta + (uint32_t)(ky * dy_bytes), a_lo = a_hi + (uint32_t)p.a_plane;
-            const uint32_t b_hi = umma::smem_u32(b_ring + sb * p.b_stage), b_lo = b_hi + (uint32_t)b_bytes;
+            const uint32_t b_hi = GRP ? sta + (uint32_t)(p.a_stage + ky * p.b_stage) : umma::smem_u32(b_ring + sb * p.b_stage);
+            const uint32_t b_lo = b_hi + (uint32_t)b_bytes;
             // descriptor low words at K offset 0; a K-step of 32 bytes adds 2 (addresses are in 16-byte units)
             const uint32_t dbh0 = umma::desc_lo_sw128(b_hi), dbl0 = umma::desc_lo_sw128(b_lo);
 #pragma unroll
@@ -249,14 +303,23 @@ __global__ void __launch_bounds__(conv_threads(SUB), 1) conv_umma_kernel(const _
               }
             }
             accumulate = 1u;
-            if (TWO) umma::mma_commit_2sm(&emptyB[sb], 3); else umma::mma_commit(&emptyB[sb]);
-            if (++sb == p.nstB) { sb = 0; phb ^= 1; }
+            if (!GRP) {
+              if (TWO) umma::mma_commit_2sm(&emptyB[sb], 3); else umma::mma_commit(&emptyB[sb]);
+              if (++sb == p.nstB) { sb = 0; phb ^= 1; }
+            }
           }
           if (TWO) umma::mma_commit_2sm(&emptyA[sa], 3); else umma::mma_commit(&emptyA[sa]);
           if (++sa == p.nstA) { sa = 0; pha ^= 1; }
         }
         if (TWO) umma::mma_commit_2sm(&tfull[acc], 3); else umma::mma_commit(&tfull[acc]);
       }
+#ifdef AS_CONV_TRACE
+      if (blockIdx.x == 0) {
+        tr[3] = clock64() - t_loop;
+        tr[4] = (long long)niter * ngroups * p.KH * 4 * NS * SUB;
+        for (int i = 0; i < 5; ++i) g_conv_trace[i] = tr[i];
+      }
+#endif
     }
     __syncwarp();
   } else if (warp >= 4) {
@@ -402,9 +465,9 @@ __global__ void __launch_bounds__(conv_threads(SUB), 1) conv_umma_kernel(const _
   }
 }
 
-template <bool TWO, int NS, int SUB>
+template <bool TWO, int NS, int SUB, bool GRP>
 int launch_conv(const ConvMaps& maps, const ConvUmmaParams& p, int sms, int smem, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<TWO, NS, SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<TWO, NS, SUB, GRP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return (int)e;
   constexpr int CS = TWO ? 2 : 1;
   int grid = p.num_tiles < sms ? p.num_tiles : sms;
@@ -423,8 +486,18 @@ int launch_conv(const ConvMaps& maps, const ConvUmmaParams& p, int sms, int smem
   static const bool pdl = !(getenv("AS_CONV_PDL") && getenv("AS_CONV_PDL")[0] == '0');   // A/B knob
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 2 : 1;
-  e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<TWO, NS, SUB>, maps, p);
+  e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<TWO, NS, SUB, GRP>, maps, p);
   if (e != cudaSuccess) return (int)e;
+#ifdef AS_CONV_TRACE
+  if (getenv("AS_CONV_TRACE_PRINT")) {
+    long long tr[8];
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(tr, g_conv_trace, sizeof(tr));
+    fprintf(stderr, "conv N=%3d Cin=%3d k=%d epi=%d tiles=%d passes=%d: loop %lld cycles, %lld MMAs (%.1f cyc/MMA); waits: patch %.1f%% weights %.1f%% accumulator %.1f%%\n",
+            p.N, p.cin_total, p.KH, p.epilogue, p.num_tiles, NS, tr[3], tr[4], (double)tr[3] / (double)(tr[4] ? tr[4] : 1),
+            100.0 * tr[0] / tr[3], 100.0 * tr[1] / tr[3], 100.0 * tr[2] / tr[3]);
+  }
+#endif
   AS_RETURN_IF_LAUNCH_FAILED();
   return AS_OK;
 }
@@ -518,6 +591,18 @@ extern "C" int as_conv2d_umma(const as_conv_umma_desc* d, as_stream_t stream) {
     }
   }
   if (p.nstB < 2) return AS_ERR_UNSUPPORTED;
+  // group stages (see the kernel): 3x3 layers with N <= 128 when at least two {patch + 3 weight tiles} stages fit
+  bool group = false;
+  {
+    static const bool allow = !(getenv("AS_CONV_GROUP") && getenv("AS_CONV_GROUP")[0] == '0');      // A/B knob
+    const int gstage = p.a_stage + d->KH * p.b_stage;
+    const int ng = (kSmemBudget - fixed) / gstage;
+    if (allow && sub == 1 && d->KH == 3 && p.N <= 128 && ng >= 2) {
+      group = true;
+      p.nstA = ng > kMaxStages ? kMaxStages : ng;
+      p.nstB = 0;
+    }
+  }
   p.bias = d->bias; p.ctx = d->ctx; p.ctx_pitch = d->ctx_pitch; p.h = d->h; p.z = d->z;
   p.out_f32 = d->out_f32; p.out_hi = (__nv_bfloat16*)d->out_hi; p.out_lo = (__nv_bfloat16*)d->out_lo;
   p.out_pitch = d->out_pitch; p.out_coff = d->out_coff; p.cout_valid = d->cout_valid;
@@ -576,7 +661,7 @@ extern "C" int as_conv2d_umma(const as_conv_umma_desc* d, as_stream_t stream) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int smem = fixed + p.nstA * p.a_stage + p.nstB * p.b_stage;
+  const int smem = group ? fixed + p.nstA * (p.a_stage + d->KH * p.b_stage) : fixed + p.nstA * p.a_stage + p.nstB * p.b_stage;
   if (two) {   // the weight tensor map's box is one CTA's half of the rows
     const uint64_t Kt = (uint64_t)d->KH * d->KW * cin;
     const uint64_t dims[2] = {Kt, (uint64_t)p.N};
@@ -588,16 +673,21 @@ extern "C" int as_conv2d_umma(const as_conv_umma_desc* d, as_stream_t stream) {
     } else {
       maps.b_lo = maps.b_hi;
     }
-#define AS_CONV_DISPATCH(TWO_)                                                                     \
-  do {                                                                                             \
-    if (sub == 2) {                                                                                \
-      if (d->nsplit == 3) return launch_conv<TWO_, 3, 2>(maps, p, sms, smem, as_cu(stream));       \
-      if (d->nsplit == 2) return launch_conv<TWO_, 2, 2>(maps, p, sms, smem, as_cu(stream));       \
-      return launch_conv<TWO_, 1, 2>(maps, p, sms, smem, as_cu(stream));                           \
-    }                                                                                              \
-    if (d->nsplit == 3) return launch_conv<TWO_, 3, 1>(maps, p, sms, smem, as_cu(stream));         \
-    if (d->nsplit == 2) return launch_conv<TWO_, 2, 1>(maps, p, sms, smem, as_cu(stream));         \
-    return launch_conv<TWO_, 1, 1>(maps, p, sms, smem, as_cu(stream));                             \
+#define AS_CONV_DISPATCH(TWO_)                                                                            \
+  do {                                                                                                    \
+    if (sub == 2) {                                                                                       \
+      if (d->nsplit == 3) return launch_conv<TWO_, 3, 2, false>(maps, p, sms, smem, as_cu(stream));       \
+      if (d->nsplit == 2) return launch_conv<TWO_, 2, 2, false>(maps, p, sms, smem, as_cu(stream));       \
+      return launch_conv<TWO_, 1, 2, false>(maps, p, sms, smem, as_cu(stream));                           \
+    }                                                                                                     \
+    if (group) {                                                                                          \
+      if (d->nsplit == 3) return launch_conv<TWO_, 3, 1, true>(maps, p, sms, smem, as_cu(stream));        \
+      if (d->nsplit == 2) return launch_conv<TWO_, 2, 1, true>(maps, p, sms, smem, as_cu(stream));        \
+      return launch_conv<TWO_, 1, 1, true>(maps, p, sms, smem, as_cu(stream));                            \
+    }                                                                                                     \
+    if (d->nsplit == 3) return launch_conv<TWO_, 3, 1, false>(maps, p, sms, smem, as_cu(stream));         \
+    if (d->nsplit == 2) return launch_conv<TWO_, 2, 1, false>(maps, p, sms, smem, as_cu(stream));         \
+    return launch_conv<TWO_, 1, 1, false>(maps, p, sms, smem, as_cu(stream));                             \
   } while (0)
     AS_CONV_DISPATCH(true);
   }
