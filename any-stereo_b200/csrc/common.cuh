@@ -124,3 +124,60 @@ __device__ __forceinline__ void as_store_lo8(void* lo, long long off, const floa
     *reinterpret_cast<uint2*>(b + 64) = c;
   }
 }
+
+// ----------------------------------------------------------------------------------------------
+// 256-bit global stores (sm_100: STG.E.ENL2.256).  Epilogues whose threads each own one pixel row write row-strided
+// pieces; with 16 bytes per lane every 32-byte sector is written in two halves by two instructions and the L2 handles
+// partial sectors (measured on the fused lookup kernel: 61 MB of output cost 16-20 us with 16-byte stores, 10 us with
+// 32-byte stores).  The address must be 32-byte aligned.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void as_stg256(void* p, const uint32_t (&w)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+               "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+}
+__device__ __forceinline__ void as_stg256f(float* p, const float* v) {     // 8 consecutive floats
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+// 32 consecutive channels of one pixel (off = element offset of the first, a multiple of 32; 32-byte aligned rows) -> the
+// 16-bit hi plane and the second plane of the format (16-bit lo, or the e5m2 pair plane of AS_FMT_F16F8), 32 bytes per store
+__device__ __forceinline__ void as_store_split32_v8(const float* y, void* out_hi, void* out_lo, long long off, int fmt) {
+  const bool f16 = fmt != 0;
+  uint32_t h[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) h[i] = as_cvt16x2(y[2 * i], y[2 * i + 1], f16);
+  {
+    const uint32_t a[8] = {h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]};
+    const uint32_t b[8] = {h[8], h[9], h[10], h[11], h[12], h[13], h[14], h[15]};
+    as_stg256(reinterpret_cast<unsigned short*>(out_hi) + off, a);
+    as_stg256(reinterpret_cast<unsigned short*>(out_hi) + off + 16, b);
+  }
+  if (!out_lo) return;
+  float r[32], hv[32];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    hv[2 * i] = as_widen_lo16(h[i], f16);
+    hv[2 * i + 1] = as_widen_hi16(h[i], f16);
+    r[2 * i] = y[2 * i] - hv[2 * i];
+    r[2 * i + 1] = y[2 * i + 1] - hv[2 * i + 1];
+  }
+  if (fmt != 2) {
+    uint32_t l[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) l[i] = as_cvt16x2(r[2 * i], r[2 * i + 1], f16);
+    const uint32_t a[8] = {l[0], l[1], l[2], l[3], l[4], l[5], l[6], l[7]};
+    const uint32_t b[8] = {l[8], l[9], l[10], l[11], l[12], l[13], l[14], l[15]};
+    as_stg256(reinterpret_cast<unsigned short*>(out_lo) + off, a);
+    as_stg256(reinterpret_cast<unsigned short*>(out_lo) + off + 16, b);
+  } else {
+    uint8_t* bp = reinterpret_cast<uint8_t*>(out_lo) + as_x8_byte(off);
+    uint32_t a[8], b[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      a[i] = as_e5m2x4(r[4 * i] * kX8ActLoScale, r[4 * i + 1] * kX8ActLoScale, r[4 * i + 2] * kX8ActLoScale, r[4 * i + 3] * kX8ActLoScale);
+      b[i] = as_e5m2x4(hv[4 * i] * kX8ActHiScale, hv[4 * i + 1] * kX8ActHiScale, hv[4 * i + 2] * kX8ActHiScale, hv[4 * i + 3] * kX8ActHiScale);
+    }
+    as_stg256(bp, a);
+    as_stg256(bp + 64, b);
+  }
+}

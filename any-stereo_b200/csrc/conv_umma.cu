@@ -52,6 +52,7 @@ struct ConvUmmaParams {
   const float* disp; const float* w2; float* u;
   bool f16;                                   // hi planes / weights are IEEE half instead of bf16
   int fmt;                                    // AS_FMT_* of the planes this launch reads and writes
+  bool wide;                                  // output planes: 32-byte aligned rows -> 256-bit stores
 };
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
@@ -72,7 +73,12 @@ __device__ long long g_conv_trace[8];
 
 // store 32 consecutive channels of one pixel as 16-bit hi planes (+ the lo plane of the format: x - hi in 16 bits, or the
 // e5m2 pair encoding of AS_FMT_F16F8, common.cuh)
-__device__ __forceinline__ void store_split32(const float* v, __nv_bfloat16* hi, __nv_bfloat16* lo, long long off, int fmt) {
+__device__ __forceinline__ void store_split32(const float* v, __nv_bfloat16* hi, __nv_bfloat16* lo, long long off, int fmt,
+                                              bool wide) {
+  if (wide) {                                   // rows are 32-byte aligned: full-sector stores
+    as_store_split32_v8(v, hi, lo, off, fmt);
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < 32; j += 8) {
     uint32_t h[4];
@@ -370,7 +376,7 @@ __global__ void __launch_bounds__(conv_threads(SUB), 1) conv_umma_kernel(const _
           if (c0 < Hd) {                                     // z = sigmoid(convz + cz)      update.py:37
             float* zp = p.z + n * Hd + c0;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(zp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            for (int j = 0; j < 32; j += 8) as_stg256f(zp + j, v + j);
           } else {                                           // r*h feeds convq                update.py:38-39
             const float* hp = p.h + n * Hd + (c0 - Hd);
 #pragma unroll
@@ -378,7 +384,7 @@ __global__ void __launch_bounds__(conv_threads(SUB), 1) conv_umma_kernel(const _
               const float4 h4 = __ldg(reinterpret_cast<const float4*>(hp + j));
               v[j] *= h4.x; v[j + 1] *= h4.y; v[j + 2] *= h4.z; v[j + 3] *= h4.w;
             }
-            store_split32(v, p.out_hi, p.out_lo, n * p.out_pitch + p.out_coff + (c0 - Hd), p.fmt);
+            store_split32(v, p.out_hi, p.out_lo, n * p.out_pitch + p.out_coff + (c0 - Hd), p.fmt, p.wide);
           }
         } else if (p.epilogue == AS_UEPI_GRU_Q) {            // h' = (1-z) h + z tanh(convq + cq)   update.py:39-40
           const float* zp = p.z + n * p.N + c0;
@@ -395,8 +401,8 @@ __global__ void __launch_bounds__(conv_threads(SUB), 1) conv_umma_kernel(const _
           }
           float* op = p.out_f32 + n * p.N + c0;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          store_split32(v, p.out_hi, p.out_lo, n * p.out_pitch + p.out_coff + c0, p.fmt);
+          for (int j = 0; j < 32; j += 8) as_stg256f(op + j, v + j);
+          store_split32(v, p.out_hi, p.out_lo, n * p.out_pitch + p.out_coff + c0, p.fmt, p.wide);
         } else if (p.epilogue == AS_UEPI_DISPHEAD) {         // relu(conv1) dotted with conv2's 9 taps  update.py:23-24
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -426,7 +432,7 @@ __global__ void __launch_bounds__(conv_threads(SUB), 1) conv_umma_kernel(const _
             v[j + 2] = fmaxf(v[j + 2] + b4.z, 0.f); v[j + 3] = fmaxf(v[j + 3] + b4.w, 0.f);
           }
           if (p.epilogue == AS_UEPI_MOTION && c0 + 32 == p.N) v[31] = __ldg(p.disp + n);   // cat(out, disp) update.py:92
-          store_split32(v, p.out_hi, p.out_lo, n * p.out_pitch + p.out_coff + c0, p.fmt);
+          store_split32(v, p.out_hi, p.out_lo, n * p.out_pitch + p.out_coff + c0, p.fmt, p.wide);
         }
         }
         __syncwarp();     // reconverge before the next warp-aligned tcgen05.ld
@@ -630,6 +636,11 @@ extern "C" int as_conv2d_umma(const as_conv_umma_desc* d, as_stream_t stream) {
     default: return AS_ERR_UNSUPPORTED;
   }
   if ((d->out_pitch & 7) || (d->out_coff & 7)) return AS_ERR_ALIGNMENT;
+  static const bool allow_wide = !(getenv("AS_CONV_WIDE") && getenv("AS_CONV_WIDE")[0] == '0');       // A/B knob
+  p.wide = allow_wide && !(d->out_pitch & 15) && !(d->out_coff & 15) && !(reinterpret_cast<uintptr_t>(d->out_hi) & 31) &&
+           !(reinterpret_cast<uintptr_t>(d->out_lo) & 31);
+  if (d->epilogue == AS_UEPI_GRU_ZR && ((reinterpret_cast<uintptr_t>(d->z) & 31) || (d->Cout & 15))) return AS_ERR_ALIGNMENT;
+  if (d->epilogue == AS_UEPI_GRU_Q && (reinterpret_cast<uintptr_t>(d->out_f32) & 31)) return AS_ERR_ALIGNMENT;
 
   ConvMaps maps;
   int rc;

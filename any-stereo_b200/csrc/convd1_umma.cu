@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(kThreads, 3)
 convd1_umma_kernel(const __grid_constant__ CUtensorMap tWh, const __grid_constant__ CUtensorMap tWl,
                    const float* __restrict__ disp, const float* __restrict__ bias, __nv_bfloat16* __restrict__ out_hi,
                    __nv_bfloat16* __restrict__ out_lo, int H, int W, int tiles_x, int tiles_y, int num_tiles, int pitch,
-                   int coff, int nsplit, bool f16, int out_fmt) {
+                   int coff, int nsplit, bool f16, int out_fmt, bool wide) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* act = smem;                                   // hi | lo
@@ -126,16 +126,22 @@ convd1_umma_kernel(const __grid_constant__ CUtensorMap tWh, const __grid_constan
       const int x = x0 + (row & 15), y = y0 + (row >> 4);
       if (x < W && y < H) {
         const long long o = ((long long)b * HW + (long long)y * W + x) * pitch + coff + half * 32;
+        if (wide) {                               // 32-byte aligned rows: full-sector stores (common.cuh)
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          uint32_t h[4];
-          float yv[8];
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + __ldg(bias + half * 32 + i), 0.f);
+          as_store_split32_v8(v, out_hi, out_lo, o, out_fmt);
+        } else {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) yv[i] = fmaxf(v[j + i] + __ldg(bias + half * 32 + j + i), 0.f);
+          for (int j = 0; j < 32; j += 8) {
+            uint32_t h[4];
+            float yv[8];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) h[i] = as_cvt16x2(yv[2 * i], yv[2 * i + 1], f16);
-          *reinterpret_cast<uint4*>(out_hi + o + j) = make_uint4(h[0], h[1], h[2], h[3]);
-          if (out_lo) as_store_lo8(out_lo, o + j, yv, h, out_fmt);                 // 16-bit lo or the e5m2 pair plane
+            for (int i = 0; i < 8; ++i) yv[i] = fmaxf(v[j + i] + __ldg(bias + half * 32 + j + i), 0.f);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) h[i] = as_cvt16x2(yv[2 * i], yv[2 * i + 1], f16);
+            *reinterpret_cast<uint4*>(out_hi + o + j) = make_uint4(h[0], h[1], h[2], h[3]);
+            if (out_lo) as_store_lo8(out_lo, o + j, yv, h, out_fmt);                 // 16-bit lo or the e5m2 pair plane
+          }
         }
       }
     }
@@ -176,9 +182,11 @@ extern "C" int as_convd1_umma(const float* disp, const void* w_hi, const void* w
   cudaError_t e = cudaFuncSetAttribute(convd1_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
   if (e != cudaSuccess) return (int)e;
   const int grid = nt < 3LL * sms ? (int)nt : 3 * sms;
+  const bool wide = !(out_pitch & 15) && !(out_coff & 15) && !(reinterpret_cast<uintptr_t>(out_hi) & 31) &&
+                    !(reinterpret_cast<uintptr_t>(out_lo) & 31);                       // 256-bit stores need 32-byte aligned rows
   convd1_umma_kernel<<<grid, kThreads, kSmem, as_cu(stream)>>>(tWh, tWl, disp, bias, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo,
                                                                H, W, tiles_x, tiles_y, (int)nt, out_pitch, out_coff, nsplit,
-                                                               as_operand_f16_internal() != 0, as_operand_fmt_internal());
+                                                               as_operand_f16_internal() != 0, as_operand_fmt_internal(), wide);
   AS_RETURN_IF_LAUNCH_FAILED();
   return AS_OK;
 }

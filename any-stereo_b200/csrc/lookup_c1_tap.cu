@@ -135,54 +135,6 @@ __device__ __forceinline__ void put4(uint32_t addr, float v0, float v1, float v2
   }
 }
 
-__device__ __forceinline__ void stg256(void* p, const uint32_t (&w)[8]) {      // one full 32-byte sector per lane
-  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
-               "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
-}
-// 32 consecutive output channels of one pixel (off = element offset of the first, a multiple of 32) -> the hi plane and
-// the second plane (16-bit lo, or the e5m2 pair plane of AS_FMT_F16F8: see as_store_lo8), in 32-byte stores: a 16-byte
-// store per lane leaves half-written sectors behind (measured: the output then costs 20 us instead of 10)
-template <bool kF16>
-__device__ __forceinline__ void store_row32(__nv_bfloat16* out_hi, __nv_bfloat16* out_lo, long long off, const float (&y)[32], int fmt) {
-  uint32_t h[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) h[i] = as_cvt16x2(y[2 * i], y[2 * i + 1], kF16);
-  {
-    const uint32_t a[8] = {h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]};
-    const uint32_t b[8] = {h[8], h[9], h[10], h[11], h[12], h[13], h[14], h[15]};
-    stg256(out_hi + off, a);
-    stg256(out_hi + off + 16, b);
-  }
-  if (!out_lo) return;
-  float r[32], hv[32];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    hv[2 * i] = as_widen_lo16(h[i], kF16);
-    hv[2 * i + 1] = as_widen_hi16(h[i], kF16);
-    r[2 * i] = y[2 * i] - hv[2 * i];
-    r[2 * i + 1] = y[2 * i + 1] - hv[2 * i + 1];
-  }
-  if (fmt != 2) {
-    uint32_t l[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) l[i] = as_cvt16x2(r[2 * i], r[2 * i + 1], kF16);
-    const uint32_t a[8] = {l[0], l[1], l[2], l[3], l[4], l[5], l[6], l[7]};
-    const uint32_t b[8] = {l[8], l[9], l[10], l[11], l[12], l[13], l[14], l[15]};
-    stg256(out_lo + off, a);
-    stg256(out_lo + off + 16, b);
-  } else {
-    uint8_t* bp = reinterpret_cast<uint8_t*>(out_lo) + as_x8_byte(off);
-    uint32_t a[8], b[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      a[i] = as_e5m2x4(r[4 * i] * kX8ActLoScale, r[4 * i + 1] * kX8ActLoScale, r[4 * i + 2] * kX8ActLoScale, r[4 * i + 3] * kX8ActLoScale);
-      b[i] = as_e5m2x4(hv[4 * i] * kX8ActHiScale, hv[4 * i + 1] * kX8ActHiScale, hv[4 * i + 2] * kX8ActHiScale, hv[4 * i + 3] * kX8ActHiScale);
-    }
-    stg256(bp, a);
-    stg256(bp + 64, b);
-  }
-}
-
 // byte offset of K index kidx inside row `row` of an A stage: K-block | row | swizzled byte inside the 128-byte row
 __device__ __forceinline__ uint32_t a_offset(int kidx, int row) {
   return (uint32_t)((kidx >> 6) * kABlock + row * 128) + ((((uint32_t)(kidx & 63)) << 1) ^ ((uint32_t)(row & 7) << 4));
@@ -419,7 +371,7 @@ geo_lookup_convc1_tap_kernel(const __grid_constant__ CUtensorMap tmW_hi, const _
 #ifdef AS_TAP_NOEPI                          // experiment: no output traffic
           if (__float_as_uint(v[0]) == 0x12345678u && __float_as_uint(v[31]) == 0x9abcdef0u)
 #endif
-          store_row32<kF16>(out_hi, out_lo, o + hf * 32, v, out_fmt);
+          as_store_split32_v8(v, out_hi, out_lo, o + hf * 32, out_fmt);   // 32-byte stores (common.cuh)
         }
       }
       TAP_TRACE(warp, t, 3);

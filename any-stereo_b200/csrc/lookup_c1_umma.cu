@@ -183,7 +183,7 @@ geo_lookup_convc1_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __gri
                          const C1Levels lv, int Dg, const float* __restrict__ disp, const float* __restrict__ coords,
                          const float* __restrict__ bias, __nv_bfloat16* __restrict__ out_hi,
                          __nv_bfloat16* __restrict__ out_lo, int HW, int W, int tiles_per_img, int num_tiles, int nsplit,
-                         int out_fmt) {
+                         int out_fmt, bool wide) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int kKB = k_blocks(GEO), kAStage = a_stage_bytes(GEO);
@@ -362,6 +362,12 @@ geo_lookup_convc1_kernel(const __grid_constant__ CUtensorMap tmW_hi, const __gri
         const long long o = ((long long)b * HW + p) * kNOut;
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
+          if (wide) {                              // 32-byte aligned rows: full-sector stores (common.cuh)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[hf][i] = fmaxf(v[hf][i] + __ldg(bias + hf * 32 + i), 0.f);
+            as_store_split32_v8(v[hf], out_hi, out_lo, o + hf * 32, out_fmt);
+            continue;
+          }
 #pragma unroll
           for (int jj = 0; jj < 32; jj += 8) {
             uint32_t h[4];
@@ -423,6 +429,7 @@ static int launch_lookup_convc1(bool geo, const float* const* geo_levels, int Dg
   // tensor pipe); under AS_FMT_F16F8 only its OUTPUT planes switch to the e5m2 pair encoding convc2 consumes
   const bool f16 = as_operand_f16_internal() != 0;
   const int out_fmt = as_operand_fmt_internal();
+  const bool wide = !((reinterpret_cast<uintptr_t>(out_hi) | reinterpret_cast<uintptr_t>(out_lo)) & 31u);   // 256-bit stores
 #define AS_C1_LAUNCH(LV, F, GEO)                                                                                          \
   do {                                                                                                                    \
     e = cudaFuncSetAttribute(geo_lookup_convc1_kernel<LV, F, GEO>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
@@ -430,7 +437,7 @@ static int launch_lookup_convc1(bool geo, const float* const* geo_levels, int Dg
     if (e != cudaSuccess) return (int)e;                                                                                  \
     geo_lookup_convc1_kernel<LV, F, GEO><<<grid, kThreads, smem_bytes(GEO), st>>>(                                        \
         tW_hi, tW_lo, lv, Dg, disp, coords, bias, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, HW, W, tiles_per_img,   \
-        (int)nt, nsplit, out_fmt);                                                                                        \
+        (int)nt, nsplit, out_fmt, wide);                                                                                  \
   } while (0)
   if (geo) {
     if (num_levels == 2) { if (f16) AS_C1_LAUNCH(2, true, true); else AS_C1_LAUNCH(2, false, true); }

@@ -1,4 +1,5 @@
-for env in "AS_CONV_GROUP=1" "AS_CONV_TALL=2" "AS_CONV_GROUP=0"; do
+# Experiment (GPU box): same-box A/B of convolution-kernel knobs on the headline step
+for env in "AS_CONV_WIDE=1" "AS_CONV_WIDE=0" "AS_CONV_WIDE=1" "AS_CONV_WIDE=0"; do
 echo "== $env"
 env $env python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-other-configs 2>/dev/null | tail -1 | python -c "
 import sys,json
