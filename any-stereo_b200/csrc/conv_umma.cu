@@ -356,23 +356,19 @@ __global__ void __launch_bounds__(conv_threads(SUB), 1) conv_umma_kernel(const _
         float v[32];
         umma::tmem_ld_32x32(trow + (uint32_t)c0, v);
         // the context row of the GRU epilogues is fetched while the TMEM load is in flight
-        float4 cpre[8];
+        float cpre[32];
         const bool gru = p.epilogue == AS_UEPI_GRU_ZR || p.epilogue == AS_UEPI_GRU_Q;
         if (gru && valid) {
           const float* cx = p.ctx + n * p.ctx_pitch + c0;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) cpre[j] = __ldg(reinterpret_cast<const float4*>(cx + 4 * j));
+          for (int j = 0; j < 32; j += 8) as_ldg256f(cx + j, cpre + j);      // 32-byte loads: whole sectors per lane
         }
         umma::tmem_ld_wait();
         if (valid) {
         if (p.epilogue == AS_UEPI_GRU_ZR) {
           const int Hd = p.N >> 1;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 c4 = cpre[j >> 2];
-            v[j] = sigmoidf_(v[j] + c4.x); v[j + 1] = sigmoidf_(v[j + 1] + c4.y);
-            v[j + 2] = sigmoidf_(v[j + 2] + c4.z); v[j + 3] = sigmoidf_(v[j + 3] + c4.w);
-          }
+          for (int j = 0; j < 32; ++j) v[j] = sigmoidf_(v[j] + cpre[j]);
           if (c0 < Hd) {                                     // z = sigmoid(convz + cz)      update.py:37
             float* zp = p.z + n * Hd + c0;
 #pragma unroll
@@ -380,9 +376,11 @@ __global__ void __launch_bounds__(conv_threads(SUB), 1) conv_umma_kernel(const _
           } else {                                           // r*h feeds convq                update.py:38-39
             const float* hp = p.h + n * Hd + (c0 - Hd);
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 h4 = __ldg(reinterpret_cast<const float4*>(hp + j));
-              v[j] *= h4.x; v[j + 1] *= h4.y; v[j + 2] *= h4.z; v[j + 3] *= h4.w;
+            for (int j = 0; j < 32; j += 8) {
+              float h8[8];
+              as_ldg256f(hp + j, h8);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[j + i] *= h8[i];
             }
             store_split32(v, p.out_hi, p.out_lo, n * p.out_pitch + p.out_coff + (c0 - Hd), p.fmt, p.wide);
           }
@@ -390,14 +388,12 @@ __global__ void __launch_bounds__(conv_threads(SUB), 1) conv_umma_kernel(const _
           const float* zp = p.z + n * p.N + c0;
           const float* hp = p.h + n * p.N + c0;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 c4 = cpre[j >> 2];
-            const float4 z4 = *reinterpret_cast<const float4*>(zp + j);
-            const float4 h4 = __ldg(reinterpret_cast<const float4*>(hp + j));
-            v[j] = (1.0f - z4.x) * h4.x + z4.x * tanhf(v[j] + c4.x);
-            v[j + 1] = (1.0f - z4.y) * h4.y + z4.y * tanhf(v[j + 1] + c4.y);
-            v[j + 2] = (1.0f - z4.z) * h4.z + z4.z * tanhf(v[j + 2] + c4.z);
-            v[j + 3] = (1.0f - z4.w) * h4.w + z4.w * tanhf(v[j + 3] + c4.w);
+          for (int j = 0; j < 32; j += 8) {
+            float z8[8], h8[8];
+            as_ld256f(zp + j, z8);              // z was written by the previous launch of this stream: coherent path
+            as_ldg256f(hp + j, h8);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[j + i] = (1.0f - z8[i]) * h8[i] + z8[i] * tanhf(v[j + i] + cpre[j + i]);
           }
           float* op = p.out_f32 + n * p.N + c0;
 #pragma unroll
@@ -639,8 +635,11 @@ extern "C" int as_conv2d_umma(const as_conv_umma_desc* d, as_stream_t stream) {
   static const bool allow_wide = !(getenv("AS_CONV_WIDE") && getenv("AS_CONV_WIDE")[0] == '0');       // A/B knob
   p.wide = allow_wide && !(d->out_pitch & 15) && !(d->out_coff & 15) && !(reinterpret_cast<uintptr_t>(d->out_hi) & 31) &&
            !(reinterpret_cast<uintptr_t>(d->out_lo) & 31);
-  if (d->epilogue == AS_UEPI_GRU_ZR && ((reinterpret_cast<uintptr_t>(d->z) & 31) || (d->Cout & 15))) return AS_ERR_ALIGNMENT;
-  if (d->epilogue == AS_UEPI_GRU_Q && (reinterpret_cast<uintptr_t>(d->out_f32) & 31)) return AS_ERR_ALIGNMENT;
+  if (d->epilogue == AS_UEPI_GRU_ZR || d->epilogue == AS_UEPI_GRU_Q) {      // 256-bit accesses to the fp32 state rows
+    const uintptr_t a = reinterpret_cast<uintptr_t>(d->z) | reinterpret_cast<uintptr_t>(d->h) | reinterpret_cast<uintptr_t>(d->ctx) |
+                        (d->epilogue == AS_UEPI_GRU_Q ? reinterpret_cast<uintptr_t>(d->out_f32) : 0);
+    if ((a & 31) || (d->ctx_pitch & 7) || (d->Cout & 15)) return AS_ERR_ALIGNMENT;
+  }
 
   ConvMaps maps;
   int rc;
