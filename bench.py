@@ -387,6 +387,8 @@ def run_ours(args):
         torch.cuda.synchronize()
         # per-kernel event timing needs eager launches: two more steps of the same loop with CUDA events around the lookup
         # launch and around the update block
+        step(dd, [], [])                                  # untimed: the eager path warms its own caches
+        torch.cuda.synchronize()
         events, uevents = [], []
         for _ in range(2):
             step(dd, events, uevents)
@@ -570,7 +572,7 @@ def run_ours(args):
         pass
     # second roofline: the update block (tensor-bound).  FLOPs per SURVEY.md 8(d); in the bf16x3 mode every MAC is
     # issued 3 times, so "issued" is what the tensor pipe executes; peak = measured sustained cuBLAS bf16.
-    upd_avg_us = sum(upd_us) / max(len(upd_us), 1)
+    upd_avg_us = sorted(upd_us)[len(upd_us) // 2] if upd_us else 0.0          # median: immune to a one-off stall
     upd_flops = 2.0 * (n_pix * (1847488 + 64 * 162) + n_pix / 4 * 1327104 + n_pix / 16 * 884736)
     issued = upd_flops * PASSES.get(args.engine, 1)
     try:
