@@ -93,6 +93,36 @@ __global__ void interp_split_kernel(const float* __restrict__ in, __nv_bfloat16*
   store_split4(o, hi, lo, idx * 4, fmt);
 }
 
+// 8 channels per thread: 256-bit loads of the four neighbours, one 16-byte hi store + the second plane.  (The 4-channel
+// kernel above ran at 1.5 TB/s: 7.7 M threads of ~80 dependent instructions each at config 2.)  Same arithmetic per channel.
+__global__ void __launch_bounds__(256) interp_split8_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi,
+                                                            __nv_bfloat16* __restrict__ lo, int Hi, int Wi, int Ho, int Wo, int C8,
+                                                            float sy, float sx, int fmt) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= Wo * C8) return;
+  const int xo = r / C8, c8 = r - xo * C8;
+  const int yo = blockIdx.y, b = blockIdx.z;
+  const float fy = sy * yo, fx = sx * xo;
+  const int y0 = (int)fy, x0 = (int)fx;
+  const int y1 = min(y0 + 1, Hi - 1), x1 = min(x0 + 1, Wi - 1);
+  const float ly = fy - y0, lx = fx - x0, hy = 1.0f - ly, hx = 1.0f - lx;
+  const int C = C8 * 8;
+  const float* base = in + (long long)b * Hi * Wi * C + c8 * 8;
+  float v00[8], v01[8], v10[8], v11[8], o[8];
+  as_ldg256f(base + ((long long)y0 * Wi + x0) * C, v00);
+  as_ldg256f(base + ((long long)y0 * Wi + x1) * C, v01);
+  as_ldg256f(base + ((long long)y1 * Wi + x0) * C, v10);
+  as_ldg256f(base + ((long long)y1 * Wi + x1) * C, v11);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = hy * (hx * v00[i] + lx * v01[i]) + ly * (hx * v10[i] + lx * v11[i]);
+  const long long off = ((((long long)b * Ho + yo) * Wo + xo) * C8 + c8) * 8;
+  uint32_t h[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = as_cvt16x2(o[2 * i], o[2 * i + 1], fmt != 0);
+  *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+  if (lo) as_store_lo8(lo, off, o, h, fmt);
+}
+
 __global__ void pack_weight_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi,
                                         __nv_bfloat16* __restrict__ lo, int Cout, int Cin, int T, int n_pad, int cin_pad,
                                         long long total, int fmt) {
@@ -247,6 +277,13 @@ extern "C" int as_interp_bilinear_nhwc_split(const float* in, void* hi, void* lo
   const float sy = Hout > 1 ? (float)(Hin - 1) / (float)(Hout - 1) : 0.f;
   const float sx = Wout > 1 ? (float)(Win - 1) / (float)(Wout - 1) : 0.f;
   if (B > 65535 || Hout > 65535 || (long long)Wout * (C / 4) >= (1LL << 31)) return AS_ERR_INDEX_RANGE;
+  if (!(C & 7) && !(reinterpret_cast<uintptr_t>(in) & 31)) {
+    dim3 grid8(as_ceil_div(Wout * (C / 8), 256), Hout, B);
+    interp_split8_kernel<<<grid8, 256, 0, as_cu(stream)>>>(in, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, Hin, Win, Hout, Wout,
+                                                            C / 8, sy, sx, as_operand_fmt_internal());
+    AS_RETURN_IF_LAUNCH_FAILED();
+    return AS_OK;
+  }
   dim3 grid(as_ceil_div(Wout * (C / 4), 256), Hout, B);
   interp_split_kernel<<<grid, 256, 0, as_cu(stream)>>>(in, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, Hin, Win, Hout, Wout, C / 4,
                                                        sy, sx, as_operand_fmt_internal());
