@@ -144,8 +144,49 @@ def run(family, H, W, iters=32, B=1, engines=("bf16x3", "fp16"), device="cuda", 
     return res
 
 
+def profile(family="igev", H=384, W=1248, iters=32, B=1, device="cuda"):
+    """Where one forward of the REAL reference graph spends its time with this library installed: CUDA-event time per
+    top-level child module (update_block = all iterations; 'other' = lookups, volume build, glue outside any child)."""
+    import anystereo_b200 as A
+    model, R = build_model(family, device)
+    img1, img2 = make_pair(B, H, W, device)
+    out = {"family": family, "image": [H, W], "batch": B, "iters": iters, "engine": A.get_update_engine(), "ms": {}}
+    with installed(model, R, family) as m:
+        forward(m, R, img1, img2, iters)                       # warm-up: weight packing, cudnn autotune
+        spans = {}
+        handles = []
+        for name, child in m.named_children():
+            def pre(mod, inp, name=name):
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                spans.setdefault(name, []).append([e, None])
+            def post(mod, inp, outp, name=name):
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                spans[name][-1][1] = e
+            handles.append(child.register_forward_pre_hook(pre))
+            handles.append(child.register_forward_hook(post))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        forward(m, R, img1, img2, iters)
+        e1.record()
+        torch.cuda.synchronize()
+        for h in handles:
+            h.remove()
+        total = e0.elapsed_time(e1)
+        acc = 0.0
+        for name, evs in spans.items():
+            t = sum(a.elapsed_time(b) for a, b in evs if b is not None)
+            out["ms"][name] = {"ms": round(t, 3), "calls": len(evs)}
+            acc += t
+        out["ms"]["other (lookups, volume build, glue)"] = {"ms": round(total - acc, 3), "calls": 1}
+        out["total_ms"] = round(total, 3)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--profile", action="store_true", help="per-module time of one drop-in forward instead of the EPE table")
     ap.add_argument("--family", default="both", choices=["igev", "raft", "both"])
     ap.add_argument("--size", default=None, help="HxW (default: 384x1248 for igev, 320x736 for raft; both for 'both')")
     ap.add_argument("--iters", type=int, default=32)
@@ -155,6 +196,18 @@ def main():
     a = ap.parse_args()
     if not reference_available():
         print(json.dumps({"unavailable": "reference tree not found (baseline/_ref; run oracle/install_ref.py in the build container)"}))
+        return
+    if a.profile:
+        fams = ["igev", "raft"] if a.family == "both" else [a.family]
+        res = []
+        for fam in fams:
+            H, W = (tuple(int(v) for v in a.size.split("x")) if a.size else (384, 1248))
+            r = profile(fam, H, W, a.iters, a.batch)
+            res.append(r)
+            print(json.dumps(r), flush=True)
+        if a.json:
+            with open(a.json, "w") as f:
+                json.dump(res, f, indent=1)
         return
     engines = [None if e == "default" else e for e in a.engines.split(",")]
     jobs = []
