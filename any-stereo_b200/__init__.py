@@ -13,13 +13,15 @@ Everything computes in hand-written CUDA kernels behind the C ABI of include/any
 """
 from . import _lib
 from . import corr_sampler
+from . import submodule
+from . import hotpath
 from . import update_umma
 from .geometry import CorrBlock1D, Combined_Geo_Encoding_Volume, set_corr_mode, get_corr_mode
-from .submodule import build_gwc_volume, disparity_regression, init_disparity
+from .submodule import build_gwc_volume, disparity_regression, init_disparity, gwc_corr_stem, DeferredGwcVolume
 from .update import (BasicMultiUpdateBlock, BasicMultiUpdateBlockRAFT, BasicMotionEncoder, ConvGRU, DispHead,
                      set_update_engine, get_update_engine)
 from .hotpath import (igev_iterations, raft_iterations, install_into_reference, HotLoopGraph, set_lookup_fusion,
-                      adopt_update_block, adopt_liif_up, set_graph_replay)
+                      adopt_update_block, adopt_liif_up, adopt_corr_stem, set_graph_replay)
 from .parallel import shard_pairs, allreduce_gradients, GradientAllReducer
 from . import liif
 from .liif import liif_out_multi_scale_Training, context_upsample_multiscale_train, upsample_disp
@@ -30,4 +32,5 @@ __all__ = [
     "set_corr_mode", "get_corr_mode", "set_update_engine", "get_update_engine",
     "igev_iterations", "raft_iterations", "install_into_reference", "HotLoopGraph",
     "shard_pairs", "allreduce_gradients", "GradientAllReducer",
+    "gwc_corr_stem", "adopt_corr_stem", "adopt_update_block", "adopt_liif_up", "set_graph_replay",
 ]

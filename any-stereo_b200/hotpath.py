@@ -8,6 +8,7 @@ from __future__ import annotations
 import os
 
 import torch
+import torch.nn as nn
 
 from . import _lib as L
 from .geometry import CorrBlock1D, Combined_Geo_Encoding_Volume
@@ -266,6 +267,79 @@ def install_into_reference(ref_igev_module=None, ref_raft_module=None):
         ref_raft_module.CorrBlock1D = CorrBlock1D
         from .liif import context_upsample_multiscale_train      # prune_raft_stereo.py:227
         ref_raft_module.context_upsample_multiscale_train = context_upsample_multiscale_train
+
+
+class _PendingStem:
+    """corr_stem applied to a DeferredGwcVolume, still not run: corr_feature_att launches the fused kernel."""
+
+    def __init__(self, vol, stem):
+        self.vol, self.stem = vol, stem
+
+    def run(self, att=None):
+        from .submodule import gwc_corr_stem
+        v, bn = self.vol, self.stem.bn
+        scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+        shift = bn.bias - bn.running_mean * scale
+        return gwc_corr_stem(v.left, v.right, v.maxdisp, v.num_groups, self.stem.conv.weight, scale, shift, 0.01, att)
+
+
+class CorrStem(nn.Module):
+    """The reference's ``corr_stem`` (submodule.BasicConv: Conv3d + BatchNorm3d + LeakyReLU, continuous_IGEVstereo.py:172)
+    around the SAME submodules (state_dict keys unchanged).  A DeferredGwcVolume input is handed on unevaluated when the
+    fused kernel applies (eval-mode BatchNorm, no gradient requested); anything else takes the reference's arithmetic."""
+
+    def __init__(self, ref):
+        super().__init__()
+        self.conv, self.bn, self.relu, self.use_bn = ref.conv, ref.bn, ref.relu, ref.use_bn
+
+    def _fusable(self):
+        c = self.conv
+        grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        return (isinstance(c, nn.Conv3d) and c.bias is None and tuple(c.weight.shape) == (8, 8, 3, 3, 3)
+                and tuple(c.stride) == (1, 1, 1) and tuple(c.padding) == (1, 1, 1) and tuple(c.dilation) == (1, 1, 1)
+                and self.use_bn and self.relu and not self.bn.training and self.bn.affine
+                and self.bn.running_mean is not None and not grad)
+
+    def forward(self, x):
+        from .submodule import DeferredGwcVolume
+        if isinstance(x, DeferredGwcVolume):
+            if self._fusable():
+                return _PendingStem(x, self)
+            x = x.materialize()
+        x = self.conv(x)                                  # submodule.py:26-32
+        if self.use_bn:
+            x = self.bn(x)
+        if self.relu:
+            x = nn.functional.leaky_relu(x)
+        return x
+
+
+class CorrFeatureAtt(nn.Module):
+    """The reference's ``corr_feature_att`` (submodule.FeatureAtt, :328-341) around the same ``feat_att`` stack; multiplies a
+    pending corr_stem inside the fused kernel, a tensor like the reference does."""
+
+    def __init__(self, ref):
+        super().__init__()
+        self.feat_att = ref.feat_att
+
+    def forward(self, cv, feat):
+        feat_att = self.feat_att(feat)
+        if isinstance(cv, _PendingStem):
+            return cv.run(torch.sigmoid(feat_att))
+        return torch.sigmoid(feat_att.unsqueeze(2)) * cv
+
+
+def adopt_corr_stem(model, ref_igev_module):
+    """fuse build_gwc_volume with corr_stem's 3-D convolution (+ BatchNorm + LeakyReLU + the FeatureAtt
+    multiply) for ``model`` (a continuous_IGEVStereo): swaps ``model.corr_stem`` / ``model.corr_feature_att`` for modules
+    around the same parameters and rebinds the module-level ``build_gwc_volume`` to the deferring variant.  Every model
+    built from ``ref_igev_module`` must be adopted (a plain corr_stem cannot take a DeferredGwcVolume).  Training
+    (gradients requested, or BatchNorm in train mode) falls back to the unfused operators automatically."""
+    from .submodule import build_gwc_volume_deferred
+    model.corr_stem = CorrStem(model.corr_stem)
+    model.corr_feature_att = CorrFeatureAtt(model.corr_feature_att)
+    ref_igev_module.build_gwc_volume = build_gwc_volume_deferred
+    return model
 
 
 def adopt_update_block(ref_update_block, family="igev"):

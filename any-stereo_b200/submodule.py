@@ -58,6 +58,62 @@ def build_gwc_volume(refimg_fea, targetimg_fea, maxdisp, num_groups):
     return vol if dt == torch.float32 else vol.to(dt)
 
 
+class DeferredGwcVolume:
+    """(left, right, maxdisp, num_groups) of one build_gwc_volume call that has not run yet: its consumer (the adopted
+    ``corr_stem`` / ``corr_feature_att`` pair, hotpath.adopt_corr_stem) evaluates it fused with the first 3-D convolution
+    (SURVEY 8(f)-3), so the correlation volume never reaches HBM.  ``materialize()`` is the plain volume."""
+
+    def __init__(self, left, right, maxdisp, num_groups):
+        self.left, self.right, self.maxdisp, self.num_groups = left, right, int(maxdisp), int(num_groups)
+        B, _, H, W = left.shape
+        self.shape = (B, self.num_groups, self.maxdisp, H, W)
+        self.dtype, self.device = left.dtype, left.device
+
+    def materialize(self):
+        return build_gwc_volume(self.left, self.right, self.maxdisp, self.num_groups)
+
+
+def build_gwc_volume_deferred(refimg_fea, targetimg_fea, maxdisp, num_groups):
+    """build_gwc_volume for models whose corr_stem has been adopted: returns a DeferredGwcVolume whenever the fused kernel
+    can take it (8 groups, maxdisp <= 48, no gradient requested), the volume itself otherwise."""
+    needs_grad = torch.is_grad_enabled() and (refimg_fea.requires_grad or targetimg_fea.requires_grad)
+    if (needs_grad or num_groups != 8 or maxdisp > 48 or refimg_fea.dim() != 4 or not refimg_fea.is_cuda
+            or refimg_fea.shape != targetimg_fea.shape or refimg_fea.shape[1] % 8):
+        return build_gwc_volume(refimg_fea, targetimg_fea, maxdisp, num_groups)
+    return DeferredGwcVolume(refimg_fea, targetimg_fea, maxdisp, num_groups)
+
+
+def gwc_corr_stem(refimg_fea, targetimg_fea, maxdisp, num_groups, conv_weight, scale, shift, negative_slope=0.01, att=None):
+    """build_gwc_volume -> Conv3d(G, G, 3, 1, 1, bias=False) -> per-channel affine (eval BatchNorm3d) -> LeakyReLU
+    [-> * att[:, :, None]] in ONE kernel (continuous_IGEVstereo.py:262-264; submodule.py:6-32, 253-271, 328-341).
+    Forward only.  refimg_fea/targetimg_fea [B,C,H,W]; conv_weight [G,G,3,3,3]; scale/shift [G]; att [B,G,H,W] or None."""
+    if refimg_fea.shape != targetimg_fea.shape or refimg_fea.dim() != 4:
+        raise RuntimeError("refimg_fea/targetimg_fea must both be [B,C,H,W]")
+    B, C, H, W = refimg_fea.shape
+    assert C % num_groups == 0  # submodule.py:255
+    L.require_cuda(refimg_fea, "refimg_fea", contiguous=False)
+    L.require_cuda(targetimg_fea, "targetimg_fea", contiguous=False)
+    if tuple(conv_weight.shape) != (num_groups, num_groups, 3, 3, 3):
+        raise RuntimeError("conv_weight must be [G,G,3,3,3]")
+    dt = refimg_fea.dtype
+    dev = refimg_fea.device
+    left = refimg_fea.detach().float().contiguous()
+    right = targetimg_fea.detach().float().contiguous()
+    w = conv_weight.detach().float().contiguous()
+    sc = scale.detach().float().contiguous()
+    sh = shift.detach().float().contiguous()
+    a = None
+    if att is not None:
+        if tuple(att.shape) != (B, num_groups, H, W):
+            raise RuntimeError("att must be [B,G,H,W]")
+        a = att.detach().float().contiguous()
+    out = torch.empty((B, num_groups, int(maxdisp), H, W), device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        L.call("as_gwc_corr_stem_fwd", left.data_ptr(), right.data_ptr(), w.data_ptr(), sc.data_ptr(), sh.data_ptr(), L.ptr(a),
+               out.data_ptr(), B, C, H, W, int(maxdisp), int(num_groups), float(negative_slope), L.stream_ptr())
+    return out if dt == torch.float32 else out.to(dt)
+
+
 def disparity_regression(x, maxdisp):
     """submodule.py:321-325: sum_d x[:, d] * d  -> [B,1,H,W]."""
     assert len(x.shape) == 4

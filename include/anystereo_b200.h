@@ -178,6 +178,15 @@ int as_gwc_build_bwd(const float* g_out, const float* left, const float* right,
                      float* g_left, float* g_right,
                      int B, int C, int H, int W, int maxdisp, int G, as_stream_t stream);
 
+/* build_gwc_volume fused with corr_stem = Conv3d(G,G,3,1,1,bias=False) + BatchNorm3d (eval: per-channel
+ * affine) + LeakyReLU, and optionally FeatureAtt's multiply (continuous_IGEVstereo.py:262-264; submodule.py:6-32,328-341):
+ *   out[b,co,d,y,x] = att[b,co,y,x] * lrelu(scale[co] * conv3d(gwc)[b,co,d,y,x] + shift[co]),  gwc as in as_gwc_build_fwd.
+ * conv_weight [G][G][3][3][3] (nn.Conv3d layout), scale/shift [G], att [B][G][H][W] or NULL (= 1), out [B][G][maxdisp][H][W],
+ * all float32.  The correlation volume itself never reaches HBM.  G must be 8 and maxdisp <= 48 (AS_ERR_UNSUPPORTED). */
+int as_gwc_corr_stem_fwd(const float* left, const float* right, const float* conv_weight, const float* scale,
+                         const float* shift, const float* att, float* out,
+                         int B, int C, int H, int W, int maxdisp, int G, float negative_slope, as_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * a8-a11  per-iteration update block  (models/(all families)/update.py:16-41,73-136)
  *

@@ -184,3 +184,44 @@ def test_inference_mode_and_invalidate_weights():
         d3, _ = A.igev_iterations(m, cu(c["f1"]), cu(c["f2"]), cu(c["geo"]), [cu(t) for t in c["net"]],
                                   [[cu(t) for t in l] for l in c["inp"]], cu(c["init_disp"]), 1)
     assert abs(float((d2 - d3).mean()) - 1.0) < 1e-4
+
+
+@needs_ref
+def test_dropin_fused_corr_stem_matches_reference():
+    """SURVEY 8(f)-3 inside the REAL graph: build_gwc_volume + corr_stem + corr_feature_att through adopt_corr_stem (one
+    fused kernel, the GWC volume never in HBM) vs the unmodified model: same final disparity as the plain drop-in; the
+    state_dict keys of the adopted modules are the reference's; train() mode falls back to the unfused operators."""
+    import anystereo_b200 as A
+    D = dropin
+    model, R = D.build_model("igev", "cuda")
+    img1, img2 = D.make_pair(1, 320, 736, "cuda")
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        keys = set(model.state_dict().keys())
+        ref = D.forward(model, R, img1, img2, 12)
+        with D.installed(model, R, "igev") as m:
+            plain = D.forward(m, R, img1, img2, 12)
+        n0 = A._lib.launch_count
+        with D.installed(model, R, "igev", fuse_corr_stem=True) as m:
+            assert set(m.state_dict().keys()) == keys
+            fused = D.forward(m, R, img1, img2, 12)
+            m.train()
+            m.freeze_bn()
+            with torch.no_grad():
+                pending = m.corr_stem(A.DeferredGwcVolume(torch.randn(1, 96, 8, 16, device="cuda"),
+                                                          torch.randn(1, 96, 8, 16, device="cuda"), 48, 8))
+            # the reference's freeze_bn() only reaches BatchNorm2d: corr_stem's BatchNorm3d is in train mode, so the adopted
+            # module takes the reference's arithmetic (batch statistics) instead of the fused eval-mode kernel
+            assert torch.is_tensor(pending) and pending.shape == (1, 8, 48, 8, 16)
+            x = torch.randn(1, 96, 8, 16, device="cuda", requires_grad=True)
+            v = R.igev_module.build_gwc_volume(x, x, 48, 8)
+            assert torch.is_tensor(v) and v.requires_grad                 # a gradient is requested: the plain operator
+            m.eval()
+        assert R.igev_module.build_gwc_volume is not A.submodule.build_gwc_volume_deferred    # restored
+        e_plain = float((plain - ref).abs().mean())
+        e_fused = float((fused - ref).abs().mean())
+        assert e_fused < 1e-3 and abs(e_fused - e_plain) < 5e-4, (e_plain, e_fused)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32

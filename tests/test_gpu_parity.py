@@ -411,3 +411,31 @@ def test_model_level_init_disparity(A, golden):
     torch.cuda.synchronize()
     ref = torch.from_numpy(g["init_disp"])
     assert float((disp.cpu() - ref).abs().max()) < 1e-4 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("shape", [(1, 96, 5, 45, 48), (2, 96, 7, 32, 20), (1, 48, 3, 70, 48), (1, 96, 4, 9, 13)])
+@pytest.mark.parametrize("with_att", [False, True])
+def test_gwc_corr_stem_matches_unfused(A, shape, with_att):
+    """build_gwc_volume + Conv3d(8,8,3) + eval BatchNorm3d + LeakyReLU (+ FeatureAtt multiply) in one kernel
+    against the same chain in torch (fp64) over the oracle's volume; ragged widths, maxdisp > W, 6 / 12 channels per group."""
+    B, C, H, W, D = shape
+    g = torch.Generator().manual_seed(H * 100 + W)
+    f1 = torch.randn(B, C, H, W, generator=g)
+    f2 = torch.randn(B, C, H, W, generator=g)
+    w = torch.randn(8, 8, 3, 3, 3, generator=g) * 0.2
+    scale = torch.rand(8, generator=g) + 0.5
+    shift = torch.randn(8, generator=g) * 0.3
+    att = torch.sigmoid(torch.randn(B, 8, H, W, generator=g)) if with_att else None
+    vol = O.gwc_volume(f1, f2, D, 8).double()
+    ref = torch.nn.functional.conv3d(vol, w.double(), padding=1)
+    ref = ref * scale.double().view(1, 8, 1, 1, 1) + shift.double().view(1, 8, 1, 1, 1)
+    ref = torch.nn.functional.leaky_relu(ref, 0.01)
+    if with_att:
+        ref = ref * att.double().unsqueeze(2)
+    got = A.gwc_corr_stem(f1.cuda(), f2.cuda(), D, 8, w.cuda(), scale.cuda(), shift.cuda(), 0.01,
+                          att.cuda() if with_att else None)
+    assert got.shape == (B, 8, D, H, W)
+    assert rel(got, ref.float()) < 1e-5
+    # unsupported shapes are refused loudly (the deferring build_gwc_volume never produces them)
+    with pytest.raises(RuntimeError):
+        A.gwc_corr_stem(f1.cuda(), f2.cuda(), 64, 8, w.cuda(), scale.cuda(), shift.cuda())

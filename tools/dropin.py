@@ -63,16 +63,20 @@ def build_model(family, device, seed=0, **over):
 
 
 @contextlib.contextmanager
-def installed(model, R, family):
-    """Rebind the reference's names to this library for the duration of the block."""
+def installed(model, R, family, fuse_corr_stem=False):
+    """Rebind the reference's names to this library for the duration of the block.
+    fuse_corr_stem (IGEV): also adopt corr_stem / corr_feature_att (build_gwc_volume fused with them)."""
     import anystereo_b200 as A
     mod = R.igev_module if family == "igev" else R.raft_module
     names = ["Combined_Geo_Encoding_Volume", "build_gwc_volume", "context_upsample_multiscale_train", "CorrBlock1D"]
     saved = {n: getattr(mod, n) for n in names if hasattr(mod, n)}
     ub, lu = model.update_block, model.liif_up
+    stem = (model.corr_stem, model.corr_feature_att) if family == "igev" else None
     try:
         if family == "igev":
             A.install_into_reference(ref_igev_module=mod)
+            if fuse_corr_stem:
+                A.adopt_corr_stem(model, mod)
         else:
             A.install_into_reference(ref_raft_module=mod)
         model.update_block = A.adopt_update_block(ub, family)
@@ -83,6 +87,8 @@ def installed(model, R, family):
         for n, v in saved.items():
             setattr(mod, n, v)
         model.update_block, model.liif_up = ub, lu
+        if stem is not None:
+            model.corr_stem, model.corr_feature_att = stem
 
 
 def forward(model, R, img1, img2, iters, scale=1.0):

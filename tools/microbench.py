@@ -198,6 +198,29 @@ def main():
         if a.json:
             json.dump(res, open(a.json, "w"), indent=1)
         return
+    if a.only == "stem":
+        # build_gwc_volume + corr_stem (Conv3d 8->8 + eval BatchNorm3d + LeakyReLU) + FeatureAtt multiply fused;
+        # bytes = the two feature maps read once + the stem output written once (the GWC volume is never stored)
+        fl = torch.randn(B, 96, H, W, device=dev) * 0.3
+        fr = torch.randn(B, 96, H, W, device=dev) * 0.3
+        wst = torch.randn(8, 8, 3, 3, 3, device=dev) * 0.2
+        sc, sh = torch.rand(8, device=dev) + 0.5, torch.randn(8, device=dev) * 0.1
+        att = torch.sigmoid(torch.randn(B, 8, H, W, device=dev))
+        alg = 4 * (2 * B * 96 * H * W + B * 8 * Dg * H * W + B * 8 * H * W)
+        med, best = timeit(lambda: A.gwc_corr_stem(fl, fr, Dg, 8, wst, sc, sh, 0.01, att))
+        rec("gwc_corr_stem_fused", med, best, alg)
+        def chain():
+            v = A.build_gwc_volume(fl, fr, Dg, 8)
+            v = torch.nn.functional.conv3d(v, wst, padding=1)
+            v = torch.nn.functional.leaky_relu(v * sc.view(1, 8, 1, 1, 1) + sh.view(1, 8, 1, 1, 1), 0.01)
+            return v * att.unsqueeze(2)
+        for tf32 in (True, False):
+            torch.backends.cudnn.allow_tf32 = tf32
+            med, best = timeit(chain)
+            rec("UNFUSED_gwc_kernel_then_torch_conv3d_affine_lrelu_mul_%s" % ("tf32" if tf32 else "fp32"), med, best, alg)
+        if a.json:
+            json.dump(res, open(a.json, "w"), indent=1)
+        return
     if a.only == "lookup":
         blk = A.Combined_Geo_Encoding_Volume(f1, f2, gwc, num_levels=2, radius=4)
         coords = torch.arange(W, device=dev, dtype=torch.float32).reshape(1, 1, W, 1).repeat(B, H, 1, 1)
