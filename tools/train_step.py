@@ -131,7 +131,7 @@ def main():
     ap.add_argument("--iters", type=int, default=16)       # train_iters, train_continuous_IGEV.py:297
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--no-overlap", action="store_true")
-    ap.add_argument("--engine", default="fp32", choices=["fp32", "bf16x3", "bf16", "fp16"],
+    ap.add_argument("--engine", default="fp32", choices=["fp32", "bf16x3", "bf16", "fp16", "f16f8"],
                     help="update-block engine: fp32 = CUDA cores; others = forward, data and weight gradients on tcgen05")
     ap.add_argument("--h", type=int, default=80)
     ap.add_argument("--w", type=int, default=184)
