@@ -101,6 +101,9 @@ SIGNATURES = {
     "as_isu_affinity": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp]),
     "as_liif_query": (_i, [C.POINTER(LiifQueryDesc), _vp]),
     "as_context_upsample_multiscale": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "as_context_upsample_multiscale_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _ll, _vp]),
+    "as_nearest_gather_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _ll, _vp]),
+    "as_nearest_gather_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _ll, _vp]),
     "as_init_disparity": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "as_disparity_regression": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "as_convd1_umma": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),

@@ -71,26 +71,102 @@ def _isu_affinity_torch(x):
     return torch.where(a < 0, torch.zeros_like(a), a)    # `affinity[affinity < 0] = 0` (liif.py:446): the gradient passes at a == 0
 
 
+class _NearestGather(torch.autograd.Function):
+    """out[b,q,:] = src[b, iy(q), ix(q), :] for a pixel-major CUDA source [B,h,w,C]; adjoint by vector reductions."""
+
+    @staticmethod
+    def forward(ctx, src, coord):
+        B, h, w, Cc = src.shape
+        Q = coord.shape[1]
+        src = src.contiguous()
+        coord = coord.detach().float().contiguous()
+        out = torch.empty((B, Q, Cc), device=src.device, dtype=torch.float32)
+        with torch.cuda.device(src.device):
+            L.call("as_nearest_gather_fwd", src.data_ptr(), coord.data_ptr(), out.data_ptr(), B, h, w, Cc, Q, L.stream_ptr())
+        ctx.save_for_backward(coord)
+        ctx.dims = (B, h, w, Cc, Q)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (coord,) = ctx.saved_tensors
+        B, h, w, Cc, Q = ctx.dims
+        g = g.contiguous()
+        gsrc = torch.empty((B, h, w, Cc), device=g.device, dtype=torch.float32)
+        with torch.cuda.device(g.device):
+            L.call("as_nearest_gather_bwd", g.data_ptr(), coord.data_ptr(), gsrc.data_ptr(), B, h, w, Cc, Q, L.stream_ptr())
+        return gsrc, None
+
+
+class _ContextUpsample(torch.autograd.Function):
+    """context_upsample_multiscale_train (submodule.py:357-372) with its adjoint as kernels."""
+
+    @staticmethod
+    def forward(ctx, disp_low, up_weights, coord):
+        B, _, h, w = disp_low.shape
+        Q = coord.shape[1]
+        d, u, c = disp_low.detach().float().contiguous(), up_weights.detach().float().contiguous(), coord.detach().float().contiguous()
+        out = torch.empty((B, Q), device=d.device, dtype=torch.float32)
+        with torch.cuda.device(d.device):
+            L.call("as_context_upsample_multiscale", d.data_ptr(), u.data_ptr(), c.data_ptr(), out.data_ptr(), B, h, w, Q,
+                   L.stream_ptr())
+        ctx.save_for_backward(d, u, c)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        d, u, c = ctx.saved_tensors
+        B, _, h, w = d.shape
+        Q = c.shape[1]
+        g = g.contiguous().float()
+        gd = torch.empty_like(d) if ctx.needs_input_grad[0] else None
+        gu = torch.empty_like(u) if ctx.needs_input_grad[1] else None
+        with torch.cuda.device(d.device):
+            L.call("as_context_upsample_multiscale_bwd", d.data_ptr(), u.data_ptr(), c.data_ptr(), g.data_ptr(), L.ptr(gd),
+                   L.ptr(gu), B, h, w, Q, L.stream_ptr())
+        return gd, gu, None
+
+
 def _logits_torch(module, feats, coord):
-    """liif_out_multi_scale_Training.forward (liif.py:652-678) in differentiable ops -> [B, 9, Q]."""
-    latent = []
+    """liif_out_multi_scale_Training.forward (liif.py:652-678), differentiable -> [B, 9, Q].
+
+    The first Linear is applied at SOURCE resolution (P = W1_slice . [feat | affinity], exact: the layer is linear and the
+    query picks single pixels), so a query gathers one 128-vector per feature map instead of 228 inputs and a 228x128
+    product; on CUDA the gather and its adjoint are kernels (csrc/liif_train.cu) -- the ATen advanced-indexing gather of
+    [B,Q,228] with its sort-based index_put adjoint was 2/3 of a training step through the real graph.  The rest
+    (affinity features, the three small Linears) stays in ATen ops and autograd."""
+    lin = module.imnet.layers[0]
+    W1, b1 = lin.weight.float(), lin.bias.float()
+    y1 = None
+    off = 0
     for f in feats:
         f = f.float()
         sf = torch.cat([f, _isu_affinity_torch(f)], dim=1)
         B, Cc, h, w = sf.shape
+        Wf, Wr = W1[:, off:off + Cc], W1[:, off + Cc:off + Cc + 2]
+        off += Cc + 2
         iy, ix = _nearest_index(coord[:, :, 0], h), _nearest_index(coord[:, :, 1], w)
-        bidx = torch.arange(B, device=sf.device).view(B, 1).expand_as(iy)
-        q = sf[bidx, :, iy, ix]                                                          # [B,Q,C+8]
         rel = torch.stack([(coord[:, :, 0].float() - _coord_axis(h, sf.device)[iy]) * h,
-                           (coord[:, :, 1].float() - _coord_axis(w, sf.device)[ix]) * w], dim=-1)
-        latent += [q, rel]
-    z = torch.cat(latent, dim=-1)
-    B, Q, _ = z.shape
-    return module.imnet.layers(z.reshape(B * Q, -1)).reshape(B, Q, -1).permute(0, 2, 1).contiguous()
+                           (coord[:, :, 1].float() - _coord_axis(w, sf.device)[ix]) * w], dim=-1)      # [B,Q,2]
+        P = torch.einsum("bchw,oc->bhwo", sf, Wf)                                     # [B,h,w,128] pixel-major
+        if P.is_cuda:
+            g = _NearestGather.apply(P, coord)
+        else:
+            bidx = torch.arange(B, device=sf.device).view(B, 1).expand_as(iy)
+            g = P[bidx, iy, ix]                                                       # [B,Q,128]
+        t = g + rel @ Wr.t()
+        y1 = t if y1 is None else y1 + t
+    assert off == W1.shape[1], (off, tuple(W1.shape))
+    y1 = y1 + b1
+    B, Q, _ = y1.shape
+    z = module.imnet.layers[1:](y1.reshape(B * Q, -1))
+    return z.reshape(B, Q, -1).permute(0, 2, 1).contiguous()
 
 
 def _context_upsample_torch(disp_low, up_weights, hr_coord):
-    """context_upsample_multiscale_train (submodule.py:357-372) in differentiable ops -> [B, Q]."""
+    """context_upsample_multiscale_train (submodule.py:357-372), differentiable -> [B, Q]."""
+    if disp_low.is_cuda:
+        return _ContextUpsample.apply(disp_low, up_weights, hr_coord)
     B, _, h, w = disp_low.shape
     iy, ix = _nearest_index(hr_coord[:, :, 0], h), _nearest_index(hr_coord[:, :, 1], w)
     pad = torch.nn.functional.pad(disp_low[:, 0].float(), (1, 1, 1, 1))

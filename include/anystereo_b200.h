@@ -438,6 +438,21 @@ int as_liif_query(const as_liif_query_desc* desc, as_stream_t stream);
 int as_context_upsample_multiscale(const float* disp_low, const float* up_weights, const float* hr_coord, float* out,
                                    int B, int h, int w, int Q, as_stream_t stream);
 
+/* Adjoint of the above: g_weights [B,9,Q] = g_out * neighbour, g_disp [B,1,h,w] += g_out * weight (either may be NULL).
+ * g_disp is zeroed by the call. */
+int as_context_upsample_multiscale_bwd(const float* disp_low, const float* up_weights, const float* hr_coord,
+                                       const float* g_out, float* g_disp, float* g_weights,
+                                       int B, int h, int w, long long Q, as_stream_t stream);
+/* The upsampler's feature query in TRAINING (liif.py:108-137 liif_feat, nearest source pixel of every query) on a
+ * pixel-major source [B,h,w,C] (C % 4 == 0): out[b,q,:] = src[b, iy(q), ix(q), :] with the reference's index convention
+ * (grid_sample nearest, align_corners=False, after the clamp of liif.py:118); hr_coord [B,Q,2] = (y, x) in [-1,1].
+ * The adjoint zeroes g_src and accumulates with vector fp32 reductions (summation order not deterministic, like the
+ * reference's own index adjoints). */
+int as_nearest_gather_fwd(const float* src, const float* hr_coord, float* out, int B, int h, int w, int C, long long Q,
+                          as_stream_t stream);
+int as_nearest_gather_bwd(const float* g_out, const float* hr_coord, float* g_src, int B, int h, int w, int C, long long Q,
+                          as_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * SURVEY 8(f)-3 (first half)  initial-disparity head before the loop
  * (continuous_IGEVstereo.py:267-268: softmax over D of Conv3d(G->1, 3x3x3, pad 1, no bias)(geo_encoding_volume),

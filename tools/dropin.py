@@ -190,8 +190,72 @@ def profile(family="igev", H=384, W=1248, iters=32, B=1, device="cuda"):
     return out
 
 
+def train_step_time(H=320, W=736, iters=16, B=4, steps=4, device="cuda"):
+    """Config-5 structure through the REAL reference graph (train() mode, frozen BatchNorm2d, sequence loss over every
+    iteration's upsampled disparity, backward): ms per forward+backward for the reference as shipped (its defaults: TF32
+    convolutions allowed) and with this library installed, plus the upsampler's share of the drop-in forward."""
+    import anystereo_b200 as A
+    model, R = build_model("igev", device)
+    img1, img2 = make_pair(B, H, W, device)
+    hr = R.make_coord([H, W]).to(device)[None].expand(B, -1, -1).contiguous()
+    sc = torch.ones(B, 1, device=device)
+    gt = torch.rand(B, 1, H * W, device=device) * 40.0
+    out = {"image": [H, W], "batch": B, "iters": iters, "engine": A.get_update_engine()}
+
+    def step(m, spans=None):
+        m.zero_grad(set_to_none=True)
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record()
+        init_disp, preds = m(img1, img2, iters=iters, test_mode=False, hr_coord=hr, scale=sc)
+        loss = sum(0.9 ** (len(preds) - 1 - i) * (p - gt).abs().mean() for i, p in enumerate(preds)) + init_disp.abs().mean()
+        e[1].record()
+        loss.backward()
+        e[2].record()
+        torch.cuda.synchronize()
+        return e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]), float(loss.detach())
+
+    def run(m, tag):
+        m.train()
+        m.freeze_bn()
+        res = [step(m) for _ in range(steps)]
+        res = res[1:]                                    # first step: autotune / weight packing
+        out[tag] = {"forward_ms": round(sorted(r[0] for r in res)[len(res) // 2], 2),
+                    "backward_ms": round(sorted(r[1] for r in res)[len(res) // 2], 2), "loss": res[-1][2],
+                    "peak_mem_GB": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)}
+        m.eval()
+
+    run(model, "reference_as_shipped")
+    torch.cuda.reset_peak_memory_stats()
+    with installed(model, R, "igev") as m:
+        run(m, "dropin")
+        # share of the upsampler (differentiable ATen formulation in training) in the drop-in forward
+        spans = []
+        lu = m.liif_up
+
+        def pre(mod, inp):
+            a = torch.cuda.Event(enable_timing=True)
+            a.record()
+            spans.append([a, None])
+
+        def post(mod, inp, outp):
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            spans[-1][1] = b
+        h1, h2 = lu.register_forward_pre_hook(pre), lu.register_forward_hook(post)
+        m.train()
+        m.freeze_bn()
+        step(m)
+        h1.remove()
+        h2.remove()
+        m.eval()
+        out["dropin"]["liif_up_forward_ms_total"] = round(sum(a.elapsed_time(b) for a, b in spans if b is not None), 2)
+        out["dropin"]["liif_up_calls"] = len(spans)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--train", action="store_true", help="time a training step through the real graph (reference vs drop-in)")
     ap.add_argument("--profile", action="store_true", help="per-module time of one drop-in forward instead of the EPE table")
     ap.add_argument("--family", default="both", choices=["igev", "raft", "both"])
     ap.add_argument("--size", default=None, help="HxW (default: 384x1248 for igev, 320x736 for raft; both for 'both')")
@@ -202,6 +266,13 @@ def main():
     a = ap.parse_args()
     if not reference_available():
         print(json.dumps({"unavailable": "reference tree not found (baseline/_ref; run oracle/install_ref.py in the build container)"}))
+        return
+    if a.train:
+        r = train_step_time(B=a.batch if a.batch > 1 else 4, iters=min(a.iters, 16))
+        print(json.dumps(r), flush=True)
+        if a.json:
+            with open(a.json, "w") as f:
+                json.dump(r, f, indent=1)
         return
     if a.profile:
         fams = ["igev", "raft"] if a.family == "both" else [a.family]
