@@ -102,6 +102,8 @@ SIGNATURES = {
     "as_liif_query": (_i, [C.POINTER(LiifQueryDesc), _vp]),
     "as_context_upsample_multiscale": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "as_context_upsample_multiscale_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _ll, _vp]),
+    "as_liif_layer1_fwd": (_i, [_i, _pp, _pp, _ip, _ip, _vp, _vp, _vp, _i, _i, _ll, _vp]),
+    "as_liif_layer1_bwd": (_i, [_i, _pp, _pp, _ip, _ip, _vp, _vp, _vp, _pp, _pp, _vp, _i, _i, _ll, _vp]),
     "as_nearest_gather_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _ll, _vp]),
     "as_nearest_gather_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _ll, _vp]),
     "as_init_disparity": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),

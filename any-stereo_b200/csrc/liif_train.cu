@@ -70,7 +70,158 @@ __global__ void __launch_bounds__(256) context_upsample_bwd_kernel(const float* 
   }
 }
 
+// ---- first MLP layer of the upsampler in training, everything after the source-resolution product fused:
+//   h1[b,q,:] = relu( sum_m ( P_m[b, iy_m(q), ix_m(q), :] + rel_m(q) . Wr_m ) + b1 )       (liif.py:108-137, 652-678)
+// rel_m = (coord - centre of the picked source pixel) * (h_m, w_m): the relative-coordinate inputs of the reference.
+struct L1Maps {
+  const float* P[3];       // [B][h][w][C] source-resolution first-layer products
+  const float* Wr[3];      // [2][C]: the two weight columns of the relative coordinates, transposed
+  float* gP[3];            // adjoint targets (zeroed by the launcher)
+  float* gWr[3];           // [2][C] accumulators (zeroed by the launcher)
+  int h[3], w[3];
+  int M;
+};
+
+__device__ __forceinline__ float axis_centre(int i, int n) {      // make_coord (liif.py:32-45): -1 + (2 i + 1) / n
+  const float r = 1.0f / (float)n;
+  return -1.0f + r + (2.0f * r) * (float)i;
+}
+
+// thread = (query, 4 channels)
+__global__ void __launch_bounds__(256) liif_layer1_fwd_kernel(const L1Maps mp, const float* __restrict__ coord,
+                                                              const float* __restrict__ b1, float4* __restrict__ out, int C4,
+                                                              long long Q, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long bq = i / C4;
+  const int c4 = (int)(i - bq * C4);
+  const long long b = bq / Q;
+  const float cy = __ldg(coord + bq * 2), cx = __ldg(coord + bq * 2 + 1);
+  float4 acc = __ldg(reinterpret_cast<const float4*>(b1) + c4);
+#pragma unroll
+  for (int m = 0; m < 3; ++m) {
+    if (m < mp.M) {
+      const int h = mp.h[m], w = mp.w[m];
+      const int iy = nearest_index(cy, h), ix = nearest_index(cx, w);
+      const float ry = (cy - axis_centre(iy, h)) * (float)h, rx = (cx - axis_centre(ix, w)) * (float)w;
+      const float4 p = __ldg(reinterpret_cast<const float4*>(mp.P[m]) + ((b * h + iy) * w + ix) * C4 + c4);
+      const float4 wy = __ldg(reinterpret_cast<const float4*>(mp.Wr[m]) + c4);
+      const float4 wx = __ldg(reinterpret_cast<const float4*>(mp.Wr[m]) + C4 + c4);
+      acc.x += p.x + ry * wy.x + rx * wx.x;
+      acc.y += p.y + ry * wy.y + rx * wx.y;
+      acc.z += p.z + ry * wy.z + rx * wx.z;
+      acc.w += p.w + ry * wy.w + rx * wx.w;
+    }
+  }
+  out[i] = make_float4(fmaxf(acc.x, 0.f), fmaxf(acc.y, 0.f), fmaxf(acc.z, 0.f), fmaxf(acc.w, 0.f));
+}
+
+// block = 8 query lanes x 32 channel quads (C = 128); every thread walks kQPT queries, scatters g = gout * (h1 > 0) into the
+// source-resolution adjoints and keeps the bias / relative-coordinate weight sums in registers; one reduction per block.
+constexpr int kQPT = 32;
+__global__ void __launch_bounds__(256) liif_layer1_bwd_kernel(const L1Maps mp, const float* __restrict__ coord,
+                                                              const float4* __restrict__ h1, const float4* __restrict__ gout,
+                                                              float* __restrict__ gb1, int C4, long long Q, long long BQ) {
+  __shared__ float4 red[8][32];
+  const int c4 = threadIdx.x & 31, ql = threadIdx.x >> 5;
+  float4 sb = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 sy[3], sx[3];
+#pragma unroll
+  for (int m = 0; m < 3; ++m) sy[m] = sx[m] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const long long q0 = (long long)blockIdx.x * (8 * kQPT);
+  if (c4 < C4) {
+    for (int t = 0; t < kQPT; ++t) {
+      const long long bq = q0 + t * 8 + ql;
+      if (bq >= BQ) break;
+      const long long b = bq / Q;
+      const float4 hv = __ldg(h1 + bq * C4 + c4), gv = __ldg(gout + bq * C4 + c4);
+      const float4 g = make_float4(hv.x > 0.f ? gv.x : 0.f, hv.y > 0.f ? gv.y : 0.f, hv.z > 0.f ? gv.z : 0.f, hv.w > 0.f ? gv.w : 0.f);
+      const float cy = __ldg(coord + bq * 2), cx = __ldg(coord + bq * 2 + 1);
+      sb.x += g.x; sb.y += g.y; sb.z += g.z; sb.w += g.w;
+#pragma unroll
+      for (int m = 0; m < 3; ++m) {
+        if (m < mp.M) {
+          const int h = mp.h[m], w = mp.w[m];
+          const int iy = nearest_index(cy, h), ix = nearest_index(cx, w);
+          const float ry = (cy - axis_centre(iy, h)) * (float)h, rx = (cx - axis_centre(ix, w)) * (float)w;
+          sy[m].x += g.x * ry; sy[m].y += g.y * ry; sy[m].z += g.z * ry; sy[m].w += g.w * ry;
+          sx[m].x += g.x * rx; sx[m].y += g.y * rx; sx[m].z += g.z * rx; sx[m].w += g.w * rx;
+          float* p = mp.gP[m] + (((b * h + iy) * w + ix) * C4 + c4) * 4;
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(g.x), "f"(g.y), "f"(g.z), "f"(g.w) : "memory");
+        }
+      }
+    }
+  }
+  // block reduction over the 8 query lanes, then one vector reduction per channel quad and quantity
+  auto block_sum = [&](float4 v, float* dst) {
+    red[ql][c4] = v;
+    __syncthreads();
+    if (ql == 0 && c4 < C4) {
+      float4 s = red[0][c4];
+#pragma unroll
+      for (int j = 1; j < 8; ++j) { const float4 o = red[j][c4]; s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w; }
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c4 * 4), "f"(s.x), "f"(s.y), "f"(s.z), "f"(s.w) : "memory");
+    }
+    __syncthreads();
+  };
+  block_sum(sb, gb1);
+  for (int m = 0; m < mp.M; ++m) {
+    block_sum(sy[m], mp.gWr[m]);
+    block_sum(sx[m], mp.gWr[m] + C4 * 4);
+  }
+}
+
 }  // namespace
+
+static int l1_fill(L1Maps& mp, int M, const float* const* P, const float* const* Wr, const int* hs, const int* ws) {
+  if (M < 1 || M > 3 || !P || !Wr || !hs || !ws) return AS_ERR_BAD_ARG;
+  mp.M = M;
+  for (int m = 0; m < M; ++m) {
+    if (!P[m] || !Wr[m] || hs[m] <= 0 || ws[m] <= 0 || !as_aligned16(P[m]) || !as_aligned16(Wr[m])) return AS_ERR_BAD_ARG;
+    mp.P[m] = P[m]; mp.Wr[m] = Wr[m]; mp.h[m] = hs[m]; mp.w[m] = ws[m];
+  }
+  return AS_OK;
+}
+
+extern "C" int as_liif_layer1_fwd(int num_maps, const float* const* P, const float* const* Wr, const int* hs, const int* ws,
+                                  const float* hr_coord, const float* b1, float* out, int B, int C, long long Q,
+                                  as_stream_t stream) {
+  if (!hr_coord || !b1 || !out || B <= 0 || Q <= 0 || C <= 0 || (C & 3) || C > 128) return AS_ERR_BAD_ARG;
+  L1Maps mp{};
+  int rc = l1_fill(mp, num_maps, P, Wr, hs, ws);
+  if (rc != AS_OK) return rc;
+  const long long total = (long long)B * Q * (C / 4);
+  if (as_ceil_div_ll(total, 256) >= (1LL << 31)) return AS_ERR_INDEX_RANGE;
+  liif_layer1_fwd_kernel<<<(unsigned)as_ceil_div_ll(total, 256), 256, 0, as_cu(stream)>>>(
+      mp, hr_coord, b1, reinterpret_cast<float4*>(out), C / 4, Q, total);
+  AS_RETURN_IF_LAUNCH_FAILED();
+  return AS_OK;
+}
+
+extern "C" int as_liif_layer1_bwd(int num_maps, const float* const* P, const float* const* Wr, const int* hs, const int* ws,
+                                  const float* hr_coord, const float* h1, const float* g_out, float* const* g_P,
+                                  float* const* g_Wr, float* g_b1, int B, int C, long long Q, as_stream_t stream) {
+  if (!hr_coord || !h1 || !g_out || !g_P || !g_Wr || !g_b1 || B <= 0 || Q <= 0 || C <= 0 || (C & 3) || C > 128) return AS_ERR_BAD_ARG;
+  L1Maps mp{};
+  int rc = l1_fill(mp, num_maps, P, Wr, hs, ws);
+  if (rc != AS_OK) return rc;
+  cudaStream_t st = as_cu(stream);
+  cudaError_t e = cudaMemsetAsync(g_b1, 0, sizeof(float) * C, st);
+  for (int m = 0; m < num_maps && e == cudaSuccess; ++m) {
+    if (!g_P[m] || !g_Wr[m]) return AS_ERR_BAD_ARG;
+    mp.gP[m] = g_P[m]; mp.gWr[m] = g_Wr[m];
+    e = cudaMemsetAsync(g_P[m], 0, sizeof(float) * (size_t)B * hs[m] * ws[m] * C, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(g_Wr[m], 0, sizeof(float) * 2 * C, st);
+  }
+  if (e != cudaSuccess) return (int)e;
+  const long long BQ = (long long)B * Q;
+  const long long blocks = as_ceil_div_ll(BQ, 8 * kQPT);
+  if (blocks >= (1LL << 31)) return AS_ERR_INDEX_RANGE;
+  liif_layer1_bwd_kernel<<<(unsigned)blocks, 256, 0, st>>>(mp, hr_coord, reinterpret_cast<const float4*>(h1),
+                                                         reinterpret_cast<const float4*>(g_out), g_b1, C / 4, Q, BQ);
+  AS_RETURN_IF_LAUNCH_FAILED();
+  return AS_OK;
+}
 
 extern "C" int as_nearest_gather_fwd(const float* src, const float* coord, float* out, int B, int h, int w, int C, long long Q,
                                      as_stream_t stream) {

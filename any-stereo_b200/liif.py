@@ -98,6 +98,47 @@ class _NearestGather(torch.autograd.Function):
         return gsrc, None
 
 
+class _Layer1(torch.autograd.Function):
+    """relu(sum_m (P_m[nearest(q)] + rel_m(q) . Wr_m) + b1) -> [B,Q,C] and its adjoint, one kernel each
+    (as_liif_layer1_fwd / _bwd).  args = P_0, Wr_0, P_1, Wr_1, ...: P_m [B,h,w,C] pixel-major, Wr_m [C,2] (y, x columns)."""
+
+    @staticmethod
+    def forward(ctx, coord, b1, *args):
+        Ps = [a.contiguous() for a in args[0::2]]
+        Wrs = [a.t().contiguous() for a in args[1::2]]                   # [2][C]
+        B, _, _, Cc = Ps[0].shape
+        Q = coord.shape[1]
+        coord = coord.detach().float().contiguous()
+        b1c = b1.detach().float().contiguous()
+        out = torch.empty((B, Q, Cc), device=coord.device, dtype=torch.float32)
+        hs, ws = [p.shape[1] for p in Ps], [p.shape[2] for p in Ps]
+        with torch.cuda.device(coord.device):
+            L.call("as_liif_layer1_fwd", len(Ps), L.ptr_array(Ps), L.ptr_array(Wrs), L.int_array(hs), L.int_array(ws),
+                   coord.data_ptr(), b1c.data_ptr(), out.data_ptr(), B, Cc, Q, L.stream_ptr())
+        ctx.save_for_backward(coord, out, *Ps, *Wrs)
+        ctx.n = len(Ps)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        coord, out = ctx.saved_tensors[:2]
+        n = ctx.n
+        Ps, Wrs = list(ctx.saved_tensors[2:2 + n]), list(ctx.saved_tensors[2 + n:2 + 2 * n])
+        B, Q, Cc = out.shape
+        g = g.contiguous().float()
+        gPs = [torch.empty_like(p) for p in Ps]
+        gWrs = [torch.empty_like(w) for w in Wrs]
+        gb1 = torch.empty((Cc,), device=g.device, dtype=torch.float32)
+        hs, ws = [p.shape[1] for p in Ps], [p.shape[2] for p in Ps]
+        with torch.cuda.device(g.device):
+            L.call("as_liif_layer1_bwd", n, L.ptr_array(Ps), L.ptr_array(Wrs), L.int_array(hs), L.int_array(ws), coord.data_ptr(),
+                   out.data_ptr(), g.data_ptr(), L.ptr_array(gPs), L.ptr_array(gWrs), gb1.data_ptr(), B, Cc, Q, L.stream_ptr())
+        grads = [None, gb1]
+        for gp, gw in zip(gPs, gWrs):
+            grads += [gp, gw.t()]
+        return tuple(grads)
+
+
 class _ContextUpsample(torch.autograd.Function):
     """context_upsample_multiscale_train (submodule.py:357-372) with its adjoint as kernels."""
 
@@ -137,29 +178,34 @@ def _logits_torch(module, feats, coord):
     (affinity features, the three small Linears) stays in ATen ops and autograd."""
     lin = module.imnet.layers[0]
     W1, b1 = lin.weight.float(), lin.bias.float()
-    y1 = None
     off = 0
+    Ps, Wrs, dims = [], [], []
     for f in feats:
         f = f.float()
         sf = torch.cat([f, _isu_affinity_torch(f)], dim=1)
         B, Cc, h, w = sf.shape
-        Wf, Wr = W1[:, off:off + Cc], W1[:, off + Cc:off + Cc + 2]
+        Ps.append(torch.einsum("bchw,oc->bhwo", sf, W1[:, off:off + Cc]))              # [B,h,w,128] pixel-major
+        Wrs.append(W1[:, off + Cc:off + Cc + 2])                                      # [128,2]: the (y, x) columns
+        dims.append((h, w))
         off += Cc + 2
-        iy, ix = _nearest_index(coord[:, :, 0], h), _nearest_index(coord[:, :, 1], w)
-        rel = torch.stack([(coord[:, :, 0].float() - _coord_axis(h, sf.device)[iy]) * h,
-                           (coord[:, :, 1].float() - _coord_axis(w, sf.device)[ix]) * w], dim=-1)      # [B,Q,2]
-        P = torch.einsum("bchw,oc->bhwo", sf, Wf)                                     # [B,h,w,128] pixel-major
-        if P.is_cuda:
-            g = _NearestGather.apply(P, coord)
-        else:
-            bidx = torch.arange(B, device=sf.device).view(B, 1).expand_as(iy)
-            g = P[bidx, iy, ix]                                                       # [B,Q,128]
-        t = g + rel @ Wr.t()
-        y1 = t if y1 is None else y1 + t
     assert off == W1.shape[1], (off, tuple(W1.shape))
-    y1 = y1 + b1
-    B, Q, _ = y1.shape
-    z = module.imnet.layers[1:](y1.reshape(B * Q, -1))
+    if Ps[0].is_cuda and W1.shape[0] % 4 == 0 and W1.shape[0] <= 128 and len(Ps) <= 3:
+        args = [t for pair in zip(Ps, Wrs) for t in pair]
+        h1 = _Layer1.apply(coord, b1, *args)                                          # gather + rel terms + bias + ReLU fused
+        rest = module.imnet.layers[2:]
+    else:                                                                             # device-agnostic formulation
+        y1 = None
+        for P, Wr, (h, w) in zip(Ps, Wrs, dims):
+            iy, ix = _nearest_index(coord[:, :, 0], h), _nearest_index(coord[:, :, 1], w)
+            rel = torch.stack([(coord[:, :, 0].float() - _coord_axis(h, P.device)[iy]) * h,
+                               (coord[:, :, 1].float() - _coord_axis(w, P.device)[ix]) * w], dim=-1)  # [B,Q,2]
+            bidx = torch.arange(P.shape[0], device=P.device).view(-1, 1).expand_as(iy)
+            t = P[bidx, iy, ix] + rel @ Wr.t()
+            y1 = t if y1 is None else y1 + t
+        h1 = y1 + b1
+        rest = module.imnet.layers[1:]
+    B, Q, _ = h1.shape
+    z = rest(h1.reshape(B * Q, -1))
     return z.reshape(B, Q, -1).permute(0, 2, 1).contiguous()
 
 

@@ -453,6 +453,18 @@ int as_nearest_gather_fwd(const float* src, const float* hr_coord, float* out, i
 int as_nearest_gather_bwd(const float* g_out, const float* hr_coord, float* g_src, int B, int h, int w, int C, long long Q,
                           as_stream_t stream);
 
+/* First MLP layer of the upsampler in training with everything after the source-resolution product fused (num_maps = 1..3
+ * feature maps, C <= 128 hidden channels, C % 4 == 0):
+ *   h1[b,q,:] = relu( sum_m ( P_m[b, iy_m(q), ix_m(q), :] + rel_m(q) . Wr_m ) + b1 )
+ * P_m [B,h_m,w_m,C] = first-layer weights applied to [feat | affinity] at source resolution; Wr_m [2][C] = the layer's two
+ * relative-coordinate columns (y, x) transposed; rel_m = (coord - centre of the picked pixel) * (h_m, w_m).
+ * The adjoint takes h1 (for the ReLU mask) and g_out and fills g_P[m], g_Wr[m] [2][C], g_b1 [C] (all zeroed by the call). */
+int as_liif_layer1_fwd(int num_maps, const float* const* P, const float* const* Wr, const int* hs, const int* ws,
+                       const float* hr_coord, const float* b1, float* out, int B, int C, long long Q, as_stream_t stream);
+int as_liif_layer1_bwd(int num_maps, const float* const* P, const float* const* Wr, const int* hs, const int* ws,
+                       const float* hr_coord, const float* h1, const float* g_out, float* const* g_P, float* const* g_Wr,
+                       float* g_b1, int B, int C, long long Q, as_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * SURVEY 8(f)-3 (first half)  initial-disparity head before the loop
  * (continuous_IGEVstereo.py:267-268: softmax over D of Conv3d(G->1, 3x3x3, pad 1, no bias)(geo_encoding_volume),

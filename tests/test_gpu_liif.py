@@ -199,3 +199,41 @@ def test_upsample_disp_normalised_variants(A, mode):
     up = LO.context_upsample_multiscale(disp / w * k, mask, coords).unsqueeze(1)
     ref = up / k * torch.round(w * 4.0 * scale.view(-1, 1, 1))
     assert rel(got, ref) < 1e-4
+
+
+@pytest.mark.parametrize("scale", [1.0, 1.7, 3.3])
+def test_upsampler_training_kernels_match_oracle_autograd(A, scale):
+    """The upsampler in TRAINING on the GPU (first Linear at source resolution, fused gather + relative-coordinate terms +
+    bias + ReLU kernel, context-upsample kernel, and their hand-written adjoints, csrc/liif_train.cu) against autograd over
+    the oracle restatement of the reference on the CPU: value, d disp, d features, d parameters."""
+    torch.manual_seed(0)
+    lc = cases.liif_case(2, h=9, w=13, scale=scale, extra_q=7)
+    chanels = [f.shape[1] for f in lc["feats"]]
+    m = A.liif_out_multi_scale_Training(encoder_dim=sum(chanels), mlphidden_list=[128, 64, 64], pos_dim=0,
+                                        unfold="with_v2ISU", affinity_settings=AFF, number_input=2, chanels=chanels)
+    lp = LO.make_liif_params(lc["in_dim"], seed=2)
+    m.load_state_dict(lp, strict=True)
+    m = m.cuda().train()
+    feats = [f.clone().cuda().requires_grad_(True) for f in lc["feats"]]
+    disp = lc["disp"].clone().cuda().requires_grad_(True)
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        out = A.upsample_disp(m, disp, feats[0][:, 48:], feats[0][:, :48], feats[1], None, hr_coord=lc["coords"].cuda(),
+                              scale=lc["scale"].cuda())
+        assert out.grad_fn is not None
+        wgt = torch.linspace(0.5, 1.5, out.numel()).view_as(out)
+        (out * wgt.cuda()).sum().backward()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+    p2 = {k: v.clone().requires_grad_(True) for k, v in lp.items()}
+    f2 = [f.clone().requires_grad_(True) for f in lc["feats"]]
+    d2 = lc["disp"].clone().requires_grad_(True)
+    ref = LO.upsample_disp_multiscale(p2, d2, f2, lc["coords"], lc["scale"])
+    (ref * wgt).sum().backward()
+    assert rel(out, ref) < 1e-5
+    assert rel(disp.grad, d2.grad) < 1e-5
+    for a, b in zip(feats, f2):
+        assert rel(a.grad, b.grad) < 2e-5
+    for k, v in m.state_dict(keep_vars=True).items():
+        assert rel(v.grad, p2[k].grad) < 2e-5, k
