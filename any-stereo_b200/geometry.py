@@ -457,3 +457,20 @@ class DeferredCorrLookup:
             L.call("as_corr_lookup_convc1", L.ptr_array(b._bufs), L.int_array(b._widths), L.int_array(b._pitches),
                    b.num_levels, self.disp.data_ptr(), L.ptr(self.coords), w_hi.data_ptr(), L.ptr(w_lo), bias.data_ptr(),
                    3 if w_lo is not None else 1, out_hi.data_ptr(), L.ptr(out_lo), B, H, W, b.radius, L.stream_ptr())
+
+
+class Combined_Geo_Encoding_Volume_Deferred(Combined_Geo_Encoding_Volume):
+    """Drop-in variant for models whose update block has been adopted (hotpath.adopt_update_block): ``geo_fn(disp, coords)``
+    returns the lookup UNEVALUATED (a DeferredGeoLookup) and the adopted update block fuses it with convc1
+    (continuous_IGEVstereo.py:275-295 hands the result straight to ``self.update_block``).  Gradients requested, the
+    exact-fp32 engine or unsupported shapes materialise it inside the update block, as ``deferred`` documents."""
+
+    def __call__(self, disp, coords):
+        return self.deferred(disp, coords)
+
+
+class CorrBlock1D_Deferred(CorrBlock1D):
+    """RAFT-family twin of Combined_Geo_Encoding_Volume_Deferred (prune_raft_stereo.py:267-290)."""
+
+    def __call__(self, disp, coords):
+        return self.deferred(disp, coords)

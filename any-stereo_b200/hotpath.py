@@ -246,7 +246,7 @@ class HotLoopGraph:
         return self.out_disp, self.out_net
 
 
-def install_into_reference(ref_igev_module=None, ref_raft_module=None):
+def install_into_reference(ref_igev_module=None, ref_raft_module=None, defer_lookup=False):
     """Rebind the names the reference's model graphs resolve at call time:
 
         models.coreContinuous_IGEV.continuous_IGEVstereo.{Combined_Geo_Encoding_Volume, build_gwc_volume}
@@ -257,14 +257,20 @@ def install_into_reference(ref_igev_module=None, ref_raft_module=None):
     ``adopt_liif_up``.  Everything installed is differentiable (training, config 5): the cost-volume objects,
     ``build_gwc_volume`` and the update block through hand-written adjoint kernels; the upsampler pieces (forward-only
     fused kernels) switch to the same arithmetic in differentiable ATen ops whenever a gradient is requested through
-    them, so no ``disp_preds`` loss term ever loses its graph."""
+    them, so no ``disp_preds`` loss term ever loses its graph.
+
+    defer_lookup=True binds the *_Deferred cost-volume classes instead: ``geo_fn(disp, coords)`` / ``corr_fn(disp, coords)``
+    return the lookup unevaluated and the ADOPTED update block runs it fused with convc1 (SURVEY 8(f)-1 inside the
+    reference's own loop).  Requires ``adopt_update_block`` on every model built from that module."""
+    if defer_lookup:
+        from .geometry import Combined_Geo_Encoding_Volume_Deferred, CorrBlock1D_Deferred
     if ref_igev_module is not None:
-        ref_igev_module.Combined_Geo_Encoding_Volume = Combined_Geo_Encoding_Volume
+        ref_igev_module.Combined_Geo_Encoding_Volume = Combined_Geo_Encoding_Volume_Deferred if defer_lookup else Combined_Geo_Encoding_Volume
         ref_igev_module.build_gwc_volume = build_gwc_volume
         from .liif import context_upsample_multiscale_train      # SURVEY 8(f)-2, continuous_IGEVstereo.py:219
         ref_igev_module.context_upsample_multiscale_train = context_upsample_multiscale_train
     if ref_raft_module is not None:
-        ref_raft_module.CorrBlock1D = CorrBlock1D
+        ref_raft_module.CorrBlock1D = CorrBlock1D_Deferred if defer_lookup else CorrBlock1D
         from .liif import context_upsample_multiscale_train      # prune_raft_stereo.py:227
         ref_raft_module.context_upsample_multiscale_train = context_upsample_multiscale_train
 

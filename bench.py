@@ -496,6 +496,26 @@ def run_ours(args):
                 for _ in range(2):
                     dropin_step()
                 dms = ev_ms(dropin_step, 3)
+                # the same loop with install_into_reference(defer_lookup=True): geo_fn returns the lookup unevaluated and the
+                # adopted update block runs it fused with convc1
+                def dropin_step_deferred():
+                    geo = A.build_gwc_volume(dd["ml"], dd["mr"], GEO_D, GROUPS)
+                    geo_fn = A.geometry.Combined_Geo_Encoding_Volume_Deferred(dd["ml"].float(), dd["mr"].float(), geo.float(),
+                                                                              radius=4, num_levels=2)
+                    coords = A.hotpath.pixel_coords(B, H4, W4, dev)
+                    net, disp = list(dd["net"]), dd["disp"]
+                    for _ in range(ITERS):
+                        feat = geo_fn(disp, coords)
+                        net, delta = block(net, dd["inp"], feat, disp, iter16=True, iter08=True)
+                        disp = disp + delta
+                    return disp
+                for _ in range(2):
+                    dropin_step_deferred()
+                dms2 = ev_ms(dropin_step_deferred, 3)
+                other["dropin_call_pattern_deferred_lookup_same_step"] = {
+                    "pairs_per_s": world * B / (dms2 / 1e3), "ms_per_step": dms2,
+                    "what": "the same reference call pattern with install_into_reference(defer_lookup=True): the lookup is "
+                            "fused with convc1 inside the adopted update block"}
                 other["dropin_call_pattern_same_step"] = {
                     "pairs_per_s": world * B / (dms / 1e3), "ms_per_step": dms,
                     "what": "reference call pattern (continuous_IGEVstereo.py:275-295) on this library's operators: "

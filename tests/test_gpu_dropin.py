@@ -227,3 +227,35 @@ def test_dropin_fused_corr_stem_matches_reference():
         assert e_fused < 1e-3 and abs(e_fused - e_plain) < 5e-4, (e_plain, e_fused)
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+
+
+@needs_ref
+@pytest.mark.parametrize("family", ["igev", "raft"])
+def test_dropin_deferred_lookup_matches_plain_dropin(family):
+    """install_into_reference(defer_lookup=True): the reference's own loop hands an unevaluated lookup to the adopted update
+    block, which runs it fused with convc1.  Same final disparity as the plain drop-in (K order of the fp32
+    accumulation differs) and within the EPE gate of the unmodified model; fewer launches."""
+    import anystereo_b200 as A
+    D = dropin
+    model, R = D.build_model(family, "cuda")
+    img1, img2 = D.make_pair(1, 320, 736, "cuda")
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        ref = D.forward(model, R, img1, img2, 12)
+        with D.installed(model, R, family) as m:
+            D.forward(m, R, img1, img2, 12)
+            n0 = A._lib.launch_count
+            plain = D.forward(m, R, img1, img2, 12)
+            n_plain = A._lib.launch_count - n0
+        with D.installed(model, R, family, defer_lookup=True) as m:
+            D.forward(m, R, img1, img2, 12)
+            n0 = A._lib.launch_count
+            fused = D.forward(m, R, img1, img2, 12)
+            n_fused = A._lib.launch_count - n0
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    assert n_fused <= n_plain - 12, (n_plain, n_fused)            # at least one launch fewer per iteration
+    assert float((fused - ref).abs().mean()) < 1e-3
+    assert float((fused - plain).abs().mean()) < 5e-4

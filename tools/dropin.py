@@ -63,7 +63,7 @@ def build_model(family, device, seed=0, **over):
 
 
 @contextlib.contextmanager
-def installed(model, R, family, fuse_corr_stem=False):
+def installed(model, R, family, fuse_corr_stem=False, defer_lookup=False):
     """Rebind the reference's names to this library for the duration of the block.
     fuse_corr_stem (IGEV): also adopt corr_stem / corr_feature_att (build_gwc_volume fused with them)."""
     import anystereo_b200 as A
@@ -74,11 +74,11 @@ def installed(model, R, family, fuse_corr_stem=False):
     stem = (model.corr_stem, model.corr_feature_att) if family == "igev" else None
     try:
         if family == "igev":
-            A.install_into_reference(ref_igev_module=mod)
+            A.install_into_reference(ref_igev_module=mod, defer_lookup=defer_lookup)
             if fuse_corr_stem:
                 A.adopt_corr_stem(model, mod)
         else:
-            A.install_into_reference(ref_raft_module=mod)
+            A.install_into_reference(ref_raft_module=mod, defer_lookup=defer_lookup)
         model.update_block = A.adopt_update_block(ub, family)
         hd = model.args.hidden_dims[2]
         model.liif_up = A.adopt_liif_up(lu, chanels=[48 + hd, 32])          # agg_type 'type5': [stem_4x|hidden, stem_2x]
