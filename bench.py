@@ -495,7 +495,7 @@ def run_ours(args):
                     return disp
                 for _ in range(2):
                     dropin_step()
-                dms = ev_ms(dropin_step, 3)
+                dms = ev_ms(dropin_step, 6)
                 # the same loop with install_into_reference(defer_lookup=True): geo_fn returns the lookup unevaluated and the
                 # adopted update block runs it fused with convc1
                 def dropin_step_deferred():
@@ -511,7 +511,7 @@ def run_ours(args):
                     return disp
                 for _ in range(2):
                     dropin_step_deferred()
-                dms2 = ev_ms(dropin_step_deferred, 3)
+                dms2 = ev_ms(dropin_step_deferred, 6)
                 other["dropin_call_pattern_deferred_lookup_same_step"] = {
                     "pairs_per_s": world * B / (dms2 / 1e3), "ms_per_step": dms2,
                     "what": "the same reference call pattern with install_into_reference(defer_lookup=True): the lookup is "
