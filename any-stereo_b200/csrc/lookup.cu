@@ -577,6 +577,72 @@ __global__ void geo_lookup_bwd_kernel(LevelSetRW ggeo, int G, int Dg, LevelSetRW
   }
 }
 
+// Same adjoint for the IGEV shape (G = 8, radius 4), coalesced on both sides: the generic kernel above walks a pixel's
+// taps with one thread per (pixel, level, group), i.e. 1.5 KB between the lanes of every read-modify-write (408 us per
+// call at config-5 size).  Here a CTA stages the 162 gradient rows of 32 pixels through shared memory (reads: lanes =
+// pixels), then 8 lanes = the 8 groups of one (pixel, level) update one 32-byte sector per tap.
+template <int L>
+__global__ void __launch_bounds__(256) geo_lookup_bwd_tiled_kernel(LevelSetRW ggeo, int Dg, LevelSetRW gcorr,
+                                                                   const float* __restrict__ disp,
+                                                                   const float* __restrict__ coords,
+                                                                   const float* __restrict__ gout, int HW, int W,
+                                                                   int tiles_per_img) {
+  constexpr int G = 8, R = 4, K = 9, C = L * (G + 1) * K, TP = 32;
+  __shared__ float s[C][TP + 1];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x / tiles_per_img;
+  const int p0 = (blockIdx.x - b * tiles_per_img) * TP;
+  const float* go = gout + (long long)b * C * HW + p0;
+  for (int c = warp; c < C; c += 8) s[c][lane] = (p0 + lane < HW) ? __ldg(go + (long long)c * HW + lane) : 0.f;
+  __syncthreads();
+  const long long nbase = (long long)b * HW + p0;
+  // geometry part: item = (pixel, level), 8 lanes per item
+  const int g = lane & 7;
+  for (int item = warp * 4 + (lane >> 3); item < TP * L; item += 32) {
+    const int l = item / TP, pp = item - l * TP;
+    if (p0 + pp >= HW) continue;
+    const long long n = nbase + pp;
+    int t0; float f;
+    split_pos(__ldg(disp + n) * level_scale(l), R, t0, f);
+    const float omf = 1.0f - f;
+    const int Dl = Dg >> l;
+    float* base = ggeo.ptr[l] + n * Dl * G + g;
+    const float* sg = &s[(l * (G + 1) + g) * K][pp];
+    float gm1 = 0.f;
+#pragma unroll
+    for (int j = 0; j <= K; ++j) {
+      const float g0 = (j < K) ? sg[j * (TP + 1)] : 0.f;
+      const int x1 = t0 + j;
+      if (x1 >= 0 && x1 < Dl) base[(long long)x1 * G] += gm1 * f + g0 * omf;
+      gm1 = g0;
+    }
+  }
+  // correlation part: thread = (pixel, level)
+  if (tid < TP * L) {
+    const int l = tid / TP, pp = tid - l * TP;
+    if (p0 + pp < HW) {
+      const long long n = nbase + pp;
+      const float d = __ldg(disp + n);
+      const float c = coords ? __ldg(coords + n) : (float)((p0 + pp) % W);
+      const float sc = level_scale(l);
+      int t0; float f;
+      split_pos(c * sc - d * sc, R, t0, f);
+      const float omf = 1.0f - f;
+      const int limit = gcorr.width[l];
+      float* base = gcorr.ptr[l] + n * gcorr.pitch[l];
+      const float* sg = &s[(l * (G + 1) + G) * K][pp];
+      float gm1 = 0.f;
+#pragma unroll
+      for (int j = 0; j <= K; ++j) {
+        const float g0 = (j < K) ? sg[j * (TP + 1)] : 0.f;
+        const int x1 = t0 + j;
+        if (x1 >= 0 && x1 < limit) base[x1] += gm1 * f + g0 * omf;
+        gm1 = g0;
+      }
+    }
+  }
+}
+
 __global__ void lookup_taps_kernel(const float* __restrict__ disp, const float* __restrict__ coords, int HW,
                                    int W, int r, int level, int kind, int32_t* __restrict__ tap0,
                                    float* __restrict__ frac, long long N) {
@@ -728,6 +794,17 @@ extern "C" int as_geo_lookup_bwd(float* const* g_geo_levels, int G, int Dg, floa
     if (!g_geo_levels[l] || !g_corr_levels[l] || corr_pitches[l] < corr_widths[l]) return AS_ERR_BAD_ARG;
     cs.ptr[l] = g_corr_levels[l]; cs.width[l] = corr_widths[l]; cs.pitch[l] = corr_pitches[l];
     gs.ptr[l] = g_geo_levels[l]; gs.width[l] = Dg >> l; gs.pitch[l] = (Dg >> l) * G;
+  }
+  static const bool tiled_ok = !(getenv("AS_GEO_LOOKUP_BWD_TILED") && getenv("AS_GEO_LOOKUP_BWD_TILED")[0] == '0');   // A/B knob
+  if (tiled_ok && G == 8 && radius == 4 && (num_levels == 1 || num_levels == 2) && (long long)B * as_ceil_div(H * W, 32) < (1LL << 31)) {
+    const int tiles_per_img = as_ceil_div(H * W, 32);
+    const unsigned grid = (unsigned)((long long)B * tiles_per_img);
+    if (num_levels == 2)
+      geo_lookup_bwd_tiled_kernel<2><<<grid, 256, 0, as_cu(stream)>>>(gs, Dg, cs, disp, coords, g_out, H * W, W, tiles_per_img);
+    else
+      geo_lookup_bwd_tiled_kernel<1><<<grid, 256, 0, as_cu(stream)>>>(gs, Dg, cs, disp, coords, g_out, H * W, W, tiles_per_img);
+    AS_RETURN_IF_LAUNCH_FAILED();
+    return AS_OK;
   }
   const long long total = (long long)B * H * W * num_levels * (G + 1);
   geo_lookup_bwd_kernel<<<(unsigned)as_ceil_div_ll(total, 256), 256, 0, as_cu(stream)>>>(
