@@ -98,7 +98,8 @@ def _graph_key(kind, ub, tensors, scalars):
     from .update_umma import _OVERLAP
     shapes = tuple((tuple(t.shape), t.dtype, t.device.index) for t in tensors)
     params = tuple((p.data_ptr(), L.version_of(p)) for p in ub.parameters())
-    return (kind, id(ub), shapes, params, scalars, get_update_engine(), _FUSION["on"], _OVERLAP["on"],
+    from .geometry import get_corr_mode
+    return (kind, id(ub), shapes, params, scalars, get_update_engine(), get_corr_mode(), _FUSION["on"], _OVERLAP["on"],
             torch.cuda.current_device())
 
 
