@@ -208,3 +208,56 @@ def test_no_predicated_tensor_core_mma_in_sass():
     assert len(mma) > 50
     bad = [l.strip() for l in mma if re.search(r"@!?UP\d+\s+UTCHMMA", l)]
     assert not bad, bad[:3]
+
+
+def test_round2_entry_points_reject_bad_arguments(A):
+    """The entry points added in round 2 validate before any CUDA call (no GPU here)."""
+    lib = A._lib.lib()
+    assert lib.as_geo_lookup_convc1_tap(None, 8, 48, None, None, None, 2, None, None, None, None, None, 3, None, None,
+                                        1, 4, 4, 4, None) == -1
+    assert lib.as_gwc_corr_stem_fwd(None, None, None, None, None, None, None, 1, 96, 4, 4, 48, 8, 0.01, None) == -1
+    assert lib.as_nearest_gather_fwd(None, None, None, 1, 4, 4, 128, 16, None) == -1
+    assert lib.as_nearest_gather_bwd(None, None, None, 1, 4, 4, 128, 16, None) == -1
+    assert lib.as_context_upsample_multiscale_bwd(None, None, None, None, None, None, 1, 4, 4, 16, None) == -1
+    assert lib.as_liif_layer1_fwd(2, None, None, None, None, None, None, None, 1, 128, 16, None) == -1
+    assert lib.as_liif_layer1_bwd(2, None, None, None, None, None, None, None, None, None, None, 1, 128, 16, None) == -1
+
+
+def test_deferred_wrappers_host_logic(A):
+    """Host side of the round-2 fusions: the tap-major K order of the fused lookup's weights, and what the deferring
+    build_gwc_volume / corr_stem pair does when the fused kernel does not apply (CPU tensors, gradients, train-mode BN)."""
+    import torch.nn as nn
+    # K order: channel (level l, group g, tap k) -> l*96 + k*8 + g; correlation taps -> l*96 + 72 + k; bias -> column 81
+    c = torch.arange(162)
+    g, k = (c % 81) // 9, c % 9
+    kidx = (c // 81) * 96 + torch.where(g < 8, k * 8 + g, 72 + k)
+    assert len(set(kidx.tolist())) == 162 and 81 not in set(kidx.tolist()) and int(kidx.max()) < 192
+    assert int(kidx[0]) == 0 and int(kidx[9]) == 1 and int(kidx[72]) == 72 and int(kidx[81]) == 96
+    # build_gwc_volume_deferred: CPU tensors / gradients / unsupported shapes take the plain operator (which then raises
+    # its own "must be a CUDA tensor" here), CUDA-eligible inputs would be deferred
+    from anystereo_b200.submodule import build_gwc_volume_deferred
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        build_gwc_volume_deferred(torch.zeros(1, 96, 2, 8), torch.zeros(1, 96, 2, 8), 48, 8)
+    # CorrStem: same submodules (state_dict keys), plain tensors take the reference's arithmetic on any device
+    class Ref(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv = nn.Conv3d(8, 8, 3, 1, 1, bias=False)
+            self.bn = nn.BatchNorm3d(8)
+            self.relu, self.use_bn = True, True
+    ref = Ref().eval()
+    ours = A.hotpath.CorrStem(ref)
+    assert list(ours.state_dict().keys()) == list(ref.state_dict().keys())
+    x = torch.randn(1, 8, 4, 3, 5)
+    want = nn.functional.leaky_relu(ref.bn(ref.conv(x)))
+    assert torch.allclose(ours(x), want)
+    with torch.no_grad():
+        assert ours._fusable()
+        ours.train()
+        assert not ours._fusable()                   # batch statistics: never the fused eval-mode kernel
+        ours.eval()
+    with torch.enable_grad():
+        assert not ours._fusable()                   # parameters want gradients
+    # the deferring cost-volume classes only change __call__
+    assert A.geometry.Combined_Geo_Encoding_Volume_Deferred.__mro__[1] is A.Combined_Geo_Encoding_Volume
+    assert A.geometry.CorrBlock1D_Deferred.__mro__[1] is A.CorrBlock1D
