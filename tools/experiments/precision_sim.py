@@ -66,9 +66,14 @@ def run(family, iters, H, W, modes):
     img1, img2 = dropin.make_pair(1, H, W, "cpu")
     convs = [m for m in model.update_block.modules() if isinstance(m, torch.nn.Conv2d)]
     out = {}
+    names = {id(m): n for n, m in model.update_block.named_modules()}
     for mode in modes:
-        fn = conv_mode(mode)
+        # mixed modes "mix_<pattern>[+<pattern>]": the convolutions whose name contains a pattern run single-pass fp16, the rest
+        # f16f8 (e.g. mix_convz+convr: the GRU gates z, r in one pass; mix_gru16+gru08: the low-resolution GRUs)
+        pats = mode[4:].split("+") if mode.startswith("mix_") else None
         for m in convs:
+            mm = mode if pats is None else ("fp16" if any(p in names[id(m)] for p in pats) else "f16f8")
+            fn = conv_mode(mm)
             m.forward = (lambda x, m=m, fn=fn: fn(x.float(), m.weight, m.bias, m.padding))
         res = dropin.forward(model, R, img1, img2, iters)
         out[mode] = res
