@@ -471,6 +471,19 @@ def run_ours(args):
                 other["engine_fp16_same_step"] = {"pairs_per_s": world * B / (fms / 1e3), "ms_per_step": fms}
                 A.set_update_engine(args.engine)
                 block.reset_caches()
+            if args.engine in ("f16f8", "bf16x3"):           # opt-in: low-resolution GRUs in one tensor-core pass
+                A.set_lowres_single_pass(True)
+                block.reset_caches()
+                for _ in range(2):
+                    step(dd)
+                lms = ev_ms(lambda: step(dd), 6)
+                other["engine_%s_lowres_single_pass_same_step" % args.engine] = {
+                    "pairs_per_s": world * B / (lms / 1e3), "ms_per_step": lms,
+                    "what": "set_lowres_single_pass(True): gru08 / gru16 in one pass (final-disparity EPE 1.5e-4 -> ~2e-4 px on the "
+                            "real IGEV graph, tests/test_gpu_dropin.py; the low-resolution hidden states carry half-precision "
+                            "error, so it is not the default)"}
+                A.set_lowres_single_pass(False)
+                block.reset_caches()
             if args.engine == "f16f8":                       # the 3-pass split of round 1, same step, for context
                 A.set_update_engine("bf16x3")
                 block.reset_caches()

@@ -259,3 +259,33 @@ def test_dropin_deferred_lookup_matches_plain_dropin(family):
     assert n_fused <= n_plain - 12, (n_plain, n_fused)            # at least one launch fewer per iteration
     assert float((fused - ref).abs().mean()) < 1e-3
     assert float((fused - plain).abs().mean()) < 5e-4
+
+
+@needs_ref
+@pytest.mark.parametrize("family,size", [("igev", (384, 1248)), ("raft", (320, 736))])
+def test_dropin_lowres_single_pass_knob_epe(family, size):
+    """Opt-in speed mode (set_lowres_single_pass): the 1/8- and 1/16-resolution GRUs in one tensor-core pass.  The final
+    full-resolution disparity of the REAL graphs stays inside the 1e-3 px bar of the default engine (the simulation said
+    1.3e-4 / 3.4e-4 px); recorded live here."""
+    import anystereo_b200 as A
+    D = dropin
+    model, R = D.build_model(family, "cuda")
+    img1, img2 = D.make_pair(1, size[0], size[1], "cuda")
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    prev = A.set_lowres_single_pass(False)
+    try:
+        ref = D.forward(model, R, img1, img2, 32)
+        with D.installed(model, R, family) as m:
+            two = D.forward(m, R, img1, img2, 32)
+            A.set_lowres_single_pass(True)
+            one = D.forward(m, R, img1, img2, 32)
+    finally:
+        A.set_lowres_single_pass(prev)
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    e2, e1 = float((two - ref).abs().mean()), float((one - ref).abs().mean())
+    _record({"family": family, "image": list(size), "lowres_single_pass": {"epe_default_px": e2, "epe_knob_px": e1,
+                                                                       "epe_knob_max_px": float((one - ref).abs().max())}})
+    assert e2 < 1e-3 and e1 < 1e-3, (e2, e1)
+    assert not torch.equal(one, two)
