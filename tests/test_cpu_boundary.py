@@ -120,6 +120,13 @@ def test_update_block_state_dict_matches_reference_names(A):
         assert sum(int(np.prod(s)) for s in ours.values()) in (4071488, 4063424)
 
 
+def test_lowres_single_pass_default(A):
+    """The f16f8 engine's low-resolution GRUs run one pass by default; the switch returns the previous state."""
+    assert A.update_umma._LOWRES_1PASS["on"] is True
+    assert A.set_lowres_single_pass(False) is True
+    assert A.set_lowres_single_pass(True) is False
+
+
 def test_default_engine_is_tensor_core_parity(A):
     """VERDICT r1 weak #5: rebinding the names alone must select the tcgen05 parity engine, not the CUDA-core one."""
     import subprocess

@@ -134,7 +134,9 @@ def test_dropin_training_step_matches_reference():
         noise = float((g_ref2[n] - g_ref[n]).abs().max() / scale)      # up to 3.5e-3 on `desc.weight` (measured)
         # both sides accumulate their gather adjoints with atomics (run-to-run noise on both): seen failing once in ~10
         # runs at max(2e-3, 3 x noise)
-        assert err <= max(3e-3, 4.0 * noise), (n, err, noise)
+        # (`desc.weight`: the reference differs from ITSELF by up to 3.5e-3 between runs, and a two-run noise estimate can come
+        #  out at 2e-4 on the same box: the floor has to cover the noise, not its estimate)
+        assert err <= max(5e-3, 4.0 * noise), (n, err, noise)
 
 
 def test_lookup_rejects_mismatched_disp():

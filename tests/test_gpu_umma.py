@@ -690,3 +690,30 @@ def test_iterations_replay_their_captured_step_by_default(A):
         A.hotpath.graph_cache_clear()
         A.set_update_engine("fp32")
         A.set_corr_mode("fp32")
+
+
+@pytest.mark.parametrize("family", ["igev", "raft"])
+def test_lowres_single_pass_operator_errors(A, golden, family):
+    """The default "f16f8" engine runs the 1/8- and 1/16-resolution GRUs in ONE half pass (set_lowres_single_pass): one
+    update-block call against the reference golden stays inside the 2e-4 operator tolerance on every output (measured
+    net0 1.9e-5, net1 1.1e-4, net2 8e-5, delta 2e-5), and two passes everywhere (the knob off) differ measurably."""
+    g = golden("update_block_" + family)
+    c = cases.update_block_case(family)
+    m = make_block(A, family, 11)
+    A.set_update_engine("f16f8")
+    prev = A.set_lowres_single_pass(True)
+    try:
+        inp = [[t.cuda() for t in lst] for lst in c["inp"]]
+        with torch.no_grad():
+            net, delta = m([t.cuda() for t in c["net"]], inp, c["corr"].cuda(), c["disp"].cuda())
+            A.set_lowres_single_pass(False)
+            m.reset_caches()
+            net2, delta2 = m([t.cuda() for t in c["net"]], inp, c["corr"].cuda(), c["disp"].cuda())
+        errs = [rel(net[i], g["full_net%d" % i]) for i in range(3)] + [rel(delta, g["full_delta"])]
+        errs2 = [rel(net2[i], g["full_net%d" % i]) for i in range(3)] + [rel(delta2, g["full_delta"])]
+    finally:
+        A.set_lowres_single_pass(prev)
+        A.set_update_engine("fp32")
+    assert max(errs) < 2e-4, errs
+    assert max(errs2) < 2e-4 and not torch.equal(net[1], net2[1]), errs2
+    print("%s: one pass at low resolution %s | two passes everywhere %s" % (family, ["%.1e" % e for e in errs], ["%.1e" % e for e in errs2]))
