@@ -16,7 +16,7 @@ from . import corr_sampler
 from . import submodule
 from . import hotpath
 from . import update_umma
-from .update_umma import set_lowres_single_pass
+from .update_umma import set_lowres_single_pass, set_gate_weight_residual_only
 from .geometry import CorrBlock1D, Combined_Geo_Encoding_Volume, set_corr_mode, get_corr_mode
 from .submodule import build_gwc_volume, disparity_regression, init_disparity, gwc_corr_stem, DeferredGwcVolume
 from .update import (BasicMultiUpdateBlock, BasicMultiUpdateBlockRAFT, BasicMotionEncoder, ConvGRU, DispHead,

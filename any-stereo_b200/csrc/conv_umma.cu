@@ -97,7 +97,9 @@ __device__ __forceinline__ void store_split32(const float* v, __nv_bfloat16* hi,
 //   full barriers live in the leader (both producers arm them remotely, TMA credits them with cta_group::2),
 //   "slot free" / "accumulator ready" are multicast commits to both CTAs, "accumulator drained" arrives remotely.
 // NS = tensor-core passes per K-step: 1 = hi*hi; 3 = hi*hi + hi*lo + lo*hi (16-bit hi/lo planes); 2 = hi*hi in kind::f16 plus
-// ONE kind::f8f6f4 MMA over the e5m2 pair planes of AS_FMT_F16F8 (both cross terms, common.cuh).  Compile-time so that no
+// ONE kind::f8f6f4 MMA over the e5m2 pair planes of AS_FMT_F16F8 (both cross terms, common.cuh); 4 = like 2 with only the
+// weight-residual cross term hi_a*lo_w (half of the e5m2 row: 6 MMAs per K-block instead of 8) -- for layers whose
+// activation rounding the result does not see.  Compile-time so that no
 // MMA sits under a run-time branch (see the predicated-MMA lint in tests/test_cpu_boundary.py).
 // SUB = 128-pixel sub-tiles per CTA and weight pass.  SUB = 2 ("tall" tile, 16 x 16 pixels): ONE (16+2)-row activation patch
 // per (dx, channel chunk) and ONE weight stage feed two accumulators, so the L2 -> shared-memory weight traffic per
@@ -305,6 +307,8 @@ __global__ void __launch_bounds__(conv_threads(SUB), 1) conv_umma_kernel(const _
                   umma::mma_ss_lohi<TWO, false>(tmem_d, dal0 + k2, dbh0 + k2, idesc, 1u);
                 } else if (NS == 2) {  // [a_lo*2^6 | a_hi*2^-8] . [w_hi*2^-6 | w_lo*2^8] in e5m2: 32 of the 128 K-bytes per step
                   umma::mma_ss_lohi<TWO, true>(tmem_d, dal0 + k2, dbl0 + k2, idesc8, 1u);
+                } else if (NS == 4) {  // the weight-residual half of that row only: a_hi*2^-8 . w_lo*2^8 (K-bytes 64..127)
+                  if (k >= 2) umma::mma_ss_lohi<TWO, true>(tmem_d, dal0 + k2, dbl0 + k2, idesc8, 1u);
                 }
               }
             }
@@ -517,10 +521,10 @@ extern "C" int as_conv2d_umma(const as_conv_umma_desc* d, as_stream_t stream) {
   if (d->B <= 0 || d->H <= 0 || d->W <= 0 || d->num_src < 1 || d->num_src > 3) return AS_ERR_BAD_ARG;
   if (!((d->KH == 1 && d->KW == 1) || (d->KH == 3 && d->KW == 3))) return AS_ERR_UNSUPPORTED;
   if (d->Cout < 32 || d->Cout > 256 || (d->Cout & 31)) return AS_ERR_UNSUPPORTED;
-  if (d->nsplit < 1 || d->nsplit > 3) return AS_ERR_BAD_ARG;
+  if (d->nsplit < 1 || d->nsplit > 4) return AS_ERR_BAD_ARG;
   if (d->nsplit > 1 && !d->w_lo) return AS_ERR_BAD_ARG;
   // 2 passes = the e5m2 pair planes of AS_FMT_F16F8; 3 passes = 16-bit hi/lo planes: the plane format must match
-  if ((d->nsplit == 2) != (as_operand_fmt_internal() == AS_FMT_F16F8) && d->nsplit != 1) return AS_ERR_BAD_ARG;
+  if ((d->nsplit == 2 || d->nsplit == 4) != (as_operand_fmt_internal() == AS_FMT_F16F8) && d->nsplit != 1) return AS_ERR_BAD_ARG;
   ConvUmmaParams p{};
   p.B = d->B; p.H = d->H; p.W = d->W; p.KH = d->KH; p.KW = d->KW;
   // 128-pixel patch 16 (x) x 8 (y).  Measured on B200 at 312x96: the 8x16 orientation tiles the image exactly (2.5 %
@@ -686,15 +690,18 @@ extern "C" int as_conv2d_umma(const as_conv_umma_desc* d, as_stream_t stream) {
 #define AS_CONV_DISPATCH(TWO_)                                                                            \
   do {                                                                                                    \
     if (sub == 2) {                                                                                       \
+      if (d->nsplit == 4) return launch_conv<TWO_, 2, 2, false>(maps, p, sms, smem, as_cu(stream));       \
       if (d->nsplit == 3) return launch_conv<TWO_, 3, 2, false>(maps, p, sms, smem, as_cu(stream));       \
       if (d->nsplit == 2) return launch_conv<TWO_, 2, 2, false>(maps, p, sms, smem, as_cu(stream));       \
       return launch_conv<TWO_, 1, 2, false>(maps, p, sms, smem, as_cu(stream));                           \
     }                                                                                                     \
     if (group) {                                                                                          \
+      if (d->nsplit == 4) return launch_conv<TWO_, 2, 1, true>(maps, p, sms, smem, as_cu(stream));        \
       if (d->nsplit == 3) return launch_conv<TWO_, 3, 1, true>(maps, p, sms, smem, as_cu(stream));        \
       if (d->nsplit == 2) return launch_conv<TWO_, 2, 1, true>(maps, p, sms, smem, as_cu(stream));        \
       return launch_conv<TWO_, 1, 1, true>(maps, p, sms, smem, as_cu(stream));                            \
     }                                                                                                     \
+    if (d->nsplit == 4) return launch_conv<TWO_, 4, 1, false>(maps, p, sms, smem, as_cu(stream));         \
     if (d->nsplit == 3) return launch_conv<TWO_, 3, 1, false>(maps, p, sms, smem, as_cu(stream));         \
     if (d->nsplit == 2) return launch_conv<TWO_, 2, 1, false>(maps, p, sms, smem, as_cu(stream));         \
     return launch_conv<TWO_, 1, 1, false>(maps, p, sms, smem, as_cu(stream));                             \

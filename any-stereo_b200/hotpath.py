@@ -95,12 +95,12 @@ def set_graph_replay(on: bool) -> bool:
 
 
 def _graph_key(kind, ub, tensors, scalars):
-    from .update_umma import _OVERLAP, _LOWRES_1PASS
+    from .update_umma import _OVERLAP, _LOWRES_1PASS, _GATE_WL
     shapes = tuple((tuple(t.shape), t.dtype, t.device.index) for t in tensors)
     params = tuple((p.data_ptr(), L.version_of(p)) for p in ub.parameters())
     from .geometry import get_corr_mode
     return (kind, id(ub), shapes, params, scalars, get_update_engine(), get_corr_mode(), _FUSION["on"], _OVERLAP["on"],
-            _LOWRES_1PASS["on"], torch.cuda.current_device())
+            _LOWRES_1PASS["on"], _GATE_WL["on"], torch.cuda.current_device())
 
 
 def _graph_eligible(ub, tensors, keep_all, events):

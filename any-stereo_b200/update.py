@@ -155,6 +155,8 @@ class BasicMultiUpdateBlock(nn.Module):
 
     #: 8 geometry groups feed the motion encoder in the IGEV family, 0 in the RAFT family
     GEO_GROUPS = 8
+    #: "f16f8" engine: the 1/4-resolution gate convolutions keep only the weight-residual cross term (update_umma._GATE_WL)
+    gate_weight_residual_only = True
 
     def __init__(self, args, hidden_dims=[]):
         super().__init__()
@@ -316,3 +318,4 @@ class BasicMultiUpdateBlock(nn.Module):
 class BasicMultiUpdateBlockRAFT(BasicMultiUpdateBlock):
     """The corePrune_RAFT flavour (models/corePrune_RAFT/update.py:77: cor_planes = L*(2r+1))."""
     GEO_GROUPS = 0
+    gate_weight_residual_only = False         # RAFT's EPE sits closer to the 1e-3 px bar: both cross terms everywhere

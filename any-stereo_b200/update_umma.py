@@ -55,6 +55,21 @@ def set_lowres_single_pass(on: bool) -> bool:
     return prev
 
 
+# The 1/4-resolution gates z, r of the "f16f8" engine can drop the ACTIVATION-residual cross term lo_a*hi_w (kernel mode
+# nsplit = 4: 6 MMAs per K-block instead of 8 on the largest layer of the iteration).  Simulated per layer
+# (tools/experiments/precision_sim.py --modes mixw_gru04.convz+gru04.convr): IGEV 9.9e-5 -> 1.04e-4 px, RAFT 3.4e-4 -> 4.5e-4 px
+# -- the weight residual is the systematic error that accumulates over iterations, the activation residual averages out.
+# Default: on for the IGEV update block, off for the RAFT one (its EPE sits closer to the 1e-3 px bar); None = class default.
+_GATE_WL = {"on": {"1": True, "0": False}.get(os.environ.get("AS_GATE_WEIGHT_RESIDUAL_ONLY", ""), None)}
+
+
+def set_gate_weight_residual_only(on):
+    """True / False / None (= the update-block class' default).  Returns the previous setting."""
+    prev = _GATE_WL["on"]
+    _GATE_WL["on"] = on if on is None else bool(on)
+    return prev
+
+
 def _side_stream(dev):
     key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
     st = _SIDE.get(key)
@@ -281,9 +296,13 @@ def forward(ub, net, inp, corr=None, disp=None, iter04=True, iter08=True, iter16
         z = torch.empty_like(h)
         rh = _Planes(h.shape, dev, split)
         ns = 1 if (idx > 0 and engine == "f16f8" and _LOWRES_1PASS["on"]) else nsplit   # low-resolution GRUs: one half pass
-        _conv(B, H, W, [hS] + xs, wzr, ns, L.UEPI_GRU_ZR, out=rh, bias=False, ctx=ctx_zr, h=h, z=z)
+        wl = _GATE_WL["on"] if _GATE_WL["on"] is not None else getattr(ub, "gate_weight_residual_only", False)
+        ns_zr = 4 if (idx == 0 and engine == "f16f8" and wl) else ns                    # 1/4-resolution gates: hi*hi + hi_a*lo_w
+        _conv(B, H, W, [hS] + xs, wzr, ns_zr, L.UEPI_GRU_ZR, out=rh, bias=False, ctx=ctx_zr, h=h, z=z)
         hn = torch.empty_like(h)
         hnS = _Planes(h.shape, dev, split)
+        # (q stays 2-pass: dropping its activation residual was measured -- no gain, the N = 128 layers are fill-bound,
+        #  and the final EPE goes 1.4e-4 -> 2.1e-4 px)
         _conv(B, H, W, [rh] + xs, wq, ns, L.UEPI_GRU_Q, out=hnS, bias=False, ctx=ctx_q, h=h, z=z, out_f32=hn)
         _remember(ub, hn, hnS)
         return hn

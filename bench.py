@@ -471,17 +471,19 @@ def run_ours(args):
                 other["engine_fp16_same_step"] = {"pairs_per_s": world * B / (fms / 1e3), "ms_per_step": fms}
                 A.set_update_engine(args.engine)
                 block.reset_caches()
-            if args.engine == "f16f8":                       # two passes everywhere (the default runs gru08 / gru16 in one)
-                A.set_lowres_single_pass(False)
+            if args.engine == "f16f8":                       # both cross terms everywhere (the default: one pass in gru08 / gru16,
+                A.set_lowres_single_pass(False)              # weight-residual term only in the 1/4-resolution gates)
+                A.set_gate_weight_residual_only(False)
                 block.reset_caches()
                 for _ in range(2):
                     step(dd)
                 lms = ev_ms(lambda: step(dd), 6)
                 other["engine_f16f8_two_passes_everywhere_same_step"] = {
                     "pairs_per_s": world * B / (lms / 1e3), "ms_per_step": lms,
-                    "what": "set_lowres_single_pass(False): gru08 / gru16 in two passes like the 1/4-resolution layers (final-disparity "
-                            "EPE 1.51e-4 px instead of 1.35e-4 px on the real IGEV graph, tests/test_gpu_dropin.py)"}
+                    "what": "set_lowres_single_pass(False) + set_gate_weight_residual_only(False): every layer hi*hi + both cross "
+                            "terms (final-disparity EPE 1.51e-4 px instead of 1.44e-4 px on the real IGEV graph, tests/test_gpu_dropin.py)"}
                 A.set_lowres_single_pass(True)
+                A.set_gate_weight_residual_only(None)
                 block.reset_caches()
             if args.engine == "f16f8":                       # the 3-pass split of round 1, same step, for context
                 A.set_update_engine("bf16x3")
@@ -609,6 +611,8 @@ def run_ours(args):
     issued = upd_flops * PASSES.get(args.engine, 1)
     if args.engine == "f16f8" and A.update_umma._LOWRES_1PASS["on"]:      # gru08 / gru16 run one pass
         issued -= 2.0 * (n_pix / 4 * 1327104 + n_pix / 16 * 884736)
+    if args.engine == "f16f8" and A.update_umma._GATE_WL["on"] is not False and block.gate_weight_residual_only:
+        issued -= 0.5 * n_pix * 2.0 * 9 * 384 * 256                      # gru04 z|r: half of the e5m2 pass dropped
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             tpeak = float(json.load(f)["bf16_tflops_sustained"])
@@ -622,7 +626,8 @@ def run_ours(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"fp32": "f32", "bf16x3": "f32 (3x split-bf16 on tcgen05, fp32 accumulate)",
                   "f16f8": "f32 (2-pass split on tcgen05: IEEE-half hi*hi + one e5m2 pass for both cross terms, fp32 accumulate; "
-                           "the 1/8- and 1/16-resolution GRUs in one IEEE-half pass)",
+                           "the 1/8- and 1/16-resolution GRUs in one IEEE-half pass, the 1/4-resolution gates with the weight-residual "
+                           "cross term only)",
                   "bf16": "bf16",
                   "fp16": "f16 (IEEE half operands, fp32 accumulate; mixed-precision analogue)"}[args.engine],
         "data": "synthetic",

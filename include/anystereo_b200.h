@@ -258,7 +258,9 @@ int as_add_f32(const float* a, const float* b, float* y, long long n, as_stream_
 /* ------------------------------------------------------------------------------------------
  * a8-a11 on tensor cores (tcgen05 + TMA).  Activations are pixel-major bf16 planes [B*H*W][C]:
  * `hi` = round-to-nearest bf16 of the value, `lo` = bf16 of the remainder (fp32-parity mode, nsplit = 3:
- * hi*hi + hi*lo + lo*hi with fp32 accumulation in TMEM); nsplit = 1 is the single-bf16 fast mode.
+ * hi*hi + hi*lo + lo*hi with fp32 accumulation in TMEM); nsplit = 1 is the single-pass fast mode (hi planes only).
+ * Under AS_FMT_F16F8 (IEEE-half hi planes + e5m2 pair planes): nsplit = 2 = hi*hi + one e5m2 pass for both cross terms;
+ * nsplit = 4 = hi*hi + the weight-residual cross term hi_a*lo_w only (half of the e5m2 pass).
  * Channels per source must be multiples of 64; Cout a multiple of 32, <= 256.
  * ------------------------------------------------------------------------------------------ */
 #define AS_UEPI_RELU_SPLIT 0 /* relu(acc+bias) -> hi/lo planes at channel offset out_coff               */

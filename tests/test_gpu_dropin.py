@@ -291,3 +291,31 @@ def test_dropin_lowres_single_pass_knob_epe(family, size):
                                                                        "epe_knob_max_px": float((one - ref).abs().max())}})
     assert e2 < 1e-3 and e1 < 1e-3, (e2, e1)
     assert not torch.equal(one, two)
+
+
+@needs_ref
+def test_dropin_gate_weight_residual_only_epe():
+    """IGEV default: the 1/4-resolution gates keep only the weight-residual cross term.  Final disparity of the REAL graph at
+    384x1248 vs the unmodified model, with the mode on (default) and off: both inside the 1e-3 px bar (recorded live)."""
+    import anystereo_b200 as A
+    D = dropin
+    model, R = D.build_model("igev", "cuda")
+    img1, img2 = D.make_pair(1, 384, 1248, "cuda")
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    prev = A.set_gate_weight_residual_only(None)
+    try:
+        ref = D.forward(model, R, img1, img2, 32)
+        with D.installed(model, R, "igev") as m:
+            on = D.forward(m, R, img1, img2, 32)
+            A.set_gate_weight_residual_only(False)
+            off = D.forward(m, R, img1, img2, 32)
+    finally:
+        A.set_gate_weight_residual_only(prev)
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    e_on, e_off = float((on - ref).abs().mean()), float((off - ref).abs().mean())
+    _record({"family": "igev", "image": [384, 1248], "gate_weight_residual_only": {"epe_on_px": e_on, "epe_off_px": e_off,
+                                                                                 "epe_on_max_px": float((on - ref).abs().max())}})
+    assert e_on < 1e-3 and e_off < 1e-3, (e_on, e_off)
+    assert not torch.equal(on, off)

@@ -717,3 +717,30 @@ def test_lowres_single_pass_operator_errors(A, golden, family):
     assert max(errs) < 2e-4, errs
     assert max(errs2) < 2e-4 and not torch.equal(net[1], net2[1]), errs2
     print("%s: one pass at low resolution %s | two passes everywhere %s" % (family, ["%.1e" % e for e in errs], ["%.1e" % e for e in errs2]))
+
+
+def test_gate_weight_residual_only_operator_errors(A, golden):
+    """The IGEV update block's 1/4-resolution gates under "f16f8": hi*hi + the weight-residual cross term only (kernel mode
+    nsplit = 4).  One call against the reference golden stays inside the 2e-4 operator tolerance; both cross terms
+    (set_gate_weight_residual_only(False)) differ measurably; the RAFT block's default is both."""
+    g = golden("update_block_igev")
+    c = cases.update_block_case("igev")
+    m = make_block(A, "igev", 11)
+    assert m.gate_weight_residual_only and not make_block(A, "raft", 11).gate_weight_residual_only
+    A.set_update_engine("f16f8")
+    prev = A.set_gate_weight_residual_only(None)
+    try:
+        inp = [[t.cuda() for t in lst] for lst in c["inp"]]
+        with torch.no_grad():
+            net, delta = m([t.cuda() for t in c["net"]], inp, c["corr"].cuda(), c["disp"].cuda())
+            A.set_gate_weight_residual_only(False)
+            m.reset_caches()
+            net2, delta2 = m([t.cuda() for t in c["net"]], inp, c["corr"].cuda(), c["disp"].cuda())
+        errs = [rel(net[i], g["full_net%d" % i]) for i in range(3)] + [rel(delta, g["full_delta"])]
+        errs2 = [rel(net2[i], g["full_net%d" % i]) for i in range(3)] + [rel(delta2, g["full_delta"])]
+    finally:
+        A.set_gate_weight_residual_only(prev)
+        A.set_update_engine("fp32")
+    print("weight residual only %s | both cross terms %s" % (["%.1e" % e for e in errs], ["%.1e" % e for e in errs2]))
+    assert max(errs) < 2e-4, errs
+    assert max(errs2) < 2e-4 and not torch.equal(net[0], net2[0]), errs2

@@ -57,6 +57,15 @@ def conv_mode(mode, s_act=6, t_act=8):
             c1 = F.conv2d(q(al * sa, f8), q(wh / sa, hi8 if mode != "f16f8_e4m3hi" else f8), None, padding=pad)
             c2 = F.conv2d(q(ah / ta, f8), q(wl * ta, f8), None, padding=pad)
             return main + c1 + c2
+        if mode in ("f16f8_wl", "f16f8_al"):          # ONE cross term only (half of the e5m2 pass): weight residual / activation residual
+            ah, al = split(x, torch.float16)
+            wh, wl = split(w, torch.float16)
+            main = F.conv2d(ah, wh, b, padding=pad)
+            f8 = torch.float8_e5m2
+            sa, ta = 2.0 ** s_act, 2.0 ** t_act
+            if mode == "f16f8_wl":
+                return main + F.conv2d(q(ah / ta, f8), q(wl * ta, f8), None, padding=pad)
+            return main + F.conv2d(q(al * sa, f8), q(wh / sa, f8), None, padding=pad)
         raise ValueError(mode)
     return conv
 
@@ -70,9 +79,11 @@ def run(family, iters, H, W, modes):
     for mode in modes:
         # mixed modes "mix_<pattern>[+<pattern>]": the convolutions whose name contains a pattern run single-pass fp16, the rest
         # f16f8 (e.g. mix_convz+convr: the GRU gates z, r in one pass; mix_gru16+gru08: the low-resolution GRUs)
-        pats = mode[4:].split("+") if mode.startswith("mix_") else None
+        # "mixw_<patterns>": the named convolutions keep only the WEIGHT-residual cross term (half of the e5m2 pass)
+        cheap = "f16f8_wl" if mode.startswith("mixw_") else "fp16"
+        pats = mode[5:].split("+") if mode.startswith("mixw_") else (mode[4:].split("+") if mode.startswith("mix_") else None)
         for m in convs:
-            mm = mode if pats is None else ("fp16" if any(p in names[id(m)] for p in pats) else "f16f8")
+            mm = mode if pats is None else (cheap if any(p in names[id(m)] for p in pats) else "f16f8")
             fn = conv_mode(mm)
             m.forward = (lambda x, m=m, fn=fn: fn(x.float(), m.weight, m.bias, m.padding))
         res = dropin.forward(model, R, img1, img2, iters)
