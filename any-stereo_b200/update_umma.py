@@ -397,6 +397,7 @@ def forward(ub, net, inp, corr=None, disp=None, iter04=True, iter08=True, iter16
         B, H, W, Hd = hs[0].shape
         sw = _small_weights(ub)
         u = torch.empty((B, H, W, 9), device=dev, dtype=torch.float32)
+        # (the disparity head stays 2-pass: weight residual only was measured at +2 % throughput for EPE 1.44e-4 -> 2.19e-4 px)
         _conv(B, H, W, [_planes_of(ub, hs[0], split)], _weights(ub, "dh1", [ub.disp_head.conv1], split=split), nsplit,
               L.UEPI_DISPHEAD, w2=sw["w2"], u=u)
         delta = torch.empty((B, 1, H, W), device=dev, dtype=torch.float32)
