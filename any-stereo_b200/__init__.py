@@ -16,7 +16,7 @@ from . import corr_sampler
 from . import submodule
 from . import hotpath
 from . import update_umma
-from .update_umma import set_lowres_single_pass, set_gate_weight_residual_only
+from .update_umma import set_lowres_single_pass, set_gate_weight_residual_only, set_call_replay
 from .geometry import CorrBlock1D, Combined_Geo_Encoding_Volume, set_corr_mode, get_corr_mode
 from .submodule import build_gwc_volume, disparity_regression, init_disparity, gwc_corr_stem, DeferredGwcVolume
 from .update import (BasicMultiUpdateBlock, BasicMultiUpdateBlockRAFT, BasicMotionEncoder, ConvGRU, DispHead,
@@ -25,6 +25,8 @@ from .hotpath import (igev_iterations, raft_iterations, install_into_reference, 
                       adopt_update_block, adopt_liif_up, adopt_corr_stem, set_graph_replay)
 from .parallel import shard_pairs, allreduce_gradients, GradientAllReducer
 from . import liif
+from . import extractor
+from .extractor import adopt_context_encoder, ContextEncoder
 from .liif import liif_out_multi_scale_Training, context_upsample_multiscale_train, upsample_disp
 
 __all__ = [

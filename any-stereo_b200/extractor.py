@@ -1,0 +1,161 @@
+"""SURVEY 8(f)-4, first step: the context encoder ``cnet`` (reference: models/*/extractor.py:200-300 MultiBasicEncoder,
+ResidualBlock :9-58; call sites continuous_IGEVstereo.py:270, prune_raft_stereo.py:253).
+
+With the iteration loop on the tensor cores, one 384x1248 pair spends 7 ms of a 36 ms forward in this module -- and only
+2.4 ms of those in convolutions (profiles/cnet_prof_r02.txt): 2.8 ms are 33 eval-mode BatchNorm2d kernels, 1.1 ms NCHW <->
+NHWC conversions around every cuDNN call, 1.1 ms separate ReLU / add kernels.  None of that is arithmetic the model needs
+at inference: an eval-mode BatchNorm is a per-channel affine map of the convolution in front of it.
+
+``adopt_context_encoder(model.cnet)`` wraps the SAME submodules (state_dict keys unchanged) and, when no gradient is
+requested and every BatchNorm2d is in eval mode, runs
+
+    conv(x, w * s) + ((b - mean) * s + beta),   s = gamma / sqrt(var + eps)
+
+per Conv2d + BatchNorm2d pair, channels-last end to end, ReLU and the residual add in place.  The convolutions themselves
+stay cuDNN library calls (SURVEY names "channels-last cuDNN or custom kernels" for this row; the tensor-core kernels of
+this library cover stride-1 3x3 layers with 64-multiple channels, which is layer1 only -- DESIGN 9).  Anything else
+(training, gradients, GroupNorm / InstanceNorm variants) takes the reference module's own forward.
+"""
+from __future__ import annotations
+
+import itertools
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib as L
+
+
+class _Folded:
+    """One Conv2d with the eval-mode BatchNorm2d behind it folded in (channels-last weights)."""
+    __slots__ = ("w", "b", "stride", "padding")
+
+    def __init__(self, conv, bn=None):
+        w = conv.weight.detach().float()
+        b = conv.bias.detach().float() if conv.bias is not None else torch.zeros(w.shape[0], device=w.device)
+        if isinstance(bn, nn.BatchNorm2d):
+            s = torch.rsqrt(bn.running_var.detach().float() + bn.eps)
+            if bn.weight is not None:
+                s = s * bn.weight.detach().float()
+            w = w * s.view(-1, 1, 1, 1)
+            b = (b - bn.running_mean.detach().float()) * s
+            if bn.bias is not None:
+                b = b + bn.bias.detach().float()
+        self.w = w.contiguous(memory_format=torch.channels_last)
+        self.b = b.contiguous()
+        self.stride, self.padding = conv.stride, conv.padding
+
+    def __call__(self, x, relu=False):
+        y = F.conv2d(x, self.w, self.b, self.stride, self.padding)
+        return y.relu_() if relu else y
+
+
+class _FoldedBlock:
+    """ResidualBlock (extractor.py:9-58): relu(x' + relu(bn2(conv2(relu(bn1(conv1(x))))))), x' = bn3(conv1x1(x)) or x."""
+    __slots__ = ("c1", "c2", "down")
+
+    def __init__(self, blk):
+        self.c1 = _Folded(blk.conv1, blk.norm1)
+        self.c2 = _Folded(blk.conv2, blk.norm2)
+        self.down = None if blk.downsample is None else _Folded(blk.downsample[0], blk.downsample[1])
+
+    def __call__(self, x):
+        y = self.c2(self.c1(x, True), True)
+        if self.down is not None:
+            x = self.down(x)
+        return y.add_(x).relu_()
+
+
+def _is_block(m):
+    return all(hasattr(m, n) for n in ("conv1", "conv2", "norm1", "norm2", "downsample"))
+
+
+class ContextEncoder(nn.Module):
+    """The reference's MultiBasicEncoder around the same submodules; see the module docstring."""
+
+    def __init__(self, ref):
+        super().__init__()
+        for name, child in ref.named_children():
+            self.add_module(name, child)
+        self.norm_fn = ref.norm_fn
+        self.downsample = ref.downsample
+        self.__dict__["_ref"] = ref            # not registered: its parameters are already ours through the children
+        self.__dict__["_fold_cache"] = None
+
+    # -- when the folded path applies --------------------------------------------------------------------------------
+    def _fusable(self, x):
+        if self.norm_fn != "batch" or not torch.is_floating_point(x):
+            return False
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            return False
+        for m in self.modules():
+            if isinstance(m, nn.BatchNorm2d):
+                if m.training or m.running_mean is None:
+                    return False
+            elif isinstance(m, (nn.GroupNorm, nn.InstanceNorm2d)):
+                return False
+        return all(_is_block(b) for layer in self._layers() for b in layer)
+
+    def _layers(self):
+        return [getattr(self, "layer%d" % i) for i in range(1, 6)]
+
+    def _folded(self):
+        key = tuple((t.data_ptr(), L.version_of(t)) for t in itertools.chain(self.parameters(), self.buffers()))
+        hit = self.__dict__["_fold_cache"]
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        with torch.no_grad():
+            f = {"stem": _Folded(self.conv1, self.norm1),
+                 "layers": [[_FoldedBlock(b) for b in layer] for layer in self._layers()],
+                 "out04": [(_FoldedBlock(h[0]), _Folded(h[1])) for h in self.outputs04],
+                 "out08": [(_FoldedBlock(h[0]), _Folded(h[1])) for h in self.outputs08],
+                 "out16": [_Folded(h) for h in self.outputs16]}
+        self.__dict__["_fold_cache"] = (key, f)
+        return f
+
+    def invalidate_weights(self):
+        """After writes that bypass the version counter (``param.data``, EMA through ``.data``)."""
+        self.__dict__["_fold_cache"] = None
+
+    # -- forward (extractor.py:280-304) --------------------------------------------------------------------------------
+    def forward(self, x, dual_inp=False, num_layers=3):
+        if not self._fusable(x):
+            return self.__dict__["_ref"](x, dual_inp=dual_inp, num_layers=num_layers)
+        f = self._folded()
+        with torch.no_grad():
+            x = f["stem"](x.float().contiguous(memory_format=torch.channels_last), True)
+            for layer in f["layers"][:3]:
+                for blk in layer:
+                    x = blk(x)
+            v = None
+            if dual_inp:
+                v = x.contiguous()
+                x = x[:(x.shape[0] // 2)]
+            # the heads leave in the reference's (NCHW-contiguous) layout: whatever consumes them may .view() them
+            outputs04 = [conv(blk(x)).contiguous() for blk, conv in f["out04"]]
+            if num_layers == 1:
+                return (outputs04, v) if dual_inp else (outputs04,)
+            y = x
+            for blk in f["layers"][3]:
+                y = blk(y)
+            outputs08 = [conv(blk(y)).contiguous() for blk, conv in f["out08"]]
+            if num_layers == 2:
+                return (outputs04, outputs08, v) if dual_inp else (outputs04, outputs08)
+            z = y
+            for blk in f["layers"][4]:
+                z = blk(z)
+            outputs16 = [conv(z).contiguous() for conv in f["out16"]]
+            return (outputs04, outputs08, outputs16, v) if dual_inp else (outputs04, outputs08, outputs16)
+
+
+def adopt_context_encoder(ref_cnet):
+    """``model.cnet = adopt_context_encoder(model.cnet)``: eval-mode BatchNorm folded into the convolutions, channels-last,
+    in-place ReLU / residual adds; same parameters, same state_dict keys, reference arithmetic whenever a gradient is
+    requested or a norm layer is not an eval-mode BatchNorm2d."""
+    if isinstance(ref_cnet, ContextEncoder):
+        return ref_cnet
+    need = ("conv1", "norm1", "layer1", "layer2", "layer3", "layer4", "layer5", "outputs04", "outputs08", "outputs16")
+    if not all(hasattr(ref_cnet, n) for n in need):
+        raise TypeError("adopt_context_encoder expects the reference's MultiBasicEncoder (models/*/extractor.py:200)")
+    return ContextEncoder(ref_cnet)

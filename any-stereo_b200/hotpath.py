@@ -41,6 +41,14 @@ def set_lookup_fusion(on: bool) -> bool:
 
 def _iterate(lookup, update_block, net_list, inp_list, disp, coords, iters, slow_fast_gru=False, keep_all=False,
              lookup_events=None, update_events=None, fused_lookup=None):
+    from .update_umma import call_replay_suspended
+    with call_replay_suspended():          # this loop is captured as a whole (HotLoopGraph), not call by call
+        return _iterate_body(lookup, update_block, net_list, inp_list, disp, coords, iters, slow_fast_gru, keep_all,
+                             lookup_events, update_events, fused_lookup)
+
+
+def _iterate_body(lookup, update_block, net_list, inp_list, disp, coords, iters, slow_fast_gru, keep_all, lookup_events,
+                  update_events, fused_lookup):
     n_layers = update_block.args.n_gru_layers
     hist = []
     net_list = list(net_list)
@@ -349,8 +357,10 @@ def adopt_corr_stem(model, ref_igev_module):
     return model
 
 
-def adopt_update_block(ref_update_block, family="igev"):
-    """Build our update block around the SAME nn.Parameter objects as a reference BasicMultiUpdateBlock."""
+def adopt_update_block(ref_update_block, family="igev", replay=None):
+    """Build our update block around the SAME nn.Parameter objects as a reference BasicMultiUpdateBlock.
+    replay=True: every inference call of the block is replayed from a CUDA graph (update_umma.set_call_replay; for loops
+    that run at the host's pace, i.e. small batches); None = the module-wide setting."""
     from .update import BasicMultiUpdateBlock, BasicMultiUpdateBlockRAFT
     cls = BasicMultiUpdateBlock if family == "igev" else BasicMultiUpdateBlockRAFT
     hd = [ref_update_block.gru16.convz.out_channels, ref_update_block.gru08.convz.out_channels,
@@ -367,6 +377,7 @@ def adopt_update_block(ref_update_block, family="igev"):
         for p in parts[:-1]:
             mod = getattr(mod, p)
         mod._parameters[parts[-1]] = ref_params[name]
+    ours.call_replay = replay
     return ours.to(next(ref_update_block.parameters()).device)
 
 

@@ -157,6 +157,8 @@ class BasicMultiUpdateBlock(nn.Module):
     GEO_GROUPS = 8
     #: "f16f8" engine: the 1/4-resolution gate convolutions keep only the weight-residual cross term (update_umma._GATE_WL)
     gate_weight_residual_only = True
+    #: replay every inference call from a CUDA graph: True / False / None = update_umma.set_call_replay's setting
+    call_replay = None
 
     def __init__(self, args, hidden_dims=[]):
         super().__init__()
@@ -188,6 +190,7 @@ class BasicMultiUpdateBlock(nn.Module):
         st = self.__dict__.get("_umma_state")
         if st is not None:
             st["w"].clear()
+            st["calls"].clear()
 
     def _pk(self, name, convs):
         if name not in self._packed:
@@ -283,6 +286,11 @@ class BasicMultiUpdateBlock(nn.Module):
         if get_update_engine() != "fp32":
             from . import update_umma
             sync_operand_format()
+            if iter04 and update and update_umma.call_replay_enabled(self):
+                # the reference's own loop, one call per iteration: replay the call from a CUDA graph (opt-in)
+                out = update_umma.forward_replayed(self, net, inp, corr, disp, iter08, iter16)
+                if out is not None:
+                    return out
             return update_umma.forward(self, net, inp, corr, disp, iter04, iter08, iter16, update)
         for t in net:
             L.require_cuda(t, "net[i]", contiguous=False)

@@ -93,7 +93,7 @@ class _Planes:
 def _state(ub):
     st = ub.__dict__.get("_umma_state")
     if st is None:
-        st = {"w": {}, "ctx": {}, "planes": {}}
+        st = {"w": {}, "ctx": {}, "planes": {}, "calls": {}}
         ub.__dict__["_umma_state"] = st
     return st
 
@@ -263,7 +263,20 @@ def _remember(ub, h_f32, pl):
     cache[h_f32.data_ptr()] = (weakref.ref(h_f32), pl, L.version_of(h_f32))
 
 
-def forward(ub, net, inp, corr=None, disp=None, iter04=True, iter08=True, iter16=True, update=True):
+def _lookup_convc1(ub, corr, c1, split):
+    """relu(convc1(lookup)) of a deferred lookup into the planes `c1` (one fused kernel)."""
+    tap = bool(getattr(corr, "tap_major", False))
+    wf = _fused_c1_weights(ub, split, type(corr), tap)
+    if tap:
+        corr.convc1_planes(wf["hi"], wf["lo"], wf["bias"], c1.hi, c1.lo, tap_major=True)
+    else:
+        corr.convc1_planes(wf["hi"], wf["lo"], wf["bias"], c1.hi, c1.lo)
+
+
+def forward(ub, net, inp, corr=None, disp=None, iter04=True, iter08=True, iter16=True, update=True, ctx_override=None,
+            c1_override=None):
+    """ctx_override: {scale index: (ctx_zr, ctx_q)}, c1_override: relu(convc1(lookup)) planes -- replayed calls read the
+    loop-invariant context and the fused lookup's result from buffers the graph owns (see _CallGraph)."""
     from .update import _nhwc_view, get_update_engine
     engine = get_update_engine()
     split = engine in ("bf16x3", "f16f8")            # conv inputs carry a second ("lo") plane
@@ -291,7 +304,7 @@ def forward(ub, net, inp, corr=None, disp=None, iter04=True, iter08=True, iter16
         wzr = _weights(ub, name + ".zr", [g.convz, g.convr], split=split)
         wq = _weights(ub, name + ".q", [g.convq], split=split)
         assert wzr["cin"] == cin
-        ctx_zr, ctx_q = _context(ub, idx, inp[idx], wzr, wq)
+        ctx_zr, ctx_q = ctx_override[idx] if ctx_override is not None else _context(ub, idx, inp[idx], wzr, wq)
         hS = _planes_of(ub, h, split)
         z = torch.empty_like(h)
         rh = _Planes(h.shape, dev, split)
@@ -309,23 +322,22 @@ def forward(ub, net, inp, corr=None, disp=None, iter04=True, iter08=True, iter16
 
     def encoder():
         """BasicMotionEncoder.forward (update.py:84-92) -> motion planes [B,H,W,128] (cat(out, disp) in the epilogue)."""
-        B, Cc, H, W = corr.shape
         e = ub.encoder
         sw = _small_weights(ub)
-        cpad = (Cc + 63) // 64 * 64
-        c1 = _Planes((B, H, W, 64), dev, split)
-        if isinstance(corr, _DEFERRED):              # lookup + convc1 + ReLU in one kernel, features stay on chip
-            tap = bool(getattr(corr, "tap_major", False))
-            wf = _fused_c1_weights(ub, split, type(corr), tap)
-            if tap:
-                corr.convc1_planes(wf["hi"], wf["lo"], wf["bias"], c1.hi, c1.lo, tap_major=True)
-            else:
-                corr.convc1_planes(wf["hi"], wf["lo"], wf["bias"], c1.hi, c1.lo)
+        if c1_override is not None:                  # replayed call: the lookup ran eagerly, outside the graph
+            c1 = c1_override
+            B, H, W = c1.shape[:3]
         else:
-            wc1 = _weights(ub, "convc1", [e.convc1], cin_pad=cpad, split=split)
-            corrS = _Planes((B, H, W, cpad), dev, split)
-            L.call("as_nchw_to_nhwc_split", corr.data_ptr(), corrS.hi.data_ptr(), L.ptr(corrS.lo), B, Cc, H, W, cpad, s())
-            _conv(B, H, W, [corrS], wc1, nsplit, L.UEPI_RELU_SPLIT, out=c1)
+            B, Cc, H, W = corr.shape
+            c1 = _Planes((B, H, W, 64), dev, split)
+            if isinstance(corr, _DEFERRED):          # lookup + convc1 + ReLU in one kernel, features stay on chip
+                _lookup_convc1(ub, corr, c1, split)
+            else:
+                cpad = (Cc + 63) // 64 * 64
+                wc1 = _weights(ub, "convc1", [e.convc1], cin_pad=cpad, split=split)
+                corrS = _Planes((B, H, W, cpad), dev, split)
+                L.call("as_nchw_to_nhwc_split", corr.data_ptr(), corrS.hi.data_ptr(), L.ptr(corrS.lo), B, Cc, H, W, cpad, s())
+                _conv(B, H, W, [corrS], wc1, nsplit, L.UEPI_RELU_SPLIT, out=c1)
         enc = _Planes((B, H, W, 128), dev, split)
         _conv(B, H, W, [c1], _weights(ub, "convc2", [e.convc2], split=split), nsplit, L.UEPI_RELU_SPLIT, out=enc)
         d1 = _Planes((B, H, W, 64), dev, split)
@@ -347,12 +359,13 @@ def forward(ub, net, inp, corr=None, disp=None, iter04=True, iter08=True, iter16
         hs = [None if t is None else _nhwc_view(t.detach().float())[0] for t in net]
         enc_job = None
         if iter04:
-            if isinstance(corr, _DEFERRED):
-                if not corr.fusable or ub.encoder.convc1.out_channels != 64:
-                    corr = corr.materialize()
-            if not isinstance(corr, _DEFERRED):
-                L.require_cuda(corr, "corr", contiguous=False)
-                corr = corr.detach().float().contiguous()
+            if c1_override is None:
+                if isinstance(corr, _DEFERRED):
+                    if not corr.fusable or ub.encoder.convc1.out_channels != 64:
+                        corr = corr.materialize()
+                if not isinstance(corr, _DEFERRED):
+                    L.require_cuda(corr, "corr", contiguous=False)
+                    corr = corr.detach().float().contiguous()
             L.require_cuda(disp, "disp", contiguous=False)
             disp = disp.detach().float().contiguous()
             if _OVERLAP["on"] and (iter16 or iter08):
@@ -403,3 +416,159 @@ def forward(ub, net, inp, corr=None, disp=None, iter04=True, iter08=True, iter16
         delta = torch.empty((B, 1, H, W), device=dev, dtype=torch.float32)
         L.call("as_disp_delta", u.data_ptr(), sw["b2"].data_ptr(), delta.data_ptr(), B, H, W, s())
     return net, delta
+
+
+# ---- replayed calls: one CUDA graph per update-block CALL (the reference's own loop, drop-in) --------------------------------
+# hotpath.igev_iterations / raft_iterations replay the whole loop; a model that keeps the reference's Python loop
+# (continuous_IGEVstereo.py:284-297) calls this block once per iteration instead: ~25 kernel launches through ctypes plus the
+# tensor bookkeeping around them, ~0.5 ms of host time per call.  At one 384x1248 pair the GPU needs less than that, so the
+# loop runs at the host's pace.  With set_call_replay(True) (or AS_CALL_REPLAY=1, or adopt_update_block(..., replay=True)) the
+# first call with a given (shapes, cost-volume buffers, parameters, engine, knobs) captures the call on static buffers and
+# every later call is: copy the hidden states / disparity in, refresh the context if `inp` changed, replay, clone the results
+# out.  Same kernels, same arithmetic, same results as the eager call; nothing is traced or compiled.
+# Off by default: a graph pins the memory of one call's intermediates, and the saving only exists where the host is the
+# bottleneck (small batches).
+_CALL_REPLAY = {"on": os.environ.get("AS_CALL_REPLAY", "0") == "1", "max": 2, "suspended": 0}
+
+
+def set_call_replay(on: bool) -> bool:
+    """Replay each update-block call from a CUDA graph (inference, tensor-core engines).  Returns the previous setting."""
+    prev = _CALL_REPLAY["on"]
+    _CALL_REPLAY["on"] = bool(on)
+    return prev
+
+
+def call_replay_enabled(ub) -> bool:
+    if _CALL_REPLAY["suspended"]:
+        return False
+    own = getattr(ub, "call_replay", None)
+    return _CALL_REPLAY["on"] if own is None else bool(own)
+
+
+class call_replay_suspended:
+    """hotpath's own loops (which are captured as a whole) run their calls eagerly."""
+
+    def __enter__(self):
+        _CALL_REPLAY["suspended"] += 1
+
+    def __exit__(self, *exc):
+        _CALL_REPLAY["suspended"] -= 1
+
+
+def call_replay_clear(ub):
+    """Release the call graphs of one update block (each pins the memory pool of one captured call)."""
+    st = ub.__dict__.get("_umma_state")
+    if st is not None:
+        st["calls"].clear()
+
+
+def _gru_weights(ub, idx, split):
+    name, g = (("gru04", ub.gru04), ("gru08", ub.gru08), ("gru16", ub.gru16))[idx]
+    return (_weights(ub, name + ".zr", [g.convz, g.convr], split=split), _weights(ub, name + ".q", [g.convq], split=split))
+
+
+def _call_key(ub, net, corr, disp, iter08, iter16):
+    from .update import get_update_engine
+    shapes = tuple(None if t is None else tuple(t.shape) for t in net)
+    params = tuple((p.data_ptr(), L.version_of(p)) for p in ub.parameters())
+    ck = (type(corr).__name__, tuple(corr.shape), bool(getattr(corr, "tap_major", False)))
+    return (shapes, params, ck, tuple(disp.shape), bool(iter08), bool(iter16), get_update_engine(), L.operand_format(),
+            _OVERLAP["on"], _LOWRES_1PASS["on"], _GATE_WL["on"], net[0].device.index)
+
+
+class _CallGraph:
+    """One update-block call (all scales the flags select + the disparity head) captured on static buffers."""
+
+    def __init__(self, ub, net, inp, corr, disp, iter08, iter16):
+        from .update import get_update_engine
+        dev = net[0].device
+        self.flags = (bool(iter08), bool(iter16))
+        self.split = get_update_engine() in ("bf16x3", "f16f8")
+        self.net = []
+        for t in net:                                  # pixel-major storage behind an NCHW-shaped view, like our outputs
+            if t is None:
+                self.net.append(None)
+            else:
+                B, C, H, W = t.shape
+                self.net.append(torch.empty((B, H, W, C), device=dev, dtype=torch.float32).permute(0, 3, 1, 2))
+        self.disp = torch.empty(tuple(disp.shape), device=dev, dtype=torch.float32)
+        # A deferred lookup reads cost-volume buffers that are reallocated by every forward: its fused kernel stays OUTSIDE
+        # the graph (one eager launch per call, straight from the live volume / disparity into the graph's c1 planes), so a
+        # graph is captured once per shape, not once per image pair.  A materialised lookup tensor is copied in.
+        self.c1 = self.corr_t = None
+        if isinstance(corr, _DEFERRED):
+            B, _, H, W = disp.shape
+            self.c1 = _Planes((B, H, W, 64), dev, self.split)
+        else:
+            self.corr_t = torch.empty(tuple(corr.shape), device=dev, dtype=torch.float32)
+        self.active = [0] + ([1] if iter08 else []) + ([2] if iter16 else [])
+        self.ctx, self.ctx_src = {}, {}
+        for idx in self.active:
+            zr, q = _context(ub, idx, inp[idx], *_gru_weights(ub, idx, self.split))
+            self.ctx[idx] = (torch.empty_like(zr), torch.empty_like(q))
+        self.load(ub, net, inp, corr, disp)
+
+        def run():
+            with torch.no_grad():
+                return forward(ub, list(self.net), None, self.corr_t, self.disp, True, iter08, iter16, True,
+                               ctx_override=self.ctx, c1_override=self.c1)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            run()                                      # packs whatever weights this call needs outside the capture
+        torch.cuda.current_stream().wait_stream(side)
+        planes = _state(ub)["planes"]
+        for t in self.net:                             # the static inputs must be split inside the graph, every replay
+            if t is not None:
+                planes.pop(t.data_ptr(), None)
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = L.launch_count
+        with torch.cuda.graph(self.graph):
+            self.out_net, self.out_delta = run()
+        self.launches = L.launch_count - n0
+
+    def load(self, ub, net, inp, corr, disp):
+        for d, s in zip(self.net, net):
+            if d is not None:
+                d.copy_(s, non_blocking=True)
+        self.disp.copy_(disp, non_blocking=True)
+        if self.c1 is not None:
+            _lookup_convc1(ub, corr, self.c1, self.split)
+        else:
+            self.corr_t.copy_(corr, non_blocking=True)
+        for idx in self.active:                        # loop-invariant: copied once per `inp` (i.e. once per forward)
+            zr, q = _context(ub, idx, inp[idx], *_gru_weights(ub, idx, self.split))
+            src = self.ctx_src.get(idx)
+            if src is None or src() is not zr:
+                self.ctx[idx][0].copy_(zr, non_blocking=True)
+                self.ctx[idx][1].copy_(q, non_blocking=True)
+                self.ctx_src[idx] = weakref.ref(zr)
+
+    def replay(self):
+        self.graph.replay()
+        L.launch_count += self.launches
+        return [None if t is None else t.clone() for t in self.out_net], self.out_delta.clone()
+
+
+def forward_replayed(ub, net, inp, corr, disp, iter08=True, iter16=True):
+    """update_block(net, inp, corr, disp, iter04=True, update=True) through a cached CUDA graph; None when this call
+    cannot be replayed (the caller then runs it eagerly)."""
+    if corr is None or disp is None or torch.cuda.is_current_stream_capturing():
+        return None
+    deferred = isinstance(corr, _DEFERRED)
+    if deferred and (not corr.fusable or ub.encoder.convc1.out_channels != 64 or corr.disp.shape != disp.shape):
+        return None
+    if any(t is not None and (not t.is_cuda or t.requires_grad) for t in list(net) + [disp]):
+        return None
+    with torch.cuda.device(net[0].device):
+        key = _call_key(ub, net, corr, disp, iter08, iter16)
+        cache = _state(ub)["calls"]
+        g = cache.get(key)
+        if g is None:
+            while len(cache) >= _CALL_REPLAY["max"]:
+                cache.pop(next(iter(cache)))           # oldest first
+            g = _CallGraph(ub, net, inp, corr, disp, iter08, iter16)
+            cache[key] = g
+        else:
+            g.load(ub, net, inp, corr, disp)
+        return g.replay()

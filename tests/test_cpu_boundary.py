@@ -127,6 +127,31 @@ def test_lowres_single_pass_default(A):
     assert A.set_lowres_single_pass(True) is False
 
 
+def test_call_replay_switches(A):
+    """Per-call graph replay is opt-in: module switch, per-block override (adopt_update_block(..., replay=...)), suspended
+    inside the library's own loops (those are captured as a whole), and never taken without corr / disp."""
+    import types
+    um = A.update_umma
+    assert um._CALL_REPLAY["on"] is False
+    args = types.SimpleNamespace(corr_levels=2, corr_radius=4, n_gru_layers=3)
+    ub = A.BasicMultiUpdateBlock(args, hidden_dims=[128, 128, 128])
+    assert ub.call_replay is None and not um.call_replay_enabled(ub)
+    assert A.set_call_replay(True) is False
+    try:
+        assert um.call_replay_enabled(ub)
+        ub.call_replay = False
+        assert not um.call_replay_enabled(ub)
+        ub.call_replay = True
+        with um.call_replay_suspended():
+            assert not um.call_replay_enabled(ub)
+        assert um.call_replay_enabled(ub)
+    finally:
+        assert A.set_call_replay(False) is True
+    assert um.forward_replayed(ub, [], [], None, None) is None
+    ours = A.hotpath.adopt_update_block(ub, "igev", replay=True)
+    assert ours.call_replay is True and ours.gru04.convz.weight is ub.gru04.convz.weight
+
+
 def test_default_engine_is_tensor_core_parity(A):
     """VERDICT r1 weak #5: rebinding the names alone must select the tcgen05 parity engine, not the CUDA-core one."""
     import subprocess
@@ -268,3 +293,58 @@ def test_deferred_wrappers_host_logic(A):
     # the deferring cost-volume classes only change __call__
     assert A.geometry.Combined_Geo_Encoding_Volume_Deferred.__mro__[1] is A.Combined_Geo_Encoding_Volume
     assert A.geometry.CorrBlock1D_Deferred.__mro__[1] is A.CorrBlock1D
+
+
+def test_adopted_context_encoder_matches_reference_module(A):
+    """adopt_context_encoder folds the eval-mode BatchNorm2d layers of the reference's MultiBasicEncoder
+    (models/*/extractor.py:200-300) into its convolutions.  Same outputs as the reference module (fp32, CPU), same
+    state_dict keys, reference arithmetic when a gradient is requested or a BatchNorm is in training mode."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference tree absent")
+    ref_loader.load_models()
+    from models.coreContinuous_IGEV.extractor import MultiBasicEncoder
+    torch.manual_seed(0)
+    ref = MultiBasicEncoder(output_dim=[[128] * 3, [128] * 3], norm_fn="batch", downsample=2)
+    for m in ref.modules():                       # non-trivial running statistics and affine parameters
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.3)
+            m.running_var.uniform_(0.5, 2.0)
+            m.weight.data.uniform_(0.5, 1.5)
+            m.bias.data.normal_(0, 0.2)
+    ref.eval()
+    x = torch.randn(2, 3, 32, 64)
+    with torch.no_grad():
+        want = ref(x, num_layers=3)
+    ours = A.adopt_context_encoder(ref)
+    assert A.adopt_context_encoder(ours) is ours
+    assert list(ours.state_dict().keys()) == list(ref.state_dict().keys())
+    with torch.no_grad():
+        got = ours(x, num_layers=3)
+        assert ours.__dict__["_fold_cache"] is not None            # the folded path ran
+        for lw, lg in zip(want, got):
+            for w, g in zip(lw, lg):
+                assert g.shape == w.shape and g.is_contiguous()
+                assert float((g - w).abs().max()) <= 2e-5 * float(w.abs().max())
+        for n in (1, 2):
+            w_, g_ = ref(x, num_layers=n), ours(x, num_layers=n)
+            assert len(w_) == len(g_) == n
+            assert float((g_[-1][1] - w_[-1][1]).abs().max()) <= 2e-5 * float(w_[-1][1].abs().max())
+        wd, gd = ref(x, dual_inp=True, num_layers=3), ours(x, dual_inp=True, num_layers=3)
+        assert gd[0][0].shape[0] == 1 and float((gd[3] - wd[3]).abs().max()) <= 2e-5 * float(wd[3].abs().max())
+        assert float((gd[0][0] - wd[0][0]).abs().max()) <= 2e-5 * float(wd[0][0].abs().max())
+        # a parameter update refolds
+        ref.conv1.weight.mul_(1.5)
+        w2, g2 = ref(x), ours(x)
+        assert float((g2[0][0] - w2[0][0]).abs().max()) <= 2e-5 * float(w2[0][0].abs().max())
+    # gradients requested -> the reference's own forward (autograd graph intact)
+    out = ours(x, num_layers=1)
+    assert out[0][0].requires_grad
+    # a BatchNorm in training mode -> reference arithmetic (batch statistics), bit-identical to the reference module
+    ours.train()
+    torch.manual_seed(1)
+    with torch.no_grad():
+        a = ours(x, num_layers=1)[0][0]
+    with pytest.raises(TypeError):
+        A.adopt_context_encoder(torch.nn.Conv2d(3, 3, 1))
+    assert a.shape == want[0][0].shape

@@ -63,14 +63,16 @@ def build_model(family, device, seed=0, **over):
 
 
 @contextlib.contextmanager
-def installed(model, R, family, fuse_corr_stem=False, defer_lookup=False):
+def installed(model, R, family, fuse_corr_stem=False, defer_lookup=False, replay=None, fold_cnet=False):
     """Rebind the reference's names to this library for the duration of the block.
-    fuse_corr_stem (IGEV): also adopt corr_stem / corr_feature_att (build_gwc_volume fused with them)."""
+    fuse_corr_stem (IGEV): also adopt corr_stem / corr_feature_att (build_gwc_volume fused with them).
+    replay: adopt_update_block(..., replay=...) -- every update-block call replayed from a CUDA graph.
+    fold_cnet: model.cnet = adopt_context_encoder(model.cnet) (eval BatchNorm folded, channels-last)."""
     import anystereo_b200 as A
     mod = R.igev_module if family == "igev" else R.raft_module
     names = ["Combined_Geo_Encoding_Volume", "build_gwc_volume", "context_upsample_multiscale_train", "CorrBlock1D"]
     saved = {n: getattr(mod, n) for n in names if hasattr(mod, n)}
-    ub, lu = model.update_block, model.liif_up
+    ub, lu, cnet = model.update_block, model.liif_up, model.cnet
     stem = (model.corr_stem, model.corr_feature_att) if family == "igev" else None
     try:
         if family == "igev":
@@ -79,14 +81,16 @@ def installed(model, R, family, fuse_corr_stem=False, defer_lookup=False):
                 A.adopt_corr_stem(model, mod)
         else:
             A.install_into_reference(ref_raft_module=mod, defer_lookup=defer_lookup)
-        model.update_block = A.adopt_update_block(ub, family)
+        model.update_block = A.adopt_update_block(ub, family, replay=replay)
+        if fold_cnet:
+            model.cnet = A.adopt_context_encoder(cnet)
         hd = model.args.hidden_dims[2]
         model.liif_up = A.adopt_liif_up(lu, chanels=[48 + hd, 32])          # agg_type 'type5': [stem_4x|hidden, stem_2x]
         yield model
     finally:
         for n, v in saved.items():
             setattr(mod, n, v)
-        model.update_block, model.liif_up = ub, lu
+        model.update_block, model.liif_up, model.cnet = ub, lu, cnet
         if stem is not None:
             model.corr_stem, model.corr_feature_att = stem
 
@@ -150,15 +154,22 @@ def run(family, H, W, iters=32, B=1, engines=("bf16x3", "fp16"), device="cuda", 
     return res
 
 
-def profile(family="igev", H=384, W=1248, iters=32, B=1, device="cuda"):
+def profile(family="igev", H=384, W=1248, iters=32, B=1, device="cuda", **kw):
     """Where one forward of the REAL reference graph spends its time with this library installed: CUDA-event time per
     top-level child module (update_block = all iterations; 'other' = lookups, volume build, glue outside any child)."""
     import anystereo_b200 as A
     model, R = build_model(family, device)
     img1, img2 = make_pair(B, H, W, device)
-    out = {"family": family, "image": [H, W], "batch": B, "iters": iters, "engine": A.get_update_engine(), "ms": {}}
-    with installed(model, R, family) as m:
+    out = {"family": family, "image": [H, W], "batch": B, "iters": iters, "engine": A.get_update_engine(), "options": kw,
+           "ms": {}}
+    import gc
+    with installed(model, R, family, **kw) as m:
         forward(m, R, img1, img2, iters)                       # warm-up: weight packing, cudnn autotune
+        forward(m, R, img1, img2, iters)
+        # a generation-2 collection in the middle of a forward starves the GPU for 50-150 ms and lands in whichever module
+        # is running (seen: cnet 48 ms instead of 7): no collections inside the measured forward
+        gc.collect()
+        gc.disable()
         spans = {}
         handles = []
         for name, child in m.named_children():
@@ -177,6 +188,7 @@ def profile(family="igev", H=384, W=1248, iters=32, B=1, device="cuda"):
         forward(m, R, img1, img2, iters)
         e1.record()
         torch.cuda.synchronize()
+        gc.enable()
         for h in handles:
             h.remove()
         total = e0.elapsed_time(e1)
@@ -279,9 +291,11 @@ def main():
         res = []
         for fam in fams:
             H, W = (tuple(int(v) for v in a.size.split("x")) if a.size else (384, 1248))
-            r = profile(fam, H, W, a.iters, a.batch)
-            res.append(r)
-            print(json.dumps(r), flush=True)
+            for kw in ({}, dict(defer_lookup=True, replay=True, fold_cnet=True,
+                                **({"fuse_corr_stem": True} if fam == "igev" else {}))):
+                r = profile(fam, H, W, a.iters, a.batch, **kw)
+                res.append(r)
+                print(json.dumps(r), flush=True)
         if a.json:
             with open(a.json, "w") as f:
                 json.dump(res, f, indent=1)
