@@ -26,7 +26,7 @@ from .hotpath import (igev_iterations, raft_iterations, install_into_reference, 
 from .parallel import shard_pairs, allreduce_gradients, GradientAllReducer
 from . import liif
 from . import extractor
-from .extractor import adopt_context_encoder, ContextEncoder
+from .extractor import adopt_context_encoder, adopt_feature_encoder, ContextEncoder, FeatureEncoder
 from .liif import liif_out_multi_scale_Training, context_upsample_multiscale_train, upsample_disp
 
 __all__ = [

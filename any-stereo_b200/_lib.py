@@ -116,6 +116,8 @@ SIGNATURES = {
     "as_gwc_build_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "as_gwc_build_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "as_gwc_corr_stem_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, C.c_float, _vp]),
+    "as_instnorm_workspace_bytes": (C.c_size_t, [_i, _i]),
+    "as_instnorm_nhwc": (_i, [_vp, _vp, _vp, _vp, C.c_size_t, _i, _ll, _i, C.c_float, _i, _vp]),
     "as_pack_conv_weight": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "as_conv2d_fp32": (_i, [C.POINTER(ConvDesc), _vp]),
     "as_pool2x_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),

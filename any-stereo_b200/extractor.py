@@ -149,6 +149,104 @@ class ContextEncoder(nn.Module):
             return (outputs04, outputs08, outputs16, v) if dual_inp else (outputs04, outputs08, outputs16)
 
 
+def _instnorm_(y, eps, relu=True, resid=None):
+    """In place on a channels-last fp32 tensor [B,C,H,W]: InstanceNorm2d (no affine, no running stats) + ReLU, or the
+    block's final relu(resid + relu(norm(y))) -- csrc/instnorm.cu."""
+    B, C, H, W = y.shape
+    ws_bytes = L.lib().as_instnorm_workspace_bytes(B, C)
+    ws = torch.empty((ws_bytes,), device=y.device, dtype=torch.uint8)
+    L.call("as_instnorm_nhwc", y.data_ptr(), L.ptr(resid), y.data_ptr(), ws.data_ptr(), ws_bytes, B, H * W, C, float(eps),
+           1 if relu else 0, L.stream_ptr())
+    L.launch_count += 2                              # stats + finalize + apply
+    return y
+
+
+def _cl(t):
+    return t if t.is_contiguous(memory_format=torch.channels_last) else t.contiguous(memory_format=torch.channels_last)
+
+
+class FeatureEncoder(nn.Module):
+    """The reference's BasicEncoder(norm_fn='instance') -- RAFT's ``fnet`` (corePrune_RAFT/extractor.py:126-201; call site
+    prune_raft_stereo.py:108,252) -- around the same submodules.  Inference on CUDA: channels-last cuDNN convolutions, every
+    InstanceNorm2d + ReLU (+ the block's residual add + ReLU) in ONE elementwise pass over the tensor after a one-read
+    statistics kernel (csrc/instnorm.cu) instead of ATen's reshaped batch norm + separate ReLU / add kernels.  Gradients,
+    CPU tensors, other norm layers: the reference module's own forward."""
+
+    def __init__(self, ref):
+        super().__init__()
+        for name, child in ref.named_children():
+            self.add_module(name, child)
+        self.norm_fn = ref.norm_fn
+        self.downsample = ref.downsample
+        self.__dict__["_ref"] = ref
+        self.__dict__["_fold_cache"] = None
+
+    def _fusable(self, xs):
+        if self.norm_fn != "instance":
+            return False
+        if not all(t.is_cuda and t.dtype == torch.float32 for t in xs):
+            return False
+        if torch.is_grad_enabled() and (any(t.requires_grad for t in xs) or any(p.requires_grad for p in self.parameters())):
+            return False
+        if self.training and getattr(self, "dropout", None) is not None:
+            return False
+        for m in self.modules():
+            if isinstance(m, nn.InstanceNorm2d):
+                if m.affine or m.track_running_stats:
+                    return False
+            elif isinstance(m, (nn.BatchNorm2d, nn.GroupNorm)):
+                return False
+        return all(_is_block(b) for layer in (self.layer1, self.layer2, self.layer3) for b in layer)
+
+    def _weights(self):
+        key = tuple((t.data_ptr(), L.version_of(t)) for t in self.parameters())
+        hit = self.__dict__["_fold_cache"]
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        with torch.no_grad():
+            f = {"stem": _Folded(self.conv1), "out": _Folded(self.conv2),
+                 "layers": [[(_Folded(b.conv1), _Folded(b.conv2), None if b.downsample is None else _Folded(b.downsample[0]),
+                              b.norm1.eps, b.norm2.eps, None if b.downsample is None else b.downsample[1].eps)
+                             for b in layer] for layer in (self.layer1, self.layer2, self.layer3)]}
+        self.__dict__["_fold_cache"] = (key, f)
+        return f
+
+    def invalidate_weights(self):
+        self.__dict__["_fold_cache"] = None
+
+    def forward(self, x, dual_inp=False):
+        is_list = isinstance(x, (tuple, list))
+        if not self._fusable(list(x) if is_list else [x]):
+            return self.__dict__["_ref"](x, dual_inp=dual_inp)
+        f = self._weights()
+        with torch.no_grad(), torch.cuda.device(x[0].device if is_list else x.device):
+            if is_list:
+                batch_dim = x[0].shape[0]
+                x = torch.cat(x, dim=0)
+            x = _instnorm_(_cl(f["stem"](_cl(x))), self.norm1.eps)
+            for layer in f["layers"]:
+                for c1, c2, down, e1, e2, e3 in layer:
+                    y = _instnorm_(_cl(c1(x)), e1)
+                    y = _cl(c2(y))
+                    if down is not None:
+                        x = _instnorm_(_cl(down(x)), e3, relu=False)
+                    x = _instnorm_(y, e2, relu=True, resid=x)
+            x = f["out"](x).contiguous()
+            if is_list:
+                x = x.split(split_size=batch_dim, dim=0)
+        return x
+
+
+def adopt_feature_encoder(ref_fnet):
+    """``model.fnet = adopt_feature_encoder(model.fnet)`` (RAFT family): same parameters and state_dict keys; see FeatureEncoder."""
+    if isinstance(ref_fnet, FeatureEncoder):
+        return ref_fnet
+    need = ("conv1", "norm1", "layer1", "layer2", "layer3", "conv2")
+    if not all(hasattr(ref_fnet, n) for n in need) or hasattr(ref_fnet, "outputs04"):
+        raise TypeError("adopt_feature_encoder expects the reference's BasicEncoder (models/corePrune_RAFT/extractor.py:126)")
+    return FeatureEncoder(ref_fnet)
+
+
 def adopt_context_encoder(ref_cnet):
     """``model.cnet = adopt_context_encoder(model.cnet)``: eval-mode BatchNorm folded into the convolutions, channels-last,
     in-place ReLU / residual adds; same parameters, same state_dict keys, reference arithmetic whenever a gradient is

@@ -178,6 +178,16 @@ int as_gwc_build_bwd(const float* g_out, const float* left, const float* right,
                      float* g_left, float* g_right,
                      int B, int C, int H, int W, int maxdisp, int G, as_stream_t stream);
 
+/* SURVEY 8(f)-4 (RAFT feature encoder, models/corePrune_RAFT/extractor.py:126-201 with norm_fn='instance'; ResidualBlock
+ * :9-58): nn.InstanceNorm2d(affine=False, track_running_stats=False) on a channels-last tensor, fused with what follows it:
+ *   y = (x - mean_hw) * rsqrt(var_hw + eps)  per image and channel (biased variance);  relu != 0: y = max(y, 0);
+ *   resid != NULL: y = max(resid + y, 0)   (the block's final relu(x' + y), extractor.py:58).
+ * x, resid, out: float32 [B][HW][C] (pixel-major), 16-byte aligned, C % 4 == 0, C <= 1024; out may alias x or resid.
+ * workspace: as_instnorm_workspace_bytes(B, C) bytes of device memory (fp64 sums + fp32 mean / rstd), 16-byte aligned. */
+size_t as_instnorm_workspace_bytes(int B, int C);
+int as_instnorm_nhwc(const float* x, const float* resid, float* out, void* workspace, size_t workspace_bytes, int B,
+                     long long HW, int C, float eps, int relu, as_stream_t stream);
+
 /* build_gwc_volume fused with corr_stem = Conv3d(G,G,3,1,1,bias=False) + BatchNorm3d (eval: per-channel
  * affine) + LeakyReLU, and optionally FeatureAtt's multiply (continuous_IGEVstereo.py:262-264; submodule.py:6-32,328-341):
  *   out[b,co,d,y,x] = att[b,co,y,x] * lrelu(scale[co] * conv3d(gwc)[b,co,d,y,x] + shift[co]),  gwc as in as_gwc_build_fwd.

@@ -253,6 +253,14 @@ def test_round2_entry_points_reject_bad_arguments(A):
     assert lib.as_context_upsample_multiscale_bwd(None, None, None, None, None, None, 1, 4, 4, 16, None) == -1
     assert lib.as_liif_layer1_fwd(2, None, None, None, None, None, None, None, 1, 128, 16, None) == -1
     assert lib.as_liif_layer1_bwd(2, None, None, None, None, None, None, None, None, None, None, 1, 128, 16, None) == -1
+    # as_instnorm_nhwc: null / sizes / workspace, channel count, alignment
+    ws = lib.as_instnorm_workspace_bytes(2, 64)
+    assert ws == 2 * 64 * 24 and lib.as_instnorm_workspace_bytes(0, 64) == 0
+    assert lib.as_instnorm_nhwc(None, None, 16, 16, ws, 2, 100, 64, 1e-5, 1, None) == -1
+    assert lib.as_instnorm_nhwc(16, None, 16, 16, ws - 1, 2, 100, 64, 1e-5, 1, None) == -1
+    assert lib.as_instnorm_nhwc(16, None, 16, 16, ws, 2, 100, 64, 0.0, 1, None) == -1
+    assert lib.as_instnorm_nhwc(16, None, 16, 16, ws, 2, 100, 66, 1e-5, 1, None) == -2
+    assert lib.as_instnorm_nhwc(16, 8, 16, 16, ws, 2, 100, 64, 1e-5, 1, None) == -4
 
 
 def test_deferred_wrappers_host_logic(A):
@@ -348,3 +356,35 @@ def test_adopted_context_encoder_matches_reference_module(A):
     with pytest.raises(TypeError):
         A.adopt_context_encoder(torch.nn.Conv2d(3, 3, 1))
     assert a.shape == want[0][0].shape
+
+
+def test_adopted_feature_encoder_host_logic(A):
+    """SURVEY 8(f)-4, RAFT: adopt_feature_encoder wraps the reference's BasicEncoder(norm_fn='instance') around the same
+    submodules; without CUDA tensors (or with gradients / other norms) it is the reference module's own forward."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference tree absent")
+    ref_loader.load_models()
+    from models.corePrune_RAFT.extractor import BasicEncoder, MultiBasicEncoder
+    torch.manual_seed(0)
+    ref = BasicEncoder(output_dim=256, norm_fn="instance", downsample=2).eval()
+    ours = A.adopt_feature_encoder(ref)
+    assert A.adopt_feature_encoder(ours) is ours
+    assert list(ours.state_dict().keys()) == list(ref.state_dict().keys())
+    x = torch.randn(1, 3, 32, 64)
+    assert not ours._fusable([x])                                   # CPU tensor: no kernel, no fallback arithmetic of ours
+    with torch.no_grad():
+        a, b = ours([x, x + 1])
+        c, d = ref([x, x + 1])
+    assert torch.equal(a, c) and torch.equal(b, d)
+    f = ours._weights()
+    assert len(f["layers"]) == 3 and f["layers"][0][0][2] is None and f["layers"][1][0][2] is not None
+    assert ours._weights() is f
+    with torch.no_grad():
+        ref.conv2.weight.mul_(2.0)
+    assert ours._weights() is not f                                 # parameter update: repacked
+    with pytest.raises(TypeError):
+        A.adopt_feature_encoder(MultiBasicEncoder(output_dim=[[128] * 3], norm_fn="batch", downsample=2))
+    with pytest.raises(TypeError):
+        A.adopt_context_encoder(ref)
+    assert not A.adopt_feature_encoder(BasicEncoder(output_dim=64, norm_fn="batch", downsample=2))._fusable([x])

@@ -456,3 +456,78 @@ def test_dropin_everything_adopted_epe(family):
     epe = float((ours - ref).abs().mean())
     _record({"test": "everything_adopted", "family": family, "epe_mean_px": epe, "options": kw})
     assert epe < 2e-3, epe
+
+
+@pytest.mark.parametrize("B,C,H,W", [(2, 64, 37, 53), (1, 96, 48, 80), (3, 128, 9, 7), (1, 4, 1, 2), (2, 64, 384, 416)])
+def test_instnorm_kernel_matches_torch(B, C, H, W):
+    """csrc/instnorm.cu vs F.instance_norm in fp64 (biased variance, eps 1e-5): plain, + ReLU, + residual; in place; a
+    channel mean 300x its standard deviation (the shifted sums must not cancel); ragged sizes, a single pixel."""
+    import torch.nn.functional as F
+    from anystereo_b200 import extractor
+    torch.manual_seed(B * 1000 + C)
+    x = torch.randn(B, C, H, W, device="cuda")
+    x[:, 1] = x[:, 1] * 0.01 + 3.0                                   # mean >> std
+    x[:, 2] = x[:, 2] * 50.0 - 20.0
+    x = x.contiguous(memory_format=torch.channels_last)
+    r = torch.randn(B, C, H, W, device="cuda").contiguous(memory_format=torch.channels_last)
+    want = F.instance_norm(x.double(), eps=1e-5)
+    for relu, resid in ((False, None), (True, None), (True, r), (False, r)):
+        w = want.relu() if relu else want
+        if resid is not None:
+            w = (w + resid.double()).relu()
+        got = extractor._instnorm_(x.clone(memory_format=torch.channels_last), 1e-5, relu=relu, resid=resid)
+        assert got.is_contiguous(memory_format=torch.channels_last)
+        err = float((got.double() - w).abs().max())
+        # (the mean is held in fp32: a channel whose mean is 300x its standard deviation sees ulp(mean) * rstd ~ 3e-5)
+        assert err <= 5e-5 * max(1.0, float(w.abs().max())), (relu, resid is not None, err)
+    # out aliasing the residual (the block's running tensor) is allowed
+    rr = r.clone(memory_format=torch.channels_last)
+    import anystereo_b200 as A
+    L = A._lib
+    ws_bytes = L.lib().as_instnorm_workspace_bytes(B, C)
+    ws = torch.empty(ws_bytes, device="cuda", dtype=torch.uint8)
+    L.call("as_instnorm_nhwc", x.data_ptr(), rr.data_ptr(), rr.data_ptr(), ws.data_ptr(), ws_bytes, B, H * W, C, 1e-5, 1,
+           L.stream_ptr())
+    w = (want.relu() + r.double()).relu()
+    assert float((rr.double() - w).abs().max()) <= 5e-5 * max(1.0, float(w.abs().max()))
+
+
+@needs_ref
+def test_adopted_feature_encoder_matches_reference_module_and_graph():
+    """SURVEY 8(f)-4, RAFT: adopt_feature_encoder(model.fnet) -- channels-last convolutions + the fused InstanceNorm kernels --
+    against the reference module in strict fp32 (list input as prune_raft_stereo.py:252 passes it, and a single tensor),
+    then inside the real graph with everything else adopted: final disparity within the bar."""
+    import anystereo_b200 as A
+    D = dropin
+    model, R = D.build_model("raft", "cuda")
+    img1, img2 = D.make_pair(1, 320, 736, "cuda")
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        a = (2 * (img1 / 255.0) - 1.0).contiguous()
+        b = (2 * (img2 / 255.0) - 1.0).contiguous()
+        ours = A.adopt_feature_encoder(model.fnet)
+        with torch.no_grad():
+            w1, w2 = model.fnet([a, b])
+            n0 = A._lib.launch_count
+            g1, g2 = ours([a, b])
+            assert A._lib.launch_count - n0 == 3 * 15           # 15 normalisations, 3 kernels each
+            ws, gs = model.fnet(a), ours(a)
+        for w, g in ((w1, g1), (w2, g2), (ws, gs)):
+            assert g.shape == w.shape and g.is_contiguous()
+            assert float((g - w).abs().max()) <= 1e-4 * float(w.abs().max())
+        # gradients requested -> the reference's forward
+        a_req = a.clone().requires_grad_(True)
+        assert ours(a_req).requires_grad
+        ref = D.forward(model, R, img1, img2, 32)
+        with D.installed(model, R, "raft", defer_lookup=True, replay=True, fold_cnet=True, fused_fnet=True) as m:
+            assert isinstance(m.fnet, A.FeatureEncoder)
+            D.forward(m, R, img1, img2, 32)
+            got = D.forward(m, R, img1, img2, 32)
+        assert not isinstance(model.fnet, A.FeatureEncoder)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    epe = float((got - ref).abs().mean())
+    _record({"test": "raft_everything_adopted_incl_fnet", "epe_mean_px": epe})
+    assert epe < 2e-3, epe

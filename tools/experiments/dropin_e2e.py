@@ -41,6 +41,8 @@ for collect in (False,):
     print("  reference as shipped (TF32 default):", reps(lambda: dropin.forward(model, R, img1, img2, 32), 4), flush=True)
     variants = [{}, {"defer_lookup": True}, {"defer_lookup": True, "replay": True},
                 {"defer_lookup": True, "replay": True, "fold_cnet": True}]
+    if fam == "raft":
+        variants.append({"defer_lookup": True, "replay": True, "fold_cnet": True, "fused_fnet": True})
     if fam == "igev":
         variants.append({"fuse_corr_stem": True, "defer_lookup": True})
         variants.append({"fuse_corr_stem": True, "defer_lookup": True, "replay": True, "fold_cnet": True})
