@@ -198,6 +198,30 @@ def main():
         if a.json:
             json.dump(res, open(a.json, "w"), indent=1)
         return
+    if a.only == "instnorm":
+        # InstanceNorm2d + ReLU (+ residual add + ReLU) on channels-last tensors at the sizes RAFT's fnet runs
+        # them for one 384x1248 pair (both images in one batch).  Algorithmic bytes: x read twice (statistics, apply) + written
+        # once (+ the residual read once).  Beside it: the ATen formulation the reference executes.
+        from anystereo_b200 import extractor
+        import torch.nn.functional as F
+        for (Bn, Cn, Hn, Wn) in ((2, 64, 384, 1248), (2, 96, 192, 624), (2, 128, 96, 312)):
+            x = torch.randn(Bn, Cn, Hn, Wn, device=dev).contiguous(memory_format=torch.channels_last)
+            r = torch.randn(Bn, Cn, Hn, Wn, device=dev).contiguous(memory_format=torch.channels_last)
+            nb = 4 * x.numel()
+            tag = "%dx%dx%dx%d" % (Bn, Cn, Hn, Wn)
+            med, best = timeit(lambda: extractor._instnorm_(x, 1e-5, relu=True))
+            rec("instnorm_relu_" + tag, med, best, 3 * nb)
+            med, best = timeit(lambda: extractor._instnorm_(x, 1e-5, relu=True, resid=r))
+            rec("instnorm_relu_add_relu_" + tag, med, best, 4 * nb)
+            xn = x.contiguous()
+            rn = r.contiguous()
+            med, best = timeit(lambda: F.relu(F.instance_norm(xn, eps=1e-5), inplace=True))
+            rec("ATEN_instance_norm_relu_nchw_" + tag, med, best, 3 * nb)
+            med, best = timeit(lambda: F.relu(rn + F.relu(F.instance_norm(xn, eps=1e-5), inplace=True)))
+            rec("ATEN_instance_norm_relu_add_relu_nchw_" + tag, med, best, 4 * nb)
+        if a.json:
+            json.dump(res, open(a.json, "w"), indent=1)
+        return
     if a.only == "stem":
         # build_gwc_volume + corr_stem (Conv3d 8->8 + eval BatchNorm3d + LeakyReLU) + FeatureAtt multiply fused;
         # bytes = the two feature maps read once + the stem output written once (the GWC volume is never stored)
