@@ -530,6 +530,37 @@ def run_ours(args):
                     "pairs_per_s": world * B / (dms2 / 1e3), "ms_per_step": dms2,
                     "what": "the same reference call pattern with install_into_reference(defer_lookup=True): the lookup is "
                             "fused with convc1 inside the adopted update block"}
+                # one pair per forward (the reference's evaluation / demo batch size): the Python loop then runs at the host's pace;
+                # adopt_update_block(..., replay=True) replays each update-block call from a CUDA graph (bit-identical results)
+                one = {k: (v[:1].contiguous() if torch.is_tensor(v) else v) for k, v in dd.items()}
+                one["net"] = [t[:1].contiguous() for t in dd["net"]]
+                one["inp"] = [[t[:1].contiguous() for t in lst] for lst in dd["inp"]]
+
+                def dropin_one_pair():
+                    geo = A.build_gwc_volume(one["ml"], one["mr"], GEO_D, GROUPS)
+                    geo_fn = A.geometry.Combined_Geo_Encoding_Volume_Deferred(one["ml"].float(), one["mr"].float(), geo.float(),
+                                                                              radius=4, num_levels=2)
+                    coords = A.hotpath.pixel_coords(1, H4, W4, dev)
+                    net, disp = list(one["net"]), one["disp"]
+                    for _ in range(ITERS):
+                        feat = geo_fn(disp, coords)
+                        net, delta = block(net, one["inp"], feat, disp, iter16=True, iter08=True)
+                        disp = disp + delta
+                    return disp
+                one_ms = {}
+                for tag, flag in (("eager", False), ("replayed", True)):
+                    block.call_replay = flag
+                    for _ in range(3):
+                        d_one = dropin_one_pair()
+                    one_ms[tag] = ev_ms(dropin_one_pair, 6)
+                    one[tag] = d_one
+                block.call_replay = None
+                A.update_umma.call_replay_clear(block)
+                other["dropin_call_pattern_one_pair"] = {
+                    "eager_ms_per_pair": one_ms["eager"], "replayed_ms_per_pair": one_ms["replayed"],
+                    "bit_identical": bool(torch.equal(one["eager"], one["replayed"])),
+                    "what": "the reference call pattern at batch 1 (384x1248, 32 iterations, deferred lookup): launch by launch vs "
+                            "adopt_update_block(..., replay=True) (each update-block call replayed from a CUDA graph)"}
                 other["dropin_call_pattern_same_step"] = {
                     "pairs_per_s": world * B / (dms / 1e3), "ms_per_step": dms,
                     "what": "reference call pattern (continuous_IGEVstereo.py:275-295) on this library's operators: "
