@@ -222,7 +222,8 @@ class HotLoopGraph:
         update_block.reset_caches()
         self.graph = torch.cuda.CUDAGraph()
         n0 = L.launch_count
-        with torch.cuda.graph(self.graph):
+        # thread_local: CUDA calls of OTHER host threads (a DataLoader's pin-memory thread, say) do not invalidate the capture
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self.out_disp, self.out_net = self._run()
         self.launches = L.launch_count - n0          # kernel-launching ABI calls recorded in the graph (per replay)
 

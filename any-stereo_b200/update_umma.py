@@ -523,7 +523,8 @@ class _CallGraph:
                 planes.pop(t.data_ptr(), None)
         self.graph = torch.cuda.CUDAGraph()
         n0 = L.launch_count
-        with torch.cuda.graph(self.graph):
+        # thread_local: CUDA calls of OTHER host threads (a DataLoader's pin-memory thread, say) do not invalidate the capture
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self.out_net, self.out_delta = run()
         self.launches = L.launch_count - n0
 
@@ -564,10 +565,18 @@ def forward_replayed(ub, net, inp, corr, disp, iter08=True, iter16=True):
         key = _call_key(ub, net, corr, disp, iter08, iter16)
         cache = _state(ub)["calls"]
         g = cache.get(key)
+        if g is False:                                 # this call could not be captured: stay eager
+            return None
         if g is None:
             while len(cache) >= _CALL_REPLAY["max"]:
                 cache.pop(next(iter(cache)))           # oldest first
-            g = _CallGraph(ub, net, inp, corr, disp, iter08, iter16)
+            try:
+                g = _CallGraph(ub, net, inp, corr, disp, iter08, iter16)
+            except RuntimeError as e:                  # capture refused (another capture under way on the device, ...)
+                import warnings
+                warnings.warn("anystereo_b200: update-block call not captured, running it eagerly (%s)" % str(e)[:200])
+                cache[key] = False
+                return None
             cache[key] = g
         else:
             g.load(ub, net, inp, corr, disp)
