@@ -123,7 +123,8 @@ class ContextEncoder(nn.Module):
         if not self._fusable(x):
             return self.__dict__["_ref"](x, dual_inp=dual_inp, num_layers=num_layers)
         f = self._folded()
-        with torch.no_grad():
+        # (the reference calls this module under autocast(enabled=args.mixed_precision): the folded path keeps fp32 / TF32)
+        with torch.no_grad(), torch.autocast(device_type=x.device.type, enabled=False):
             x = f["stem"](x.float().contiguous(memory_format=torch.channels_last), True)
             for layer in f["layers"][:3]:
                 for blk in layer:
@@ -219,7 +220,8 @@ class FeatureEncoder(nn.Module):
         if not self._fusable(list(x) if is_list else [x]):
             return self.__dict__["_ref"](x, dual_inp=dual_inp)
         f = self._weights()
-        with torch.no_grad(), torch.cuda.device(x[0].device if is_list else x.device):
+        # autocast off: the normalisation kernels read fp32 (the reference calls this module under autocast(mixed_precision))
+        with torch.no_grad(), torch.cuda.device(x[0].device if is_list else x.device), torch.autocast("cuda", enabled=False):
             if is_list:
                 batch_dim = x[0].shape[0]
                 x = torch.cat(x, dim=0)

@@ -341,6 +341,10 @@ def test_adopted_context_encoder_matches_reference_module(A):
         wd, gd = ref(x, dual_inp=True, num_layers=3), ours(x, dual_inp=True, num_layers=3)
         assert gd[0][0].shape[0] == 1 and float((gd[3] - wd[3]).abs().max()) <= 2e-5 * float(wd[3].abs().max())
         assert float((gd[0][0] - wd[0][0]).abs().max()) <= 2e-5 * float(wd[0][0].abs().max())
+        # under autocast (the reference wraps the call in autocast(enabled=args.mixed_precision)) the folded path stays fp32
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            ga = ours(x, num_layers=1)
+        assert ga[0][0].dtype == torch.float32 and torch.equal(ga[0][0], got[0][0])
         # a parameter update refolds
         ref.conv1.weight.mul_(1.5)
         w2, g2 = ref(x), ours(x)

@@ -514,6 +514,9 @@ def test_adopted_feature_encoder_matches_reference_module_and_graph():
             g1, g2 = ours([a, b])
             assert A._lib.launch_count - n0 == 3 * 15           # 15 normalisations, 3 kernels each
             ws, gs = model.fnet(a), ours(a)
+            with torch.autocast("cuda", dtype=torch.float16):          # prune_raft_stereo.py:251 autocast(mixed_precision)
+                ga = ours(a)
+            assert ga.dtype == torch.float32 and torch.equal(ga, gs)
         for w, g in ((w1, g1), (w2, g2), (ws, gs)):
             assert g.shape == w.shape and g.is_contiguous()
             assert float((g - w).abs().max()) <= 1e-4 * float(w.abs().max())
