@@ -26,7 +26,8 @@ from .hotpath import (igev_iterations, raft_iterations, install_into_reference, 
 from .parallel import shard_pairs, allreduce_gradients, GradientAllReducer
 from . import liif
 from . import extractor
-from .extractor import adopt_context_encoder, adopt_feature_encoder, ContextEncoder, FeatureEncoder
+from .extractor import (adopt_context_encoder, adopt_feature_encoder, ContextEncoder, FeatureEncoder, fold_basic_convs,
+                        unfold_basic_convs, FoldedBasicConv)
 from .liif import liif_out_multi_scale_Training, context_upsample_multiscale_train, upsample_disp
 
 __all__ = [

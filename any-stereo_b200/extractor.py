@@ -259,3 +259,89 @@ def adopt_context_encoder(ref_cnet):
     if not all(hasattr(ref_cnet, n) for n in need):
         raise TypeError("adopt_context_encoder expects the reference's MultiBasicEncoder (models/*/extractor.py:200)")
     return ContextEncoder(ref_cnet)
+
+
+# ---- BasicConv (submodule.py:6-32): Conv / ConvTranspose (2-D or 3-D, bias=False) + BatchNorm + LeakyReLU -------------------
+# The reference builds its 3-D hourglass (continuous_IGEVstereo.py:22-89), FeatureAtt (submodule.py:328-341), the Conv2x
+# up-blocks of `Feature` (extractor.py) and corr_stem out of this one block.  At inference each is three launches (conv,
+# batch norm, out-of-place LeakyReLU) over small tensors; with the BatchNorm folded it is one convolution and an in-place
+# LeakyReLU.  fold_basic_convs(model) swaps every such block for a wrapper around the SAME conv / bn submodules.
+class FoldedBasicConv(nn.Module):
+    _OPS = {nn.Conv2d: F.conv2d, nn.Conv3d: F.conv3d, nn.ConvTranspose2d: F.conv_transpose2d,
+            nn.ConvTranspose3d: F.conv_transpose3d}
+
+    def __init__(self, ref):
+        super().__init__()
+        self.conv, self.bn = ref.conv, ref.bn
+        self.relu, self.use_bn = ref.relu, ref.use_bn
+        self.__dict__["_ref"] = ref
+        self.__dict__["_fold_cache"] = None
+
+    def _fusable(self, x):
+        c = self.conv
+        if type(c) not in self._OPS or c.groups != 1 or c.bias is not None or c.padding_mode != "zeros":
+            return False
+        if self.use_bn and (self.bn.training or self.bn.running_mean is None):
+            return False
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            return False
+        return torch.is_floating_point(x)
+
+    def _folded(self):
+        ts = list(self.conv.parameters()) + (list(self.bn.parameters()) + list(self.bn.buffers()) if self.use_bn else [])
+        key = tuple((t.data_ptr(), L.version_of(t)) for t in ts)
+        hit = self.__dict__["_fold_cache"]
+        if hit is not None and hit[0] == key:
+            return hit[1], hit[2]
+        with torch.no_grad():
+            w = self.conv.weight.detach().float()
+            b = None
+            if self.use_bn:
+                bn = self.bn
+                s = torch.rsqrt(bn.running_var.detach().float() + bn.eps)
+                if bn.weight is not None:
+                    s = s * bn.weight.detach().float()
+                transposed = isinstance(self.conv, (nn.ConvTranspose2d, nn.ConvTranspose3d))
+                shape = [1] * w.dim()
+                shape[1 if transposed else 0] = -1          # output channels: dim 1 of a transposed convolution's weight
+                w = (w * s.view(shape)).contiguous()
+                b = -bn.running_mean.detach().float() * s
+                if bn.bias is not None:
+                    b = b + bn.bias.detach().float()
+        self.__dict__["_fold_cache"] = (key, w, b)
+        return w, b
+
+    def forward(self, x):
+        if not self._fusable(x):
+            return self.__dict__["_ref"](x)
+        w, b = self._folded()
+        c = self.conv
+        with torch.no_grad(), torch.autocast(device_type=x.device.type, enabled=False):
+            x = x.float()
+            if isinstance(c, (nn.ConvTranspose2d, nn.ConvTranspose3d)):
+                y = self._OPS[type(c)](x, w, b, c.stride, c.padding, c.output_padding, 1, c.dilation)
+            else:
+                y = self._OPS[type(c)](x, w, b, c.stride, c.padding, c.dilation, 1)
+            return F.leaky_relu_(y, 0.01) if self.relu else y          # nn.LeakyReLU() default slope, submodule.py:30
+
+
+def _is_basic_conv(m):
+    return (type(m).__name__ == "BasicConv" and all(hasattr(m, n) for n in ("conv", "bn", "use_bn", "relu"))
+            and isinstance(getattr(m, "bn"), (nn.BatchNorm2d, nn.BatchNorm3d)))
+
+
+def fold_basic_convs(model):
+    """Swap every reference ``BasicConv`` under ``model`` for a FoldedBasicConv (same conv / bn submodules, same state_dict
+    keys).  Returns the handles ``unfold_basic_convs`` takes to put the originals back."""
+    handles = []
+    for parent in list(model.modules()):
+        for name, child in list(parent._modules.items()):
+            if child is not None and _is_basic_conv(child):
+                parent._modules[name] = FoldedBasicConv(child)
+                handles.append((parent, name, child))
+    return handles
+
+
+def unfold_basic_convs(handles):
+    for parent, name, child in handles:
+        parent._modules[name] = child

@@ -392,3 +392,44 @@ def test_adopted_feature_encoder_host_logic(A):
     with pytest.raises(TypeError):
         A.adopt_context_encoder(ref)
     assert not A.adopt_feature_encoder(BasicEncoder(output_dim=64, norm_fn="batch", downsample=2))._fusable([x])
+
+
+def test_fold_basic_convs_matches_reference_hourglass(A):
+    """fold_basic_convs swaps every reference BasicConv (Conv / ConvTranspose 2-D or 3-D + BatchNorm +
+    LeakyReLU, submodule.py:6-32) for a wrapper with the eval-mode BatchNorm folded into the convolution.  Checked on the
+    reference's 3-D hourglass (continuous_IGEVstereo.py:22-89: strided Conv3d, ConvTranspose3d, 1x1x1, FeatureAtt's 2-D
+    blocks, a block without BatchNorm / activation): same output, same state_dict keys, originals restored by unfold."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference tree absent")
+    R = ref_loader.load_models()
+    torch.manual_seed(0)
+    hg = R.igev_module.hourglass(8)
+    for m in hg.modules():
+        if isinstance(m, (torch.nn.BatchNorm2d, torch.nn.BatchNorm3d)):
+            m.running_mean.normal_(0, 0.3)
+            m.running_var.uniform_(0.5, 2.0)
+            m.weight.data.uniform_(0.5, 1.5)
+            m.bias.data.normal_(0, 0.2)
+    hg.eval()
+    x = torch.randn(1, 8, 8, 16, 24)
+    feats = [None, torch.randn(1, 64, 8, 12), torch.randn(1, 192, 4, 6), torch.randn(1, 160, 2, 3)]
+    with torch.no_grad():
+        want = hg(x, feats)
+    keys = list(hg.state_dict().keys())
+    n_blocks = sum(1 for m in hg.modules() if type(m).__name__ == "BasicConv")
+    handles = A.fold_basic_convs(hg)
+    assert len(handles) == n_blocks >= 20
+    assert list(hg.state_dict().keys()) == keys
+    assert not any(type(m).__name__ == "BasicConv" for m in hg.modules())
+    with torch.no_grad():
+        got = hg(x, feats)
+    assert got.shape == want.shape
+    assert float((got - want).abs().max()) <= 5e-5 * float(want.abs().max())
+    # gradients requested / training-mode BatchNorm: the reference block's own forward
+    blk = hg.conv1[0]
+    assert isinstance(blk, A.FoldedBasicConv) and blk(torch.randn(1, 8, 8, 16, 24)).requires_grad
+    A.unfold_basic_convs(handles)
+    assert sum(1 for m in hg.modules() if type(m).__name__ == "BasicConv") == n_blocks
+    with torch.no_grad():
+        assert torch.equal(hg(x, feats), want)

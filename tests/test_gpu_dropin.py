@@ -446,11 +446,14 @@ def test_dropin_everything_adopted_epe(family):
         kw = dict(defer_lookup=True, replay=True, fold_cnet=True)
         if family == "igev":
             kw["fuse_corr_stem"] = True
+            kw["fold_bn"] = True
         with D.installed(model, R, family, **kw) as m:
             assert isinstance(m.cnet, A.ContextEncoder)
+            assert family != "igev" or isinstance(m.cost_agg.conv1[0], A.FoldedBasicConv)
             D.forward(m, R, img1, img2, 32)
             ours = D.forward(m, R, img1, img2, 32)
         assert not isinstance(model.cnet, A.ContextEncoder)
+        assert family != "igev" or type(model.cost_agg.conv1[0]).__name__ == "BasicConv"
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
     epe = float((ours - ref).abs().mean())

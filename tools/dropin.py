@@ -63,18 +63,20 @@ def build_model(family, device, seed=0, **over):
 
 
 @contextlib.contextmanager
-def installed(model, R, family, fuse_corr_stem=False, defer_lookup=False, replay=None, fold_cnet=False, fused_fnet=False):
+def installed(model, R, family, fuse_corr_stem=False, defer_lookup=False, replay=None, fold_cnet=False, fused_fnet=False, fold_bn=False):
     """Rebind the reference's names to this library for the duration of the block.
     fuse_corr_stem (IGEV): also adopt corr_stem / corr_feature_att (build_gwc_volume fused with them).
     replay: adopt_update_block(..., replay=...) -- every update-block call replayed from a CUDA graph.
     fold_cnet: model.cnet = adopt_context_encoder(model.cnet) (eval BatchNorm folded, channels-last).
-    fused_fnet (RAFT): model.fnet = adopt_feature_encoder(model.fnet) (InstanceNorm + ReLU / residual kernels)."""
+    fused_fnet (RAFT): model.fnet = adopt_feature_encoder(model.fnet) (InstanceNorm + ReLU / residual kernels).
+    fold_bn: fold_basic_convs(model) -- every reference BasicConv (hourglass, FeatureAtt, Conv2x) with its BatchNorm folded."""
     import anystereo_b200 as A
     mod = R.igev_module if family == "igev" else R.raft_module
     names = ["Combined_Geo_Encoding_Volume", "build_gwc_volume", "context_upsample_multiscale_train", "CorrBlock1D"]
     saved = {n: getattr(mod, n) for n in names if hasattr(mod, n)}
     ub, lu, cnet = model.update_block, model.liif_up, model.cnet
     fnet = getattr(model, "fnet", None)
+    folded = []
     stem = (model.corr_stem, model.corr_feature_att) if family == "igev" else None
     try:
         if family == "igev":
@@ -88,10 +90,13 @@ def installed(model, R, family, fuse_corr_stem=False, defer_lookup=False, replay
             model.cnet = A.adopt_context_encoder(cnet)
         if fused_fnet and family == "raft":
             model.fnet = A.adopt_feature_encoder(fnet)
+        if fold_bn:
+            folded = A.fold_basic_convs(model)
         hd = model.args.hidden_dims[2]
         model.liif_up = A.adopt_liif_up(lu, chanels=[48 + hd, 32])          # agg_type 'type5': [stem_4x|hidden, stem_2x]
         yield model
     finally:
+        A.unfold_basic_convs(folded)
         for n, v in saved.items():
             setattr(mod, n, v)
         model.update_block, model.liif_up, model.cnet = ub, lu, cnet
@@ -298,7 +303,7 @@ def main():
         for fam in fams:
             H, W = (tuple(int(v) for v in a.size.split("x")) if a.size else (384, 1248))
             for kw in ({}, dict(defer_lookup=True, replay=True, fold_cnet=True,
-                                **({"fuse_corr_stem": True} if fam == "igev" else {"fused_fnet": True}))):
+                                **({"fuse_corr_stem": True, "fold_bn": True} if fam == "igev" else {"fused_fnet": True}))):
                 r = profile(fam, H, W, a.iters, a.batch, **kw)
                 res.append(r)
                 print(json.dumps(r), flush=True)

@@ -46,6 +46,7 @@ for collect in (False,):
     if fam == "igev":
         variants.append({"fuse_corr_stem": True, "defer_lookup": True})
         variants.append({"fuse_corr_stem": True, "defer_lookup": True, "replay": True, "fold_cnet": True})
+        variants.append({"fuse_corr_stem": True, "defer_lookup": True, "replay": True, "fold_cnet": True, "fold_bn": True})
     for kw in variants:
         with dropin.installed(model, R, fam, **kw) as m:
             print("  drop-in %s:" % kw, reps(lambda: dropin.forward(m, R, img1, img2, 32)), flush=True)
