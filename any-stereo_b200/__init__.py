@@ -22,7 +22,7 @@ from .submodule import build_gwc_volume, disparity_regression, init_disparity, g
 from .update import (BasicMultiUpdateBlock, BasicMultiUpdateBlockRAFT, BasicMotionEncoder, ConvGRU, DispHead,
                      set_update_engine, get_update_engine)
 from .hotpath import (igev_iterations, raft_iterations, install_into_reference, HotLoopGraph, set_lookup_fusion,
-                      adopt_update_block, adopt_liif_up, adopt_corr_stem, set_graph_replay)
+                      adopt_update_block, adopt_liif_up, adopt_corr_stem, adopt_model, set_graph_replay)
 from .parallel import shard_pairs, allreduce_gradients, GradientAllReducer
 from . import liif
 from . import extractor
@@ -37,4 +37,6 @@ __all__ = [
     "igev_iterations", "raft_iterations", "install_into_reference", "HotLoopGraph",
     "shard_pairs", "allreduce_gradients", "GradientAllReducer",
     "gwc_corr_stem", "adopt_corr_stem", "adopt_update_block", "adopt_liif_up", "set_graph_replay",
+    "adopt_model", "adopt_context_encoder", "adopt_feature_encoder", "fold_basic_convs", "unfold_basic_convs",
+    "set_call_replay", "set_lowres_single_pass", "set_gate_weight_residual_only",
 ]

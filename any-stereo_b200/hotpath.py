@@ -399,3 +399,54 @@ def adopt_liif_up(ref_liif_up, chanels):
             mod = getattr(mod, p)
         mod._parameters[parts[-1]] = ref_params[name]
     return ours.to(next(ref_liif_up.parameters()).device)
+
+
+def adopt_model(model, ref_module, family="igev", defer_lookup=True, replay=None, encoders=True, corr_stem=True,
+                liif_chanels=None):
+    """Everything this library can take over in one reference model, in one call (INTEGRATION.md section 1 spelled out):
+
+        import models.coreContinuous_IGEV.continuous_IGEVstereo as igev_mod
+        A.adopt_model(model.module, igev_mod, "igev", replay=True)
+
+    * rebinds the module-level names (``install_into_reference``; ``defer_lookup``: lookups fused with convc1),
+    * ``model.update_block`` -> adopt_update_block(..., replay=replay),
+    * ``model.liif_up`` -> adopt_liif_up when it is the multi-scale upsampler this library builds (``liif_chanels`` =
+      channel counts of its feature maps in call order; default: from ``model.args`` as continuous_IGEVstereo.py:104-168 /
+      prune_raft_stereo.py:100-189 derive them); variants outside the built set keep the reference module,
+    * ``encoders``: ``model.cnet`` -> adopt_context_encoder, RAFT's ``model.fnet`` -> adopt_feature_encoder,
+    * ``corr_stem`` (IGEV): adopt_corr_stem.
+    Every model built from ``ref_module`` must be adopted (the rebound names are module-wide).  Returns ``model``."""
+    from .extractor import adopt_context_encoder, adopt_feature_encoder
+    igev = family == "igev"
+    if family not in ("igev", "raft"):
+        raise ValueError("family must be 'igev' or 'raft'")
+    install_into_reference(ref_igev_module=ref_module if igev else None, ref_raft_module=None if igev else ref_module,
+                           defer_lookup=defer_lookup)
+    model.update_block = adopt_update_block(model.update_block, family, replay=replay)
+    lu = getattr(model, "liif_up", None)
+    if lu is not None and type(lu).__name__ == "liif_out_multi_scale_Training":
+        if liif_chanels is None:
+            hd = model.args.hidden_dims[2]
+            agg = str(getattr(model.args, "agg_type", "type5"))
+            if "type2" in agg:
+                liif_chanels = [8, 32, 48 + hd]
+            elif any(t in agg for t in ("type1", "type3", "type4", "type5")):
+                liif_chanels = [48 + hd, 32]
+        if liif_chanels is not None:
+            try:
+                model.liif_up = adopt_liif_up(lu, chanels=list(liif_chanels))
+            except (NotImplementedError, RuntimeError):
+                pass                                     # an upsampler variant outside the built set: the reference's stays
+    if encoders:
+        try:
+            model.cnet = adopt_context_encoder(model.cnet)
+        except (TypeError, AttributeError):
+            pass
+        if not igev and hasattr(model, "fnet"):
+            try:
+                model.fnet = adopt_feature_encoder(model.fnet)
+            except TypeError:
+                pass
+    if corr_stem and igev and hasattr(model, "corr_stem") and hasattr(model, "corr_feature_att"):
+        adopt_corr_stem(model, ref_module)
+    return model

@@ -433,3 +433,42 @@ def test_fold_basic_convs_matches_reference_hourglass(A):
     assert sum(1 for m in hg.modules() if type(m).__name__ == "BasicConv") == n_blocks
     with torch.no_grad():
         assert torch.equal(hg(x, feats), want)
+
+
+@pytest.mark.parametrize("family", ["igev", "raft"])
+def test_adopt_model_swaps_everything_in_one_call(A, family):
+    """adopt_model = install_into_reference + adopt_update_block + adopt_liif_up + the encoders (+ adopt_corr_stem) on a real
+    reference model instance (CPU here: only the wiring; tests/test_gpu_dropin.py runs it)."""
+    import contextlib
+    import io
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference tree absent")
+    R = ref_loader.load_models()
+    mod = R.igev_module if family == "igev" else R.raft_module
+    names = ["Combined_Geo_Encoding_Volume", "build_gwc_volume", "context_upsample_multiscale_train", "CorrBlock1D"]
+    saved = {n: getattr(mod, n) for n in names if hasattr(mod, n)}
+    try:
+        torch.manual_seed(0)
+        with contextlib.redirect_stdout(io.StringIO()):
+            model = (R.IGEV if family == "igev" else R.RAFT)(ref_loader.model_args(family)).eval()
+        keys = list(model.state_dict().keys())
+        out = A.adopt_model(model, mod, family, replay=True)
+        assert out is model
+        assert isinstance(model.update_block, A.BasicMultiUpdateBlock) and model.update_block.call_replay is True
+        assert isinstance(model.liif_up, A.liif_out_multi_scale_Training)
+        assert isinstance(model.cnet, A.ContextEncoder)
+        if family == "igev":
+            assert mod.Combined_Geo_Encoding_Volume is A.geometry.Combined_Geo_Encoding_Volume_Deferred
+            assert isinstance(model.corr_stem, A.hotpath.CorrStem) and isinstance(model.corr_feature_att, A.hotpath.CorrFeatureAtt)
+            assert mod.build_gwc_volume is A.submodule.build_gwc_volume_deferred
+        else:
+            assert mod.CorrBlock1D is A.geometry.CorrBlock1D_Deferred
+            assert isinstance(model.fnet, A.FeatureEncoder)
+        assert mod.context_upsample_multiscale_train is A.liif.context_upsample_multiscale_train
+        assert list(model.state_dict().keys()) == keys            # a reference checkpoint still loads unchanged
+        with pytest.raises(ValueError):
+            A.adopt_model(model, mod, "psm")
+    finally:
+        for n, v in saved.items():
+            setattr(mod, n, v)
